@@ -1,0 +1,14 @@
+"""Import shim: the package directory is named ``gnn.cpp_b200`` (after the reference repo), which is
+not a valid Python identifier.  ``import gnn_cpp_b200`` loads that directory as a regular package."""
+import importlib.util
+import os
+import sys
+
+_here = os.path.dirname(os.path.abspath(__file__))
+_pkg_dir = os.path.join(_here, "gnn.cpp_b200")
+_spec = importlib.util.spec_from_file_location(
+    "gnn_cpp_b200", os.path.join(_pkg_dir, "__init__.py"), submodule_search_locations=[_pkg_dir]
+)
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["gnn_cpp_b200"] = _mod
+_spec.loader.exec_module(_mod)

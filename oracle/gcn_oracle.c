@@ -1,0 +1,511 @@
+/* gcn_oracle.c — CPU restatement of walexi/gnn.cpp's GCN hot path (plain C, ctypes-callable).
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs may load this.  The product path (gnn.cpp_b200/, include/) never does.
+ *
+ * PARITY PINNING: every function below is checked against outputs of the reference itself
+ * (oracle/_ref/ref_gcn, built by oracle/build_ref.sh from /root/reference) through the committed
+ * fixtures in tests/golden/ (tests/test_oracle_vs_reference.py).  Exceptions, where the reference has
+ * no working implementation ("parity unpinned" in the reference, pinned by this file only):
+ *   - orc_csc_from_csr, orc_partition_*  (no sparse formats / no multi-GPU in the reference)
+ *   - orc_sgd_step                       (nn::SGD::step segfaults, SURVEY.md bug B4; torch semantics
+ *                                         per include/nn.h:165-167)
+ *   - dZ of the loss                     (nn::cross_entropy_loss backward throws, bug B3; analytic
+ *                                         (softmax - onehot)/N from nn::softmax, src/nn.cpp:270-278)
+ *
+ * "Reference order" = the accumulation order the reference arithmetic uses, so that this file and
+ * ref_gcn agree to the last bit where possible:
+ *   - matmul dot products: k DESCENDING, sequential fp32, no FMA   include/functional.h:432-439 +
+ *     libstdc++ _Expr::sum (valarray_after.h)
+ *   - sum along a dim / whole tensor: ASCENDING sequential fp32     include/functional.h:266-296
+ * Compile with -ffp-contract=off.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+ORC_API int orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+ORC_API void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic inputs.  Counter-based splitmix64 so numpy (gnn.cpp_b200/synth.py), this
+ * file and the C++ driver generate bit-identical problems.
+ * ---------------------------------------------------------------------------------------------- */
+static inline uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static inline uint64_t hash3(uint64_t seed, uint64_t stream, uint64_t i) {
+    return mix64(mix64(seed * 0x9E3779B97F4A7C15ULL + stream * 0xD1B54A32D192ED03ULL) + i);
+}
+ORC_API uint64_t orc_hash3(uint64_t seed, uint64_t stream, uint64_t i) { return hash3(seed, stream, i); }
+
+/* U[lo,hi) floats: 24 random bits -> exact float in [0,1) -> lo + (hi-lo)*u in fp32 */
+ORC_API void orc_synth_uniform(uint64_t seed, uint64_t stream, int64_t n, float lo, float hi, float *out) {
+    const float span = hi - lo;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        float u = (float)(hash3(seed, stream, (uint64_t)i) >> 40) * 0x1p-24f;
+        float t = span * u;
+        out[i] = lo + t;
+    }
+}
+ORC_API void orc_synth_labels(uint64_t seed, uint64_t stream, int64_t n, int32_t C, int32_t *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) out[i] = (int32_t)(hash3(seed, stream, (uint64_t)i) % (uint64_t)C);
+}
+static inline int32_t synth_endpoint(uint64_t h, int32_t N, int powerlaw, uint64_t pa, uint64_t pb) {
+    if (!powerlaw) return (int32_t)(h % (uint64_t)N);
+    /* Chung-Lu style skew: id = floor(N * u^1.5), then an affine bijection scatters hot ids */
+    double x = (double)(h >> 32) * 0x1p-32;
+    double s = sqrt(x);
+    double t = x * s;
+    int64_t id = (int64_t)(t * (double)N);
+    if (id >= N) id = N - 1;
+    return (int32_t)((pa * (uint64_t)id + pb) % (uint64_t)N);
+}
+static uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
+/* E directed entries = npairs undirected pairs, symmetrised: src=[u,v], dst=[v,u].  Self loops and
+ * duplicates are left in on purpose (the structure build must collapse them like graph.cpp:21-75). */
+ORC_API void orc_synth_edges(uint64_t seed, int64_t E, int32_t N, int powerlaw, int32_t *src, int32_t *dst) {
+    int64_t npairs = E / 2;
+    uint64_t pa = 0x9E3779B1ULL % (uint64_t)N;
+    if (pa == 0) pa = 1;
+    while (gcd_u64(pa, (uint64_t)N) != 1) pa++;
+    uint64_t pb = 0x7F4A7C15ULL % (uint64_t)N;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < npairs; k++) {
+        int32_t u = synth_endpoint(hash3(seed, 1, (uint64_t)k), N, powerlaw, pa, pb);
+        int32_t v = synth_endpoint(hash3(seed, 2, (uint64_t)k), N, powerlaw, pa, pb);
+        src[k] = u; dst[k] = v;
+        src[npairs + k] = v; dst[npairs + k] = u;
+    }
+    if (E & 1) { /* odd E: one extra directed entry */
+        src[E - 1] = synth_endpoint(hash3(seed, 1, (uint64_t)npairs), N, powerlaw, pa, pb);
+        dst[E - 1] = synth_endpoint(hash3(seed, 2, (uint64_t)npairs), N, powerlaw, pa, pb);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Structure: COO -> row-major sorted, de-duplicated CSR with the diagonal forced.
+ *   edge_to_adj_mat  (src/graph.cpp:21-44):  A[src*N+dst] = 1  — assignment, duplicates collapse,
+ *                                            row = edge_index[0], col = edge_index[1]
+ *   fill_diagonal_   (include/tensor.h:806-817): diagonal := fill (0 removes loops, 1 adds them)
+ *   adj_to_edge_list (src/graph.cpp:46-67):  row-major scan, keeps int(a)!=0  => rows ascending,
+ *                                            cols ascending inside a row
+ * fill_mode: 0 = diagonal removed, 1 = diagonal present on every row, 2 = leave as given.
+ * Returns nnz; rowptr has N+1 int64 entries; colidx capacity must be >= E + N.
+ * ---------------------------------------------------------------------------------------------- */
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return (x > y) - (x < y);
+}
+static void radix_sort_u64(uint64_t *keys, int64_t n, int bits) {
+    if (n < 4096) { qsort(keys, (size_t)n, 8, cmp_u64); return; }
+    uint64_t *tmp = (uint64_t *)malloc((size_t)n * 8);
+    uint64_t *a = keys, *b = tmp;
+    for (int shift = 0; shift < bits; shift += 16) {
+        int64_t *cnt = (int64_t *)calloc(65537, sizeof(int64_t));
+        for (int64_t i = 0; i < n; i++) cnt[((a[i] >> shift) & 0xFFFF) + 1]++;
+        for (int i = 0; i < 65536; i++) cnt[i + 1] += cnt[i];
+        for (int64_t i = 0; i < n; i++) b[cnt[(a[i] >> shift) & 0xFFFF]++] = a[i];
+        free(cnt);
+        uint64_t *t = a; a = b; b = t;
+    }
+    if (a != keys) memcpy(keys, a, (size_t)n * 8);
+    free(tmp);
+}
+ORC_API int64_t orc_csr_build(const int32_t *src, const int32_t *dst, int64_t E, int32_t N, int fill_mode,
+                              int64_t *rowptr, int32_t *colidx) {
+    int64_t cap = E + (fill_mode == 1 ? N : 0);
+    uint64_t *keys = (uint64_t *)malloc((size_t)(cap > 0 ? cap : 1) * 8);
+    int64_t m = 0;
+    for (int64_t e = 0; e < E; e++) {
+        if (fill_mode == 0 && src[e] == dst[e]) continue;
+        keys[m++] = ((uint64_t)(uint32_t)src[e] << 32) | (uint32_t)dst[e];
+    }
+    if (fill_mode == 1)
+        for (int32_t i = 0; i < N; i++) keys[m++] = ((uint64_t)(uint32_t)i << 32) | (uint32_t)i;
+    radix_sort_u64(keys, m, 64);
+    int64_t nnz = 0;
+    memset(rowptr, 0, (size_t)(N + 1) * 8);
+    for (int64_t i = 0; i < m; i++) {
+        if (i > 0 && keys[i] == keys[i - 1]) continue;
+        int32_t r = (int32_t)(keys[i] >> 32);
+        colidx[nnz++] = (int32_t)(keys[i] & 0xFFFFFFFFu);
+        rowptr[r + 1]++;
+    }
+    for (int32_t r = 0; r < N; r++) rowptr[r + 1] += rowptr[r];
+    free(keys);
+    return nnz;
+}
+
+/* CSR -> CSC (= CSR of the transpose), rows ascending inside each column, and the permutation
+ * perm[k] = CSR position of CSC entry k.  No counterpart in the reference (it transposes the dense
+ * matrix, include/functional.h:330-357; include/operation.h:526-528). */
+ORC_API void orc_csc_from_csr(int32_t N, const int64_t *rowptr, const int32_t *colidx, int64_t *colptr,
+                              int32_t *rowidx, int64_t *perm) {
+    int64_t nnz = rowptr[N];
+    memset(colptr, 0, (size_t)(N + 1) * 8);
+    for (int64_t k = 0; k < nnz; k++) colptr[colidx[k] + 1]++;
+    for (int32_t c = 0; c < N; c++) colptr[c + 1] += colptr[c];
+    int64_t *cur = (int64_t *)malloc((size_t)N * 8);
+    memcpy(cur, colptr, (size_t)N * 8);
+    for (int32_t r = 0; r < N; r++)
+        for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++) {
+            int64_t p = cur[colidx[k]]++;
+            rowidx[p] = r;
+            perm[p] = k;
+        }
+    free(cur);
+}
+
+/* Degree / D^-1/2 / edge values.
+ *   deg  = rowsum(A0 + I)                 src/graph.cpp:178 (sum(-1,true) + 1), exact integer in fp32
+ *   dinv = std::pow(deg, -0.5f)           src/graph.cpp:183 -> include/functional.h:253
+ *   val  = (1 * dinv[r]) * dinv[c]        mode-B composition (A*dinv)*dinv^T, functional.h:189-213 */
+ORC_API void orc_degree_norm(int32_t N, const int64_t *rowptr, const int32_t *colidx, int32_t *deg, float *dinv,
+                             float *val) {
+    for (int32_t r = 0; r < N; r++) {
+        deg[r] = (int32_t)(rowptr[r + 1] - rowptr[r]);
+        dinv[r] = powf((float)deg[r], -0.5f);
+    }
+    if (val)
+        for (int32_t r = 0; r < N; r++)
+            for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++) val[k] = (1.0f * dinv[r]) * dinv[colidx[k]];
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Aggregation  Y[N,F] = Ahat * P   (src/graph.cpp:208 -> include/functional.h:398-441).
+ * Reference order: for each output, columns DESCENDING, fp32 sequential; the dense zeros contribute
+ * +0.0f terms that do not change an fp32 running sum.
+ * order=1: fp64 accumulation (the "exact" variant used at sizes where sequential fp32 is itself
+ * less accurate than 1e-5).
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API void orc_spmm(int32_t N, const int64_t *ptr, const int32_t *idx, const float *val, const float *P,
+                      int64_t ldp, int32_t F, float *Y, int64_t ldy, int order) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int32_t r = 0; r < N; r++) {
+        if (order == 0) {
+            for (int32_t f = 0; f < F; f++) Y[(int64_t)r * ldy + f] = 0.0f;
+            for (int64_t k = ptr[r + 1] - 1; k >= ptr[r]; k--) {
+                const float a = val[k];
+                const float *p = P + (int64_t)idx[k] * ldp;
+                float *y = Y + (int64_t)r * ldy;
+                for (int32_t f = 0; f < F; f++) { float t = p[f] * a; y[f] = y[f] + t; }
+            }
+        } else {
+            double acc[1024];
+            for (int32_t f0 = 0; f0 < F; f0 += 1024) {
+                int32_t fn = F - f0 < 1024 ? F - f0 : 1024;
+                for (int32_t f = 0; f < fn; f++) acc[f] = 0.0;
+                for (int64_t k = ptr[r]; k < ptr[r + 1]; k++) {
+                    const double a = val[k];
+                    const float *p = P + (int64_t)idx[k] * ldp + f0;
+                    for (int32_t f = 0; f < fn; f++) acc[f] += a * (double)p[f];
+                }
+                for (int32_t f = 0; f < fn; f++) Y[(int64_t)r * ldy + f0 + f] = (float)acc[f];
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense feature transforms (nn::Linear, src/nn.cpp:205-211; MatMul::_backward, operation.h:504-534;
+ * Transpose::_backward, operation.h:416-433).  All row-major.
+ *   NT: C[M,N] = A[M,K] * B[N,K]^T     forward  P = H * W^T
+ *   NN: C[M,N] = A[M,K] * B[K,N]       backward dH = dP * W
+ *   TN: C[K1,K2] = A[M,K1]^T * B[M,K2] backward dW = dP^T * H   (reduction over the M rows)
+ * order 0 = reference order (descending reduction index, fp32, no FMA); order 1 = fp64 accumulate.
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API void orc_gemm_nt(int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B, int64_t ldb,
+                         float *C, int64_t ldc, int order) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < M; i++)
+        for (int32_t j = 0; j < N; j++) {
+            const float *a = A + i * lda, *b = B + (int64_t)j * ldb;
+            if (order == 0) {
+                float s = 0.0f;
+                for (int32_t k = K - 1; k >= 0; k--) { float t = b[k] * a[k]; s = s + t; }
+                C[i * ldc + j] = s;
+            } else {
+                double s = 0.0;
+                for (int32_t k = 0; k < K; k++) s += (double)a[k] * (double)b[k];
+                C[i * ldc + j] = (float)s;
+            }
+        }
+}
+ORC_API void orc_gemm_nn(int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B, int64_t ldb,
+                         float *C, int64_t ldc, int order) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < M; i++) {
+        const float *a = A + i * lda;
+        if (order == 0) {
+            for (int32_t j = 0; j < N; j++) {
+                float s = 0.0f;
+                for (int32_t k = K - 1; k >= 0; k--) { float t = B[(int64_t)k * ldb + j] * a[k]; s = s + t; }
+                C[i * ldc + j] = s;
+            }
+        } else {
+            double acc[2048];
+            for (int32_t j = 0; j < N; j++) acc[j] = 0.0;
+            for (int32_t k = 0; k < K; k++) {
+                const double av = a[k];
+                const float *b = B + (int64_t)k * ldb;
+                for (int32_t j = 0; j < N; j++) acc[j] += av * (double)b[j];
+            }
+            for (int32_t j = 0; j < N; j++) C[i * ldc + j] = (float)acc[j];
+        }
+    }
+}
+ORC_API void orc_gemm_tn(int64_t M, int32_t K1, int32_t K2, const float *A, int64_t lda, const float *B, int64_t ldb,
+                         float *C, int64_t ldc, int order) {
+    if (order == 0) {
+        /* out[k1][k2] = sum_{i desc} B[i][k2]*A[i][k1]; running sums updated row by row from the
+         * last row to the first give exactly that order for every output at once. */
+        for (int32_t a = 0; a < K1; a++)
+            for (int32_t b = 0; b < K2; b++) C[(int64_t)a * ldc + b] = 0.0f;
+#pragma omp parallel for schedule(static)
+        for (int32_t a = 0; a < K1; a++) {
+            float *c = C + (int64_t)a * ldc;
+            for (int64_t i = M - 1; i >= 0; i--) {
+                const float av = A[i * lda + a];
+                const float *b = B + i * ldb;
+                for (int32_t j = 0; j < K2; j++) { float t = b[j] * av; c[j] = c[j] + t; }
+            }
+        }
+    } else {
+        double *acc = (double *)calloc((size_t)K1 * K2, sizeof(double));
+#pragma omp parallel
+        {
+            double *loc = (double *)calloc((size_t)K1 * K2, sizeof(double));
+#pragma omp for schedule(static)
+            for (int64_t i = 0; i < M; i++) {
+                const float *a = A + i * lda, *b = B + i * ldb;
+                for (int32_t x = 0; x < K1; x++) {
+                    const double av = a[x];
+                    double *l = loc + (size_t)x * K2;
+                    for (int32_t j = 0; j < K2; j++) l[j] += av * (double)b[j];
+                }
+            }
+#pragma omp critical
+            for (size_t t = 0; t < (size_t)K1 * K2; t++) acc[t] += loc[t];
+            free(loc);
+        }
+        for (int32_t x = 0; x < K1; x++)
+            for (int32_t j = 0; j < K2; j++) C[(int64_t)x * ldc + j] = (float)acc[(size_t)x * K2 + j];
+        free(acc);
+    }
+}
+
+/* Bias add (Add, operation.h:102-129 / functional.h:162-187) and ReLU (nn.cpp:229-237 ->
+ * functional::mask, functional.h:443-471: out = x>0 ? x : 0, NaN -> 0). H may alias Z or be NULL. */
+ORC_API void orc_bias_relu(int64_t N, int32_t F, const float *Y, int64_t ldy, const float *bias, float *Z, int64_t ldz,
+                           float *H, int64_t ldh) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; i++)
+        for (int32_t f = 0; f < F; f++) {
+            float z = Y[i * ldy + f] + (bias ? bias[f] : 0.0f);
+            if (Z) Z[i * ldz + f] = z;
+            if (H) H[i * ldh + f] = z > 0.0f ? z : 0.0f;
+        }
+}
+/* ReLU mask backward (Mask::_backward, operation.h:557-562: grad zeroed where cond<=0) */
+ORC_API void orc_relu_bwd(int64_t N, int32_t F, const float *dH, int64_t ldd, const float *Z, int64_t ldz, float *dZ,
+                          int64_t ldo) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; i++)
+        for (int32_t f = 0; f < F; f++) dZ[i * ldo + f] = Z[i * ldz + f] > 0.0f ? dH[i * ldd + f] : 0.0f;
+}
+/* Bias gradient: db[f] = sum over rows ASCENDING (Add::_backward -> sum_to_size -> sum(0),
+ * tensor.h:618-638, functional.h:285-288). */
+ORC_API void orc_bias_grad(int64_t N, int32_t F, const float *dZ, int64_t ldd, float *db, int order) {
+#pragma omp parallel for schedule(static)
+    for (int32_t f = 0; f < F; f++) {
+        if (order == 0) {
+            float s = 0.0f;
+            for (int64_t i = 0; i < N; i++) s = s + dZ[i * ldd + f];
+            db[f] = s;
+        } else {
+            double s = 0.0;
+            for (int64_t i = 0; i < N; i++) s += (double)dZ[i * ldd + f];
+            db[f] = (float)s;
+        }
+    }
+}
+
+/* Loss: nn::cross_entropy_loss (src/nn.cpp:442-453):
+ *   L = (1/N) * sum_i -log( exp(z[i,y_i]) / (sum_c exp(z[i,c]) + 1e-20) )     no max-shift
+ * dZ (optional) = (softmax(Z) - onehot(y)) / N with softmax = exp(z - log(sum exp z))
+ * (nn::softmax, src/nn.cpp:270-278). Returns the loss. */
+ORC_API float orc_softmax_xent(int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y, float *dZ,
+                               int64_t ldd, int order) {
+    float *li = (float *)malloc((size_t)N * 4);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; i++) {
+        const float *z = Z + i * ldz;
+        float s = 0.0f;
+        for (int32_t c = 0; c < C; c++) s = s + expf(z[c]);
+        float num = expf(z[y[i]]);
+        float q = num / (s + 1e-20f);
+        li[i] = -logf(q);
+        if (dZ) {
+            float ls = logf(s);
+            for (int32_t c = 0; c < C; c++) {
+                float sm = expf(z[c] - ls);
+                if (c == y[i]) sm -= 1.0f;
+                dZ[i * ldd + c] = sm / (float)N;
+            }
+        }
+    }
+    float loss;
+    if (order == 0) {
+        float s = 0.0f;
+        for (int64_t i = 0; i < N; i++) s = s + li[i];
+        loss = s / (float)N;
+    } else {
+        double s = 0.0;
+        for (int64_t i = 0; i < N; i++) s += (double)li[i];
+        loss = (float)(s / (double)N);
+    }
+    free(li);
+    return loss;
+}
+
+/* SGD with torch.optim.SGD semantics (the documented intent of nn::SGD, include/nn.h:165-178; the
+ * reference body, src/nn.cpp:395-417, is broken — bug B4).  `first` = no momentum buffer yet. */
+ORC_API void orc_sgd_step(int64_t n, float *p, const float *g, float *vel, float lr, float momentum, float dampening,
+                          float weight_decay, int nesterov, int first) {
+    for (int64_t i = 0; i < n; i++) {
+        float d = g[i];
+        if (weight_decay != 0.0f) d = d + weight_decay * p[i];
+        if (momentum != 0.0f) {
+            float v = first ? d : momentum * vel[i] + (1.0f - dampening) * d;
+            vel[i] = v;
+            d = nesterov ? d + momentum * v : v;
+        }
+        p[i] = p[i] - lr * d;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * 1-D row partition.  No counterpart in the reference.
+ *   part_ptr[p] = min(N, p * ceil(N/P)),  p = 0..P
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API void orc_partition_ptr(int64_t N, int32_t P, int64_t *part_ptr) {
+    int64_t chunk = (N + P - 1) / P;
+    for (int32_t p = 0; p <= P; p++) {
+        int64_t v = (int64_t)p * chunk;
+        part_ptr[p] = v < N ? v : N;
+    }
+}
+/* Local CSR block of rank p: rows [lo,hi) of the global CSR with rowptr rebased to 0 (column ids stay
+ * global: the halo exchange materialises the full feature matrix in global row order). */
+ORC_API int64_t orc_partition_rows(const int64_t *rowptr, const int32_t *colidx, const float *val, int64_t lo,
+                                   int64_t hi, int64_t *l_rowptr, int32_t *l_colidx, float *l_val) {
+    int64_t base = rowptr[lo];
+    for (int64_t r = lo; r <= hi; r++) l_rowptr[r - lo] = rowptr[r] - base;
+    int64_t n = rowptr[hi] - base;
+    memcpy(l_colidx, colidx + base, (size_t)n * 4);
+    if (val && l_val) memcpy(l_val, val + base, (size_t)n * 4);
+    return n;
+}
+/* interior flag per local row: 1 when every column lies in [lo,hi) (no halo needed) */
+ORC_API int64_t orc_partition_interior(const int64_t *l_rowptr, const int32_t *l_colidx, int64_t nrows, int64_t lo,
+                                       int64_t hi, uint8_t *interior) {
+    int64_t cnt = 0;
+    for (int64_t r = 0; r < nrows; r++) {
+        uint8_t in = 1;
+        for (int64_t k = l_rowptr[r]; k < l_rowptr[r + 1]; k++)
+            if (l_colidx[k] < lo || l_colidx[k] >= hi) { in = 0; break; }
+        interior[r] = in;
+        cnt += in;
+    }
+    return cnt;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole train step (forward + loss + backward + SGD) for an L-layer GCN in the reference's operation
+ * order:  Z_l = Ahat (H_{l-1} W_l^T) + b_l,  H_l = ReLU(Z_l) for l < L;  logits = Z_L.
+ * Outputs (any may be NULL): Zs[l] (N x F_l), dWs[l], dbs[l], dZL. Weights updated in place when lr>0
+ * (plain SGD).  CSC arrays give Ahat^T for the backward aggregation (operation.h:524-531).
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API float orc_gcn_train_step(int32_t N, int32_t L, const int32_t *dims, const int64_t *rowptr,
+                                 const int32_t *colidx, const float *val, const int64_t *colptr, const int32_t *rowidx,
+                                 const float *valT, const float *X, const int32_t *y, float **W, float **b, float **Zs,
+                                 float **dWs, float **dbs, float *dZL, float lr, int order) {
+    float **H = (float **)calloc((size_t)L + 1, sizeof(float *));
+    float **Z = (float **)calloc((size_t)L + 1, sizeof(float *));
+    H[0] = (float *)X;
+    for (int32_t l = 1; l <= L; l++) {
+        int32_t Fi = dims[l - 1], Fo = dims[l];
+        float *P = (float *)malloc((size_t)N * Fo * 4);
+        float *Y = (float *)malloc((size_t)N * Fo * 4);
+        Z[l] = (float *)malloc((size_t)N * Fo * 4);
+        orc_gemm_nt(N, Fo, Fi, H[l - 1], Fi, W[l - 1], Fi, P, Fo, order);
+        orc_spmm(N, rowptr, colidx, val, P, Fo, Fo, Y, Fo, order);
+        if (l < L) {
+            H[l] = (float *)malloc((size_t)N * Fo * 4);
+            orc_bias_relu(N, Fo, Y, Fo, b[l - 1], Z[l], Fo, H[l], Fo);
+        } else {
+            orc_bias_relu(N, Fo, Y, Fo, b[l - 1], Z[l], Fo, NULL, 0);
+        }
+        if (Zs && Zs[l - 1]) memcpy(Zs[l - 1], Z[l], (size_t)N * Fo * 4);
+        free(P); free(Y);
+    }
+    int32_t C = dims[L];
+    float *dZ = (float *)malloc((size_t)N * C * 4);
+    float loss = orc_softmax_xent(N, C, Z[L], C, y, dZ, C, order);
+    if (dZL) memcpy(dZL, dZ, (size_t)N * C * 4);
+    for (int32_t l = L; l >= 1; l--) {
+        int32_t Fi = dims[l - 1], Fo = dims[l];
+        float *db = (float *)malloc((size_t)Fo * 4);
+        float *dW = (float *)malloc((size_t)Fo * Fi * 4);
+        float *dP = (float *)malloc((size_t)N * Fo * 4);
+        orc_bias_grad(N, Fo, dZ, Fo, db, order);
+        orc_spmm(N, colptr, rowidx, valT, dZ, Fo, Fo, dP, Fo, order);
+        /* dW = (H^T dP)^T : out[fo][fi] = sum_i dP[i][fo] * H[i][fi] */
+        orc_gemm_tn(N, Fo, Fi, dP, Fo, H[l - 1], Fi, dW, Fi, order);
+        float *dHprev = NULL;
+        if (l > 1) {
+            dHprev = (float *)malloc((size_t)N * Fi * 4);
+            orc_gemm_nn(N, Fi, Fo, dP, Fo, W[l - 1], Fi, dHprev, Fi, order);
+        }
+        if (dWs && dWs[l - 1]) memcpy(dWs[l - 1], dW, (size_t)Fo * Fi * 4);
+        if (dbs && dbs[l - 1]) memcpy(dbs[l - 1], db, (size_t)Fo * 4);
+        if (lr > 0.0f) {
+            orc_sgd_step((int64_t)Fo * Fi, W[l - 1], dW, NULL, lr, 0, 0, 0, 0, 1);
+            orc_sgd_step(Fo, b[l - 1], db, NULL, lr, 0, 0, 0, 0, 1);
+        }
+        free(db); free(dW); free(dP); free(dZ);
+        dZ = NULL;
+        if (l > 1) {
+            dZ = (float *)malloc((size_t)N * Fi * 4);
+            orc_relu_bwd(N, Fi, dHprev, Fi, Z[l - 1], Fi, dZ, Fi);
+            free(dHprev);
+        }
+    }
+    for (int32_t l = 1; l <= L; l++) { free(Z[l]); if (l < L) free(H[l]); }
+    free(H); free(Z);
+    return loss;
+}

@@ -1,0 +1,254 @@
+"""ctypes front end of the CPU oracle (oracle/gcn_oracle.c).
+
+TEST INFRASTRUCTURE ONLY — importable from tests/, __graft_entry__.smoke() and bench.py's CPU legs.
+The product package (gnn.cpp_b200/) must never import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "gcn_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_max_threads.restype = C.c_int
+        L.orc_hash3.restype = C.c_uint64
+        L.orc_hash3.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+        L.orc_synth_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_float, C.c_float, _f32p]
+        L.orc_synth_labels.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, _i32p]
+        L.orc_synth_edges.argtypes = [C.c_uint64, C.c_int64, C.c_int32, C.c_int, _i32p, _i32p]
+        L.orc_csr_build.restype = C.c_int64
+        L.orc_csr_build.argtypes = [_i32p, _i32p, C.c_int64, C.c_int32, C.c_int, _i64p, _i32p]
+        L.orc_csc_from_csr.argtypes = [C.c_int32, _i64p, _i32p, _i64p, _i32p, _i64p]
+        L.orc_degree_norm.argtypes = [C.c_int32, _i64p, _i32p, _i32p, _f32p, _f32p]
+        L.orc_spmm.argtypes = [C.c_int32, _i64p, _i32p, _f32p, _f32p, C.c_int64, C.c_int32, _f32p, C.c_int64, C.c_int]
+        for fn in (L.orc_gemm_nt, L.orc_gemm_nn):
+            fn.argtypes = [C.c_int64, C.c_int32, C.c_int32, _f32p, C.c_int64, _f32p, C.c_int64, _f32p, C.c_int64, C.c_int]
+        L.orc_gemm_tn.argtypes = [C.c_int64, C.c_int32, C.c_int32, _f32p, C.c_int64, _f32p, C.c_int64, _f32p, C.c_int64, C.c_int]
+        L.orc_bias_relu.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.orc_relu_bwd.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _f32p, C.c_int64, _f32p, C.c_int64]
+        L.orc_bias_grad.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _f32p, C.c_int]
+        L.orc_softmax_xent.restype = C.c_float
+        L.orc_softmax_xent.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _i32p, C.c_void_p, C.c_int64, C.c_int]
+        L.orc_sgd_step.argtypes = [C.c_int64, _f32p, _f32p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.orc_partition_ptr.argtypes = [C.c_int64, C.c_int32, _i64p]
+        L.orc_partition_rows.restype = C.c_int64
+        L.orc_partition_rows.argtypes = [_i64p, _i32p, C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, C.c_void_p]
+        L.orc_partition_interior.restype = C.c_int64
+        L.orc_partition_interior.argtypes = [_i64p, _i32p, C.c_int64, C.c_int64, C.c_int64, _u8p]
+        L.orc_gcn_train_step.restype = C.c_float
+        _LIB = L
+    return _LIB
+
+
+def max_threads():
+    return lib().orc_max_threads()
+
+
+def set_threads(n):
+    lib().orc_set_threads(int(n))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ---- synthetic inputs (must equal gnn.cpp_b200/synth.py bit for bit) ---------------------------------
+def synth_uniform(seed, stream, n, lo, hi):
+    out = np.empty(n, dtype=np.float32)
+    lib().orc_synth_uniform(seed, stream, n, lo, hi, out)
+    return out
+
+
+def synth_labels(seed, stream, n, Cn):
+    out = np.empty(n, dtype=np.int32)
+    lib().orc_synth_labels(seed, stream, n, Cn, out)
+    return out
+
+
+def synth_edges(seed, E, N, powerlaw):
+    src = np.empty(E, dtype=np.int32)
+    dst = np.empty(E, dtype=np.int32)
+    lib().orc_synth_edges(seed, E, N, int(powerlaw), src, dst)
+    return src, dst
+
+
+# ---- structure -------------------------------------------------------------------------------------
+def csr_build(src, dst, N, fill_mode=1):
+    src = np.ascontiguousarray(src, dtype=np.int32)
+    dst = np.ascontiguousarray(dst, dtype=np.int32)
+    E = len(src)
+    rowptr = np.zeros(N + 1, dtype=np.int64)
+    colidx = np.empty(max(E + N, 1), dtype=np.int32)
+    nnz = lib().orc_csr_build(src, dst, E, N, fill_mode, rowptr, colidx)
+    return rowptr, colidx[:nnz].copy()
+
+
+def csc_from_csr(N, rowptr, colidx):
+    nnz = int(rowptr[N])
+    colptr = np.zeros(N + 1, dtype=np.int64)
+    rowidx = np.empty(max(nnz, 1), dtype=np.int32)
+    perm = np.empty(max(nnz, 1), dtype=np.int64)
+    lib().orc_csc_from_csr(N, rowptr, colidx, colptr, rowidx, perm)
+    return colptr, rowidx[:nnz], perm[:nnz]
+
+
+def degree_norm(N, rowptr, colidx):
+    deg = np.empty(N, dtype=np.int32)
+    dinv = np.empty(N, dtype=np.float32)
+    val = np.empty(max(int(rowptr[N]), 1), dtype=np.float32)
+    lib().orc_degree_norm(N, rowptr, colidx, deg, dinv, val)
+    return deg, dinv, val[: int(rowptr[N])]
+
+
+class Graph:
+    """CSR/CSC/normalisation of A_hat = D^-1/2 (A0 + I) D^-1/2 built by the oracle."""
+
+    def __init__(self, src, dst, N):
+        self.N = N
+        self.rowptr, self.colidx = csr_build(src, dst, N, 1)
+        self.nnz = int(self.rowptr[N])
+        self.deg, self.dinv, self.val = degree_norm(N, self.rowptr, self.colidx)
+        self.colptr, self.rowidx, self.perm = csc_from_csr(N, self.rowptr, self.colidx)
+        self.valT = self.val[self.perm].copy()
+
+
+# ---- compute ---------------------------------------------------------------------------------------
+def spmm(N, ptr, idx, val, P, order=0):
+    P = np.ascontiguousarray(P, dtype=np.float32)
+    F = P.shape[1]
+    Y = np.empty((N, F), dtype=np.float32)
+    lib().orc_spmm(N, ptr, np.ascontiguousarray(idx), np.ascontiguousarray(val), P, F, F, Y, F, order)
+    return Y
+
+
+def gemm_nt(A, B, order=0):
+    A = np.ascontiguousarray(A, dtype=np.float32); B = np.ascontiguousarray(B, dtype=np.float32)
+    M, K = A.shape; Nn = B.shape[0]
+    Cm = np.empty((M, Nn), dtype=np.float32)
+    lib().orc_gemm_nt(M, Nn, K, A, K, B, K, Cm, Nn, order)
+    return Cm
+
+
+def gemm_nn(A, B, order=0):
+    A = np.ascontiguousarray(A, dtype=np.float32); B = np.ascontiguousarray(B, dtype=np.float32)
+    M, K = A.shape; Nn = B.shape[1]
+    Cm = np.empty((M, Nn), dtype=np.float32)
+    lib().orc_gemm_nn(M, Nn, K, A, K, B, Nn, Cm, Nn, order)
+    return Cm
+
+
+def gemm_tn(A, B, order=0):
+    A = np.ascontiguousarray(A, dtype=np.float32); B = np.ascontiguousarray(B, dtype=np.float32)
+    M, K1 = A.shape; K2 = B.shape[1]
+    Cm = np.empty((K1, K2), dtype=np.float32)
+    lib().orc_gemm_tn(M, K1, K2, A, K1, B, K2, Cm, K2, order)
+    return Cm
+
+
+def bias_relu(Y, bias):
+    Y = np.ascontiguousarray(Y, dtype=np.float32)
+    N, F = Y.shape
+    Z = np.empty_like(Y); H = np.empty_like(Y)
+    lib().orc_bias_relu(N, F, Y, F, _ptr(bias), _ptr(Z), F, _ptr(H), F)
+    return Z, H
+
+
+def relu_bwd(dH, Z):
+    dH = np.ascontiguousarray(dH, dtype=np.float32); Z = np.ascontiguousarray(Z, dtype=np.float32)
+    N, F = Z.shape
+    out = np.empty_like(Z)
+    lib().orc_relu_bwd(N, F, dH, F, Z, F, out, F)
+    return out
+
+
+def bias_grad(dZ, order=0):
+    dZ = np.ascontiguousarray(dZ, dtype=np.float32)
+    N, F = dZ.shape
+    db = np.empty(F, dtype=np.float32)
+    lib().orc_bias_grad(N, F, dZ, F, db, order)
+    return db
+
+
+def softmax_xent(Z, y, order=0, want_grad=True):
+    Z = np.ascontiguousarray(Z, dtype=np.float32)
+    N, Cn = Z.shape
+    dZ = np.empty_like(Z) if want_grad else None
+    loss = lib().orc_softmax_xent(N, Cn, Z, Cn, np.ascontiguousarray(y, dtype=np.int32), _ptr(dZ), Cn, order)
+    return float(loss), dZ
+
+
+def sgd_step(p, g, vel=None, lr=0.01, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, first=True):
+    lib().orc_sgd_step(p.size, p.reshape(-1), np.ascontiguousarray(g, dtype=np.float32).reshape(-1), _ptr(vel), lr,
+                       momentum, dampening, weight_decay, int(nesterov), int(first))
+
+
+def partition_ptr(N, P):
+    out = np.empty(P + 1, dtype=np.int64)
+    lib().orc_partition_ptr(N, P, out)
+    return out
+
+
+def partition_rows(rowptr, colidx, val, lo, hi):
+    n = int(rowptr[hi] - rowptr[lo])
+    lr = np.empty(hi - lo + 1, dtype=np.int64)
+    lc = np.empty(max(n, 1), dtype=np.int32)
+    lv = np.empty(max(n, 1), dtype=np.float32) if val is not None else None
+    lib().orc_partition_rows(rowptr, colidx, _ptr(val), lo, hi, lr, lc, _ptr(lv))
+    return lr, lc[:n], (lv[:n] if lv is not None else None)
+
+
+def partition_interior(l_rowptr, l_colidx, lo, hi):
+    nrows = len(l_rowptr) - 1
+    flags = np.empty(max(nrows, 1), dtype=np.uint8)
+    cnt = lib().orc_partition_interior(l_rowptr, np.ascontiguousarray(l_colidx), nrows, lo, hi, flags)
+    return flags[:nrows], int(cnt)
+
+
+def train_step(g, dims, X, y, W, b, lr=0.0, order=0):
+    """Full fwd+loss+bwd(+SGD when lr>0, in place on W/b). Returns dict of Z1..ZL, dW*, db*, dZ, loss."""
+    L = len(dims) - 1
+    N = g.N
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    Zs = [np.empty((N, dims[l + 1]), dtype=np.float32) for l in range(L)]
+    dWs = [np.empty((dims[l + 1], dims[l]), dtype=np.float32) for l in range(L)]
+    dbs = [np.empty(dims[l + 1], dtype=np.float32) for l in range(L)]
+    dZL = np.empty((N, dims[L]), dtype=np.float32)
+    PP = C.c_void_p * L
+
+    def arr(lst):
+        return PP(*[a.ctypes.data_as(C.c_void_p) for a in lst])
+
+    for a in list(W) + list(b):
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    fn = lib().orc_gcn_train_step
+    fn.argtypes = [C.c_int32, C.c_int32, _i32p, _i64p, _i32p, _f32p, _i64p, _i32p, _f32p, _f32p, _i32p, PP, PP, PP, PP,
+                   PP, _f32p, C.c_float, C.c_int]
+    loss = fn(N, L, np.asarray(dims, dtype=np.int32), g.rowptr, g.colidx, g.val, g.colptr,
+              np.ascontiguousarray(g.rowidx), g.valT, X, np.ascontiguousarray(y, dtype=np.int32), arr(W), arr(b),
+              arr(Zs), arr(dWs), arr(dbs), dZL, lr, order)
+    out = {"loss": float(loss), "dZ": dZL}
+    for l in range(L):
+        out["Z%d" % (l + 1)] = Zs[l]
+        out["dW%d" % (l + 1)] = dWs[l]
+        out["db%d" % (l + 1)] = dbs[l]
+    return out

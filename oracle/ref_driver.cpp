@@ -1,0 +1,213 @@
+// ref_driver.cpp — drives the UNMODIFIED arithmetic of walexi/gnn.cpp (patched only so it
+// compiles, see oracle/build_ref.sh) to produce oracle outputs for the GCN hot path.
+//
+// TEST INFRASTRUCTURE ONLY: built into oracle/_ref/ref_gcn, used by tests/golden/make_golden.py
+// to pin oracle/gcn_oracle.c, and by `bench.py --impl reference` as the timed CPU reference.
+// Nothing here is on the product path.
+//
+// "Mode B" (SURVEY.md §0.1, §8c): the standard Kipf-Welling layer composed from the reference's
+// own primitives —
+//   A   = graph::edge_to_adj_mat(ei, nullptr, N)           src/graph.cpp:21-44
+//   A->fill_diagonal_(1)                                   include/tensor.h:806-817
+//   deg = A->sum(-1,true); dinv = deg->pow(-0.5)           src/graph.cpp:178,183
+//   Ahat= (A*dinv)*dinv->t()                               functional.h:189-213 (broadcast mul)
+//   Z_l = Ahat->mm(H->mm(W->t())) + b ; H = ReLU(Z)        nn.cpp:205-211, graph.cpp:208, nn.cpp:229-237
+//   loss= nn::cross_entropy_loss(Z_L, y)                   nn.cpp:442-453
+//   dZ_L= (nn::softmax(Z_L) - onehot(y))/N                 nn.cpp:270-278 (reference CE backward throws, bug B3)
+//   Z_L->backward(dZ_L)                                    tensor.h:260-276, operation.h:504-534 ...
+//
+// usage:
+//   ref_gcn structure <problem.gcnp> <out.gcno>
+//   ref_gcn step      <problem.gcnp> <out.gcno>
+//   ref_gcn time      <problem.gcnp> <steps>         (prints one JSON line with per-stage ms)
+#include "graph.h"
+#include "nn.h"
+#include REF_NN_CPP
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+using cyg::tensor;
+using cyg::tptr;
+
+namespace {
+
+struct Problem {
+    int64_t N = 0, E = 0, L = 0;
+    std::vector<int64_t> dims;
+    std::vector<int> src, dst;
+    std::vector<float> X;
+    std::vector<int> y;
+    std::vector<std::vector<float>> W, b;
+};
+
+void rd(std::ifstream &f, void *p, size_t n) {
+    f.read(reinterpret_cast<char *>(p), n);
+    if (!f) { fprintf(stderr, "ref_driver: short read\n"); exit(2); }
+}
+
+Problem load(const char *path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { fprintf(stderr, "ref_driver: cannot open %s\n", path); exit(2); }
+    Problem p;
+    int64_t magic;
+    rd(f, &magic, 8);
+    if (magic != 0x47434E50) { fprintf(stderr, "ref_driver: bad magic\n"); exit(2); }
+    rd(f, &p.N, 8); rd(f, &p.E, 8); rd(f, &p.L, 8);
+    p.dims.resize(p.L + 1);
+    rd(f, p.dims.data(), 8 * (p.L + 1));
+    p.src.resize(p.E); p.dst.resize(p.E);
+    if (p.E) { rd(f, p.src.data(), 4 * p.E); rd(f, p.dst.data(), 4 * p.E); }
+    p.X.resize(p.N * p.dims[0]); rd(f, p.X.data(), 4 * p.X.size());
+    p.y.resize(p.N); rd(f, p.y.data(), 4 * p.N);
+    p.W.resize(p.L); p.b.resize(p.L);
+    for (int64_t l = 0; l < p.L; l++) {
+        p.W[l].resize(p.dims[l + 1] * p.dims[l]); rd(f, p.W[l].data(), 4 * p.W[l].size());
+        p.b[l].resize(p.dims[l + 1]);             rd(f, p.b[l].data(), 4 * p.b[l].size());
+    }
+    return p;
+}
+
+struct Writer {
+    std::ofstream f;
+    explicit Writer(const char *path) : f(path, std::ios::binary) {}
+    void put(const std::string &name, int dtype, const std::vector<int64_t> &shape, const void *data, size_t bytes) {
+        int32_t nl = name.size(), nd = shape.size(), dt = dtype;
+        f.write(reinterpret_cast<char *>(&nl), 4); f.write(name.data(), nl);
+        f.write(reinterpret_cast<char *>(&dt), 4); f.write(reinterpret_cast<char *>(&nd), 4);
+        f.write(reinterpret_cast<const char *>(shape.data()), 8 * nd);
+        f.write(reinterpret_cast<const char *>(data), bytes);
+    }
+    void f32(const std::string &name, const std::valarray<float> &v, std::vector<size_t> shape) {
+        std::vector<int64_t> s(shape.begin(), shape.end());
+        put(name, 0, s, &v[0], 4 * v.size());
+    }
+    void i32(const std::string &name, const std::valarray<int> &v, std::vector<size_t> shape) {
+        std::vector<int64_t> s(shape.begin(), shape.end());
+        put(name, 1, s, v.size() ? &v[0] : nullptr, 4 * v.size());
+    }
+};
+
+tptr<float> make_f(const std::vector<float> &v, std::vector<size_t> dims, bool rg) {
+    auto *d = new std::valarray<float>(v.data(), v.size());
+    return std::make_shared<tensor<float>>(dims, d, rg);
+}
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Ahat built exactly from reference primitives (mode B).
+tptr<float> build_ahat(const Problem &p, tptr<float> *deg_out = nullptr, tptr<float> *dinv_out = nullptr) {
+    auto ei = graph::vec_to_edge_list(p.src, p.dst);
+    auto A = graph::edge_to_adj_mat(*ei, nullptr, p.N);
+    A->fill_diagonal_(1);
+    auto deg = A->sum(-1, true);
+    auto dinv = deg->pow(-0.5);
+    auto Ahat = (A * dinv) * dinv->t(-1, -2);
+    if (deg_out) *deg_out = deg;
+    if (dinv_out) *dinv_out = dinv;
+    return Ahat;
+}
+
+int cmd_structure(const Problem &p, const char *out) {
+    Writer w(out);
+    auto ei = graph::vec_to_edge_list(p.src, p.dst);
+    for (int fill = 0; fill <= 1; fill++) {
+        // add_self_loops = edge_to_adj_mat + fill_diagonal_ + adj_to_edge_list  (src/graph.cpp:68-75)
+        auto [el, ew] = graph::add_self_loops(*ei, nullptr, (float)fill, (int)p.N);
+        w.i32(std::string("coo_fill") + char('0' + fill), *el->data(), el->shape());
+    }
+    tptr<float> deg, dinv;
+    auto Ahat = build_ahat(p, &deg, &dinv);
+    w.f32("deg", *deg->data(), {(size_t)p.N});
+    w.f32("dinv", *dinv->data(), {(size_t)p.N});
+    // nonzero values of Ahat in row-major order (positions == coo_fill1)
+    auto &ad = *Ahat->data();
+    std::vector<float> nz;
+    for (size_t i = 0; i < ad.size(); i++) if (ad[i] != 0.0f) nz.push_back(ad[i]);
+    std::valarray<float> nzv(nz.data(), nz.size());
+    w.f32("ahat_val", nzv, {nz.size()});
+    return 0;
+}
+
+struct StepTimes { double ahat = 0, fwd = 0, loss = 0, bwd = 0; };
+
+int run_step(const Problem &p, Writer *w, StepTimes *tm) {
+    double t0 = now_ms();
+    auto Ahat = build_ahat(p);
+    double t1 = now_ms();
+    size_t N = p.N;
+    std::vector<tptr<float>> W(p.L), B(p.L), Z(p.L);
+    for (int64_t l = 0; l < p.L; l++) {
+        W[l] = make_f(p.W[l], {(size_t)p.dims[l + 1], (size_t)p.dims[l]}, true);
+        B[l] = make_f(p.b[l], {(size_t)p.dims[l + 1]}, true);
+    }
+    auto H = make_f(p.X, {N, (size_t)p.dims[0]}, false);
+    nn::ReLU relu;
+    for (int64_t l = 0; l < p.L; l++) {
+        auto P = H->mm(W[l]->t(-1, -2));      // nn::Linear::forward without bias (nn.cpp:205-211)
+        auto Y = Ahat->mm(P);                 // aggregation (graph.cpp:208)
+        Z[l] = Y + B[l];                      // bias (graph.cpp:188)
+        if (w) w->f32("Z" + std::to_string(l + 1), *Z[l]->data(), Z[l]->shape());
+        if (l + 1 < p.L) H = relu.forward(Z[l]);
+    }
+    double t2 = now_ms();
+    auto logits = Z[p.L - 1];
+    auto *yd = new std::valarray<int>(p.y.data(), p.y.size());
+    auto yt = std::make_shared<tensor<int>>(std::vector<size_t>{N}, yd, false);
+    // loss forward on a detached copy: the reference's own CE backward is broken (bug B3) and
+    // logits must keep fan-out 1 for the reference autograd to be a valid gradient oracle (bug B2).
+    // (a requires_grad leaf clone: cross_entropy_loss dereferences out->grad_fn, nn.cpp:451)
+    auto logits_detached = logits->clone(true);
+    auto loss = nn::cross_entropy_loss(logits_detached, yt);
+    auto S = nn::softmax(logits_detached, -1);
+    size_t C = p.dims[p.L];
+    auto *dz = new std::valarray<float>(*S->data());
+    for (size_t i = 0; i < N; i++) (*dz)[i * C + p.y[i]] -= 1.0f;
+    *dz /= (float)N;
+    auto dZ = std::make_shared<tensor<float>>(std::vector<size_t>{N, C}, dz, false);
+    double t3 = now_ms();
+    logits->backward(dZ);
+    double t4 = now_ms();
+    if (w) {
+        w->f32("loss", *loss->data(), {1});
+        w->f32("dZ", *dZ->data(), dZ->shape());
+        for (int64_t l = 0; l < p.L; l++) {
+            w->f32("dW" + std::to_string(l + 1), *W[l]->grad(), W[l]->shape());
+            w->f32("db" + std::to_string(l + 1), *B[l]->grad(), B[l]->shape());
+        }
+    }
+    if (tm) { tm->ahat += t1 - t0; tm->fwd += t2 - t1; tm->loss += t3 - t2; tm->bwd += t4 - t3; }
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 4) {
+        fprintf(stderr, "usage: %s structure|step|time <problem.gcnp> <out.gcno|steps>\n", argv[0]);
+        return 2;
+    }
+    std::string cmd = argv[1];
+    Problem p = load(argv[2]);
+    if (cmd == "structure") return cmd_structure(p, argv[3]);
+    if (cmd == "step") { Writer w(argv[3]); return run_step(p, &w, nullptr); }
+    if (cmd == "time") {
+        int steps = atoi(argv[3]);
+        StepTimes tm;
+        double t0 = now_ms();
+        for (int s = 0; s < steps; s++) run_step(p, nullptr, &tm);
+        double total = now_ms() - t0;
+        printf("{\"steps\": %d, \"ms_per_step\": %.3f, \"ahat_ms\": %.3f, \"fwd_ms\": %.3f, \"loss_ms\": %.3f, \"bwd_ms\": %.3f, \"threads\": 1}\n",
+               steps, total / steps, tm.ahat / steps, tm.fwd / steps, tm.loss / steps, tm.bwd / steps);
+        return 0;
+    }
+    fprintf(stderr, "unknown command %s\n", cmd.c_str());
+    return 2;
+}

@@ -1,0 +1,109 @@
+"""Pins oracle/gcn_oracle.c against outputs of the REAL reference (tests/golden/*.npz, produced by
+oracle/_ref/ref_gcn via tests/golden/make_golden.py).  CPU only.
+
+The restatement follows the reference's accumulation order, so everything is required BIT-EXACT here
+(far inside the 1e-5 bar the GPU path is held to)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, load_problem
+
+SMALL = ["toy", "tiny", "directed", "tiny_pl", "cora"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_structure_bit_exact(oracle, name):
+    p, g = load_problem(name), load_golden(name)
+    N = p.cfg.N
+    for fill in (0, 1):  # add_self_loops(fillValue=0) removes loops, fillValue=1 adds them (graph.cpp:68-75)
+        rp, ci = oracle.csr_build(p.src, p.dst, N, fill)
+        rows = np.repeat(np.arange(N, dtype=np.int32), np.diff(rp))
+        coo = g["s_coo_fill%d" % fill]
+        assert np.array_equal(coo[0], rows)
+        assert np.array_equal(coo[1], ci)
+    G = oracle.Graph(p.src, p.dst, N)
+    assert np.array_equal(G.deg.astype(np.float32), g["s_deg"])
+    assert np.array_equal(G.dinv, g["s_dinv"])
+    assert np.array_equal(G.val, g["s_ahat_val"])
+
+
+def test_toy_graph_known_answer(oracle):
+    """The reference's own 8-edge fixture (tests/graph.test.cpp:19-20), N=5; SURVEY.md §8c lists the expected COO."""
+    src = np.array([1, 2, 3, 0, 4, 1, 2, 3], dtype=np.int32)
+    dst = np.array([1, 2, 0, 1, 2, 2, 1, 1], dtype=np.int32)
+    rp, ci = oracle.csr_build(src, dst, 5, 2)
+    assert list(np.repeat(np.arange(5), np.diff(rp))) == [0, 1, 1, 2, 2, 3, 3, 4] and list(ci) == [1, 1, 2, 1, 2, 0, 1, 2]
+    rp, ci = oracle.csr_build(src, dst, 5, 0)
+    assert list(np.repeat(np.arange(5), np.diff(rp))) == [0, 1, 2, 3, 3, 4] and list(ci) == [1, 2, 1, 0, 1, 2]
+    rp, ci = oracle.csr_build(src, dst, 5, 1)
+    assert rp[5] == 11
+
+
+@pytest.mark.parametrize("name", SMALL + ["pubmed"])
+def test_train_step_bit_exact(oracle, name):
+    import os
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, name + ".npz")):
+        pytest.skip("fixture %s.npz not generated" % name)
+    p, g = load_problem(name), load_golden(name)
+    G = oracle.Graph(p.src, p.dst, p.cfg.N)
+    W = [w.copy() for w in p.W]
+    b = [x.copy() for x in p.b]
+    out = oracle.train_step(G, p.cfg.dims, p.X, p.y, W, b, lr=0.0, order=0)
+    assert out["loss"] == float(g["loss"][0])
+    for k in g.files:
+        if k.startswith("s_") or k == "loss" or k.endswith("_rows"):
+            continue
+        mine = out[k]
+        if k + "_rows" in g.files:
+            mine = mine[g[k + "_rows"]]
+        assert np.array_equal(mine, g[k]), k
+
+
+@pytest.mark.parametrize("name", ["tiny", "directed", "cora"])
+def test_fp64_order_close_to_reference_order(oracle, name):
+    """order=1 (fp64 accumulate) is the large-size checker; it must agree with the reference order."""
+    from conftest import rel_err
+    p = load_problem(name)
+    G = oracle.Graph(p.src, p.dst, p.cfg.N)
+    o0 = oracle.train_step(G, p.cfg.dims, p.X, p.y, [w.copy() for w in p.W], [x.copy() for x in p.b], order=0)
+    o1 = oracle.train_step(G, p.cfg.dims, p.X, p.y, [w.copy() for w in p.W], [x.copy() for x in p.b], order=1)
+    for k in o0:
+        if k == "loss":
+            assert abs(o0[k] - o1[k]) <= 1e-5 * abs(o0[k])
+        else:
+            assert rel_err(o1[k], o0[k]) <= 1e-5, k
+
+
+def test_csc_is_transpose(oracle):
+    p = load_problem("directed")
+    G = oracle.Graph(p.src, p.dst, p.cfg.N)
+    N = p.cfg.N
+    A = np.zeros((N, N), dtype=np.float32)
+    rows = np.repeat(np.arange(N), np.diff(G.rowptr))
+    A[rows, G.colidx] = G.val
+    At = np.zeros((N, N), dtype=np.float32)
+    cols = np.repeat(np.arange(N), np.diff(G.colptr))
+    At[cols, G.rowidx] = G.valT
+    assert np.array_equal(A.T, At)
+    assert np.all(np.diff(G.rowidx.astype(np.int64))[np.diff(cols) == 0] > 0)  # rows ascending inside a column
+    assert np.array_equal(G.colidx[G.perm], cols)
+
+
+def test_sgd_matches_torch(oracle):
+    """nn::SGD's documented intent is torch.optim.SGD (include/nn.h:165-167); the reference body is broken (B4)."""
+    import torch
+    rng = np.random.default_rng(0)
+    for kw in [dict(), dict(momentum=0.9), dict(momentum=0.9, dampening=0.1, weight_decay=1e-2),
+               dict(momentum=0.8, nesterov=True, weight_decay=1e-3)]:
+        p0 = rng.standard_normal(257).astype(np.float32)
+        tp = torch.tensor(p0.copy(), requires_grad=True)
+        opt = torch.optim.SGD([tp], lr=0.05, **kw)
+        mine = p0.copy()
+        vel = np.zeros_like(mine)
+        for it in range(4):
+            g = rng.standard_normal(257).astype(np.float32)
+            tp.grad = torch.tensor(g)
+            opt.step()
+            oracle.sgd_step(mine, g, vel, lr=0.05, first=(it == 0), **kw)
+            np.testing.assert_allclose(mine, tp.detach().numpy(), rtol=2e-6, atol=1e-7)
