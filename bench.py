@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — full-batch GCN train step (fwd + loss + bwd + SGD) on a synthetic BASELINE.json config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config products] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  Metric: GCN train-step ms (BASELINE.json), lower is better, with the SpMM
+roofline (algorithmic GB/s of all aggregation launches vs measured HBM peak), the CPU baseline timed on the same
+box, and the end-to-end number through the host-buffer C ABI entry point.
+
+N > 1 (launched by torchrun, one rank per GPU): nodes are 1-D row-partitioned; every aggregation all-gathers its
+input rows over NCCL; gradients are all-reduced.  Total work is fixed => "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import gnn_cpp_b200  # noqa: E402,F401
+from gnn_cpp_b200 import synth  # noqa: E402
+
+LR = 0.01
+CPU_SAMPLE_DIV = {"products": 16, "reddit": 32, "arxiv": 1, "pubmed": 1, "cora": 1, "tiny_pl": 1}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_step_ms(cfg_name, steps=1, warmup=0):
+    """The reference's algorithm on the host cores.  cora: the real reference binary (oracle/_ref, 1 thread, dense);
+    every other config: the oracle port (sparse restatement in the reference's operation order, OpenMP over rows)
+    on a 1/div-scale sample of the same generator, time scaled by div."""
+    cfg = synth.CONFIGS[cfg_name]
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_gcn")
+    if cfg_name == "cora" and os.path.exists(ref_bin):
+        from gnn_cpp_b200 import problem_io
+        p = synth.make_problem(cfg)
+        with tempfile.TemporaryDirectory() as td:
+            pin = os.path.join(td, "p.gcnp")
+            problem_io.write_problem(pin, p)
+            out = subprocess.check_output([ref_bin, "time", pin, str(max(1, steps))], text=True)
+        r = json.loads(out.strip().splitlines()[-1])
+        return r["ms_per_step"], {"kind": "reference", "cores": 1,
+                                  "sample": "full Cora-shaped step through the patched reference binary (mode B, dense A_hat rebuilt per step)"}
+    from oracle import oracle as orc
+    div = CPU_SAMPLE_DIV.get(cfg_name, 1)
+    scfg = synth.Config(cfg.name + "_s", max(cfg.N // div, 64), max(cfg.E // div, 2), cfg.dims, cfg.powerlaw, cfg.config_id)
+    p = synth.make_problem(scfg)
+    G = orc.Graph(p.src, p.dst, scfg.N)
+    W = [w.copy() for w in p.W]; b = [x.copy() for x in p.b]
+    cores = orc.max_threads()
+    ts = []
+    for i in range(warmup + max(1, steps)):
+        t0 = time.perf_counter()
+        orc.train_step(G, scfg.dims, p.X, p.y, W, b, lr=LR, order=0)
+        if i >= warmup:
+            ts.append((time.perf_counter() - t0) * 1e3)
+    ms = float(np.mean(ts)) * div
+    sample = ("oracle port (sparse CSR restatement, reference op order, fp32, OpenMP) on a 1/%d-scale sample "
+              "(N=%d, E=%d, nnz=%d, same dims/generator), time x%d" % (div, scfg.N, scfg.E, G.nnz, div)) if div > 1 else \
+             "oracle port (sparse CSR restatement, reference op order, fp32, OpenMP), full workload"
+    return ms, {"kind": "port", "cores": cores, "sample": sample}
+
+
+def workload_desc(cfg, nnz=None):
+    d = {"workload": "%s-shaped synthetic graph, %d-layer GCN full-batch train step (fwd+loss+bwd+SGD)" % (cfg.name, len(cfg.dims) - 1),
+         "nodes": cfg.N, "edges": cfg.E, "dims": cfg.dims, "graph": "power-law (Chung-Lu)" if cfg.powerlaw else "uniform (Erdos-Renyi)",
+         "lr": LR, "optimizer": "SGD"}
+    if nnz is not None:
+        d["nnz_with_self_loops"] = int(nnz)
+    return d
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = synth.CONFIGS[args.config]
+    ms, info = cpu_step_ms(args.config, steps=args.steps if args.config == "cora" else 1, warmup=0)
+    cfgd = workload_desc(cfg)
+    cfgd["parallelism"] = "host CPU"
+    line = {"impl": "reference", "metric": "gcn_train_step_ms", "value": ms, "unit": "ms", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgd,
+            "cpu_baseline": dict(info, value=ms, unit="ms"),
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gnn_cpp_b200 import host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = synth.CONFIGS[args.config]
+    L = len(cfg.dims) - 1
+    t0 = time.time()
+    p = synth.make_problem(cfg)
+    if rank == 0:
+        log("[bench] generated %s: N=%d E=%d in %.1fs" % (cfg.name, cfg.N, cfg.E, time.time() - t0))
+
+    ctx = host.Context(local_rank)
+    if world > 1:
+        ctx.init_comm_from_torch()
+    t0 = time.time()
+    src_d = torch.from_numpy(p.src).to(ctx.device)
+    dst_d = torch.from_numpy(p.dst).to(ctx.device)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    gfull = host.Graph.build(ctx, src_d, dst_d, cfg.N)
+    ev1.record()
+    torch.cuda.synchronize()
+    build_ms = ev0.elapsed_time(ev1)
+    nnz = gfull.nnz
+    del src_d, dst_d
+    if world > 1:
+        chunk = (cfg.N + world - 1) // world
+        lo, hi = min(cfg.N, rank * chunk), min(cfg.N, (rank + 1) * chunk)
+        g = gfull.slice_rows(lo, hi)
+        gfull.close()
+        rows_alloc = chunk
+    else:
+        lo, hi, g, rows_alloc = 0, cfg.N, gfull, cfg.N
+    torch.cuda.empty_cache()
+    n_loc = hi - lo
+    if rank == 0:
+        log("[bench] structure build %.1f ms on device (nnz=%d, symmetric=%s), wall %.1fs" % (build_ms, nnz, gfull.symmetric if world == 1 else "n/a", time.time() - t0))
+
+    ld0 = (cfg.dims[0] + 3) // 4 * 4
+    Xbuf = torch.zeros((rows_alloc, ld0), dtype=torch.float32, device=ctx.device)
+    X = Xbuf[:n_loc, :cfg.dims[0]]
+    X.copy_(torch.from_numpy(p.X[lo:hi]))
+    ybuf = torch.zeros(rows_alloc, dtype=torch.int32, device=ctx.device)
+    ybuf[:n_loc].copy_(torch.from_numpy(p.y[lo:hi]))
+    model = host.GCN(ctx, g, cfg.dims)
+    model.set_option("precision", args.precision)
+    model.set_params(p.W, p.b)
+    loss_d = torch.zeros(1, dtype=torch.float32, device=ctx.device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=ctx.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    step = lambda: model.train_step(X, ybuf, LR, loss_d)  # noqa: E731
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    total_ms = timed(step, args.steps)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    final_loss = float(loss_d.cpu()[0])
+
+    # per-class device time (CUDA events around every launch group inside the trainer), separate pass
+    model.set_option("profile", 1)
+    bd_acc = None
+    nprof = max(2, min(args.steps, 5))
+    for _ in range(nprof):
+        step()
+        bd = model.breakdown()
+        bd_acc = bd if bd_acc is None else {k: bd_acc[k] + bd[k] for k in bd}
+    model.set_option("profile", 0)
+    bd = {k: v / nprof for k, v in bd_acc.items()}
+    st = model.stats()
+    peak, peak_src = peaks()
+    spmm_gbs = st["spmm_alg_bytes"] / (bd["spmm"] * 1e-3) / 1e9 if bd["spmm"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.config)
+
+    # end to end through the host-buffer entry point: H2D of the step's inputs (pinned) + step + D2H of the loss
+    Xh = torch.from_numpy(np.ascontiguousarray(p.X[lo:hi])).pin_memory()
+    yh = torch.from_numpy(np.ascontiguousarray(p.y[lo:hi])).pin_memory()
+    e2e_fn = lambda: model.train_step_host(Xh, yh, LR)  # noqa: E731
+    e2e_fn()
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_fn()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=ctx.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cms, info = cpu_step_ms(args.config)
+            cpu = dict(info, value=cms, unit="ms")
+        cfgd = workload_desc(cfg, nnz)
+        cfgd.update({"parallelism": "1-D row partition x%d, NCCL all-gather of aggregation inputs + grad all-reduce" % world if world > 1 else "single GPU",
+                     "l2_policy": "working set (feature matrices %.1f GB) larger than L2; no flush needed" % (cfg.N * max(cfg.dims) * 4 / 1e9)
+                     if cfg.N * max(cfg.dims) * 4 > 2.5e8 else "small working set (L2-resident): launch-bound config",
+                     "gemm_precision": "fp32 FMA" if args.precision == 0 else "3xTF32 tcgen05",
+                     "spmm_launches_per_step": st["n_spmm"], "structure_build_ms": build_ms, "final_loss": final_loss})
+        line = {"metric": "gcn_train_step_ms", "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgd,
+                "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel (all aggregation launches of one step, per rank)",
+                             "achieved": spmm_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                             "frac": spmm_gbs / peak, "traffic": traffic,
+                             "alg_bytes_per_step": st["spmm_alg_bytes"], "spmm_ms_per_step": bd["spmm"]},
+                "breakdown_ms": bd,
+                "gemm_tflops": st["gemm_flops"] / (bd["gemm"] * 1e-3) / 1e12 if bd["gemm"] > 0 else None,
+                "cpu_baseline": cpu,
+                "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(Xh.numel() * 4 + yh.numel() * 4),
+                        "d2h_bytes_per_step": 4, "api": "gnn_gcn_train_step_h (pinned host buffers)"},
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    model.close(); g.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="products", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--precision", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

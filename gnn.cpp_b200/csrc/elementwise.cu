@@ -1,0 +1,329 @@
+// elementwise.cu — epilogue, loss, optimiser and cyg::tensor-surface kernels (K7, K8, K9).
+// All HBM-bound streaming kernels: grid-stride over whole waves of the SMs, fixed-order reductions
+// (per-block partials combined by one block) so results are deterministic run to run.
+#include "common.cuh"
+
+namespace gnn {
+
+static inline unsigned stream_grid(gnn_ctx *ctx, int64_t n, int threads, int per_thread = 4) {
+    int64_t want = ceil_div(n, (int64_t)threads * per_thread);
+    int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (want < 1) want = 1;
+    return (unsigned)(want < cap ? want : cap);
+}
+
+__global__ void fill_kernel(float *__restrict__ p, float v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void bias_relu_kernel(int64_t N, int32_t F, const float *__restrict__ Y, int64_t ldy,
+                                 const float *__restrict__ bias, int relu, float *__restrict__ out, int64_t ldo) {
+    const int64_t total = N * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / F;
+        const int32_t c = (int32_t)(i - r * F);
+        float v = Y[r * ldy + c];
+        if (bias) v += bias[c];
+        if (relu) v = v > 0.f ? v : 0.f;
+        out[r * ldo + c] = v;
+    }
+}
+
+__global__ void relu_bwd_kernel(int64_t N, int32_t F, const float *__restrict__ dH, int64_t ldd,
+                                const float *__restrict__ act, int64_t lda, float *__restrict__ dZ, int64_t ldo) {
+    const int64_t total = N * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / F;
+        const int32_t c = (int32_t)(i - r * F);
+        dZ[r * ldo + c] = act[r * lda + c] > 0.f ? dH[r * ldd + c] : 0.f;
+    }
+}
+
+// column sums, stage 1: block b sums rows [b*rows_per_block, ...) for every column (threads over columns,
+// coalesced across a row); stage 2: one block adds the per-block partials in ascending block order.
+constexpr int CS_THREADS = 256;
+__global__ void __launch_bounds__(CS_THREADS) colsum_partial_kernel(int64_t N, int32_t F, const float *__restrict__ A,
+                                                                    int64_t lda, int64_t rows_per_block,
+                                                                    float *__restrict__ partial) {
+    // 2-D thread layout: tx over columns (32 wide), ty over rows (8 deep); smem combine over ty in fixed order
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(N, r0 + rows_per_block);
+    for (int32_t c0 = 0; c0 < F; c0 += 32) {
+        const int32_t c = c0 + tx;
+        float s = 0.f;
+        if (c < F)
+            for (int64_t r = r0 + ty; r < r1; r += 8) s += A[r * lda + c];
+        red[ty][tx] = s;
+        __syncthreads();
+        if (ty == 0 && c < F) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) t += red[j][tx];
+            partial[(int64_t)blockIdx.x * F + c] = t;
+        }
+        __syncthreads();
+    }
+}
+__global__ void colsum_final_kernel(int32_t F, int nblocks, const float *__restrict__ partial, float *__restrict__ out) {
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= F) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; b++) s += partial[(int64_t)b * F + c];
+    out[c] = s;
+}
+
+// softmax cross-entropy: one warp per row, classes strided over lanes.
+constexpr int XE_THREADS = 256;
+__global__ void __launch_bounds__(XE_THREADS)
+    softmax_xent_kernel(int64_t N, int32_t C, const float *__restrict__ Z, int64_t ldz, const int32_t *__restrict__ y,
+                        float inv_n, float *__restrict__ dZ, int64_t ldd, float *__restrict__ partial) {
+    __shared__ float wsum[XE_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * (XE_THREADS / 32);
+    float local = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * (XE_THREADS / 32) + warp; r < N; r += nwarps) {
+        const float *z = Z + r * ldz;
+        float m = -INFINITY;
+        for (int32_t c = lane; c < C; c += 32) m = fmaxf(m, z[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int32_t c = lane; c < C; c += 32) s += expf(z[c] - m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const int32_t yi = y[r];
+        const float zy = z[yi];
+        // reference: -log( exp(z_y) / (sum exp(z) + 1e-20) )  (src/nn.cpp:446-450), evaluated with the row
+        // max factored out so it cannot overflow: exp(z_y-m) / (sum exp(z-m) + 1e-20*exp(-m))
+        const float eps = (m > -60.f) ? 1e-20f * expf(-m) : INFINITY;
+        const float li = -logf(expf(zy - m) / (s + eps));
+        if (lane == 0) local += li;
+        if (dZ) {
+            const float inv_s = 1.f / s;
+            for (int32_t c = lane; c < C; c += 32) {
+                float p = expf(z[c] - m) * inv_s;       // nn::softmax (src/nn.cpp:270-278)
+                if (c == yi) p -= 1.f;
+                dZ[r * ldd + c] = p * inv_n;
+            }
+        }
+    }
+    if (lane == 0) wsum[warp] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < XE_THREADS / 32; w++) t += wsum[w];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void xent_final_kernel(int nblocks, const float *__restrict__ partial, float inv_n, float *__restrict__ loss) {
+    // one warp, fixed order: lane-strided partial sums then a shuffle tree
+    float s = 0.f;
+    for (int b = threadIdx.x; b < nblocks; b += 32) s += partial[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *loss = s * inv_n;
+}
+
+__global__ void sgd_kernel(int64_t n, float *__restrict__ p, const float *__restrict__ g, float *__restrict__ vel,
+                           float lr, float momentum, float dampening, float wd, int nesterov, int first) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float d = g[i];
+        const float pi = p[i];
+        if (wd != 0.f) d = d + wd * pi;
+        if (momentum != 0.f) {
+            const float v = first ? d : momentum * vel[i] + (1.f - dampening) * d;
+            vel[i] = v;
+            d = nesterov ? d + momentum * v : v;
+        }
+        p[i] = pi - lr * d;
+    }
+}
+
+__global__ void binary_kernel(int op, int64_t rows, int64_t cols, const float *__restrict__ a, int64_t a_rs,
+                              int64_t a_cs, const float *__restrict__ b, int64_t b_rs, int64_t b_cs,
+                              float *__restrict__ out) {
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        const float x = a[r * a_rs + c * a_cs], y = b[r * b_rs + c * b_cs];
+        float v;
+        switch (op) {
+        case GNN_OP_ADD: v = x + y; break;
+        case GNN_OP_MUL: v = x * y; break;
+        case GNN_OP_DIV: v = x / y; break;
+        case GNN_OP_POW: v = powf(x, y); break;
+        default: v = x > y ? 1.f : 0.f; break;
+        }
+        out[i] = v;
+    }
+}
+__global__ void unary_kernel(int op, int64_t n, const float *__restrict__ a, float *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = a[i];
+        out[i] = op == GNN_UOP_EXP ? expf(x) : (op == GNN_UOP_LOG ? logf(x) : -x);
+    }
+}
+__global__ void where_kernel(int64_t n, const float *__restrict__ cond, const float *__restrict__ t,
+                             const float *__restrict__ f, float *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = cond[i] > 0.f ? t[i] : f[i];
+}
+// row sums: one warp per row
+__global__ void rowsum_kernel(int64_t rows, int64_t cols, const float *__restrict__ a, float *__restrict__ out) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= rows) return;
+    float s = 0.f;
+    for (int64_t c = lane; c < cols; c += 32) s += a[w * cols + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[w] = s;
+}
+__global__ void transpose_kernel(int64_t rows, int64_t cols, int64_t tiles_c, const float *__restrict__ a,
+                                 float *__restrict__ out) {
+    __shared__ float tile[32][33];
+    const int64_t c0 = ((int64_t)blockIdx.x % tiles_c) * 32, r0 = ((int64_t)blockIdx.x / tiles_c) * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = a[r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+__global__ void gather_cols_kernel(int64_t rows, int64_t cols, const float *__restrict__ a,
+                                   const int32_t *__restrict__ idx, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) out[i] = a[i * cols + idx[i]];
+}
+
+int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out) {
+    int64_t nblocks = (int64_t)ctx->sm_count * 4;
+    int64_t rows_per_block = ceil_div(N, nblocks);
+    if (rows_per_block < 64) rows_per_block = 64;
+    rows_per_block = round_up(rows_per_block, 8);
+    nblocks = ceil_div(N, rows_per_block);
+    void *ws = nullptr;
+    GNN_TRY(ctx->workspace((size_t)nblocks * F * 4, &ws));
+    colsum_partial_kernel<<<(unsigned)nblocks, CS_THREADS, 0, ctx->stream>>>(N, F, A, lda, rows_per_block, (float *)ws);
+    GNN_LAUNCHED(ctx);
+    colsum_final_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, ctx->stream>>>(F, (int)nblocks, (const float *)ws, out);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+} // namespace gnn
+
+using namespace gnn;
+
+extern "C" {
+
+int gnn_fill_f32(gnn_ctx_t *ctx, float *ptr, float value, int64_t n) {
+    GNN_REQUIRE(ctx && (ptr || n == 0), "gnn_fill_f32: NULL argument");
+    if (n <= 0) return 0;
+    fill_kernel<<<stream_grid(ctx, n, 256), 256, 0, ctx->stream>>>(ptr, value, n);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_bias_relu_fwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *Y, int64_t ldy, const float *bias, int relu,
+                      float *out, int64_t ldo) {
+    GNN_REQUIRE(ctx && Y && out && N > 0 && F > 0, "gnn_bias_relu_fwd: bad argument");
+    bias_relu_kernel<<<stream_grid(ctx, N * F, 256), 256, 0, ctx->stream>>>(N, F, Y, ldy, bias, relu, out, ldo);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_relu_bwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *dH, int64_t ldd, const float *act, int64_t lda,
+                 float *dZ, int64_t ldo) {
+    GNN_REQUIRE(ctx && dH && act && dZ && N > 0 && F > 0, "gnn_relu_bwd: bad argument");
+    relu_bwd_kernel<<<stream_grid(ctx, N * F, 256), 256, 0, ctx->stream>>>(N, F, dH, ldd, act, lda, dZ, ldo);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_bias_grad(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *dZ, int64_t ldd, float *db) {
+    GNN_REQUIRE(ctx && dZ && db && N > 0 && F > 0, "gnn_bias_grad: bad argument");
+    return colsum(ctx, N, F, dZ, ldd, db);
+}
+
+int gnn_softmax_xent(gnn_ctx_t *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
+                     int64_t n_total, float *loss, float *dZ, int64_t ldd) {
+    GNN_REQUIRE(ctx && Z && y && loss, "gnn_softmax_xent: NULL argument");
+    GNN_REQUIRE(N > 0 && C > 0 && ldz >= C, "invalid input, logits must be of rank 2 and targets must be 1D tensor");
+    if (n_total <= 0) n_total = N;
+    int64_t nblocks = ceil_div(N, XE_THREADS / 32);
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (nblocks > cap) nblocks = cap;
+    void *ws = nullptr;
+    GNN_TRY(ctx->workspace((size_t)nblocks * 4, &ws));
+    const float inv_n = 1.0f / (float)n_total;
+    softmax_xent_kernel<<<(unsigned)nblocks, XE_THREADS, 0, ctx->stream>>>(N, C, Z, ldz, y, inv_n, dZ, ldd, (float *)ws);
+    GNN_LAUNCHED(ctx);
+    xent_final_kernel<<<1, 32, 0, ctx->stream>>>((int)nblocks, (const float *)ws, inv_n, loss);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_sgd_step(gnn_ctx_t *ctx, int64_t n, float *p, const float *g, float *vel, float lr, float momentum,
+                 float dampening, float weight_decay, int nesterov, int first) {
+    GNN_REQUIRE(ctx && p && g && n > 0, "gnn_sgd_step: bad argument");
+    GNN_REQUIRE(momentum == 0.f || vel, "gnn_sgd_step: momentum needs a velocity buffer");
+    sgd_kernel<<<stream_grid(ctx, n, 256, 1), 256, 0, ctx->stream>>>(n, p, g, vel, lr, momentum, dampening, weight_decay,
+                                                                   nesterov, first);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_binary_f32(gnn_ctx_t *ctx, int op, int64_t rows, int64_t cols, const float *a, int64_t a_rs, int64_t a_cs,
+                   const float *b, int64_t b_rs, int64_t b_cs, float *out) {
+    GNN_REQUIRE(ctx && a && b && out && rows > 0 && cols > 0 && op >= 0 && op <= GNN_OP_GT, "gnn_binary_f32: bad argument");
+    binary_kernel<<<stream_grid(ctx, rows * cols, 256), 256, 0, ctx->stream>>>(op, rows, cols, a, a_rs, a_cs, b, b_rs,
+                                                                             b_cs, out);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+int gnn_unary_f32(gnn_ctx_t *ctx, int op, int64_t n, const float *a, float *out) {
+    GNN_REQUIRE(ctx && a && out && n > 0 && op >= 0 && op <= GNN_UOP_NEG, "gnn_unary_f32: bad argument");
+    unary_kernel<<<stream_grid(ctx, n, 256), 256, 0, ctx->stream>>>(op, n, a, out);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+int gnn_where_f32(gnn_ctx_t *ctx, int64_t n, const float *cond, const float *t, const float *f, float *out) {
+    GNN_REQUIRE(ctx && cond && t && f && out && n > 0, "gnn_where_f32: bad argument");
+    where_kernel<<<stream_grid(ctx, n, 256), 256, 0, ctx->stream>>>(n, cond, t, f, out);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+int gnn_sum_f32(gnn_ctx_t *ctx, int64_t rows, int64_t cols, const float *a, int dim, float *out) {
+    GNN_REQUIRE(ctx && a && out && rows > 0 && cols > 0, "gnn_sum_f32: bad argument");
+    if (dim == 0) return colsum(ctx, rows, (int32_t)cols, a, cols, out);
+    if (dim == 1) {
+        rowsum_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, ctx->stream>>>(rows, cols, a, out);
+        GNN_LAUNCHED(ctx);
+        return 0;
+    }
+    // all elements: treat as one long column
+    return colsum(ctx, rows * cols, 1, a, 1, out);
+}
+int gnn_transpose_f32(gnn_ctx_t *ctx, int64_t rows, int64_t cols, const float *a, float *out) {
+    GNN_REQUIRE(ctx && a && out && rows > 0 && cols > 0 && a != out, "gnn_transpose_f32: bad argument");
+    const int64_t tiles_c = ceil_div(cols, 32), tiles_r = ceil_div(rows, 32);
+    dim3 block(32, 8);
+    transpose_kernel<<<(unsigned)(tiles_c * tiles_r), block, 0, ctx->stream>>>(rows, cols, tiles_c, a, out);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+int gnn_gather_cols_f32(gnn_ctx_t *ctx, int64_t rows, int64_t cols, const float *a, const int32_t *idx, float *out) {
+    GNN_REQUIRE(ctx && a && idx && out && rows > 0 && cols > 0, "gnn_gather_cols_f32: bad argument");
+    gather_cols_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, ctx->stream>>>(rows, cols, a, idx, out);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+} // extern "C"

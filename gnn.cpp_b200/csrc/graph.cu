@@ -1,0 +1,435 @@
+// graph.cu — device structure build (K1-K3): COO -> CSR (sorted, de-duplicated, diagonal policy),
+// CSR -> CSC + permutation, degree / D^-1/2 / edge values.  Integer results are bit-exact against the
+// CPU oracle, which is itself pinned to the reference's dense round trip (src/graph.cpp:21-75).
+#include "common.cuh"
+
+namespace gnn {
+
+static int bits_for(int64_t n) { // bits to represent values in [0, n)
+    int b = 1;
+    while (((int64_t)1 << b) < n) b++;
+    return b;
+}
+
+__global__ void make_keys_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int64_t E,
+                                 int32_t n_rows, int32_t n_cols, int cb, int add_diag, uint64_t *__restrict__ keys,
+                                 int *__restrict__ err) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < E) {
+        const int32_t r = src[i], c = dst[i];
+        if (r < 0 || r >= n_rows || c < 0 || c >= n_cols) {
+            *err = 1;
+            keys[i] = 0;
+        } else {
+            keys[i] = ((uint64_t)(uint32_t)r << cb) | (uint32_t)c;
+        }
+    } else if (add_diag && i < E + n_rows) {
+        const uint64_t d = (uint64_t)(i - E);
+        keys[i] = (d << cb) | d;
+    }
+}
+
+__global__ void unique_flags_kernel(const uint64_t *__restrict__ keys, int64_t m, int cb, int drop_diag,
+                                    uint32_t *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint64_t k = keys[i];
+    bool keep = (i == 0) || (k != keys[i - 1]);
+    if (drop_diag && (k >> cb) == (k & (((uint64_t)1 << cb) - 1))) keep = false;
+    flags[i] = keep ? 1u : 0u;
+}
+
+// pos has m+1 entries (exclusive scan incl. total): element i was kept iff pos[i+1] != pos[i]
+__global__ void compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pos, int64_t m, int cb,
+                               uint64_t *__restrict__ ukeys, int32_t *__restrict__ colidx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t p = pos[i];
+    if (pos[i + 1] != p) {
+        const uint64_t k = keys[i];
+        ukeys[p] = k;
+        colidx[p] = (int32_t)(k & (((uint64_t)1 << cb) - 1));
+    }
+}
+
+// ptr[r] = first position in sorted `ukeys` whose (key >> shift) & mask... >= r  (lower bound)
+__global__ void lower_bound_kernel(const uint64_t *__restrict__ ukeys, int64_t nnz, int shift, uint64_t field_mask,
+                                   int32_t n, int32_t *__restrict__ ptr) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    int64_t lo = 0, hi = nnz;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const uint64_t f = (ukeys[mid] >> shift) & field_mask;
+        if (f < (uint64_t)r) lo = mid + 1;
+        else hi = mid;
+    }
+    ptr[r] = (int32_t)lo;
+}
+
+__global__ void max_diff_kernel(const int32_t *__restrict__ ptr, int32_t n, int32_t *__restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t d = (r < n) ? ptr[r + 1] - ptr[r] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0 && d > 0) atomicMax(out, d);
+}
+
+// one warp per row: keys[k] = row << cb | col, vals[k] = k
+__global__ void csr_to_keys_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                   int32_t n_rows, int cb, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    const int32_t b = rowptr[w], e = rowptr[w + 1];
+    for (int32_t k = b + lane; k < e; k += 32) {
+        keys[k] = ((uint64_t)(uint32_t)w << cb) | (uint32_t)colidx[k];
+        vals[k] = (uint32_t)k;
+    }
+}
+
+__global__ void unpack_csc_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t nnz,
+                                  int cb, int32_t *__restrict__ rowidx, int32_t *__restrict__ perm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    rowidx[i] = (int32_t)(keys[i] >> cb);
+    perm[i] = (int32_t)vals[i];
+}
+
+__global__ void arrays_equal_kernel(const int32_t *__restrict__ a, const int32_t *__restrict__ b, int64_t n,
+                                    int *__restrict__ differ) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && a[i] != b[i]) *differ = 1;
+}
+
+__global__ void degree_kernel(const int32_t *__restrict__ rowptr, int32_t n, int32_t *__restrict__ deg,
+                              float *__restrict__ dinv) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int32_t d = rowptr[r + 1] - rowptr[r];
+    deg[r] = d;
+    // deg^-1/2, correctly rounded from fp64 (the reference's std::pow(float,-0.5f) is within 1 ulp of this)
+    dinv[r] = d > 0 ? (float)(1.0 / sqrt((double)d)) : 0.0f;
+}
+
+// one warp per row: val[k] = dinv[row] * dinv[col]
+__global__ void edge_val_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                const float *__restrict__ dinv, int32_t n_rows, float *__restrict__ val) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    const int32_t b = rowptr[w], e = rowptr[w + 1];
+    const float dr = dinv[w];
+    for (int32_t k = b + lane; k < e; k += 32) val[k] = dr * dinv[colidx[k]];
+}
+
+__global__ void gather_f32_kernel(const float *__restrict__ src, const int32_t *__restrict__ idx, int64_t n,
+                                  float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+__global__ void to_dense_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                const float *__restrict__ val, int32_t n_rows, float *__restrict__ out, int64_t ld) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    for (int32_t k = rowptr[w] + lane; k < rowptr[w + 1]; k += 32) out[w * ld + colidx[k]] = val ? val[k] : 1.0f;
+}
+
+__global__ void rebase_kernel(const int32_t *__restrict__ in, int64_t n, int32_t base, int32_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] - base;
+}
+
+static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)ceil_div(n > 0 ? n : 1, threads); }
+
+static int finish_stats(gnn_ctx *ctx, gnn_graph *g) {
+    int32_t *d_max = nullptr;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&d_max, 8, ctx->stream));
+    GNN_CHECK_CUDA(cudaMemsetAsync(d_max, 0, 8, ctx->stream));
+    max_diff_kernel<<<grid_for(g->n_rows, 256), 256, 0, ctx->stream>>>(g->rowptr, g->n_rows, d_max);
+    GNN_LAUNCHED(ctx);
+    if (g->colptr) {
+        max_diff_kernel<<<grid_for(g->t_rows, 256), 256, 0, ctx->stream>>>(g->colptr, g->t_rows, d_max + 1);
+        GNN_LAUNCHED(ctx);
+    }
+    int32_t h[2] = {0, 0};
+    GNN_CHECK_CUDA(cudaMemcpyAsync(h, d_max, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    GNN_CHECK_CUDA(cudaFreeAsync(d_max, ctx->stream));
+    g->max_row_nnz = h[0];
+    if (g->colptr) g->max_col_nnz = h[1];
+    return 0;
+}
+
+} // namespace gnn
+
+using namespace gnn;
+
+extern "C" {
+
+int gnn_graph_build(gnn_ctx_t *ctx, const int32_t *src, const int32_t *dst, int64_t E, int32_t N, int fill_mode,
+                    gnn_graph_t **out) {
+    GNN_REQUIRE(ctx && out, "gnn_graph_build: NULL argument");
+    GNN_REQUIRE(N > 0, "dims cannot be empty or zero");
+    GNN_REQUIRE(E >= 0 && fill_mode >= 0 && fill_mode <= 2, "gnn_graph_build: bad E or fill_mode");
+    GNN_REQUIRE(E == 0 || (src && dst), "gnn_graph_build: NULL edge arrays");
+    const int cb = bits_for(N);
+    const int64_t m = E + (fill_mode == 1 ? N : 0);
+    GNN_REQUIRE(m < (int64_t)0x7FFFFFFF, "gnn_graph_build: E + N = %lld exceeds int32 positions", (long long)m);
+    cudaStream_t s = ctx->stream;
+    gnn_graph *g = new gnn_graph();
+    g->n_rows = g->n_cols = N;
+    g->t_rows = N;
+    g->fill_mode = fill_mode;
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->rowptr, (size_t)(N + 1) * 4));
+    if (m == 0) {
+        GNN_CHECK_CUDA(cudaMemsetAsync(g->rowptr, 0, (size_t)(N + 1) * 4, s));
+        GNN_CHECK_CUDA(cudaMalloc((void **)&g->colidx, 4));
+        g->nnz = 0;
+        *out = g;
+        return 0;
+    }
+    uint64_t *keys = nullptr, *ukeys = nullptr;
+    uint32_t *flags = nullptr;
+    int *err_d = nullptr;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&keys, (size_t)m * 8, s));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&flags, (size_t)(m + 2) * 4, s));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&err_d, 4, s));
+    GNN_CHECK_CUDA(cudaMemsetAsync(err_d, 0, 4, s));
+    make_keys_kernel<<<grid_for(m, 256), 256, 0, s>>>(src, dst, E, N, N, cb, fill_mode == 1, keys, err_d);
+    GNN_LAUNCHED(ctx);
+    GNN_TRY(radix_sort_u64(ctx, keys, nullptr, m, 0, 2 * cb));
+    unique_flags_kernel<<<grid_for(m, 256), 256, 0, s>>>(keys, m, cb, fill_mode == 0, flags);
+    GNN_LAUNCHED(ctx);
+    // scan m+1 entries (flags[m] = 0) so that pos[m] = nnz and "kept" == pos[i+1] != pos[i] for every i
+    GNN_CHECK_CUDA(cudaMemsetAsync(flags + m, 0, 8, s));
+    GNN_TRY(exclusive_scan_u32(ctx, flags, flags, m + 1, nullptr));
+    uint32_t h_nnz = 0;
+    int h_err = 0;
+    GNN_CHECK_CUDA(cudaMemcpyAsync(&h_nnz, flags + m, 4, cudaMemcpyDeviceToHost, s));
+    GNN_CHECK_CUDA(cudaMemcpyAsync(&h_err, err_d, 4, cudaMemcpyDeviceToHost, s));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    if (h_err) {
+        cudaFreeAsync(keys, s); cudaFreeAsync(flags, s); cudaFreeAsync(err_d, s);
+        cudaFree(g->rowptr);
+        delete g;
+        // same condition and message as graph::Data's constructor (reference src/graph.cpp:87-88)
+        set_error("invalid input, max value in edge_index should be less than the number of nodes from x");
+        return 2;
+    }
+    g->nnz = h_nnz;
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->colidx, (size_t)(g->nnz ? g->nnz : 1) * 4));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&ukeys, (size_t)(g->nnz ? g->nnz : 1) * 8, s));
+    compact_kernel<<<grid_for(m, 256), 256, 0, s>>>(keys, flags, m, cb, ukeys, g->colidx);
+    GNN_LAUNCHED(ctx);
+    lower_bound_kernel<<<grid_for(N + 1, 256), 256, 0, s>>>(ukeys, g->nnz, cb, ((uint64_t)1 << (64 - cb)) - 1, N,
+                                                           g->rowptr);
+    GNN_LAUNCHED(ctx);
+    GNN_CHECK_CUDA(cudaFreeAsync(keys, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(ukeys, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(flags, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(err_d, s));
+    GNN_TRY(finish_stats(ctx, g));
+    *out = g;
+    return 0;
+}
+
+int gnn_graph_build_h(gnn_ctx_t *ctx, const int32_t *src_h, const int32_t *dst_h, int64_t E, int32_t N, int fill_mode,
+                      gnn_graph_t **out) {
+    int32_t *d = nullptr;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&d, (size_t)(E ? E : 1) * 8, ctx->stream));
+    if (E) {
+        GNN_CHECK_CUDA(cudaMemcpyAsync(d, src_h, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
+        GNN_CHECK_CUDA(cudaMemcpyAsync(d + E, dst_h, (size_t)E * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int r = gnn_graph_build(ctx, d, d + E, E, N, fill_mode, out);
+    cudaFreeAsync(d, ctx->stream);
+    return r;
+}
+
+int gnn_graph_from_csr(gnn_ctx_t *ctx, int32_t n_rows, int32_t n_cols, const int32_t *rowptr, const int32_t *colidx,
+                       const float *val, gnn_graph_t **out) {
+    GNN_REQUIRE(ctx && out && rowptr, "gnn_graph_from_csr: NULL argument");
+    GNN_REQUIRE(n_rows > 0 && n_cols > 0, "dims cannot be empty or zero");
+    cudaStream_t s = ctx->stream;
+    int32_t ends[2];
+    GNN_CHECK_CUDA(cudaMemcpyAsync(&ends[0], rowptr, 4, cudaMemcpyDeviceToHost, s));
+    GNN_CHECK_CUDA(cudaMemcpyAsync(&ends[1], rowptr + n_rows, 4, cudaMemcpyDeviceToHost, s));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    gnn_graph *g = new gnn_graph();
+    g->n_rows = n_rows; g->n_cols = n_cols; g->t_rows = n_cols; g->fill_mode = 2;
+    g->nnz = ends[1] - ends[0];
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->rowptr, (size_t)(n_rows + 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->colidx, (size_t)(g->nnz ? g->nnz : 1) * 4));
+    rebase_kernel<<<grid_for(n_rows + 1, 256), 256, 0, s>>>(rowptr, n_rows + 1, ends[0], g->rowptr);
+    GNN_LAUNCHED(ctx);
+    if (g->nnz) GNN_CHECK_CUDA(cudaMemcpyAsync(g->colidx, colidx + ends[0], (size_t)g->nnz * 4, cudaMemcpyDeviceToDevice, s));
+    if (val) {
+        GNN_CHECK_CUDA(cudaMalloc((void **)&g->val, (size_t)(g->nnz ? g->nnz : 1) * 4));
+        if (g->nnz) GNN_CHECK_CUDA(cudaMemcpyAsync(g->val, val + ends[0], (size_t)g->nnz * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    GNN_TRY(finish_stats(ctx, g));
+    *out = g;
+    return 0;
+}
+
+int gnn_graph_build_csc(gnn_ctx_t *ctx, gnn_graph_t *g) {
+    GNN_REQUIRE(ctx && g, "gnn_graph_build_csc: NULL argument");
+    if (g->colptr) return 0;
+    cudaStream_t s = ctx->stream;
+    const int cb = bits_for(g->n_cols);
+    const int64_t nnz = g->nnz;
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->colptr, (size_t)(g->n_cols + 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->rowidx, (size_t)(nnz ? nnz : 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->perm, (size_t)(nnz ? nnz : 1) * 4));
+    if (nnz == 0) {
+        GNN_CHECK_CUDA(cudaMemsetAsync(g->colptr, 0, (size_t)(g->n_cols + 1) * 4, s));
+        return 0;
+    }
+    uint64_t *keys = nullptr;
+    uint32_t *vals = nullptr;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&keys, (size_t)nnz * 8, s));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&vals, (size_t)nnz * 4, s));
+    csr_to_keys_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, s>>>(g->rowptr, g->colidx, g->n_rows, cb, keys,
+                                                                              vals);
+    GNN_LAUNCHED(ctx);
+    // CSR order is (row, col) ascending; a STABLE sort on the column bits alone yields (col, row) ascending
+    GNN_TRY(radix_sort_u64(ctx, keys, vals, nnz, 0, cb));
+    unpack_csc_kernel<<<grid_for(nnz, 256), 256, 0, s>>>(keys, vals, nnz, cb, g->rowidx, g->perm);
+    GNN_LAUNCHED(ctx);
+    lower_bound_kernel<<<grid_for(g->n_cols + 1, 256), 256, 0, s>>>(keys, nnz, 0, ((uint64_t)1 << cb) - 1, g->n_cols,
+                                                                   g->colptr);
+    GNN_LAUNCHED(ctx);
+    GNN_CHECK_CUDA(cudaFreeAsync(keys, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(vals, s));
+    // structural symmetry: CSC arrays identical to CSR arrays -> alias them (halves index traffic in L2)
+    if (g->n_rows == g->n_cols) {
+        int *differ = nullptr, h = 0;
+        GNN_CHECK_CUDA(cudaMallocAsync((void **)&differ, 4, s));
+        GNN_CHECK_CUDA(cudaMemsetAsync(differ, 0, 4, s));
+        arrays_equal_kernel<<<grid_for(g->n_rows + 1, 256), 256, 0, s>>>(g->rowptr, g->colptr, g->n_rows + 1, differ);
+        GNN_LAUNCHED(ctx);
+        arrays_equal_kernel<<<grid_for(nnz, 256), 256, 0, s>>>(g->colidx, g->rowidx, nnz, differ);
+        GNN_LAUNCHED(ctx);
+        GNN_CHECK_CUDA(cudaMemcpyAsync(&h, differ, 4, cudaMemcpyDeviceToHost, s));
+        GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+        GNN_CHECK_CUDA(cudaFreeAsync(differ, s));
+        g->symmetric = (h == 0);
+    }
+    g->nnz_t = g->nnz;
+    GNN_TRY(finish_stats(ctx, g));
+    return 0;
+}
+
+int gnn_graph_normalize(gnn_ctx_t *ctx, gnn_graph_t *g) {
+    GNN_REQUIRE(ctx && g, "gnn_graph_normalize: NULL argument");
+    GNN_REQUIRE(g->n_rows == g->n_cols, "gnn_graph_normalize: needs the square (global) graph");
+    cudaStream_t s = ctx->stream;
+    const int64_t nnz = g->nnz ? g->nnz : 1;
+    if (!g->deg) GNN_CHECK_CUDA(cudaMalloc((void **)&g->deg, (size_t)g->n_rows * 4));
+    if (!g->dinv) GNN_CHECK_CUDA(cudaMalloc((void **)&g->dinv, (size_t)g->n_rows * 4));
+    if (!g->val) GNN_CHECK_CUDA(cudaMalloc((void **)&g->val, (size_t)nnz * 4));
+    degree_kernel<<<grid_for(g->n_rows, 256), 256, 0, s>>>(g->rowptr, g->n_rows, g->deg, g->dinv);
+    GNN_LAUNCHED(ctx);
+    edge_val_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, s>>>(g->rowptr, g->colidx, g->dinv, g->n_rows,
+                                                                           g->val);
+    GNN_LAUNCHED(ctx);
+    if (g->colptr && !g->valT) {
+        GNN_CHECK_CUDA(cudaMalloc((void **)&g->valT, (size_t)nnz * 4));
+        gather_f32_kernel<<<grid_for(g->nnz, 256), 256, 0, s>>>(g->val, g->perm, g->nnz, g->valT);
+        GNN_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+int gnn_graph_destroy(gnn_ctx_t *ctx, gnn_graph_t *g) {
+    if (!g) return 0;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(g->rowptr); cudaFree(g->colidx); cudaFree(g->val);
+    cudaFree(g->colptr); cudaFree(g->rowidx); cudaFree(g->perm); cudaFree(g->valT);
+    cudaFree(g->deg); cudaFree(g->dinv);
+    cudaFree(g->split_items_csr); cudaFree(g->split_items_csc);
+    delete g;
+    return 0;
+}
+
+int64_t gnn_graph_nnz(const gnn_graph_t *g) { return g ? g->nnz : -1; }
+int32_t gnn_graph_rows(const gnn_graph_t *g) { return g ? g->n_rows : -1; }
+int32_t gnn_graph_cols(const gnn_graph_t *g) { return g ? g->n_cols : -1; }
+int gnn_graph_is_symmetric(const gnn_graph_t *g) { return g && g->symmetric; }
+
+int gnn_graph_export_h(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t *rowptr_h, int32_t *colidx_h, float *val_h,
+                       int32_t *colptr_h, int32_t *rowidx_h, int32_t *perm_h, float *valT_h, int32_t *deg_h,
+                       float *dinv_h) {
+    GNN_REQUIRE(ctx && g, "gnn_graph_export_h: NULL argument");
+    cudaStream_t s = ctx->stream;
+    const size_t nz = (size_t)g->nnz;
+#define EXPORT(dst, srcp, bytes, what)                                                          \
+    if (dst) {                                                                                  \
+        GNN_REQUIRE((srcp) != nullptr, "gnn_graph_export_h: %s not built", what);               \
+        if (bytes) GNN_CHECK_CUDA(cudaMemcpyAsync(dst, srcp, bytes, cudaMemcpyDeviceToHost, s)); \
+    }
+    EXPORT(rowptr_h, g->rowptr, (size_t)(g->n_rows + 1) * 4, "rowptr");
+    EXPORT(colidx_h, g->colidx, nz * 4, "colidx");
+    EXPORT(val_h, g->val, nz * 4, "val");
+    EXPORT(colptr_h, g->colptr, (size_t)(g->t_rows + 1) * 4, "colptr (call gnn_graph_build_csc)");
+    EXPORT(rowidx_h, g->rowidx, nz * 4, "rowidx (call gnn_graph_build_csc)");
+    EXPORT(perm_h, g->perm, nz * 4, "perm (call gnn_graph_build_csc)");
+    EXPORT(valT_h, g->valT, nz * 4, "valT (call gnn_graph_build_csc then gnn_graph_normalize)");
+    EXPORT(deg_h, g->deg, (size_t)g->n_rows * 4, "deg (call gnn_graph_normalize)");
+    EXPORT(dinv_h, g->dinv, (size_t)g->n_rows * 4, "dinv (call gnn_graph_normalize)");
+#undef EXPORT
+    GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int gnn_graph_to_dense(gnn_ctx_t *ctx, const gnn_graph_t *g, int weighted, float *out, int64_t ld) {
+    GNN_REQUIRE(ctx && g && out, "gnn_graph_to_dense: NULL argument");
+    GNN_REQUIRE(!weighted || g->val, "gnn_graph_to_dense: values not built (call gnn_graph_normalize)");
+    GNN_CHECK_CUDA(cudaMemset2DAsync(out, (size_t)ld * 4, 0, (size_t)g->n_cols * 4, g->n_rows, ctx->stream));
+    to_dense_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, ctx->stream>>>(g->rowptr, g->colidx,
+                                                                                    weighted ? g->val : nullptr,
+                                                                                    g->n_rows, out, ld);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_partition_ptr_h(int64_t N, int32_t P, int64_t *part_ptr_h) {
+    GNN_REQUIRE(N > 0 && P > 0 && part_ptr_h, "gnn_partition_ptr_h: bad argument");
+    const int64_t chunk = (N + P - 1) / P;
+    for (int32_t p = 0; p <= P; p++) {
+        const int64_t v = (int64_t)p * chunk;
+        part_ptr_h[p] = v < N ? v : N;
+    }
+    return 0;
+}
+
+int gnn_graph_slice_rows(gnn_ctx_t *ctx, const gnn_graph_t *g, int64_t lo, int64_t hi, gnn_graph_t **out) {
+    GNN_REQUIRE(ctx && g && out, "gnn_graph_slice_rows: NULL argument");
+    GNN_REQUIRE(0 <= lo && lo < hi && hi <= g->n_rows, "gnn_graph_slice_rows: bad range [%lld,%lld)", (long long)lo,
+                (long long)hi);
+    GNN_REQUIRE(g->n_rows == g->n_cols, "gnn_graph_slice_rows: needs the square (global) graph");
+    gnn_graph *l = nullptr;
+    // forward block: rows [lo,hi) of A_hat (global columns)
+    GNN_TRY(gnn_graph_from_csr(ctx, (int32_t)(hi - lo), g->n_cols, g->rowptr + lo, g->colidx, g->val, &l));
+    // backward block: rows [lo,hi) of A_hat^T = CSC columns [lo,hi) (global row ids)
+    if (g->colptr) {
+        gnn_graph *t = nullptr;
+        const int32_t *tptr = g->symmetric ? g->rowptr : g->colptr;
+        const int32_t *tidx = g->symmetric ? g->colidx : g->rowidx;
+        const float *tval = g->symmetric ? g->val : g->valT;
+        GNN_TRY(gnn_graph_from_csr(ctx, (int32_t)(hi - lo), g->n_rows, tptr + lo, tidx, tval, &t));
+        l->colptr = t->rowptr; l->rowidx = t->colidx; l->valT = t->val;
+        l->max_col_nnz = t->max_row_nnz;
+        l->t_rows = t->n_rows;
+        l->nnz_t = t->nnz;
+        t->rowptr = nullptr; t->colidx = nullptr; t->val = nullptr;
+        delete t;
+    }
+    *out = l;
+    return 0;
+}
+
+} // extern "C"

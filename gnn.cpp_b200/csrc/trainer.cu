@@ -1,0 +1,440 @@
+// trainer.cu — fused full-batch GCN train step (forward + loss + backward + SGD) over preallocated device
+// buffers: the launch sequence a main.cpp loop over graph::GCNConv / nn::cross_entropy_loss / nn::SGD issues
+// (SURVEY.md §3.5), as one fixed, CUDA-graph-capturable schedule.
+//
+// Layer l (1..L):  Z_l = A_hat (H_{l-1} W_l^T) + b_l ,  H_l = ReLU(Z_l) for l < L, logits = Z_L.
+// Because A_hat (H W^T) == (A_hat H) W^T, each layer aggregates at the narrower width:
+//   TF (transform first, F_l <= F_{l-1}):  P = H W^T ;            H_l = relu(A_hat P + b)      [GEMM, SpMM+epilogue]
+//       backward: dP = A_hat^T dZ ; dW = dP^T H_{l-1} ; dZ_{l-1} = (dP W) . [H_{l-1} > 0]
+//   AF (aggregate first, F_{l-1} < F_l):   M = A_hat H_{l-1} ;    H_l = relu(M W^T + b)        [SpMM, GEMM+epilogue]
+//       backward: dW = dZ^T M ; dM = dZ W ; dZ_{l-1} = (A_hat^T dM) . [H_{l-1} > 0]
+//       (for l = 1 no input gradient is needed, so an AF first layer has NO backward aggregation)
+// Row-partitioned multi-GPU (graph with n_rows < n_cols): every aggregation input is all-gathered into a
+// global-row-order buffer first; weight/bias gradients and the loss are all-reduced in one slab.
+#include "common.cuh"
+
+namespace gnn {
+int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out);
+}
+
+struct gnn_gcn {
+    const gnn_graph *g = nullptr;
+    int32_t L = 0;
+    std::vector<int32_t> dims, ld;   // F_l and padded leading dimension (multiple of 4)
+    std::vector<char> agg_first;     // per layer (index 1..L)
+    int64_t n_loc = 0, n_glob = 0, chunk = 0; // local rows, global nodes, rows per rank (dist)
+    bool dist = false;
+    // parameter slab: [W_1, b_1, ..., W_L, b_L] ; gradient slab same layout + 1 float (local loss sum / N)
+    float *params = nullptr, *grads = nullptr, *vel = nullptr;
+    int64_t n_params = 0;
+    std::vector<int64_t> w_off, b_off;
+    // activations
+    std::vector<float *> H;  // H[l], l = 1..L  [n_loc, ld[l]]
+    std::vector<float *> M;  // aggregated inputs of AF layers [n_loc, ld[l-1]]
+    float *S1 = nullptr, *G0 = nullptr, *G1 = nullptr; // scratch [n_loc, maxld]
+    float *AG = nullptr;                                 // all-gather buffer [world*chunk, maxld] (dist)
+    float *Xd = nullptr;                                 // staged features for *_h entry points
+    int32_t *yd = nullptr;
+    const int32_t *last_y = nullptr;
+    float *loss_d = nullptr;
+    int32_t maxld = 0;
+    // options
+    int precision = 0, profile = 0;
+    float momentum = 0.f, dampening = 0.f, weight_decay = 0.f;
+    int nesterov = 0;
+    int64_t steps = 0;
+    // stats
+    double alg_bytes = 0, gemm_flops = 0;
+    int32_t n_spmm = 0;
+    // profiling
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    size_t span_used = 0;
+    double breakdown[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace gnn {
+
+enum { CLS_SPMM = 0, CLS_GEMM = 1, CLS_LOSS = 2, CLS_BIAS = 3, CLS_SGD = 4, CLS_OTHER = 5 };
+
+struct Prof {
+    gnn_ctx *ctx;
+    gnn_gcn *m;
+    int idx = -1;
+    Prof(gnn_ctx *c, gnn_gcn *mm, int cls) : ctx(c), m(mm) {
+        if (!m->profile) return;
+        if (m->span_used == m->spans.size()) {
+            gnn_gcn::Span s;
+            s.cls = cls;
+            cudaEventCreate(&s.a);
+            cudaEventCreate(&s.b);
+            m->spans.push_back(s);
+        }
+        idx = (int)m->span_used++;
+        m->spans[idx].cls = cls;
+        cudaEventRecord(m->spans[idx].a, ctx->stream);
+    }
+    ~Prof() {
+        if (idx >= 0) cudaEventRecord(m->spans[idx].b, ctx->stream);
+    }
+};
+
+static double spmm_alg_bytes(int64_t n_out, int64_t nnz, int32_t F) {
+    // B_alg = 4(N+1) + nnz*(8 + 4F) + 4*N*F
+    return 4.0 * (n_out + 1) + (double)nnz * (8.0 + 4.0 * F) + 4.0 * n_out * F;
+}
+
+static void recompute_stats(gnn_gcn *m) {
+    // statistics for the roofline line: every SpMM of one train step
+    const gnn_graph *g = m->g;
+    m->alg_bytes = 0; m->gemm_flops = 0; m->n_spmm = 0;
+    for (int32_t l = 1; l <= m->L; l++) {
+        const int32_t Fi = m->dims[l - 1], Fo = m->dims[l];
+        if (m->agg_first[l]) {
+            m->alg_bytes += spmm_alg_bytes(m->n_loc, g->nnz, Fi); m->n_spmm++;
+            if (l > 1) { m->alg_bytes += spmm_alg_bytes(m->n_loc, g->nnz_t, Fi); m->n_spmm++; }
+        } else {
+            m->alg_bytes += spmm_alg_bytes(m->n_loc, g->nnz, Fo); m->n_spmm++;
+            m->alg_bytes += spmm_alg_bytes(m->n_loc, g->nnz_t, Fo); m->n_spmm++;
+        }
+        m->gemm_flops += 2.0 * m->n_loc * Fi * Fo * (l > 1 ? 3 : 2);
+    }
+}
+
+// aggregation input must be visible in global row order: all-gather under row partitioning
+static int gather_input(gnn_ctx *ctx, gnn_gcn *m, const float *local, int32_t ldw, const float **global_out) {
+    if (!m->dist) {
+        *global_out = local;
+        return 0;
+    }
+    Prof p(ctx, m, CLS_OTHER);
+    GNN_TRY(gnn_allgather_rows(ctx, local, m->AG, m->chunk, ldw));
+    *global_out = m->AG;
+    return 0;
+}
+
+static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
+    const gnn_graph *g = m->g;
+    const float *Hin = X;
+    int64_t ld_in = ldx;
+    for (int32_t l = 1; l <= m->L; l++) {
+        const int32_t Fi = m->dims[l - 1], Fo = m->dims[l];
+        const float *W = m->params + m->w_off[l], *b = m->params + m->b_off[l];
+        const int relu = l < m->L;
+        if (m->agg_first[l]) {
+            const float *src = nullptr;
+            // the gather needs a dense [chunk, ld] block; X may have ldx != ld[0] only in single-GPU mode
+            GNN_TRY(gather_input(ctx, m, Hin, (int32_t)ld_in, &src));
+            {
+                Prof p(ctx, m, CLS_SPMM);
+                GNN_TRY(gnn_spmm_fwd(ctx, g, src, ld_in, Fi, m->M[l], m->ld[l - 1], nullptr, 0, nullptr, 0, 1));
+            }
+            Prof p(ctx, m, CLS_GEMM);
+            GNN_TRY(gnn_gemm_nt(ctx, m->n_loc, Fo, Fi, m->M[l], m->ld[l - 1], W, Fi, m->H[l], m->ld[l], b, relu,
+                                m->precision));
+        } else {
+            {
+                Prof p(ctx, m, CLS_GEMM);
+                GNN_TRY(gnn_gemm_nt(ctx, m->n_loc, Fo, Fi, Hin, ld_in, W, Fi, m->S1, m->ld[l], nullptr, 0,
+                                    m->precision));
+            }
+            const float *src = nullptr;
+            GNN_TRY(gather_input(ctx, m, m->S1, m->ld[l], &src));
+            Prof p(ctx, m, CLS_SPMM);
+            GNN_TRY(gnn_spmm_fwd(ctx, g, src, m->ld[l], Fo, m->H[l], m->ld[l], b, relu, nullptr, 0, 1));
+        }
+        Hin = m->H[l];
+        ld_in = m->ld[l];
+    }
+    return 0;
+}
+
+static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
+    const gnn_graph *g = m->g;
+    float *dZ = m->G0, *dNext = m->G1;
+    for (int32_t l = m->L; l >= 1; l--) {
+        const int32_t Fi = m->dims[l - 1], Fo = m->dims[l];
+        const float *W = m->params + m->w_off[l];
+        float *dW = m->grads + m->w_off[l], *db = m->grads + m->b_off[l];
+        const float *Hin = l > 1 ? m->H[l - 1] : X;
+        const int64_t ld_in = l > 1 ? m->ld[l - 1] : ldx;
+        {
+            Prof p(ctx, m, CLS_BIAS);
+            GNN_TRY(colsum(ctx, m->n_loc, Fo, dZ, m->ld[l], db));
+        }
+        if (m->agg_first[l]) {
+            {
+                Prof p(ctx, m, CLS_GEMM);
+                GNN_TRY(gnn_gemm_tn(ctx, m->n_loc, Fo, Fi, dZ, m->ld[l], m->M[l], m->ld[l - 1], dW, Fi, m->precision));
+            }
+            if (l > 1) {
+                {
+                    Prof p(ctx, m, CLS_GEMM);
+                    GNN_TRY(gnn_gemm_nn(ctx, m->n_loc, Fi, Fo, dZ, m->ld[l], W, Fi, m->S1, m->ld[l - 1], nullptr, 0,
+                                        m->precision));
+                }
+                const float *src = nullptr;
+                GNN_TRY(gather_input(ctx, m, m->S1, m->ld[l - 1], &src));
+                Prof p(ctx, m, CLS_SPMM);
+                GNN_TRY(gnn_spmm_bwd(ctx, g, src, m->ld[l - 1], Fi, dNext, m->ld[l - 1], Hin, ld_in, 1));
+            }
+        } else {
+            const float *src = nullptr;
+            GNN_TRY(gather_input(ctx, m, dZ, m->ld[l], &src));
+            {
+                Prof p(ctx, m, CLS_SPMM);
+                GNN_TRY(gnn_spmm_bwd(ctx, g, src, m->ld[l], Fo, m->S1, m->ld[l], nullptr, 0, 1));
+            }
+            {
+                Prof p(ctx, m, CLS_GEMM);
+                GNN_TRY(gnn_gemm_tn(ctx, m->n_loc, Fo, Fi, m->S1, m->ld[l], Hin, ld_in, dW, Fi, m->precision));
+            }
+            if (l > 1) {
+                Prof p(ctx, m, CLS_GEMM);
+                GNN_TRY(gnn_gemm_nn(ctx, m->n_loc, Fi, Fo, m->S1, m->ld[l], W, Fi, dNext, m->ld[l - 1], Hin, ld_in,
+                                    m->precision));
+            }
+        }
+        float *t = dZ; dZ = dNext; dNext = t;
+    }
+    return 0;
+}
+
+} // namespace gnn
+
+using namespace gnn;
+
+extern "C" {
+
+int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_t *dims, gnn_gcn_t **out) {
+    GNN_REQUIRE(ctx && g && dims && out && L >= 1, "gnn_gcn_create: bad argument");
+    GNN_REQUIRE(g->val && g->colptr && (g->valT || g->symmetric),
+                "gnn_gcn_create: graph needs gnn_graph_build_csc + gnn_graph_normalize (or a slice of such a graph)");
+    for (int32_t l = 0; l <= L; l++) GNN_REQUIRE(dims[l] > 0, "dims cannot be empty or zero");
+    gnn_gcn *m = new gnn_gcn();
+    m->g = g;
+    m->L = L;
+    m->n_loc = g->n_rows;
+    m->n_glob = g->n_cols;
+    m->dist = g->n_rows != g->n_cols || ctx->world > 1;
+    if (m->dist) {
+        m->chunk = ceil_div(m->n_glob, ctx->world);
+        GNN_REQUIRE(m->n_loc <= m->chunk, "gnn_gcn_create: local rows %lld exceed the partition chunk %lld",
+                    (long long)m->n_loc, (long long)m->chunk);
+    }
+    m->dims.assign(dims, dims + L + 1);
+    m->ld.resize(L + 1);
+    m->agg_first.assign(L + 1, 0);
+    m->w_off.assign(L + 1, 0);
+    m->b_off.assign(L + 1, 0);
+    for (int32_t l = 0; l <= L; l++) {
+        m->ld[l] = (int32_t)round_up(dims[l], 4);
+        if (m->ld[l] > m->maxld) m->maxld = m->ld[l];
+    }
+    int64_t off = 0;
+    for (int32_t l = 1; l <= L; l++) {
+        m->agg_first[l] = dims[l - 1] < dims[l];
+        m->w_off[l] = off; off += (int64_t)dims[l] * dims[l - 1];
+        m->b_off[l] = off; off += dims[l];
+        off = round_up(off, 4); // keep every W 16-byte aligned
+    }
+    m->n_params = off;
+    const int64_t rows_alloc = m->dist ? m->chunk : m->n_loc; // gather sends whole chunks
+    auto alloc = [&](float **p, int64_t n) -> int {
+        GNN_CHECK_CUDA(cudaMalloc((void **)p, (size_t)n * 4));
+        GNN_CHECK_CUDA(cudaMemsetAsync(*p, 0, (size_t)n * 4, ctx->stream));
+        return 0;
+    };
+    GNN_TRY(alloc(&m->params, m->n_params));
+    GNN_TRY(alloc(&m->grads, m->n_params + 4));
+    m->H.assign(L + 1, nullptr);
+    m->M.assign(L + 1, nullptr);
+    for (int32_t l = 1; l <= L; l++) {
+        GNN_TRY(alloc(&m->H[l], rows_alloc * m->ld[l]));
+        if (m->agg_first[l]) GNN_TRY(alloc(&m->M[l], rows_alloc * m->ld[l - 1]));
+    }
+    GNN_TRY(alloc(&m->S1, rows_alloc * m->maxld));
+    GNN_TRY(alloc(&m->G0, rows_alloc * m->maxld));
+    GNN_TRY(alloc(&m->G1, rows_alloc * m->maxld));
+    if (m->dist) GNN_TRY(alloc(&m->AG, (int64_t)ctx->world * m->chunk * m->maxld));
+    GNN_TRY(alloc(&m->loss_d, 4));
+    recompute_stats(m);
+    *out = m;
+    return 0;
+}
+
+int gnn_gcn_destroy(gnn_ctx_t *ctx, gnn_gcn_t *m) {
+    if (!m) return 0;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(m->params); cudaFree(m->grads); cudaFree(m->vel);
+    for (auto p : m->H) cudaFree(p);
+    for (auto p : m->M) cudaFree(p);
+    cudaFree(m->S1); cudaFree(m->G0); cudaFree(m->G1); cudaFree(m->AG);
+    cudaFree(m->Xd); cudaFree(m->yd); cudaFree(m->loss_d);
+    for (auto &s : m->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    delete m;
+    return 0;
+}
+
+int gnn_gcn_set_params_h(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, const float *W_h, const float *b_h) {
+    GNN_REQUIRE(ctx && m && layer >= 1 && layer <= m->L, "gnn_gcn_set_params_h: bad layer");
+    const int64_t nw = (int64_t)m->dims[layer] * m->dims[layer - 1];
+    if (W_h) GNN_CHECK_CUDA(cudaMemcpyAsync(m->params + m->w_off[layer], W_h, (size_t)nw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (b_h) GNN_CHECK_CUDA(cudaMemcpyAsync(m->params + m->b_off[layer], b_h, (size_t)m->dims[layer] * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int copy_out(gnn_ctx_t *ctx, float *dst_h, const float *src, size_t n) {
+    if (!dst_h) return 0;
+    GNN_CHECK_CUDA(cudaMemcpyAsync(dst_h, src, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+int gnn_gcn_get_params_h(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, float *W_h, float *b_h) {
+    GNN_REQUIRE(ctx && m && layer >= 1 && layer <= m->L, "gnn_gcn_get_params_h: bad layer");
+    GNN_TRY(copy_out(ctx, W_h, m->params + m->w_off[layer], (size_t)m->dims[layer] * m->dims[layer - 1]));
+    GNN_TRY(copy_out(ctx, b_h, m->params + m->b_off[layer], (size_t)m->dims[layer]));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int gnn_gcn_get_grads_h(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, float *dW_h, float *db_h) {
+    GNN_REQUIRE(ctx && m && layer >= 1 && layer <= m->L, "gnn_gcn_get_grads_h: bad layer");
+    GNN_TRY(copy_out(ctx, dW_h, m->grads + m->w_off[layer], (size_t)m->dims[layer] * m->dims[layer - 1]));
+    GNN_TRY(copy_out(ctx, db_h, m->grads + m->b_off[layer], (size_t)m->dims[layer]));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int gnn_gcn_get_activation_h(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, float *out_h) {
+    GNN_REQUIRE(ctx && m && out_h && layer >= 1 && layer <= m->L, "gnn_gcn_get_activation_h: bad layer");
+    GNN_CHECK_CUDA(cudaMemcpy2DAsync(out_h, (size_t)m->dims[layer] * 4, m->H[layer], (size_t)m->ld[layer] * 4,
+                                     (size_t)m->dims[layer] * 4, (size_t)m->n_loc, cudaMemcpyDeviceToHost, ctx->stream));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int gnn_gcn_get_dlogits_h(gnn_ctx_t *ctx, gnn_gcn_t *m, float *out_h) {
+    GNN_REQUIRE(ctx && m && out_h, "gnn_gcn_get_dlogits_h: NULL argument");
+    GNN_REQUIRE(m->last_y, "gnn_gcn_get_dlogits_h: run gnn_gcn_train_step first");
+    // the dZ_L buffer is recycled by the backward ping-pong: recompute it from the kept logits
+    const int32_t C = m->dims[m->L];
+    const size_t n = (size_t)m->n_loc * m->ld[m->L];
+    float *tmp = nullptr;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&tmp, (n + 4) * 4, ctx->stream));
+    GNN_TRY(gnn_softmax_xent(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], m->last_y, m->n_glob, tmp + n, tmp, m->ld[m->L]));
+    GNN_CHECK_CUDA(cudaMemcpy2DAsync(out_h, (size_t)C * 4, tmp, (size_t)m->ld[m->L] * 4, (size_t)C * 4, (size_t)m->n_loc,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    GNN_CHECK_CUDA(cudaFreeAsync(tmp, ctx->stream));
+    return 0;
+}
+
+int gnn_gcn_set_option(gnn_gcn_t *m, const char *key, double value) {
+    GNN_REQUIRE(m && key, "gnn_gcn_set_option: NULL argument");
+    if (!strcmp(key, "precision")) m->precision = (int)value;
+    else if (!strcmp(key, "profile")) m->profile = (int)value;
+    else if (!strcmp(key, "momentum")) m->momentum = (float)value;
+    else if (!strcmp(key, "dampening")) m->dampening = (float)value;
+    else if (!strcmp(key, "weight_decay")) m->weight_decay = (float)value;
+    else if (!strcmp(key, "nesterov")) m->nesterov = (int)value;
+    else if (!strcmp(key, "agg_first_mask")) { // bit l-1 set -> layer l aggregates first (tests / ablation)
+        for (int32_t l = 1; l <= m->L; l++) m->agg_first[l] = (((int64_t)value) >> (l - 1)) & 1;
+        recompute_stats(m);
+    } else {
+        set_error("gnn_gcn_set_option: unknown key '%s'", key);
+        return 2;
+    }
+    return 0;
+}
+
+static int ensure_buffers(gnn_ctx_t *ctx, gnn_gcn_t *m) {
+    const int64_t rows_alloc = m->dist ? m->chunk : m->n_loc;
+    for (int32_t l = 1; l <= m->L; l++)
+        if (m->agg_first[l] && !m->M[l]) {
+            GNN_CHECK_CUDA(cudaMalloc((void **)&m->M[l], (size_t)rows_alloc * m->ld[l - 1] * 4));
+            GNN_CHECK_CUDA(cudaMemsetAsync(m->M[l], 0, (size_t)rows_alloc * m->ld[l - 1] * 4, ctx->stream));
+        }
+    return 0;
+}
+
+int gnn_gcn_forward(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx) {
+    GNN_REQUIRE(ctx && m && X && ldx >= m->dims[0], "gnn_gcn_forward: bad argument");
+    GNN_TRY(ensure_buffers(ctx, m));
+    GNN_REQUIRE(!m->dist || ldx == m->ld[0], "gnn_gcn_forward: row-partitioned mode needs ldx == round_up(F0,4)");
+    return forward(ctx, m, X, ldx);
+}
+
+int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx, const int32_t *y, float lr,
+                       float *loss_d) {
+    GNN_REQUIRE(ctx && m && X && y && ldx >= m->dims[0], "gnn_gcn_train_step: bad argument");
+    GNN_REQUIRE(!m->dist || ldx == m->ld[0], "gnn_gcn_train_step: row-partitioned mode needs ldx == round_up(F0,4)");
+    GNN_TRY(ensure_buffers(ctx, m));
+    m->last_y = y;
+    m->span_used = 0;
+    GNN_TRY(forward(ctx, m, X, ldx));
+    const int32_t C = m->dims[m->L];
+    float *loss_slot = m->grads + m->n_params; // rides along with the gradient all-reduce
+    {
+        Prof p(ctx, m, CLS_LOSS);
+        GNN_TRY(gnn_softmax_xent(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], y, m->n_glob, loss_slot, m->G0, m->ld[m->L]));
+    }
+    GNN_TRY(backward(ctx, m, X, ldx));
+    if (m->dist) {
+        Prof p(ctx, m, CLS_OTHER);
+        GNN_TRY(gnn_allreduce_sum(ctx, m->grads, m->n_params + 1));
+    }
+    if (m->momentum != 0.f && !m->vel) {
+        GNN_CHECK_CUDA(cudaMalloc((void **)&m->vel, (size_t)m->n_params * 4));
+        GNN_CHECK_CUDA(cudaMemsetAsync(m->vel, 0, (size_t)m->n_params * 4, ctx->stream));
+    }
+    if (lr != 0.f) {
+        Prof p(ctx, m, CLS_SGD);
+        GNN_TRY(gnn_sgd_step(ctx, m->n_params, m->params, m->grads, m->vel, lr, m->momentum, m->dampening,
+                             m->weight_decay, m->nesterov, m->steps == 0));
+    }
+    if (loss_d) GNN_CHECK_CUDA(cudaMemcpyAsync(loss_d, loss_slot, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    m->steps++;
+    if (m->profile) {
+        GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < 6; i++) m->breakdown[i] = 0;
+        for (size_t i = 0; i < m->span_used; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, m->spans[i].a, m->spans[i].b);
+            m->breakdown[m->spans[i].cls] += ms;
+        }
+    }
+    return 0;
+}
+
+int gnn_gcn_train_step_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const int32_t *y_h, float lr, float *loss_h) {
+    GNN_REQUIRE(ctx && m && X_h && y_h && loss_h, "gnn_gcn_train_step_h: NULL argument");
+    const int32_t F0 = m->dims[0];
+    const int64_t rows_alloc = m->dist ? m->chunk : m->n_loc;
+    if (!m->Xd) GNN_CHECK_CUDA(cudaMalloc((void **)&m->Xd, (size_t)rows_alloc * m->ld[0] * 4));
+    if (!m->yd) GNN_CHECK_CUDA(cudaMalloc((void **)&m->yd, (size_t)rows_alloc * 4));
+    GNN_CHECK_CUDA(cudaMemcpy2DAsync(m->Xd, (size_t)m->ld[0] * 4, X_h, (size_t)F0 * 4, (size_t)F0 * 4, (size_t)m->n_loc,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    GNN_CHECK_CUDA(cudaMemcpyAsync(m->yd, y_h, (size_t)m->n_loc * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GNN_TRY(gnn_gcn_train_step(ctx, m, m->Xd, m->ld[0], m->yd, lr, m->loss_d));
+    GNN_CHECK_CUDA(cudaMemcpyAsync(loss_h, m->loss_d, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int gnn_gcn_last_breakdown(gnn_gcn_t *m, double *ms, int n) {
+    GNN_REQUIRE(m && ms, "gnn_gcn_last_breakdown: NULL argument");
+    for (int i = 0; i < n && i < 6; i++) ms[i] = m->breakdown[i];
+    return 0;
+}
+
+int gnn_gcn_spmm_stats(gnn_gcn_t *m, double *alg_bytes, int32_t *n_spmm, double *gemm_flops) {
+    GNN_REQUIRE(m, "gnn_gcn_spmm_stats: NULL argument");
+    if (alg_bytes) *alg_bytes = m->alg_bytes;
+    if (n_spmm) *n_spmm = m->n_spmm;
+    if (gemm_flops) *gemm_flops = m->gemm_flops;
+    return 0;
+}
+
+} // extern "C"

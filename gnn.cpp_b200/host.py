@@ -1,0 +1,283 @@
+"""Thin Python host layer over the C ABI for the test/bench harness.
+
+PyTorch provides device buffers (torch.Tensor.data_ptr()), the CUDA stream and torch.distributed; all
+computation is done by libgnn_b200.so.  The user-facing API of this project is the C++ surface in
+gnn.cpp_b200/host/ (cyg::tensor, graph::GCNConv, nn::...) — this module only lets Python drive the same
+C ABI the C++ classes call.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data_as(C.c_void_p)
+    raise TypeError(type(t))
+
+
+class Context:
+    def __init__(self, device=0, use_torch_stream=True):
+        if not torch.cuda.is_available():
+            raise capi.GnnError("no CUDA device: the GCN hot path has no CPU fallback")
+        torch.cuda.set_device(device)
+        self.device = torch.device("cuda", device)
+        stream = torch.cuda.current_stream(device).cuda_stream if use_torch_stream else None
+        h = C.c_void_p()
+        capi.call("gnn_ctx_create", device, C.c_void_p(stream) if stream else None, C.byref(h))
+        self.h = h
+        self.sm_count = capi.load().gnn_ctx_sm_count(h)
+
+    def sync(self):
+        capi.call("gnn_ctx_sync", self.h)
+
+    @property
+    def launches(self):
+        return capi.load().gnn_ctx_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            capi.call("gnn_ctx_destroy", self.h)
+            self.h = None
+
+    # ---- multi-GPU -------------------------------------------------------------------------------
+    def init_comm_from_torch(self):
+        """Bootstrap the library's NCCL communicator through an initialised torch.distributed group."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            capi.call("gnn_comm_unique_id_h", _ptr(ident))
+        t = torch.from_numpy(ident).to(self.device) if dist.get_backend() == "nccl" else torch.from_numpy(ident)
+        dist.broadcast(t, 0)
+        ident = t.cpu().numpy().copy()
+        capi.call("gnn_comm_init", self.h, _ptr(ident), rank, world)
+        return rank, world
+
+
+class Graph:
+    """Device CSR/CSC of A_hat = D^-1/2 (A0 + I) D^-1/2."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    @classmethod
+    def build(cls, ctx, src, dst, N, fill_mode=1, csc=True, normalize=True):
+        """src/dst: int32 numpy (host) or torch cuda int32 tensors."""
+        h = C.c_void_p()
+        E = len(src)
+        if isinstance(src, torch.Tensor):
+            assert src.is_cuda and src.dtype == torch.int32 and dst.dtype == torch.int32
+            capi.call("gnn_graph_build", ctx.h, _ptr(src), _ptr(dst), E, N, fill_mode, C.byref(h))
+        else:
+            src = np.ascontiguousarray(src, dtype=np.int32)
+            dst = np.ascontiguousarray(dst, dtype=np.int32)
+            capi.call("gnn_graph_build_h", ctx.h, _ptr(src), _ptr(dst), E, N, fill_mode, C.byref(h))
+        g = cls(ctx, h)
+        if csc:
+            capi.call("gnn_graph_build_csc", ctx.h, h)
+        if normalize:
+            capi.call("gnn_graph_normalize", ctx.h, h)
+        return g
+
+    @property
+    def nnz(self):
+        return capi.load().gnn_graph_nnz(self.h)
+
+    @property
+    def n_rows(self):
+        return capi.load().gnn_graph_rows(self.h)
+
+    @property
+    def n_cols(self):
+        return capi.load().gnn_graph_cols(self.h)
+
+    @property
+    def symmetric(self):
+        return bool(capi.load().gnn_graph_is_symmetric(self.h))
+
+    def slice_rows(self, lo, hi):
+        h = C.c_void_p()
+        capi.call("gnn_graph_slice_rows", self.ctx.h, self.h, lo, hi, C.byref(h))
+        return Graph(self.ctx, h)
+
+    def export(self, csc=True, values=True):
+        n, nnz, nc = self.n_rows, self.nnz, self.n_cols
+        out = {"rowptr": np.empty(n + 1, np.int32), "colidx": np.empty(nnz, np.int32)}
+        if values:
+            out.update(val=np.empty(nnz, np.float32), deg=np.empty(n, np.int32), dinv=np.empty(n, np.float32))
+        if csc:
+            out.update(colptr=np.empty(nc + 1, np.int32), rowidx=np.empty(nnz, np.int32), perm=np.empty(nnz, np.int32))
+            if values:
+                out["valT"] = np.empty(nnz, np.float32)
+        g = out.get
+        capi.call("gnn_graph_export_h", self.ctx.h, self.h, _ptr(out["rowptr"]), _ptr(out["colidx"]), _ptr(g("val")),
+                  _ptr(g("colptr")), _ptr(g("rowidx")), _ptr(g("perm")), _ptr(g("valT")), _ptr(g("deg")), _ptr(g("dinv")))
+        return out
+
+    def to_dense(self, weighted=True):
+        out = torch.empty((self.n_rows, self.n_cols), dtype=torch.float32, device=self.ctx.device)
+        capi.call("gnn_graph_to_dense", self.ctx.h, self.h, int(weighted), _ptr(out), self.n_cols)
+        return out
+
+    def spmm_fwd(self, P, bias=None, relu=False, mask=None, use_values=True, out=None):
+        n, F = self.n_rows, P.shape[1]
+        Y = out if out is not None else torch.empty((n, F), dtype=torch.float32, device=P.device)
+        capi.call("gnn_spmm_fwd", self.ctx.h, self.h, _ptr(P), P.stride(0), F, _ptr(Y), Y.stride(0), _ptr(bias),
+                  int(relu), _ptr(mask), mask.stride(0) if mask is not None else 0, int(use_values))
+        return Y
+
+    def spmm_bwd(self, dZ, mask=None, use_values=True, out=None, n_out=None):
+        F = dZ.shape[1]
+        n = n_out if n_out is not None else self.n_cols
+        dP = out if out is not None else torch.empty((n, F), dtype=torch.float32, device=dZ.device)
+        capi.call("gnn_spmm_bwd", self.ctx.h, self.h, _ptr(dZ), dZ.stride(0), F, _ptr(dP), dP.stride(0), _ptr(mask),
+                  mask.stride(0) if mask is not None else 0, int(use_values))
+        return dP
+
+    def close(self):
+        if self.h:
+            capi.call("gnn_graph_destroy", self.ctx.h, self.h)
+            self.h = None
+
+
+def gemm_nt(ctx, A, B, bias=None, relu=False, precision=0, out=None):
+    M, K = A.shape
+    N = B.shape[0]
+    Cm = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=A.device)
+    capi.call("gnn_gemm_nt", ctx.h, M, N, K, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(Cm), Cm.stride(0),
+              _ptr(bias), int(relu), precision)
+    return Cm
+
+
+def gemm_nn(ctx, A, B, mask=None, precision=0, out=None):
+    M, K = A.shape
+    N = B.shape[1]
+    Cm = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=A.device)
+    capi.call("gnn_gemm_nn", ctx.h, M, N, K, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(Cm), Cm.stride(0),
+              _ptr(mask), mask.stride(0) if mask is not None else 0, precision)
+    return Cm
+
+
+def gemm_tn(ctx, A, B, precision=0, out=None):
+    M, K1 = A.shape
+    K2 = B.shape[1]
+    Cm = out if out is not None else torch.empty((K1, K2), dtype=torch.float32, device=A.device)
+    capi.call("gnn_gemm_tn", ctx.h, M, K1, K2, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(Cm), Cm.stride(0),
+              precision)
+    return Cm
+
+
+def bias_relu(ctx, Y, bias=None, relu=True):
+    out = torch.empty_like(Y)
+    capi.call("gnn_bias_relu_fwd", ctx.h, Y.shape[0], Y.shape[1], _ptr(Y), Y.stride(0), _ptr(bias), int(relu), _ptr(out),
+              out.stride(0))
+    return out
+
+
+def relu_bwd(ctx, dH, act):
+    out = torch.empty_like(dH)
+    capi.call("gnn_relu_bwd", ctx.h, dH.shape[0], dH.shape[1], _ptr(dH), dH.stride(0), _ptr(act), act.stride(0),
+              _ptr(out), out.stride(0))
+    return out
+
+
+def bias_grad(ctx, dZ):
+    db = torch.empty(dZ.shape[1], dtype=torch.float32, device=dZ.device)
+    capi.call("gnn_bias_grad", ctx.h, dZ.shape[0], dZ.shape[1], _ptr(dZ), dZ.stride(0), _ptr(db))
+    return db
+
+
+def softmax_xent(ctx, Z, y, n_total=0, want_grad=True):
+    loss = torch.empty(1, dtype=torch.float32, device=Z.device)
+    dZ = torch.empty_like(Z) if want_grad else None
+    capi.call("gnn_softmax_xent", ctx.h, Z.shape[0], Z.shape[1], _ptr(Z), Z.stride(0), _ptr(y), n_total, _ptr(loss),
+              _ptr(dZ), dZ.stride(0) if want_grad else 0)
+    return loss, dZ
+
+
+def sgd_step(ctx, p, g, vel=None, lr=0.01, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, first=True):
+    capi.call("gnn_sgd_step", ctx.h, p.numel(), _ptr(p), _ptr(g), _ptr(vel), lr, momentum, dampening, weight_decay,
+              int(nesterov), int(first))
+
+
+class GCN:
+    """Fused trainer (gnn_gcn_* entry points)."""
+
+    def __init__(self, ctx, graph, dims):
+        self.ctx, self.graph, self.dims = ctx, graph, list(dims)
+        self.L = len(dims) - 1
+        h = C.c_void_p()
+        d = np.asarray(dims, dtype=np.int32)
+        capi.call("gnn_gcn_create", ctx.h, graph.h, self.L, _ptr(d), C.byref(h))
+        self.h = h
+        self.n_loc = graph.n_rows
+
+    def set_option(self, key, value):
+        capi.call("gnn_gcn_set_option", self.h, key.encode(), float(value))
+
+    def set_params(self, Ws, bs):
+        for l, (W, b) in enumerate(zip(Ws, bs), start=1):
+            W = np.ascontiguousarray(W, dtype=np.float32)
+            b = np.ascontiguousarray(b, dtype=np.float32)
+            capi.call("gnn_gcn_set_params_h", self.ctx.h, self.h, l, _ptr(W), _ptr(b))
+
+    def params(self, l):
+        W = np.empty((self.dims[l], self.dims[l - 1]), np.float32)
+        b = np.empty(self.dims[l], np.float32)
+        capi.call("gnn_gcn_get_params_h", self.ctx.h, self.h, l, _ptr(W), _ptr(b))
+        return W, b
+
+    def grads(self, l):
+        W = np.empty((self.dims[l], self.dims[l - 1]), np.float32)
+        b = np.empty(self.dims[l], np.float32)
+        capi.call("gnn_gcn_get_grads_h", self.ctx.h, self.h, l, _ptr(W), _ptr(b))
+        return W, b
+
+    def activation(self, l):
+        out = np.empty((self.n_loc, self.dims[l]), np.float32)
+        capi.call("gnn_gcn_get_activation_h", self.ctx.h, self.h, l, _ptr(out))
+        return out
+
+    def dlogits(self):
+        out = np.empty((self.n_loc, self.dims[-1]), np.float32)
+        capi.call("gnn_gcn_get_dlogits_h", self.ctx.h, self.h, _ptr(out))
+        return out
+
+    def train_step(self, X, y, lr, loss_out=None):
+        """X: cuda float32 [n_loc, F0] (row stride = ld), y: cuda int32 [n_loc]. Returns the device loss tensor."""
+        if loss_out is None:
+            loss_out = torch.empty(1, dtype=torch.float32, device=X.device)
+        capi.call("gnn_gcn_train_step", self.ctx.h, self.h, _ptr(X), X.stride(0), _ptr(y), lr, _ptr(loss_out))
+        return loss_out
+
+    def forward(self, X):
+        capi.call("gnn_gcn_forward", self.ctx.h, self.h, _ptr(X), X.stride(0))
+
+    def train_step_host(self, X_h, y_h, lr):
+        """End-to-end step from host buffers (numpy or pinned torch CPU tensors); returns the loss as float."""
+        loss = np.zeros(1, np.float32)
+        capi.call("gnn_gcn_train_step_h", self.ctx.h, self.h, _ptr(X_h), _ptr(y_h), lr, _ptr(loss))
+        return float(loss[0])
+
+    def breakdown(self):
+        ms = np.zeros(6, np.float64)
+        capi.call("gnn_gcn_last_breakdown", self.h, _ptr(ms), 6)
+        return dict(zip(["spmm", "gemm", "loss", "bias_grad", "sgd", "other"], ms.tolist()))
+
+    def stats(self):
+        b, n, f = C.c_double(), C.c_int32(), C.c_double()
+        capi.call("gnn_gcn_spmm_stats", self.h, C.byref(b), C.byref(n), C.byref(f))
+        return {"spmm_alg_bytes": b.value, "n_spmm": n.value, "gemm_flops": f.value}
+
+    def close(self):
+        if self.h:
+            capi.call("gnn_gcn_destroy", self.ctx.h, self.h)
+            self.h = None

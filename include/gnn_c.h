@@ -1,0 +1,221 @@
+/* gnn_c.h — C ABI of the B200-native GCN hot path (libgnn_b200.so).
+ *
+ * This is the drop-in boundary: the reference (walexi/gnn.cpp) has no FFI of its own — its intended but
+ * unwritten seam is a `device::` namespace called from `functional::` (reference include/functional.h:174,180;
+ * src/device.cu and include/device.cuh are empty).  Every entry point below names the reference code whose
+ * results it reproduces (file:line relative to the reference root).  INTEGRATION.md shows the binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; gnn_last_error() gives the message
+ *     (thread-local).  The C++ host shim rethrows std::runtime_error like the reference's CHECK_* helpers
+ *     (reference include/utils.h:19-30).
+ *   - pointers are DEVICE pointers unless the parameter name ends in `_h` (host).
+ *   - all kernels are enqueued on the context's stream; nothing synchronises unless stated.
+ *   - matrices are dense row-major fp32 with an explicit leading dimension (elements).
+ *   - there is no CPU fallback: creating a context without a CUDA device fails.
+ */
+#ifndef GNN_C_H
+#define GNN_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GNN_API __attribute__((visibility("default")))
+#else
+#define GNN_API
+#endif
+
+typedef struct gnn_ctx gnn_ctx_t;
+typedef struct gnn_graph gnn_graph_t;
+typedef struct gnn_gcn gnn_gcn_t;
+
+/* ---------------------------------------------------------------- context / errors ---------------- */
+GNN_API int gnn_version(void);
+GNN_API const char *gnn_last_error(void);
+/* stream: an existing cudaStream_t to enqueue on (e.g. the caller's), or NULL to create one. */
+GNN_API int gnn_ctx_create(int device, void *stream, gnn_ctx_t **out);
+GNN_API int gnn_ctx_destroy(gnn_ctx_t *ctx);
+GNN_API int gnn_ctx_sync(gnn_ctx_t *ctx);
+GNN_API void *gnn_ctx_stream(gnn_ctx_t *ctx);
+GNN_API int gnn_ctx_sm_count(gnn_ctx_t *ctx);
+/* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
+GNN_API int64_t gnn_ctx_launch_count(gnn_ctx_t *ctx);
+
+/* ---------------------------------------------------------------- storage -------------------------
+ * Replaces the heap std::valarray storage of cyg::tensor (reference include/tensor.h:825-828). */
+GNN_API int gnn_malloc(gnn_ctx_t *ctx, void **ptr, size_t bytes);
+GNN_API int gnn_free(gnn_ctx_t *ctx, void *ptr);
+GNN_API int gnn_memset(gnn_ctx_t *ctx, void *ptr, int value, size_t bytes);
+GNN_API int gnn_memcpy_h2d(gnn_ctx_t *ctx, void *dst, const void *src_h, size_t bytes); /* async on stream */
+GNN_API int gnn_memcpy_d2h(gnn_ctx_t *ctx, void *dst_h, const void *src, size_t bytes); /* synchronises */
+GNN_API int gnn_memcpy_d2d(gnn_ctx_t *ctx, void *dst, const void *src, size_t bytes);
+GNN_API int gnn_fill_f32(gnn_ctx_t *ctx, float *ptr, float value, int64_t n);
+
+/* ---------------------------------------------------------------- graph structure (K1-K3) ----------
+ * gnn_graph_build: COO edge list -> CSR of the 0/1 adjacency, rows ascending, columns ascending and
+ * de-duplicated inside a row.  Reproduces, without the dense N x N round trip,
+ *     graph::edge_to_adj_mat      reference src/graph.cpp:21-44   (A[src][dst] = 1, duplicates collapse)
+ *     tensor::fill_diagonal_      reference include/tensor.h:806-817
+ *     graph::adj_to_edge_list     reference src/graph.cpp:46-67   (row-major scan -> sorted COO)
+ *     graph::add_self_loops       reference src/graph.cpp:68-75
+ * fill_mode: 0 = diagonal removed (add_self_loops fillValue 0, as GCNConv calls it, src/graph.cpp:172),
+ *            1 = diagonal forced on every row (fillValue 1; the A+I of the north-star layer),
+ *            2 = diagonal left as given.
+ * src/dst are device int32 arrays of length E (row = src = edge_index[0], col = dst = edge_index[1]). */
+GNN_API int gnn_graph_build(gnn_ctx_t *ctx, const int32_t *src, const int32_t *dst, int64_t E, int32_t N,
+                            int fill_mode, gnn_graph_t **out);
+GNN_API int gnn_graph_build_h(gnn_ctx_t *ctx, const int32_t *src_h, const int32_t *dst_h, int64_t E, int32_t N,
+                              int fill_mode, gnn_graph_t **out);
+/* Adopt an existing device CSR (used by the row-partitioned multi-GPU path: local rows, global columns).
+ * n_rows x n_cols, rowptr[n_rows+1] int32, colidx[nnz] int32, val[nnz] fp32 or NULL; arrays are copied. */
+GNN_API int gnn_graph_from_csr(gnn_ctx_t *ctx, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
+                               const int32_t *colidx, const float *val, gnn_graph_t **out);
+/* K2: CSC (= CSR of the transpose) + permutation, rows ascending inside a column.  The reference instead
+ * clones and transposes the dense matrix on every backward (include/operation.h:526-528). */
+GNN_API int gnn_graph_build_csc(gnn_ctx_t *ctx, gnn_graph_t *g);
+/* K3: deg = rowsum(A0+I) (src/graph.cpp:178), dinv = deg^-1/2 (src/graph.cpp:183),
+ * val[r,c] = dinv[r]*dinv[c] (mode-B composition of functional::mul, include/functional.h:189-213);
+ * also valT when the CSC exists. */
+GNN_API int gnn_graph_normalize(gnn_ctx_t *ctx, gnn_graph_t *g);
+GNN_API int gnn_graph_destroy(gnn_ctx_t *ctx, gnn_graph_t *g);
+GNN_API int64_t gnn_graph_nnz(const gnn_graph_t *g);
+GNN_API int32_t gnn_graph_rows(const gnn_graph_t *g);
+GNN_API int32_t gnn_graph_cols(const gnn_graph_t *g);
+/* 1 when the CSC arrays alias the CSR arrays (structurally symmetric graph, detected on device). */
+GNN_API int gnn_graph_is_symmetric(const gnn_graph_t *g);
+/* Copy structure arrays to host for bit-exact checks (any pointer may be NULL).  Sizes: rowptr/colptr
+ * rows+1 / cols+1 int32, colidx/rowidx/perm/val/valT nnz, deg/dinv rows. Synchronises. */
+GNN_API int gnn_graph_export_h(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t *rowptr_h, int32_t *colidx_h,
+                               float *val_h, int32_t *colptr_h, int32_t *rowidx_h, int32_t *perm_h, float *valT_h,
+                               int32_t *deg_h, float *dinv_h);
+/* Dense adjacency (graph::Data::to_adj / edge_to_adj_mat, src/graph.cpp:118-129) for API fidelity at small N:
+ * out[n_rows, n_cols] = weighted ? val : 1 at the stored positions, 0 elsewhere. */
+GNN_API int gnn_graph_to_dense(gnn_ctx_t *ctx, const gnn_graph_t *g, int weighted, float *out, int64_t ld);
+
+/* ---------------------------------------------------------------- aggregation (K4/K5/K7) -----------
+ * Forward  Y[n_rows,F] = A_hat * P           — adj_mat->mm(x), reference src/graph.cpp:208 ->
+ *                                              include/functional.h:398-441
+ * Backward dP[n_cols,F] = A_hat^T * dZ       — MatMul::_backward rhs branch, include/operation.h:524-531,
+ *                                              computed over the CSC: no atomics, fixed order.
+ * Fused epilogue (all optional):
+ *     bias[F]        Z = Y + b               — Add, include/operation.h:102-129
+ *     relu           H = Z > 0 ? Z : 0       — nn::ReLU / Mask, src/nn.cpp:229-237, operation.h:537-573
+ *     mask[.,F]      out = mask > 0 ? out : 0 (ReLU backward, operation.h:557-562)
+ * use_values = 0 treats every stored entry as 1 (plain sum aggregation, graph.cpp:204-212). */
+GNN_API int gnn_spmm_fwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *P, int64_t ldp, int32_t F, float *Y,
+                         int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm, int use_values);
+GNN_API int gnn_spmm_bwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *dZ, int64_t ldz, int32_t F, float *dP,
+                         int64_t ldp, const float *mask, int64_t ldm, int use_values);
+/* SpMM variant selection: 0 = auto (by degree skew), 1 = row-per-lane-group, 2 = row-split (long rows cut
+ * into fixed chunks, partials combined in fixed order). */
+GNN_API int gnn_set_spmm_variant(gnn_ctx_t *ctx, int variant);
+
+/* ---------------------------------------------------------------- dense transforms (K6) ------------
+ *   gnn_gemm_nt: C[M,N] = A[M,K] * B[N,K]^T (+bias[N]) (relu)   — nn::Linear::forward, src/nn.cpp:205-211
+ *   gnn_gemm_nn: C[M,N] = A[M,K] * B[K,N] (mask)                — MatMul::_backward lhs branch, operation.h:516-523
+ *   gnn_gemm_tn: C[K1,K2] = A[M,K1]^T * B[M,K2]                 — rhs branch + Transpose::_backward,
+ *                                                                  operation.h:524-531,416-433 (fixed-order split over M)
+ * precision: 0 = FP32 FMA (CUDA cores), 1 = 3xTF32 on tcgen05 tensor cores (error ~2^-21, inside 1e-5). */
+GNN_API int gnn_gemm_nt(gnn_ctx_t *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B,
+                        int64_t ldb, float *C, int64_t ldc, const float *bias, int relu, int precision);
+GNN_API int gnn_gemm_nn(gnn_ctx_t *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B,
+                        int64_t ldb, float *C, int64_t ldc, const float *mask, int64_t ldm, int precision);
+GNN_API int gnn_gemm_tn(gnn_ctx_t *ctx, int64_t M, int32_t K1, int32_t K2, const float *A, int64_t lda,
+                        const float *B, int64_t ldb, float *C, int64_t ldc, int precision);
+
+/* ---------------------------------------------------------------- epilogues, loss, optimiser -------
+ * bias+ReLU forward / ReLU mask backward / bias gradient (ascending-row column sum; Add::_backward ->
+ * sum_to_size, include/tensor.h:618-638). */
+GNN_API int gnn_bias_relu_fwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *Y, int64_t ldy, const float *bias,
+                              int relu, float *out, int64_t ldo);
+GNN_API int gnn_relu_bwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *dH, int64_t ldd, const float *act,
+                         int64_t lda, float *dZ, int64_t ldo);
+GNN_API int gnn_bias_grad(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *dZ, int64_t ldd, float *db);
+/* Fused softmax-cross-entropy: loss (device scalar) = mean_i -log(exp(z_iy)/(sum_c exp(z_ic)+1e-20))
+ * (nn::cross_entropy_loss forward, src/nn.cpp:442-453); dZ = (softmax(Z)-onehot(y))/N_total (the analytic
+ * gradient — the reference backward throws, SURVEY.md bug B3).  n_total is the divisor (global node count
+ * under row partitioning); dZ may be NULL. */
+GNN_API int gnn_softmax_xent(gnn_ctx_t *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
+                             int64_t n_total, float *loss, float *dZ, int64_t ldd);
+/* torch.optim.SGD semantics, the documented intent of nn::SGD (include/nn.h:165-178; body broken, bug B4).
+ * vel may be NULL when momentum == 0; first = 1 on the first step (velocity initialised to the gradient). */
+GNN_API int gnn_sgd_step(gnn_ctx_t *ctx, int64_t n, float *p, const float *g, float *vel, float lr, float momentum,
+                         float dampening, float weight_decay, int nesterov, int first);
+
+/* ---------------------------------------------------------------- elementwise / reductions for the
+ * cyg::tensor surface (functional::add/mul/div/exp/log/sum/transpose/mask, include/functional.h:162-471) */
+enum { GNN_OP_ADD = 0, GNN_OP_MUL = 1, GNN_OP_DIV = 2, GNN_OP_POW = 3, GNN_OP_GT = 4 };
+enum { GNN_UOP_EXP = 0, GNN_UOP_LOG = 1, GNN_UOP_NEG = 2 };
+/* out[rows,cols] = a (op) b with numpy broadcasting expressed as strides (0 = broadcast) */
+GNN_API int gnn_binary_f32(gnn_ctx_t *ctx, int op, int64_t rows, int64_t cols, const float *a, int64_t a_rs,
+                           int64_t a_cs, const float *b, int64_t b_rs, int64_t b_cs, float *out);
+GNN_API int gnn_unary_f32(gnn_ctx_t *ctx, int op, int64_t n, const float *a, float *out);
+/* out = cond > 0 ? t : f  (functional::mask, include/functional.h:443-471) */
+GNN_API int gnn_where_f32(gnn_ctx_t *ctx, int64_t n, const float *cond, const float *t, const float *f, float *out);
+/* sum over dim of a [rows, cols] view: dim 0 -> out[cols], dim 1 -> out[rows], dim -1 (all) -> out[1] */
+GNN_API int gnn_sum_f32(gnn_ctx_t *ctx, int64_t rows, int64_t cols, const float *a, int dim, float *out);
+GNN_API int gnn_transpose_f32(gnn_ctx_t *ctx, int64_t rows, int64_t cols, const float *a, float *out);
+/* out[i] = a[i, idx[i]]  (tensor::at / functional::slice, include/functional.h:482-494) */
+GNN_API int gnn_gather_cols_f32(gnn_ctx_t *ctx, int64_t rows, int64_t cols, const float *a, const int32_t *idx,
+                                float *out);
+
+/* ---------------------------------------------------------------- fused trainer --------------------
+ * One full-batch GCN train step (forward + loss + backward + SGD) for the layer stack
+ *     Z_l = A_hat (H_{l-1} W_l^T) + b_l,  H_l = ReLU(Z_l) (l < L),  logits = Z_L
+ * i.e. what a main.cpp loop over graph::GCNConv / nn::cross_entropy_loss / nn::SGD executes,
+ * with every buffer preallocated so the step is a fixed launch sequence (CUDA-graph capturable).
+ * Per layer the aggregation runs at the narrower of (F_{l-1}, F_l): A_hat(HW^T) == (A_hat H)W^T.
+ * The graph must have CSC + normalisation built.  dims has L+1 entries. */
+GNN_API int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_t *dims, gnn_gcn_t **out);
+GNN_API int gnn_gcn_destroy(gnn_ctx_t *ctx, gnn_gcn_t *m);
+/* layer = 1..L.  W[F_l, F_{l-1}] row-major (nn::Linear layout, src/nn.cpp:187-194), b[F_l]. */
+GNN_API int gnn_gcn_set_params_h(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, const float *W_h, const float *b_h);
+GNN_API int gnn_gcn_get_params_h(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, float *W_h, float *b_h);
+GNN_API int gnn_gcn_get_grads_h(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, float *dW_h, float *db_h);
+/* activations of layer l (pre-ReLU Z_l is not kept for l < L; this returns H_l = ReLU(Z_l), logits for l = L) */
+GNN_API int gnn_gcn_get_activation_h(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, float *out_h);
+GNN_API int gnn_gcn_get_dlogits_h(gnn_ctx_t *ctx, gnn_gcn_t *m, float *out_h);
+/* options: precision (0 fp32 / 1 3xTF32), keep_preact (store Z_l for parity tests), lr etc. */
+GNN_API int gnn_gcn_set_option(gnn_gcn_t *m, const char *key, double value);
+/* X[N,F0] (ld = ldx) and y[N] on the device.  loss_d: device float written by the step. */
+GNN_API int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx, const int32_t *y,
+                               float lr, float *loss_d);
+/* forward only (inference); logits stay in the model's activation buffer */
+GNN_API int gnn_gcn_forward(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx);
+/* End-to-end step from HOST buffers: copies X_h and y_h to the device (pinned or pageable), runs the step,
+ * copies the loss back and synchronises.  This is the call bench.py's `e2e` times. */
+GNN_API int gnn_gcn_train_step_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const int32_t *y_h, float lr,
+                                 float *loss_h);
+/* per-kernel-class device time of the last profiled step, ms: fills up to n entries of
+ * {spmm, gemm, loss, bias_grad, sgd, other}.  Enabled by option "profile" = 1 (adds event records). */
+GNN_API int gnn_gcn_last_breakdown(gnn_gcn_t *m, double *ms, int n);
+/* algorithmic SpMM bytes / number of SpMM launches in one train step (for the roofline line) */
+GNN_API int gnn_gcn_spmm_stats(gnn_gcn_t *m, double *alg_bytes, int32_t *n_spmm, double *gemm_flops);
+
+/* ---------------------------------------------------------------- multi-GPU (K10) ------------------
+ * 1-D contiguous row partition: part_ptr[p] = min(N, p*ceil(N/P)).  Each rank owns the CSR rows (and CSC
+ * columns) of its nodes with GLOBAL column ids; per aggregation the ranks all-gather their feature row
+ * blocks (NCCL over NVLink) into a global-order buffer and aggregate locally. */
+GNN_API int gnn_partition_ptr_h(int64_t N, int32_t P, int64_t *part_ptr_h);
+/* Extract rank-local rows [lo,hi) of g as a new graph (n_rows = hi-lo, n_cols = N, global column ids),
+ * including values and, when g has them, the matching CSC slice for the backward. */
+GNN_API int gnn_graph_slice_rows(gnn_ctx_t *ctx, const gnn_graph_t *g, int64_t lo, int64_t hi, gnn_graph_t **out);
+/* NCCL communicator owned by the context.  id_h: 128-byte ncclUniqueId produced by gnn_comm_unique_id_h on
+ * rank 0 and distributed by the caller (torch.distributed / MPI / files). */
+GNN_API int gnn_comm_unique_id_h(void *id_h /* 128 bytes */);
+GNN_API int gnn_comm_init(gnn_ctx_t *ctx, const void *id_h, int rank, int world);
+GNN_API int gnn_comm_destroy(gnn_ctx_t *ctx);
+/* all-gather equal row blocks: recv[world*rows_per_rank, F] <- send[rows_per_rank, F] (dense, ld = F) */
+GNN_API int gnn_allgather_rows(gnn_ctx_t *ctx, const float *send, float *recv, int64_t rows_per_rank, int32_t F);
+GNN_API int gnn_allreduce_sum(gnn_ctx_t *ctx, float *buf, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNN_C_H */
