@@ -286,6 +286,7 @@ int gnn_graph_build_csc(gnn_ctx_t *ctx, gnn_graph_t *g) {
     GNN_CHECK_CUDA(cudaMalloc((void **)&g->perm, (size_t)(nnz ? nnz : 1) * 4));
     if (nnz == 0) {
         GNN_CHECK_CUDA(cudaMemsetAsync(g->colptr, 0, (size_t)(g->n_cols + 1) * 4, s));
+        g->symmetric = g->n_rows == g->n_cols;
         return 0;
     }
     uint64_t *keys = nullptr;

@@ -29,7 +29,17 @@ class Context:
             raise capi.GnnError("no CUDA device: the GCN hot path has no CPU fallback")
         torch.cuda.set_device(device)
         self.device = torch.device("cuda", device)
-        stream = torch.cuda.current_stream(device).cuda_stream if use_torch_stream else None
+        # One stream for everything: torch ops (copies, allocations, events) and the library's kernels must be
+        # ordered on the SAME stream.  torch's legacy default stream has handle 0, which the C ABI reads as
+        # "create your own", so make a real stream current for torch and hand that one to the context.
+        stream = None
+        if use_torch_stream:
+            if torch.cuda.current_stream(device).cuda_stream == 0:
+                self.stream = torch.cuda.Stream(device)
+                torch.cuda.set_stream(self.stream)
+            else:
+                self.stream = torch.cuda.current_stream(device)
+            stream = self.stream.cuda_stream
         h = C.c_void_p()
         capi.call("gnn_ctx_create", device, C.c_void_p(stream) if stream else None, C.byref(h))
         self.h = h
