@@ -266,15 +266,21 @@ def run_ours(args):
     # end to end through the host-buffer entry point: H2D of the step's inputs (pinned) + step + D2H of the loss
     Xh = torch.from_numpy(np.ascontiguousarray(p.X[lo:hi])).pin_memory()
     yh = torch.from_numpy(np.ascontiguousarray(p.y[lo:hi])).pin_memory()
+    # Pipelined: every call runs the step on the batch uploaded during the previous call and starts the upload of
+    # the batch it is handed (copy stream, double-buffered) — each step's inputs cross PCIe exactly once, inside
+    # the timed region, overlapped with the previous step's kernels.  The loss comes back to the host every step.
     e2e_fn = lambda: model.train_step_host(Xh, yh, LR)  # noqa: E731
+    e2e_fn()                       # unpipelined first call (also allocates the staging slots)
+    model.prefetch_host(Xh, yh)    # prime the pipeline
     e2e_fn()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 10))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_fn()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    model.train_step_host(None, None, LR)   # drain the last prefetched batch
     if world > 1:
         t = torch.tensor([e2e_ms], device=ctx.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -70,6 +70,7 @@ SIGNATURES = {
     "gnn_gcn_train_step": (C.c_int, [vp, vp, vp, i64, vp, f32, vp]),
     "gnn_gcn_forward": (C.c_int, [vp, vp, vp, i64]),
     "gnn_gcn_train_step_h": (C.c_int, [vp, vp, vp, vp, f32, vp]),
+    "gnn_gcn_prefetch_h": (C.c_int, [vp, vp, vp, vp]),
     "gnn_gcn_last_breakdown": (C.c_int, [vp, vp, C.c_int]),
     "gnn_gcn_spmm_stats": (C.c_int, [vp, vp, vp, vp]),
     "gnn_partition_ptr_h": (C.c_int, [i64, i32, vp]),

@@ -33,8 +33,12 @@ struct gnn_gcn {
     std::vector<float *> M;  // aggregated inputs of AF layers [n_loc, ld[l-1]]
     float *S1 = nullptr, *G0 = nullptr, *G1 = nullptr; // scratch [n_loc, maxld]
     float *AG = nullptr;                                 // all-gather buffer [world*chunk, maxld] (dist)
-    float *Xd = nullptr;                                 // staged features for *_h entry points
-    int32_t *yd = nullptr;
+    float *Xs[2] = {nullptr, nullptr};                   // double-buffered staged inputs for *_h entry points
+    int32_t *ys[2] = {nullptr, nullptr};
+    int cur_slot = 0;
+    bool prefetched = false;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_uploaded = nullptr, ev_consumed = nullptr;
     const int32_t *last_y = nullptr;
     float *loss_d = nullptr;
     int32_t maxld = 0;
@@ -270,7 +274,9 @@ int gnn_gcn_destroy(gnn_ctx_t *ctx, gnn_gcn_t *m) {
     for (auto p : m->H) cudaFree(p);
     for (auto p : m->M) cudaFree(p);
     cudaFree(m->S1); cudaFree(m->G0); cudaFree(m->G1); cudaFree(m->AG);
-    cudaFree(m->Xd); cudaFree(m->yd); cudaFree(m->loss_d);
+    for (int i = 0; i < 2; i++) { cudaFree(m->Xs[i]); cudaFree(m->ys[i]); }
+    if (m->copy_stream) { cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_uploaded); cudaEventDestroy(m->ev_consumed); }
+    cudaFree(m->loss_d);
     for (auto &s : m->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     delete m;
     return 0;
@@ -408,16 +414,64 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
     return 0;
 }
 
-int gnn_gcn_train_step_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const int32_t *y_h, float lr, float *loss_h) {
-    GNN_REQUIRE(ctx && m && X_h && y_h && loss_h, "gnn_gcn_train_step_h: NULL argument");
-    const int32_t F0 = m->dims[0];
+// staging buffers for the host-buffer entry points: two (X, y) device slots so the upload of the next step's
+// inputs (copy stream) overlaps the current step's kernels (compute stream)
+static int ensure_staging(gnn_ctx_t *ctx, gnn_gcn_t *m) {
     const int64_t rows_alloc = m->dist ? m->chunk : m->n_loc;
-    if (!m->Xd) GNN_CHECK_CUDA(cudaMalloc((void **)&m->Xd, (size_t)rows_alloc * m->ld[0] * 4));
-    if (!m->yd) GNN_CHECK_CUDA(cudaMalloc((void **)&m->yd, (size_t)rows_alloc * 4));
-    GNN_CHECK_CUDA(cudaMemcpy2DAsync(m->Xd, (size_t)m->ld[0] * 4, X_h, (size_t)F0 * 4, (size_t)F0 * 4, (size_t)m->n_loc,
-                                     cudaMemcpyHostToDevice, ctx->stream));
-    GNN_CHECK_CUDA(cudaMemcpyAsync(m->yd, y_h, (size_t)m->n_loc * 4, cudaMemcpyHostToDevice, ctx->stream));
-    GNN_TRY(gnn_gcn_train_step(ctx, m, m->Xd, m->ld[0], m->yd, lr, m->loss_d));
+    for (int s = 0; s < 2; s++) {
+        if (!m->Xs[s]) {
+            GNN_CHECK_CUDA(cudaMalloc((void **)&m->Xs[s], (size_t)rows_alloc * m->ld[0] * 4));
+            GNN_CHECK_CUDA(cudaMemsetAsync(m->Xs[s], 0, (size_t)rows_alloc * m->ld[0] * 4, ctx->stream));
+        }
+        if (!m->ys[s]) GNN_CHECK_CUDA(cudaMalloc((void **)&m->ys[s], (size_t)rows_alloc * 4));
+    }
+    if (!m->copy_stream) {
+        GNN_CHECK_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        GNN_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_uploaded, cudaEventDisableTiming));
+        GNN_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_consumed, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+static int upload(gnn_gcn_t *m, int slot, const float *X_h, const int32_t *y_h, cudaStream_t s) {
+    const int32_t F0 = m->dims[0];
+    if (m->ld[0] == F0) // dense rows: one flat DMA (a 2-D copy of 400-byte rows is an order of magnitude slower)
+        GNN_CHECK_CUDA(cudaMemcpyAsync(m->Xs[slot], X_h, (size_t)m->n_loc * F0 * 4, cudaMemcpyHostToDevice, s));
+    else
+        GNN_CHECK_CUDA(cudaMemcpy2DAsync(m->Xs[slot], (size_t)m->ld[0] * 4, X_h, (size_t)F0 * 4, (size_t)F0 * 4,
+                                         (size_t)m->n_loc, cudaMemcpyHostToDevice, s));
+    GNN_CHECK_CUDA(cudaMemcpyAsync(m->ys[slot], y_h, (size_t)m->n_loc * 4, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+int gnn_gcn_prefetch_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const int32_t *y_h) {
+    GNN_REQUIRE(ctx && m && X_h && y_h, "gnn_gcn_prefetch_h: NULL argument");
+    GNN_REQUIRE(!m->prefetched, "gnn_gcn_prefetch_h: a prefetched batch is already pending");
+    GNN_TRY(ensure_staging(ctx, m));
+    const int slot = m->cur_slot ^ 1;
+    // the back slot may still be read by the step that used it last: wait for that step on the copy stream
+    GNN_CHECK_CUDA(cudaEventRecord(m->ev_consumed, ctx->stream));
+    GNN_CHECK_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_consumed, 0));
+    GNN_TRY(upload(m, slot, X_h, y_h, m->copy_stream));
+    GNN_CHECK_CUDA(cudaEventRecord(m->ev_uploaded, m->copy_stream));
+    m->prefetched = true;
+    return 0;
+}
+
+int gnn_gcn_train_step_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const int32_t *y_h, float lr, float *loss_h) {
+    GNN_REQUIRE(ctx && m && loss_h, "gnn_gcn_train_step_h: NULL argument");
+    GNN_TRY(ensure_staging(ctx, m));
+    if (m->prefetched) { // inputs were uploaded by gnn_gcn_prefetch_h: order the step after that copy
+        m->cur_slot ^= 1;
+        m->prefetched = false;
+        GNN_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_uploaded, 0));
+        // pipelined mode: the buffers passed now are the NEXT step's inputs; their upload overlaps this step
+        if (X_h && y_h) GNN_TRY(gnn_gcn_prefetch_h(ctx, m, X_h, y_h));
+    } else {
+        GNN_REQUIRE(X_h && y_h, "gnn_gcn_train_step_h: NULL inputs and nothing prefetched");
+        GNN_TRY(upload(m, m->cur_slot, X_h, y_h, ctx->stream));
+    }
+    GNN_TRY(gnn_gcn_train_step(ctx, m, m->Xs[m->cur_slot], m->ld[0], m->ys[m->cur_slot], lr, m->loss_d));
     GNN_CHECK_CUDA(cudaMemcpyAsync(loss_h, m->loss_d, 4, cudaMemcpyDeviceToHost, ctx->stream));
     GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -274,8 +274,13 @@ class GCN:
     def train_step_host(self, X_h, y_h, lr):
         """End-to-end step from host buffers (numpy or pinned torch CPU tensors); returns the loss as float."""
         loss = np.zeros(1, np.float32)
-        capi.call("gnn_gcn_train_step_h", self.ctx.h, self.h, _ptr(X_h), _ptr(y_h), lr, _ptr(loss))
+        capi.call("gnn_gcn_train_step_h", self.ctx.h, self.h, _ptr(X_h) if X_h is not None else None,
+                  _ptr(y_h) if y_h is not None else None, lr, _ptr(loss))
         return float(loss[0])
+
+    def prefetch_host(self, X_h, y_h):
+        """Start uploading the next step's host inputs (overlaps the running step); see gnn_gcn_prefetch_h."""
+        capi.call("gnn_gcn_prefetch_h", self.ctx.h, self.h, _ptr(X_h), _ptr(y_h))
 
     def breakdown(self):
         ms = np.zeros(6, np.float64)

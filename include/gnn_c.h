@@ -192,6 +192,12 @@ GNN_API int gnn_gcn_forward(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_
  * copies the loss back and synchronises.  This is the call bench.py's `e2e` times. */
 GNN_API int gnn_gcn_train_step_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const int32_t *y_h, float lr,
                                  float *loss_h);
+/* Enqueue the upload of the NEXT step's host inputs on a copy stream (double-buffered device slots), so it
+ * overlaps the current step's kernels.  The following gnn_gcn_train_step_h runs on the prefetched batch; the
+ * X_h / y_h it is given are then taken as the batch AFTER that one and prefetched in turn (pass NULL to stop
+ * pipelining).  So a loop `prefetch(b0); for k: train_step_h(b[k+1])` uploads every step's inputs exactly once,
+ * hidden behind the previous step.  Host buffers must be pinned and stay valid until consumed. */
+GNN_API int gnn_gcn_prefetch_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const int32_t *y_h);
 /* per-kernel-class device time of the last profiled step, ms: fills up to n entries of
  * {spmm, gemm, loss, bias_grad, sgd, other}.  Enabled by option "profile" = 1 (adds event records). */
 GNN_API int gnn_gcn_last_breakdown(gnn_gcn_t *m, double *ms, int n);

@@ -322,8 +322,15 @@ def test_train_step_host_entry_point(ctx, oracle):
     g = host.Graph.build(ctx, p.src, p.dst, p.cfg.N)
     m = host.GCN(ctx, g, p.cfg.dims)
     m.set_params(p.W, p.b)
-    loss = m.train_step_host(np.ascontiguousarray(p.X), np.ascontiguousarray(p.y), 0.0)
+    Xh, yh = np.ascontiguousarray(p.X), np.ascontiguousarray(p.y)
+    loss = m.train_step_host(Xh, yh, 0.0)
     assert abs(loss - ref["loss"]) <= TOL * abs(ref["loss"])
+    # pipelined mode (gnn_gcn_prefetch_h): uploads overlap the previous step; with lr = 0 every step is identical
+    m.prefetch_host(Xh, yh)
+    l2 = m.train_step_host(Xh, yh, 0.0)      # runs on the prefetched batch, prefetches the next
+    l3 = m.train_step_host(None, None, 0.0)  # drains the pipeline
+    l4 = m.train_step_host(Xh, yh, 0.0)      # back to the unpipelined path
+    assert loss == l2 == l3 == l4
     m.close(); g.close()
 
 
