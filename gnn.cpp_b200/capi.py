@@ -42,6 +42,7 @@ SIGNATURES = {
     "gnn_graph_is_symmetric": (C.c_int, [vp]),
     "gnn_graph_export_h": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "gnn_graph_to_dense": (C.c_int, [vp, vp, C.c_int, vp, i64]),
+    "gnn_dense_to_coo": (C.c_int, [vp, vp, i64, i64, i64, vp, vp, vp, i64, vp]),
     "gnn_spmm_fwd": (C.c_int, [vp, vp, vp, i64, i32, vp, i64, vp, C.c_int, vp, i64, C.c_int]),
     "gnn_spmm_bwd": (C.c_int, [vp, vp, vp, i64, i32, vp, i64, vp, i64, C.c_int]),
     "gnn_set_spmm_variant": (C.c_int, [vp, C.c_int]),

@@ -137,6 +137,30 @@ __global__ void to_dense_kernel(const int32_t *__restrict__ rowptr, const int32_
     for (int32_t k = rowptr[w] + lane; k < rowptr[w + 1]; k += 32) out[w * ld + colidx[k]] = val ? val[k] : 1.0f;
 }
 
+// flags[i] = int(A[i]) != 0 over the row-major dense matrix; flags[n] = 0 (scan sentinel)
+__global__ void dense_flags_kernel(const float *__restrict__ A, int64_t rows, int64_t cols, int64_t ld,
+                                   uint32_t *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = rows * cols;
+    if (i > n) return;
+    if (i == n) { flags[i] = 0; return; }
+    const float a = A[(i / cols) * ld + (i % cols)];
+    flags[i] = ((int)a != 0) ? 1u : 0u;
+}
+__global__ void dense_compact_kernel(const float *__restrict__ A, int64_t rows, int64_t cols, int64_t ld,
+                                     const uint32_t *__restrict__ pos, int32_t *__restrict__ out_rows,
+                                     int32_t *__restrict__ out_cols, float *__restrict__ out_vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const uint32_t p = pos[i];
+    if (pos[i + 1] != p) {
+        const int64_t r = i / cols, c = i % cols;
+        out_rows[p] = (int32_t)r;
+        out_cols[p] = (int32_t)c;
+        if (out_vals) out_vals[p] = A[r * ld + c];
+    }
+}
+
 __global__ void rebase_kernel(const int32_t *__restrict__ in, int64_t n, int32_t base, int32_t *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] - base;
@@ -394,6 +418,32 @@ int gnn_graph_to_dense(gnn_ctx_t *ctx, const gnn_graph_t *g, int weighted, float
                                                                                     weighted ? g->val : nullptr,
                                                                                     g->n_rows, out, ld);
     GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+// dense -> row-major COO of the entries with int(a) != 0  (graph::adj_to_edge_list, reference src/graph.cpp:46-67)
+int gnn_dense_to_coo(gnn_ctx_t *ctx, const float *A, int64_t rows, int64_t cols, int64_t ld, int32_t *out_rows,
+                     int32_t *out_cols, float *out_vals, int64_t capacity, int64_t *count_h) {
+    GNN_REQUIRE(ctx && A && count_h && rows > 0 && cols > 0, "gnn_dense_to_coo: bad argument");
+    const int64_t n = rows * cols;
+    GNN_REQUIRE(n < (int64_t)0x7FFFFFFF, "gnn_dense_to_coo: matrix too large for the dense path");
+    cudaStream_t s = ctx->stream;
+    uint32_t *flags = nullptr;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&flags, (size_t)(n + 1) * 4, s));
+    dense_flags_kernel<<<grid_for(n + 1, 256), 256, 0, s>>>(A, rows, cols, ld, flags);
+    GNN_LAUNCHED(ctx);
+    GNN_TRY(exclusive_scan_u32(ctx, flags, flags, n + 1, nullptr));
+    uint32_t cnt = 0;
+    GNN_CHECK_CUDA(cudaMemcpyAsync(&cnt, flags + n, 4, cudaMemcpyDeviceToHost, s));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    *count_h = cnt;
+    if (out_rows && out_cols && cnt > 0) {
+        GNN_REQUIRE((int64_t)cnt <= capacity, "gnn_dense_to_coo: %u entries exceed the output capacity %lld", cnt,
+                    (long long)capacity);
+        dense_compact_kernel<<<grid_for(n, 256), 256, 0, s>>>(A, rows, cols, ld, flags, out_rows, out_cols, out_vals);
+        GNN_LAUNCHED(ctx);
+    }
+    GNN_CHECK_CUDA(cudaFreeAsync(flags, s));
     return 0;
 }
 

@@ -1,0 +1,57 @@
+// device.h — the seam the reference left empty (include/device.cuh is 0 bytes; the commented-out
+// `device::add(out_data, lhs_data, rhs_data)` calls at include/functional.h:174,180 mark where it was meant
+// to go).  Thin C++ RAII layer over the C ABI (include/gnn_c.h): one process-wide context, device buffers
+// with shared ownership, and error translation to std::runtime_error.  No CPU fallback.
+#ifndef GNNB200_DEVICE_H
+#define GNNB200_DEVICE_H
+
+#include <cstdlib>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/gnn_c.h"
+
+namespace cyg {
+namespace device {
+
+inline void check(int rc) {
+    if (rc != 0) throw std::runtime_error(gnn_last_error());
+}
+
+// process-wide context (device from GNN_DEVICE, default 0); created on first use
+inline gnn_ctx_t *ctx() {
+    static gnn_ctx_t *c = [] {
+        gnn_ctx_t *p = nullptr;
+        const char *d = std::getenv("GNN_DEVICE");
+        check(gnn_ctx_create(d ? std::atoi(d) : 0, nullptr, &p));
+        return p;
+    }();
+    return c;
+}
+inline void sync() { check(gnn_ctx_sync(ctx())); }
+
+struct Buffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    explicit Buffer(size_t n) : bytes(n) { check(gnn_malloc(ctx(), &ptr, n)); }
+    Buffer(const Buffer &) = delete;
+    Buffer &operator=(const Buffer &) = delete;
+    ~Buffer() { gnn_free(ctx(), ptr); }
+};
+using buffer_ptr = std::shared_ptr<Buffer>;
+inline buffer_ptr alloc(size_t bytes) { return std::make_shared<Buffer>(bytes); }
+
+// owning handle of a device graph structure (CSR + CSC + normalisation)
+struct GraphHandle {
+    gnn_graph_t *g = nullptr;
+    explicit GraphHandle(gnn_graph_t *p) : g(p) {}
+    GraphHandle(const GraphHandle &) = delete;
+    GraphHandle &operator=(const GraphHandle &) = delete;
+    ~GraphHandle() { gnn_graph_destroy(ctx(), g); }
+};
+using graph_ptr = std::shared_ptr<GraphHandle>;
+
+} // namespace device
+} // namespace cyg
+#endif

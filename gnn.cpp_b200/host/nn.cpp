@@ -1,0 +1,183 @@
+// nn.cpp — see nn.h.  Registration/lookup semantics follow reference src/nn.cpp:12-151 (ordered child list,
+// recursive name maps with `parent_child` prefixing on collisions); the arithmetic is device kernels.
+#include "nn.h"
+
+#include <cmath>
+
+using namespace cyg;
+
+namespace nn {
+
+void Module::register_module(std::string n, Module *module) {
+    module->name = n;
+    _modules.push_back({n, std::shared_ptr<Module>(module)});
+}
+void Module::register_parameter(std::string n, tptr<float> p) {
+    if (!p->requires_grad() || p->grad_fn)
+        throw std::runtime_error("cannot add tensor as param, tensor requires_grad must be set to true and tensor must be non-leaf - explicitly created");
+    _parameters[n] = p;
+}
+void Module::register_buffer(std::string n, tptr<float> b) {
+    if (b->requires_grad() || b->grad_fn)
+        throw std::runtime_error("cannot add tensor as buffer, tensor requires_grad must be set to false and tensor must be non-leaf - explicitly created");
+    _buffers[n] = b;
+}
+void Module::zero_grad() {
+    for (auto &kv : _parameters) kv.second->zero_grad();
+    for (auto &kv : _modules) kv.second->zero_grad();
+}
+void Module::train(const bool &isTrain) {
+    training = isTrain;
+    for (auto &kv : _parameters) kv.second->requires_grad_(isTrain);
+    for (auto &kv : _modules) kv.second->train(isTrain);
+}
+tptr<float> Module::get_parameter(std::string n) {
+    auto params = named_parameters();
+    auto it = params.find(n);
+    if (it == params.end()) throw std::runtime_error("invalid input, no parameter with given name");
+    return it->second;
+}
+tptr<float> Module::get_buffer(std::string n) {
+    auto bufs = named_buffers();
+    auto it = bufs.find(n);
+    if (it == bufs.end()) throw std::runtime_error("invalid input, no buffer with given name");
+    return it->second;
+}
+std::shared_ptr<Module> Module::get_module(std::string n) {
+    for (auto &kv : _modules)
+        if (kv.first == n) return kv.second; // direct children first (cheap, unambiguous)
+    auto mods = named_modules();
+    auto it = mods.find(n);
+    if (it == mods.end()) throw std::runtime_error("invalid input, no Module with given name");
+    return it->second;
+}
+tptr<float> Module::operator()(const tptr<float> &input_tensor, tensor<int> *y) {
+    if (y == nullptr) return forward(input_tensor);
+    return forward(input_tensor, y);
+}
+std::vector<std::shared_ptr<Module>> Module::modules(const bool &recurse) {
+    std::vector<std::shared_ptr<Module>> out;
+    for (auto &kv : named_modules(recurse)) out.push_back(kv.second);
+    return out;
+}
+std::unordered_map<std::string, std::shared_ptr<Module>> Module::named_modules(const bool &recurse) {
+    std::unordered_map<std::string, std::shared_ptr<Module>> res;
+    if (!recurse || _modules.empty()) {
+        // a module owned by raw pointer (stack object) has no shared owner: report children only
+        auto self = this->weak_from_this().lock();
+        if (self) res[name] = self;
+        return res;
+    }
+    for (auto &kv : _modules) {
+        for (auto &sub : kv.second->named_modules(recurse)) {
+            if (res.count(sub.first)) res[kv.first + "_" + sub.first] = sub.second;
+            else res[sub.first] = sub.second;
+        }
+    }
+    return res;
+}
+std::vector<tptr<float>> Module::parameters(const bool &recurse) {
+    // deterministic order (registration order, depth first) so optimiser state lines up run to run; the reference
+    // iterates an unordered_map (nn.cpp:103-109)
+    std::vector<tptr<float>> out;
+    std::vector<std::string> keys;
+    for (auto &kv : _parameters) keys.push_back(kv.first);
+    std::sort(keys.begin(), keys.end());
+    for (auto &k : keys) out.push_back(_parameters[k]);
+    if (recurse)
+        for (auto &kv : _modules)
+            for (auto &p : kv.second->parameters(true)) out.push_back(p);
+    return out;
+}
+std::unordered_map<std::string, tptr<float>> Module::named_parameters(const bool &recurse) {
+    std::unordered_map<std::string, tptr<float>> res = _parameters;
+    if (!recurse || _modules.empty()) return res;
+    for (auto &kv : _modules) {
+        for (auto &sub : kv.second->named_parameters(recurse)) {
+            if (res.count(sub.first)) res[kv.first + "_" + sub.first] = sub.second;
+            else res[sub.first] = sub.second;
+        }
+    }
+    return res;
+}
+std::unordered_map<std::string, tptr<float>> Module::named_buffers(const bool &recurse) const {
+    std::unordered_map<std::string, tptr<float>> res = _buffers;
+    if (!recurse || _modules.empty()) return res;
+    for (auto &kv : _modules)
+        for (auto &sub : kv.second->named_buffers(recurse)) res[kv.first + "_" + sub.first] = sub.second;
+    return res;
+}
+std::vector<tptr<float>> Module::buffers(const bool &recurse) const {
+    std::vector<tptr<float>> out;
+    for (auto &kv : named_buffers(recurse)) out.push_back(kv.second);
+    return out;
+}
+
+Linear::Linear(const size_t &in_features, const size_t &out_features, const bool &bias, const std::string &n)
+    : Module(n), _bias(bias), _in_features(in_features), _out_features(out_features) {
+    register_parameter("weight", std::make_shared<tensor<float>>(std::vector<size_t>{out_features, in_features}, 1.0f, true));
+    if (_bias) register_parameter("bias", std::make_shared<tensor<float>>(std::vector<size_t>{out_features}, 1.0f, true));
+    reset_parameters();
+}
+void Linear::reset_parameters() { // U(-1/sqrt(in), 1/sqrt(in)) — reference nn.cpp:198-204
+    const float bound = 1.0f / std::sqrt((float)_in_features);
+    _parameters["weight"]->uniform(-bound, bound);
+    if (_bias) _parameters["bias"]->uniform(-bound, bound);
+}
+tptr<float> Linear::forward(const tptr<float> &x) {
+    auto op = std::make_unique<LinearOp<tensor<float>>>();
+    auto out = op->forward(x, _parameters["weight"], _bias ? _parameters["bias"] : nullptr, false);
+    if (out->requires_grad()) out->grad_fn = std::move(op);
+    return out;
+}
+
+Sequential::Sequential(std::vector<std::pair<std::string, Module *>> input, const std::string &n) : Module(n) {
+    for (auto &kv : input) register_module(kv.first, kv.second);
+}
+tptr<float> Sequential::forward(const tptr<float> &x) {
+    tptr<float> out = x;
+    for (auto &kv : _modules) out = (*kv.second)(out);
+    return out;
+}
+
+tptr<float> ReLU::forward(const tptr<float> &x) {
+    auto cond = x > 0.0f;
+    auto out = x->where(cond, 0.0f);
+    if (out->grad_fn) out->grad_fn->name = name;
+    return out;
+}
+
+tptr<float> softmax(const tptr<float> &x, int dim) {
+    auto sum_ = x->exp()->sum(dim, true);
+    auto out = (x - sum_->log())->exp();
+    if (out->grad_fn) out->grad_fn->name = "SoftmaxOp";
+    return out;
+}
+
+tptr<float> cross_entropy_loss(const tptr<float> logits, const tptr<int> target) {
+    auto op = std::make_unique<SoftmaxCrossEntropy<tensor<float>>>();
+    auto out = op->forward(logits, target);
+    if (out->requires_grad()) out->grad_fn = std::move(op);
+    return out;
+}
+
+void Optimizer::zero_grad() {
+    for (auto &p : _parameters) p->zero_grad();
+}
+
+void SGD::step() {
+    if (_velocity.size() != _parameters.size()) _velocity.assign(_parameters.size(), nullptr);
+    for (size_t i = 0; i < _parameters.size(); i++) {
+        auto &p = _parameters[i];
+        float *vel = nullptr;
+        if (_momentum != 0.0f) {
+            if (!_velocity[i]) _velocity[i] = device::alloc(p->numel() * 4);
+            vel = static_cast<float *>(_velocity[i]->ptr);
+        }
+        device::check(gnn_sgd_step(device::ctx(), (int64_t)p->numel(), p->dptr(), p->grad_dptr(), vel, _lr, _momentum, _dampening,
+                                   _weight_decay, _nestorov, _steps == 0));
+    }
+    _steps++;
+}
+
+} // namespace nn

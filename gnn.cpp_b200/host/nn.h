@@ -1,0 +1,99 @@
+// nn.h — Module tree, Linear, ReLU, Sequential, softmax, cross-entropy loss and the optimisers of the GCN
+// training loop (counterpart of reference include/nn.h:28-91,155-191).  Out of scope here: BatchNorm,
+// LayerNorm, Dropout, Sigmoid, tanh, Adam, MLP, Embedding.
+#ifndef GNNB200_NN_H
+#define GNNB200_NN_H
+
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "tensor.h"
+
+namespace nn {
+
+/** parameter / submodule registry — reference nn.h:28-61, nn.cpp:12-151 */
+class Module : public std::enable_shared_from_this<Module> {
+  public:
+    explicit Module(std::string n = "Module") : name(std::move(n)) {}
+    virtual ~Module() = default; // the reference's destructor is non-virtual (bug B5)
+    bool training = true;
+    std::string name;
+    void register_module(std::string name, Module *module);
+    void register_parameter(std::string name, cyg::tptr<float> p);
+    void register_buffer(std::string name, cyg::tptr<float> p);
+    void zero_grad();
+    void eval() { train(false); }
+    void train(const bool &isTrain = true);
+    cyg::tptr<float> get_parameter(std::string name);
+    cyg::tptr<float> get_buffer(std::string name);
+    std::shared_ptr<Module> get_module(std::string name);
+    cyg::tptr<float> operator()(const cyg::tptr<float> &input_tensor, cyg::tensor<int> *y = nullptr);
+    virtual cyg::tptr<float> forward(const cyg::tptr<float> &) { throw std::runtime_error("not implemented"); }
+    virtual cyg::tptr<float> forward(const cyg::tptr<float> &, cyg::tensor<int> *) { throw std::runtime_error("not implemented"); }
+    std::vector<std::shared_ptr<Module>> modules(const bool &recurse = true);
+    std::unordered_map<std::string, std::shared_ptr<Module>> named_modules(const bool &recurse = true);
+    std::vector<cyg::tptr<float>> parameters(const bool &recurse = true);
+    std::unordered_map<std::string, cyg::tptr<float>> named_parameters(const bool &recurse = true);
+    std::vector<cyg::tptr<float>> buffers(const bool &recurse = true) const;
+    std::unordered_map<std::string, cyg::tptr<float>> named_buffers(const bool &recurse = true) const;
+
+    std::vector<std::pair<std::string, std::shared_ptr<Module>>> _modules;
+    std::unordered_map<std::string, cyg::tptr<float>> _parameters;
+    std::unordered_map<std::string, cyg::tptr<float>> _buffers;
+};
+
+/** y = x W^T + b, W[out,in] — reference nn.h:63-73, nn.cpp:187-211.  One fused NT-GEMM node. */
+class Linear : public Module {
+  public:
+    Linear(const size_t &in_features, const size_t &out_features, const bool &bias = true, const std::string &n = "Linear");
+    void reset_parameters();
+    cyg::tptr<float> forward(const cyg::tptr<float> &input_tensor) override;
+    bool _bias;
+    size_t _in_features, _out_features;
+};
+
+class Sequential : public Module { // reference nn.h:75-82
+  public:
+    explicit Sequential(const std::string &n = "seq") : Module(n) {}
+    Sequential(std::vector<std::pair<std::string, Module *>> input, const std::string &n = "seq");
+    void add_module(std::string n, Module *m) { register_module(n, m); }
+    cyg::tptr<float> forward(const cyg::tptr<float> &input_tensor) override;
+};
+
+class ReLU : public Module { // reference nn.h:84-91, nn.cpp:229-237
+  public:
+    explicit ReLU(const std::string &n = "ReLU") : Module(n) {}
+    cyg::tptr<float> forward(const cyg::tptr<float> &input_tensor) override;
+};
+
+/** softmax(x) = exp(x - log(sum(exp(x)))) composed from tensor ops like the reference (nn.cpp:270-278) */
+cyg::tptr<float> softmax(const cyg::tptr<float> &input_tensor, int dim);
+
+/** mean_i -log(exp(z_iy)/(sum_c exp(z_ic)+1e-20)) — reference nn.h:191, nn.cpp:442-453 — one fused kernel; its
+ *  backward is the analytic (softmax - onehot)/N (the reference's own backward throws, bug B3). */
+cyg::tptr<float> cross_entropy_loss(const cyg::tptr<float> logits, const cyg::tptr<int> target);
+
+class Optimizer { // reference nn.h:155-162
+  public:
+    explicit Optimizer(std::vector<cyg::tptr<float>> parameters) : _parameters(std::move(parameters)) {}
+    void zero_grad();
+    std::vector<cyg::tptr<float>> _parameters;
+};
+
+/** torch.optim.SGD semantics (the documented intent, nn.h:165-167; the reference body segfaults, bug B4) */
+class SGD : public Optimizer {
+  public:
+    SGD(std::vector<cyg::tptr<float>> parameters, float lr, float momentum = 0, float dampening = 0, float weight_decay = 0,
+        bool nestorov = false)
+        : Optimizer(std::move(parameters)), _lr(lr), _dampening(dampening), _momentum(momentum), _weight_decay(weight_decay), _nestorov(nestorov) {}
+    void step();
+    float _lr, _dampening, _momentum, _weight_decay;
+    bool _nestorov;
+    std::vector<cyg::device::buffer_ptr> _velocity;
+    size_t _steps = 0;
+};
+
+} // namespace nn
+#endif

@@ -97,6 +97,12 @@ GNN_API int gnn_graph_export_h(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t *ro
 /* Dense adjacency (graph::Data::to_adj / edge_to_adj_mat, src/graph.cpp:118-129) for API fidelity at small N:
  * out[n_rows, n_cols] = weighted ? val : 1 at the stored positions, 0 elsewhere. */
 GNN_API int gnn_graph_to_dense(gnn_ctx_t *ctx, const gnn_graph_t *g, int weighted, float *out, int64_t ld);
+/* Dense matrix -> row-major sorted COO of the entries with int(a) != 0 (graph::adj_to_edge_list,
+ * src/graph.cpp:46-67).  Two passes (flag + scan + compact); *count_h receives the number of entries; when
+ * out_rows/out_cols are NULL only the count is produced. Synchronises. */
+GNN_API int gnn_dense_to_coo(gnn_ctx_t *ctx, const float *A, int64_t rows, int64_t cols, int64_t ld,
+                             int32_t *out_rows, int32_t *out_cols, float *out_vals, int64_t capacity,
+                             int64_t *count_h);
 
 /* ---------------------------------------------------------------- aggregation (K4/K5/K7) -----------
  * Forward  Y[n_rows,F] = A_hat * P           — adj_mat->mm(x), reference src/graph.cpp:208 ->
