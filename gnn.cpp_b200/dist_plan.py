@@ -1,0 +1,55 @@
+"""Host-side description of the row-partitioned (multi-GPU) train step: who owns which rows, which tensors are
+all-gathered when, and how many bytes cross NVLink per step.  Mirrors the schedule csrc/trainer.cu executes
+(same layer-order rule, same padded widths) so the CPU tests and bench.py can reason about it without a GPU."""
+import ctypes
+
+import numpy as np
+
+from . import capi
+
+
+def partition(N, world):
+    """part_ptr[p] = min(N, p*ceil(N/world)) — computed by the library (gnn_partition_ptr_h)."""
+    out = np.empty(world + 1, dtype=np.int64)
+    capi.call("gnn_partition_ptr_h", int(N), int(world), out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def chunk_rows(N, world):
+    return (N + world - 1) // world
+
+
+def padded(F):
+    return (F + 3) // 4 * 4
+
+
+def layer_order(dims):
+    """True = aggregate first (A_hat H, then the GEMM): chosen when the input is narrower than the output."""
+    return [dims[l - 1] < dims[l] for l in range(1, len(dims))]
+
+
+def exchange_schedule(dims):
+    """[(phase, layer, tensor, width)] of every all-gather in one train step, in execution order."""
+    L = len(dims) - 1
+    af = layer_order(dims)
+    sched = []
+    for l in range(1, L + 1):
+        if af[l - 1]:
+            sched.append(("fwd", l, "H%d" % (l - 1), padded(dims[l - 1])))
+        else:
+            sched.append(("fwd", l, "P%d" % l, padded(dims[l])))
+    for l in range(L, 0, -1):
+        if af[l - 1]:
+            if l > 1:
+                sched.append(("bwd", l, "dM%d" % l, padded(dims[l - 1])))
+        else:
+            sched.append(("bwd", l, "dZ%d" % l, padded(dims[l])))
+    return sched
+
+
+def comm_bytes_per_step(N, dims, world):
+    """bytes RECEIVED per rank per step: all-gathers of (world-1) remote chunks + the gradient all-reduce."""
+    c = chunk_rows(N, world)
+    gathers = sum(w for _, _, _, w in exchange_schedule(dims)) * 4 * c * (world - 1)
+    n_params = sum(dims[l] * dims[l - 1] + dims[l] for l in range(1, len(dims)))
+    return gathers + (2 * 4 * n_params * (world - 1)) // max(world, 1)
