@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="products", choices=sorted(synth.CONFIGS))
-    ap.add_argument("--precision", type=int, default=0)
+    ap.add_argument("--precision", type=int, default=1, help="dense transforms: 1 = 3xTF32 on tcgen05 (default), 0 = FP32 FMA")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -1,20 +1,730 @@
-// gemm_tc.cu — tensor-core (tcgen05, 3xTF32) variants of the dense feature transforms.
-// Entry points return -1 when a shape is not supported so gemm.cu falls back to the FP32 FMA kernel.
+// gemm_tc.cu — tensor-core (tcgen05, 3xTF32) variants of the dense feature transforms K6.
+//
+// Every FP32 operand a is split as a = hi + lo with hi = rna_tf32(a), lo = rna_tf32(a - hi); the product is
+// accumulated in FP32 (TMEM) as  lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  (error ~2^-21, inside the 1e-5 contract;
+// the dropped lo*lo term is ~2^-22).  The big, streamed operand is split ON CHIP: TMA lands the raw FP32 tile in
+// shared memory (128-byte swizzle), four converter warps rewrite it as hi (in place) + lo (second buffer), and one
+// thread issues the tcgen05.mma triple.  The small operand (weights) is pre-split once per call.
+//
+//   rows kernel (NT, NN):  C[M,N] = A[M,K] * Bt[N,K]^T   A streamed by 128-row tiles, persistent CTAs,
+//                          two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1,
+//                          fused bias / ReLU / mask epilogue with coalesced row stores.
+//   tn kernel:             C[K1,K2] = A[M,K1]^T * B[M,K2] reduction over the (millions of) node rows: both operands
+//                          are MN-major straight out of TMA, every CTA owns a contiguous node range and writes one
+//                          partial; a fixed-order pass sums the partials (deterministic, no atomics).
+//
+// Entry points return -1 when a shape/alignment is not supported so gemm.cu falls back to the FP32 FMA kernel.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace gnn {
+namespace tc {
 
-int gemm_tc_nt(gnn_ctx *, int64_t, int32_t, int32_t, const float *, int64_t, const float *, int64_t, float *, int64_t,
-               const float *, int) {
-    return -1;
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-int gemm_tc_nn(gnn_ctx *, int64_t, int32_t, int32_t, const float *, int64_t, const float *, int64_t, float *, int64_t,
-               const float *, int64_t) {
-    return -1;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-int gemm_tc_tn(gnn_ctx *, int64_t, int32_t, int32_t, const float *, int64_t, const float *, int64_t, float *,
-               int64_t) {
-    return -1;
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :
+                 : "r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread for the CTA
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :
+                 : "r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+// arrives on the mbarrier when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base+i), columns c..c+15
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+// in-place hi, separate lo for one 16-byte vector
+__device__ __forceinline__ void split4(float4 *hi_ptr, float4 *lo_ptr) {
+    const float4 v = *hi_ptr;
+    float4 h, l;
+    h.x = __uint_as_float(rna_tf32(v.x)); l.x = __uint_as_float(rna_tf32(v.x - h.x));
+    h.y = __uint_as_float(rna_tf32(v.y)); l.y = __uint_as_float(rna_tf32(v.y - h.y));
+    h.z = __uint_as_float(rna_tf32(v.z)); l.z = __uint_as_float(rna_tf32(v.z - h.z));
+    h.w = __uint_as_float(rna_tf32(v.w)); l.w = __uint_as_float(rna_tf32(v.w - h.w));
+    *hi_ptr = h;
+    *lo_ptr = l;
+}
+
+// shared-memory matrix descriptor, descriptor version 1 (sm_100).  layout 2 = 128-byte swizzle of 16-byte chunks
+// (TMA SWIZZLE_128B), layout 1 = 128-byte swizzle of 32-byte chunks (TMA SWIZZLE_128B_ATOM_32B) — the only layout
+// the tensor core accepts for MN-major 32-bit operands.
+constexpr uint64_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint64_t layout = LAYOUT_SW128) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    d |= layout << 61;
+    return d;
+}
+// instruction descriptor: D=F32, A=B=TF32, M x N tile, operand majors (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t instr_desc(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ rows kernel
+constexpr int ROWS_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2-5 converters, warps 6-9 epilogue
+constexpr int TILE_M = 128;
+constexpr int BK = 32;                      // floats per k-block = one 128-byte swizzle row
+constexpr uint32_t A_TILE_BYTES = TILE_M * BK * 4; // 16 KB
+constexpr uint32_t CTRL_BYTES = 1024;
+constexpr uint32_t STAGING_BYTES = 4 * 32 * 128; // 4 epilogue warps x 32 rows x 32 columns
+
+struct RowsArgs {
+    int64_t M;
+    int32_t N, Npad, kblocks, num_tiles, stages;
+    uint32_t tmem_cols, acc_stride, stage_bytes, b_bytes;
+    float *C;
+    int64_t ldc;
+    const float *bias;
+    int relu;
+    const float *mask;
+    int64_t ldm;
+};
+
+__global__ void __launch_bounds__(ROWS_THREADS, 1)
+    tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const RowsArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw_u32);
+
+    const uint32_t bar_full = base, bar_conv = base + 64, bar_empty = base + 128;
+    const uint32_t bar_tfull = base + 192, bar_tempty = base + 208, tmem_slot = base + 224;
+    const uint32_t staging = base + CTRL_BYTES;
+    const uint32_t stage0 = staging + STAGING_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < a.stages; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 4);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gbase + 224);
+
+    const int32_t first_tile = blockIdx.x, tile_step = gridDim.x;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            const uint32_t tx = A_TILE_BYTES + 2 * a.b_bytes;
+            for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step) {
+                for (int32_t kb = 0; kb < a.kblocks; kb++, it++) {
+                    const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t st = stage0 + s * a.stage_bytes;
+                    mbar_arrive_expect_tx(bar_full + 8 * s, tx);
+                    tma_load_2d(st, &tmA, bar_full + 8 * s, kb * BK, tile * TILE_M);
+                    tma_load_2d(st + 2 * A_TILE_BYTES, &tmB, bar_full + 8 * s, kb * BK, 0);
+                    tma_load_2d(st + 2 * A_TILE_BYTES + a.b_bytes, &tmB, bar_full + 8 * s, kb * BK, a.Npad);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc(TILE_M, (uint32_t)a.Npad, 0, 0);
+            uint32_t it = 0, tile_it = 0;
+            for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step, tile_it++) {
+                const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * a.acc_stride;
+                for (int32_t kb = 0; kb < a.kblocks; kb++, it++) {
+                    const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    mbar_wait(bar_conv + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t st = stage0 + s * a.stage_bytes;
+                    const uint64_t a_hi = smem_desc(st, 16, 1024), a_lo = smem_desc(st + A_TILE_BYTES, 16, 1024);
+                    const uint64_t b_hi = smem_desc(st + 2 * A_TILE_BYTES, 16, 1024);
+                    const uint64_t b_lo = smem_desc(st + 2 * A_TILE_BYTES + a.b_bytes, 16, 1024);
+#pragma unroll
+                    for (uint32_t k = 0; k < BK / 8; k++) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4); // 8 tf32 = 32 bytes along the swizzled row
+                        mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+                        mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+                        mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+                    }
+                    mma_commit(bar_empty + 8 * s);
+                }
+                mma_commit(bar_tfull + 8 * acc);
+            }
+        }
+    } else if (warp < 6) {
+        const int t = threadIdx.x - 64; // 0..127
+        uint32_t it = 0;
+        for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step) {
+            for (int32_t kb = 0; kb < a.kblocks; kb++, it++) {
+                const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                mbar_wait(bar_full + 8 * s, ph);
+                uint8_t *st = gbase + CTRL_BYTES + STAGING_BYTES + (size_t)s * a.stage_bytes;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    float4 *hp = reinterpret_cast<float4 *>(st) + (i * 128 + t);
+                    split4(hp, hp + A_TILE_BYTES / 16);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+            }
+        }
+    } else {
+        const int q = warp & 3; // TMEM lane quadrant this warp may read
+        uint8_t *stg = gbase + CTRL_BYTES + q * 4096;
+        const int rsub = lane >> 3, j = lane & 7;
+        uint32_t tile_it = 0;
+        for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step, tile_it++) {
+            const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * acc, acc_ph);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * a.acc_stride;
+            const int64_t row0 = (int64_t)tile * TILE_M + q * 32;
+            for (int32_t c0 = 0; c0 < a.Npad; c0 += 32) {
+                uint32_t r[32];
+                const bool two = c0 + 16 < a.Npad;
+                tmem_ld16(t_row + c0, r);
+                if (two) tmem_ld16(t_row + c0 + 16, r + 16);
+                tmem_ld_wait();
+                if (c0 + 32 >= a.Npad) { // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                }
+                // phase 1: thread = row, scatter its 32 columns into the warp's staging rows (xor-swizzled chunks)
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    if (c < 4 || two) {
+                        float4 v = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                               __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
+                        *reinterpret_cast<float4 *>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = v;
+                    }
+                }
+                __syncwarp();
+                // phase 2: 8 lanes cover one 128-byte row segment -> coalesced global stores, fused epilogue
+                const int32_t col = c0 + 4 * j;
+                if (col < a.N) {
+                    const bool full = col + 3 < a.N;
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (a.bias) { // scalar loads: the bias vector sits anywhere in the parameter slab
+                        bv.x = __ldg(a.bias + col);
+                        if (col + 1 < a.N) bv.y = __ldg(a.bias + col + 1);
+                        if (col + 2 < a.N) bv.z = __ldg(a.bias + col + 2);
+                        if (col + 3 < a.N) bv.w = __ldg(a.bias + col + 3);
+                    }
+                    // all mask vectors of this chunk are fetched before the first store so the loads overlap
+                    float4 mk[8];
+                    if (a.mask && full) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; itr++) {
+                            const int64_t grow = row0 + itr * 4 + rsub;
+                            mk[itr] = grow < a.M ? __ldg(reinterpret_cast<const float4 *>(a.mask + grow * a.ldm + col))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int itr = 0; itr < 8; itr++) {
+                        const int rr = itr * 4 + rsub;
+                        const int64_t grow = row0 + rr;
+                        if (grow >= a.M) continue;
+                        float4 v = *reinterpret_cast<const float4 *>(stg + rr * 128 + ((j ^ (rr & 7)) << 4));
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        if (a.relu) {
+                            v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+                            v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+                        }
+                        float *dst = a.C + grow * a.ldc + col;
+                        if (full) {
+                            if (a.mask) {
+                                v.x = mk[itr].x > 0.f ? v.x : 0.f; v.y = mk[itr].y > 0.f ? v.y : 0.f;
+                                v.z = mk[itr].z > 0.f ? v.z : 0.f; v.w = mk[itr].w > 0.f ? v.w : 0.f;
+                            }
+                            *reinterpret_cast<float4 *>(dst) = v;
+                        } else {
+                            const float vv[3] = {v.x, v.y, v.z};
+                            for (int e = 0; e < 3 && col + e < a.N; e++) {
+                                float o = vv[e];
+                                if (a.mask) o = a.mask[grow * a.ldm + col + e] > 0.f ? o : 0.f;
+                                dst[e] = o;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tn kernel
+// The tensor core adds into its FP32 accumulator with truncation, so a reduction over millions of node rows cannot
+// stay in one TMEM accumulator (measured: error grows linearly, ~2e-6 per 96 accumulations).  The node range of a
+// CTA is therefore cut into chunks of TN_CHUNK stages; chunks alternate between two TMEM accumulators, and while
+// the MMAs of chunk c+1 run, the converter warps drain chunk c into per-thread FP32 register sums (round to
+// nearest).  grid = (node splits, 128-row halves of the output).
+constexpr int TN_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2-9 converters + accumulator drain
+constexpr int TN_BK = 16;       // node rows per stage (two K=8 MMA steps)
+constexpr int TN_CHUNK = 16;    // stages per TMEM accumulation chunk (256 node rows, 96 accumulating MMAs)
+constexpr uint32_t BOX_BYTES = TN_BK * 128; // one TMA box: 16 node rows x 32 floats
+
+struct TnArgs {
+    int64_t M, nodes_per_cta;
+    int32_t K1, nbB, N, stages;
+    uint32_t tmem_cols, stage_bytes, hi_bytes;
+    int64_t part_stride; // floats per node split: gridDim.y * 128 * N
+    float *partial;      // [splits][gridDim.y*128][N]
+};
+
+__global__ void __launch_bounds__(TN_THREADS, 1)
+    tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw_u32);
+
+    const uint32_t bar_full = base, bar_conv = base + 64, bar_empty = base + 128;
+    const uint32_t bar_tfull = base + 192, bar_tempty = base + 208, tmem_slot = base + 224;
+    const uint32_t stage0 = base + CTRL_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int32_t half = blockIdx.y;
+    const int32_t colsA = min(128, a.K1 - half * 128);  // output rows of this half
+    const int32_t nbA = (colsA + 31) / 32;              // real A boxes (of the 4 the MMA reads)
+
+    // operand rows/columns beyond K1/K2 only feed ignored accumulator entries; zero them once anyway
+    {
+        float4 *z = reinterpret_cast<float4 *>(gbase + CTRL_BYTES);
+        const uint32_t n16 = (uint32_t)a.stages * a.stage_bytes / 16;
+        for (uint32_t i = threadIdx.x; i < n16; i += TN_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < a.stages; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 8);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gbase + 224);
+
+    const int64_t n_begin = (int64_t)blockIdx.x * a.nodes_per_cta;
+    const int64_t n_end = min(a.M, n_begin + a.nodes_per_cta);
+    const int32_t iters = (int32_t)((n_end - n_begin + TN_BK - 1) / TN_BK);
+    const int32_t nchunks = (iters + TN_CHUNK - 1) / TN_CHUNK;
+    constexpr uint32_t A_HI_BYTES = 4 * BOX_BYTES;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)(nbA + a.nbB) * BOX_BYTES;
+            for (int32_t it = 0; it < iters; it++) {
+                const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                const uint32_t st = stage0 + s * a.stage_bytes;
+                const int32_t node = (int32_t)(n_begin + (int64_t)it * TN_BK);
+                mbar_arrive_expect_tx(bar_full + 8 * s, tx);
+                for (int32_t b = 0; b < nbA; b++)
+                    tma_load_2d(st + b * BOX_BYTES, &tmA, bar_full + 8 * s, half * 128 + b * 32, node);
+                for (int32_t b = 0; b < a.nbB; b++)
+                    tma_load_2d(st + A_HI_BYTES + b * BOX_BYTES, &tmB, bar_full + 8 * s, b * 32, node);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc(128, (uint32_t)a.N, 1, 1);
+            int32_t it = 0;
+            for (int32_t chunk = 0; chunk < nchunks; chunk++) {
+                const uint32_t accb = chunk & 1, acc_ph = (chunk >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * accb, acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + accb * a.N;
+                const int32_t nst = min(TN_CHUNK, iters - chunk * TN_CHUNK);
+                for (int32_t jst = 0; jst < nst; jst++, it++) {
+                    const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    mbar_wait(bar_conv + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t st = stage0 + s * a.stage_bytes;
+                    // MN-major, 32-byte-atom 128-byte swizzle: LBO = distance between 32-float column boxes,
+                    // SBO = distance between groups of 4 node rows
+                    const uint64_t a_hi = smem_desc(st, BOX_BYTES, 512, LAYOUT_SW128_BASE32B);
+                    const uint64_t a_lo = smem_desc(st + a.hi_bytes, BOX_BYTES, 512, LAYOUT_SW128_BASE32B);
+                    const uint64_t b_hi = smem_desc(st + A_HI_BYTES, BOX_BYTES, 512, LAYOUT_SW128_BASE32B);
+                    const uint64_t b_lo = smem_desc(st + A_HI_BYTES + a.hi_bytes, BOX_BYTES, 512, LAYOUT_SW128_BASE32B);
+#pragma unroll
+                    for (uint32_t k = 0; k < TN_BK / 8; k++) {
+                        const uint64_t adv = (uint64_t)(k * 1024 >> 4); // next group of 8 node rows
+                        mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (jst | k) != 0);
+                        mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+                        mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+                    }
+                    mma_commit(bar_empty + 8 * s);
+                }
+                mma_commit(bar_tfull + 8 * accb);
+            }
+        }
+    } else {
+        const int t = threadIdx.x - 64; // 0..255
+        const int q = warp & 3;         // TMEM lane quadrant this warp may read
+        const int colhalf = (warp - 2) >> 2;
+        const int32_t Nh = a.N >> 1;    // columns summed by this thread (multiple of 16, <= 128)
+        float acc[128];
+#pragma unroll
+        for (int i = 0; i < 128; i++) acc[i] = 0.f;
+
+        auto drain = [&](int32_t chunk) {
+            const uint32_t accb = chunk & 1, acc_ph = (chunk >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * accb, acc_ph);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + accb * a.N + colhalf * Nh;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (c * 16 < Nh) {
+                    uint32_t r[16];
+                    tmem_ld16(t_row + c * 16, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; e++) acc[c * 16 + e] += __uint_as_float(r[e]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * accb);
+        };
+
+        int32_t drained = 0;
+        const int32_t nboxes = nbA + a.nbB; // a box is 2 KB = 128 float4
+        for (int32_t it = 0; it < iters; it++) {
+            const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            uint8_t *st = gbase + CTRL_BYTES + (size_t)s * a.stage_bytes;
+            for (int32_t i = t; i < nboxes * 128; i += 256) {
+                const int32_t b = i >> 7, e = i & 127;
+                const uint32_t off = (b < nbA ? b * BOX_BYTES : A_HI_BYTES + (b - nbA) * BOX_BYTES) + e * 16;
+                float4 *hp = reinterpret_cast<float4 *>(st + off);
+                split4(hp, hp + a.hi_bytes / 16);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+            // chunk `drained` is complete once the pipeline has moved a.stages stages past its end
+            if (it + 1 == (drained + 1) * TN_CHUNK + a.stages) drain(drained++);
+        }
+        while (drained < nchunks) drain(drained++);
+
+        float *orow = a.partial + (size_t)blockIdx.x * a.part_stride + (size_t)(half * 128 + q * 32 + lane) * a.N +
+                      colhalf * Nh;
+#pragma unroll
+        for (int c = 0; c < 32; c++)
+            if (c * 4 < Nh)
+                *reinterpret_cast<float4 *>(orow + c * 4) =
+                    make_float4(acc[c * 4], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+// C[r, c] = sum over CTAs (ascending) of partial[cta][r][c]
+__global__ void tn_reduce_kernel(const float *__restrict__ partial, int32_t n_parts, int64_t part_stride, int32_t N,
+                                 int32_t K1, int32_t K2, float *__restrict__ C, int64_t ldc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)K1 * K2) return;
+    const int32_t r = (int32_t)(i / K2), c = (int32_t)(i % K2);
+    const float *p = partial + (size_t)r * N + c;
+    float s = 0.f;
+    for (int32_t z = 0; z < n_parts; z++) s += p[(size_t)z * part_stride];
+    C[(int64_t)r * ldc + c] = s;
+}
+
+// weights -> [2*Npad, Kpad]: rows [0,Npad) = hi, rows [Npad,2Npad) = lo of Bt[n][k], zero padded.
+// transpose = 0: Bt[n][k] = B[n*ldb + k] (NT);  1: Bt[n][k] = B[k*ldb + n] (NN)
+__global__ void prep_weights_kernel(const float *__restrict__ B, int64_t ldb, int32_t N, int32_t K, int transpose,
+                                    float *__restrict__ out, int32_t Npad, int32_t Kpad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Npad * Kpad) return;
+    const int32_t n = (int32_t)(i / Kpad), k = (int32_t)(i % Kpad);
+    float v = 0.f;
+    if (n < N && k < K) v = transpose ? B[(int64_t)k * ldb + n] : B[(int64_t)n * ldb + k];
+    float hi = __uint_as_float(rna_tf32(v));
+    if (!isfinite(hi)) hi = v; // keep inf/nan (and values that would round up to inf) in the hi part alone
+    const float lo = isfinite(hi) ? __uint_as_float(rna_tf32(v - hi)) : 0.f;
+    out[i] = hi;
+    out[(int64_t)Npad * Kpad + i] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// 2-D FP32 row-major view [rows, cols] with leading dimension ld; box = {32 floats, box_rows}, 128-byte swizzle,
+// out-of-bounds elements read as zero
+static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+    EncodeTiledFn fn = encode_fn();
+    GNN_REQUIRE(fn, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GNN_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+                (long long)rows, (long long)cols, (long long)ld);
+    return 0;
+}
+
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+static uint32_t pow2_cols(uint32_t c) {
+    uint32_t p = 32;
+    while (p < c) p <<= 1;
+    return p;
+}
+constexpr uint32_t SMEM_MAX = 227 * 1024;
+
+// C[M, N] (N <= 256) = A[M,K] * Bt^T with Bt given through `transpose` as in prep_weights_kernel
+static int rows_gemm(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B,
+                     int64_t ldb, int transpose, float *C, int64_t ldc, const float *bias, int relu, const float *mask,
+                     int64_t ldm) {
+    const int32_t Npad = (int32_t)round_up(N, 16), Kpad = (int32_t)round_up(K, BK);
+    void *ws = nullptr;
+    GNN_TRY(ctx->workspace((size_t)2 * Npad * Kpad * 4, &ws));
+    float *Bs = (float *)ws;
+    {
+        const int64_t n = (int64_t)Npad * Kpad;
+        prep_weights_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(B, ldb, N, K, transpose, Bs, Npad, Kpad);
+        GNN_LAUNCHED(ctx);
+    }
+    CUtensorMap tmA, tmB;
+    GNN_TRY(make_map(&tmA, A, M, K, lda, TILE_M));
+    GNN_TRY(make_map(&tmB, Bs, 2 * (int64_t)Npad, Kpad, Kpad, (uint32_t)Npad));
+
+    RowsArgs a;
+    a.M = M; a.N = N; a.Npad = Npad; a.kblocks = Kpad / BK;
+    a.num_tiles = (int32_t)ceil_div(M, TILE_M);
+    a.b_bytes = (uint32_t)Npad * 128;
+    a.stage_bytes = 2 * A_TILE_BYTES + 2 * a.b_bytes;
+    const uint32_t fixed = 1024 /*align slack*/ + CTRL_BYTES + STAGING_BYTES;
+    int stages = (int)((SMEM_MAX - fixed) / a.stage_bytes);
+    if (stages > 6) stages = 6;
+    GNN_REQUIRE(stages >= 2, "gemm_tc: tile does not fit shared memory");
+    a.stages = stages;
+    a.acc_stride = pow2_cols((uint32_t)Npad);
+    a.tmem_cols = 2 * a.acc_stride;
+    a.C = C; a.ldc = ldc; a.bias = bias; a.relu = relu; a.mask = mask; a.ldm = ldm;
+    const uint32_t smem = fixed + (uint32_t)stages * a.stage_bytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        attr_set = true;
+    }
+    const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+    tc_rows_kernel<<<grid, ROWS_THREADS, smem, ctx->stream>>>(tmA, tmB, a);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+// C[K1, K2 (<=256)] = A[M,K1]^T B[M,K2]
+static int tn_gemm(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float *A, int64_t lda, const float *B,
+                   int64_t ldb, float *C, int64_t ldc) {
+    TnArgs a;
+    a.M = M;
+    a.K1 = K1;
+    const int32_t halves = (int32_t)ceil_div(K1, 128);
+    a.nbB = (int32_t)ceil_div(K2, 32);
+    a.N = a.nbB * 32;
+    a.hi_bytes = (uint32_t)(4 + a.nbB) * BOX_BYTES;
+    a.stage_bytes = 2 * a.hi_bytes;
+    const uint32_t fixed = 1024 + CTRL_BYTES;
+    int stages = (int)((SMEM_MAX - fixed) / a.stage_bytes);
+    if (stages > 6) stages = 6;
+    GNN_REQUIRE(stages >= 2, "gemm_tc: tile does not fit shared memory");
+    a.stages = stages;
+    a.tmem_cols = pow2_cols((uint32_t)(2 * a.N));
+    int64_t splits = ctx->sm_count / halves;
+    if (splits < 1) splits = 1;
+    const int64_t max_splits = ceil_div(M, TN_BK);
+    if (splits > max_splits) splits = max_splits;
+    a.nodes_per_cta = round_up(ceil_div(M, splits), TN_BK);
+    splits = ceil_div(M, a.nodes_per_cta);
+    a.part_stride = (int64_t)halves * 128 * a.N;
+    void *ws = nullptr;
+    GNN_TRY(ctx->workspace((size_t)splits * a.part_stride * 4, &ws));
+    a.partial = (float *)ws;
+    CUtensorMap tmA, tmB;
+    GNN_TRY(make_map(&tmA, A, M, K1, lda, TN_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    GNN_TRY(make_map(&tmB, B, M, K2, ldb, TN_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    const uint32_t smem = fixed + (uint32_t)stages * a.stage_bytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        attr_set = true;
+    }
+    tc_tn_kernel<<<dim3((unsigned)splits, (unsigned)halves), TN_THREADS, smem, ctx->stream>>>(tmA, tmB, a);
+    GNN_LAUNCHED(ctx);
+    const int64_t n = (int64_t)K1 * K2;
+    tn_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(a.partial, (int32_t)splits, a.part_stride, a.N,
+                                                                        K1, K2, C, ldc);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+} // namespace tc
+
+// The TMA path needs 16-byte aligned rows; anything else goes back to the FP32 FMA kernel (return -1).
+// The rows kernel keeps a whole reduction in one TMEM accumulator, whose truncating adds cost ~2e-6 of relative
+// error per 256 of K (measured): reductions longer than 512 stay on the FP32 FMA kernel to hold the 1e-5 contract.
+constexpr int32_t TC_MAX_K = 512;
+int gemm_tc_nt(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B, int64_t ldb,
+               float *C, int64_t ldc, const float *bias, int relu) {
+    if (!tc::aligned16(A) || !tc::aligned16(C) || (lda & 3) || (ldc & 3)) return -1;
+    if (M >= (1ll << 31) || K > TC_MAX_K) return -1;
+    for (int32_t n0 = 0; n0 < N; n0 += 256) { // wider outputs: column panels of 256
+        const int32_t nn = N - n0 < 256 ? N - n0 : 256;
+        GNN_TRY(tc::rows_gemm(ctx, M, nn, K, A, lda, B + (int64_t)n0 * ldb, ldb, 0, C + n0, ldc, bias ? bias + n0 : nullptr,
+                              relu, nullptr, 0));
+    }
+    return 0;
+}
+
+int gemm_tc_nn(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B, int64_t ldb,
+               float *C, int64_t ldc, const float *mask, int64_t ldm) {
+    if (!tc::aligned16(A) || !tc::aligned16(C) || (lda & 3) || (ldc & 3)) return -1;
+    if (mask && (!tc::aligned16(mask) || (ldm & 3))) return -1;
+    if (M >= (1ll << 31) || K > TC_MAX_K) return -1;
+    for (int32_t n0 = 0; n0 < N; n0 += 256) {
+        const int32_t nn = N - n0 < 256 ? N - n0 : 256;
+        GNN_TRY(tc::rows_gemm(ctx, M, nn, K, A, lda, B + n0, ldb, 1, C + n0, ldc, nullptr, 0, mask ? mask + n0 : nullptr,
+                              ldm));
+    }
+    return 0;
+}
+
+int gemm_tc_tn(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float *A, int64_t lda, const float *B,
+               int64_t ldb, float *C, int64_t ldc) {
+    if (!tc::aligned16(A) || !tc::aligned16(B) || (lda & 3) || (ldb & 3)) return -1;
+    if (M >= (1ll << 31)) return -1;
+    for (int32_t c0 = 0; c0 < K2; c0 += 256) { // wider outputs: column panels of 256
+        const int32_t kc = K2 - c0 < 256 ? K2 - c0 : 256;
+        GNN_TRY(tc::tn_gemm(ctx, M, K1, kc, A, lda, B + c0, ldb, C + c0, ldc));
+    }
+    return 0;
 }
 
 } // namespace gnn

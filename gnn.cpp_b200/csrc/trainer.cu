@@ -43,7 +43,7 @@ struct gnn_gcn {
     float *loss_d = nullptr;
     int32_t maxld = 0;
     // options
-    int precision = 0, profile = 0;
+    int precision = 1, profile = 0; // dense transforms: 1 = 3xTF32 on tcgen05 (falls back per shape), 0 = FP32 FMA
     float momentum = 0.f, dampening = 0.f, weight_decay = 0.f;
     int nesterov = 0;
     int64_t steps = 0;

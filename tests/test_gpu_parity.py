@@ -201,14 +201,73 @@ def test_gemms_vs_oracle(ctx, oracle, M, N, K):
     assert np.array_equal(got, host.gemm_tn(ctx, _dev(dP, ctx), _dev(A, ctx)).cpu().numpy())  # deterministic split-K
 
 
-def test_gemm_tn_long_reduction(ctx, oracle):
-    """dW = dP^T H over 300k node rows: fixed-order split reduction stays inside 1e-5 of the fp64 oracle."""
+@pytest.mark.parametrize("precision", [0, 1])
+def test_gemm_tn_long_reduction(ctx, oracle, precision):
+    """dW = dP^T H over 300k node rows: fixed-order split reduction stays inside 1e-5 of the fp64 oracle.
+    precision=1: the tcgen05 kernel drains its TMEM accumulator every 256 rows (truncating adds) into FP32 sums."""
     from gnn_cpp_b200 import host
     rng = np.random.default_rng(3)
     M = 300000
     A = rng.uniform(-1, 1, (M, 40)).astype(np.float32)
     B = rng.uniform(-1, 1, (M, 24)).astype(np.float32)
-    assert rel_err(host.gemm_tn(ctx, _dev(A, ctx), _dev(B, ctx)).cpu().numpy(), oracle.gemm_tn(A, B, order=1)) <= TOL
+    got = host.gemm_tn(ctx, _dev(A, ctx), _dev(B, ctx), precision=precision).cpu().numpy()
+    assert rel_err(got, oracle.gemm_tn(A, B, order=1)) <= TOL
+    # all-positive operands: partial sums grow linearly, the worst case for a truncating accumulator
+    A = np.abs(A); B = np.abs(B)
+    got = host.gemm_tn(ctx, _dev(A, ctx), _dev(B, ctx), precision=precision).cpu().numpy()
+    assert rel_err(got, oracle.gemm_tn(A, B, order=1)) <= TOL
+
+
+def _padded(a, ctx):
+    """device copy whose row stride is a multiple of 4 floats (the TMA path needs 16-byte aligned rows)"""
+    import torch
+    ld = (a.shape[1] + 3) // 4 * 4
+    buf = torch.zeros((a.shape[0], ld), dtype=torch.float32, device=ctx.device)
+    buf[:, :a.shape[1]].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+    return buf[:, :a.shape[1]]
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (200, 16, 24), (3001, 47, 256), (4099, 256, 100), (1000, 130, 257),
+                                   (777, 3, 64), (20000, 300, 100), (2708, 16, 1433), (40000, 256, 256)])
+def test_gemms_tensor_core_vs_oracle(ctx, oracle, M, N, K):
+    """3xTF32 on tcgen05 (precision=1) against the fp64-accumulate oracle, ragged shapes included; the launch
+    counter proves the tensor-core kernels ran (weight split + GEMM, or GEMM + partial reduction = 2 launches)
+    except where the documented K > 512 rule hands the reduction to the FP32 FMA kernel."""
+    from gnn_cpp_b200 import host
+    import torch
+    rng = np.random.default_rng(M + N + K)
+    A = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    W = rng.uniform(-1, 1, (N, K)).astype(np.float32)
+    bias = rng.uniform(-1, 1, N).astype(np.float32)
+    dP = rng.uniform(-1, 1, (M, N)).astype(np.float32)
+    Ad, dPd, Wd = _padded(A, ctx), _padded(dP, ctx), _dev(W, ctx)
+    ldn = (N + 3) // 4 * 4; ldk = (K + 3) // 4 * 4
+    out = torch.full((M, ldn), 7.0, device=ctx.device)
+
+    def launches(fn):
+        n0 = ctx.launches
+        r = fn()
+        return r, ctx.launches - n0
+
+    P = oracle.gemm_nt(A, W, order=1)
+    _, n = launches(lambda: host.gemm_nt(ctx, Ad, Wd, precision=1, out=out[:, :N]))
+    assert n == (2 * ((N + 255) // 256) if K <= 512 else 1)
+    assert rel_err(out[:, :N].cpu().numpy(), P) <= TOL
+    if ldn != N:
+        assert bool((out[:, N:] == 7.0).all()), "padding columns must not be written"
+    _, H = oracle.bias_relu(P, bias)
+    host.gemm_nt(ctx, Ad, Wd, bias=_dev(bias, ctx), relu=True, precision=1, out=out[:, :N])
+    assert rel_err(out[:, :N].cpu().numpy(), H) <= TOL
+    dH = oracle.gemm_nn(dP, W, order=1)
+    outk = torch.full((M, ldk), 7.0, device=ctx.device)
+    _, n = launches(lambda: host.gemm_nn(ctx, dPd, Wd, mask=Ad, precision=1, out=outk[:, :K]))
+    assert n == (2 * ((K + 255) // 256) if N <= 512 else 1)
+    assert rel_err(outk[:, :K].cpu().numpy(), oracle.relu_bwd(dH, A)) <= TOL
+    dW = oracle.gemm_tn(dP, A, order=1)
+    got, n = launches(lambda: host.gemm_tn(ctx, dPd, Ad, precision=1))
+    assert n == 2 * ((K + 255) // 256)
+    assert rel_err(got.cpu().numpy(), dW) <= TOL
+    assert torch.equal(got, host.gemm_tn(ctx, dPd, Ad, precision=1))  # deterministic: fixed-order partial sum
 
 
 @pytest.mark.parametrize("N,C", [(5, 4), (200, 5), (2708, 7), (19717, 3), (5000, 47), (1234, 70)])
@@ -251,7 +310,7 @@ def test_bias_relu_sgd_vs_oracle(ctx, oracle):
 
 
 # ------------------------------------------------------------------------------------------------ whole train step
-def _run_trainer(ctx, p, lr=0.0, agg_mask=None, precision=0):
+def _run_trainer(ctx, p, lr=0.0, agg_mask=None, precision=1):
     from gnn_cpp_b200 import host
     g = host.Graph.build(ctx, p.src, p.dst, p.cfg.N)
     m = host.GCN(ctx, g, p.cfg.dims)
@@ -273,11 +332,12 @@ def _run_trainer(ctx, p, lr=0.0, agg_mask=None, precision=0):
 
 @pytest.mark.parametrize("name", ["toy", "tiny", "directed", "tiny_pl", "cora", "pubmed"])
 @pytest.mark.parametrize("agg_mask", [None, 0, 0xFF])
-def test_train_step_vs_reference_golden(ctx, name, agg_mask):
+@pytest.mark.parametrize("precision", [0, 1])
+def test_train_step_vs_reference_golden(ctx, name, agg_mask, precision):
     """fwd + loss + bwd against outputs of the REAL reference (mode B), for the automatic layer order and for both
     forced orders (transform-first everywhere == the reference's own order; aggregate-first everywhere)."""
     p, g = load_problem(name), load_golden(name)
-    out = _run_trainer(ctx, p, lr=0.0, agg_mask=agg_mask)
+    out = _run_trainer(ctx, p, lr=0.0, agg_mask=agg_mask, precision=precision)
     L = len(p.cfg.dims) - 1
     assert abs(out["loss"] - float(g["loss"][0])) <= TOL * abs(float(g["loss"][0]))
     for l in range(1, L + 1):
@@ -334,7 +394,8 @@ def test_train_step_host_entry_point(ctx, oracle):
     m.close(); g.close()
 
 
-def test_medium_graph_train_step_vs_fp64_oracle(ctx, oracle):
+@pytest.mark.parametrize("precision", [0, 1])
+def test_medium_graph_train_step_vs_fp64_oracle(ctx, oracle, precision):
     """arxiv-like slice (N=40k, power-law, 3 layers incl. F=256): sequential-fp32 order is no longer the better
     reference at this size, so the checker is the oracle's fp64-accumulate mode."""
     from gnn_cpp_b200 import synth
@@ -342,7 +403,7 @@ def test_medium_graph_train_step_vs_fp64_oracle(ctx, oracle):
     p = synth.make_problem(cfg)
     G = oracle.Graph(p.src, p.dst, cfg.N)
     ref = oracle.train_step(G, cfg.dims, p.X, p.y, [w.copy() for w in p.W], [x.copy() for x in p.b], order=1)
-    out = _run_trainer(ctx, p)
+    out = _run_trainer(ctx, p, precision=precision)
     assert abs(out["loss"] - ref["loss"]) <= TOL * abs(ref["loss"])
     L = 3
     for l in range(1, L + 1):
