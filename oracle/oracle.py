@@ -252,3 +252,32 @@ def train_step(g, dims, X, y, W, b, lr=0.0, order=0):
         out["dW%d" % (l + 1)] = dWs[l]
         out["db%d" % (l + 1)] = dbs[l]
     return out
+
+
+def train_step_composed(g, dims, X, y, W, b, order=0, masks=None):
+    """The same fwd+loss+bwd as orc_gcn_train_step, composed from the primitives above in the reference's own
+    (transform-first) order.  `masks` (list of L-1 boolean [N, F_l] arrays, entries may be None) overrides which side
+    of the ReLU kink the BACKWARD takes for hidden layer l: a checker for pre-activations that sit within the forward
+    tolerance of zero, where `Z > 0` (operation.h:560) is not a continuous function of the inputs."""
+    L = len(dims) - 1
+    H = np.ascontiguousarray(X, dtype=np.float32)
+    Hs, Zs = [H], []
+    for l in range(L):
+        P = gemm_nt(Hs[l], W[l], order)
+        Z, Hn = bias_relu(spmm(g.N, g.rowptr, g.colidx, g.val, P, order), b[l])
+        Zs.append(Z)
+        Hs.append(Hn)
+    loss, dZ = softmax_xent(Zs[-1], y, order)
+    out = {"loss": loss, "dZ": dZ}
+    for l in range(L - 1, -1, -1):
+        out["Z%d" % (l + 1)] = Zs[l]
+        out["db%d" % (l + 1)] = bias_grad(dZ, order)
+        dP = spmm(g.N, g.colptr, g.rowidx, g.valT, dZ, order)
+        out["dW%d" % (l + 1)] = gemm_tn(dP, Hs[l], order)
+        if l > 0:
+            dH = gemm_nn(dP, W[l], order)
+            if masks is not None and masks[l - 1] is not None:
+                dZ = np.where(masks[l - 1], dH, np.float32(0)).astype(np.float32)
+            else:
+                dZ = relu_bwd(dH, Zs[l - 1])
+    return out

@@ -330,10 +330,37 @@ def _run_trainer(ctx, p, lr=0.0, agg_mask=None, precision=1):
     return out
 
 
+def _check_grads(out, ref, p, oracle, order):
+    """dW/db/dZ within TOL of `ref`.  `Z > 0` (operation.h:560) is discontinuous: a hidden pre-activation that lies
+    within the forward tolerance of zero may legitimately land on the other side of the kink, which moves a whole
+    row of dW.  When the direct comparison fails, the check therefore (1) requires every ReLU-mask difference to sit
+    at |Z_oracle| <= TOL*max|Z| and to be rare, and (2) re-runs the oracle's backward on the device's side of those
+    kinks and compares again at the same TOL."""
+    L = len(p.cfg.dims) - 1
+    names = ["dW%d" % l for l in range(1, L + 1)] + ["db%d" % l for l in range(1, L + 1)] + ["dZ"]
+    bad = [k for k in names if rel_err(out[k], ref[k]) > TOL]
+    if not bad:
+        return
+    G = oracle.Graph(p.src, p.dst, p.cfg.N)
+    base = oracle.train_step_composed(G, p.cfg.dims, p.X, p.y, p.W, p.b, order=order)
+    masks, flips = [], 0
+    for l in range(1, L):
+        Z = base["Z%d" % l]
+        m = out["A%d" % l] > 0
+        diff = m != (Z > 0)
+        assert np.abs(Z[diff]).max(initial=0.0) <= TOL * np.abs(Z).max(), "layer %d: mask differs away from the kink" % l
+        flips += int(diff.sum())
+        masks.append(m)
+    assert 0 < flips <= max(1, int(1e-4 * sum(m.size for m in masks))), (bad, flips)
+    ref2 = oracle.train_step_composed(G, p.cfg.dims, p.X, p.y, p.W, p.b, order=order, masks=masks)
+    for k in names:
+        assert rel_err(out[k], ref2[k]) <= TOL, "%s (after %d kink flips)" % (k, flips)
+
+
 @pytest.mark.parametrize("name", ["toy", "tiny", "directed", "tiny_pl", "cora", "pubmed"])
 @pytest.mark.parametrize("agg_mask", [None, 0, 0xFF])
 @pytest.mark.parametrize("precision", [0, 1])
-def test_train_step_vs_reference_golden(ctx, name, agg_mask, precision):
+def test_train_step_vs_reference_golden(ctx, oracle, name, agg_mask, precision):
     """fwd + loss + bwd against outputs of the REAL reference (mode B), for the automatic layer order and for both
     forced orders (transform-first everywhere == the reference's own order; aggregate-first everywhere)."""
     p, g = load_problem(name), load_golden(name)
@@ -347,9 +374,7 @@ def test_train_step_vs_reference_golden(ctx, name, agg_mask, precision):
             A = A[g["Z%d_rows" % l]]
         ref = np.maximum(Z, 0) if l < L else Z          # H_l = ReLU(Z_l); logits for l = L
         assert rel_err(A, ref) <= TOL, "activation %d" % l
-        assert rel_err(out["dW%d" % l], g["dW%d" % l]) <= TOL, "dW%d" % l
-        assert rel_err(out["db%d" % l], g["db%d" % l]) <= TOL, "db%d" % l
-    assert rel_err(out["dZ"], g["dZ"]) <= TOL
+    _check_grads(out, g, p, oracle, order=0)   # order 0 = the restatement that is bit-exact with the reference
 
 
 @pytest.mark.parametrize("name", ["tiny", "cora"])
@@ -409,5 +434,4 @@ def test_medium_graph_train_step_vs_fp64_oracle(ctx, oracle, precision):
     for l in range(1, L + 1):
         Z = ref["Z%d" % l]
         assert rel_err(out["A%d" % l], np.maximum(Z, 0) if l < L else Z) <= TOL
-        assert rel_err(out["dW%d" % l], ref["dW%d" % l]) <= TOL
-        assert rel_err(out["db%d" % l], ref["db%d" % l]) <= TOL
+    _check_grads(out, ref, p, oracle, order=1)

@@ -107,3 +107,22 @@ def test_sgd_matches_torch(oracle):
             opt.step()
             oracle.sgd_step(mine, g, vel, lr=0.05, first=(it == 0), **kw)
             np.testing.assert_allclose(mine, tp.detach().numpy(), rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_pl", "cora"])
+def test_composed_step_equals_c_step(oracle, name):
+    """The primitive-by-primitive composition (used by the kink-aware gradient checks) is bit-identical to
+    orc_gcn_train_step, with and without an explicit ReLU-mask override equal to the natural mask."""
+    p = load_problem(name)
+    G = oracle.Graph(p.src, p.dst, p.cfg.N)
+    L = len(p.cfg.dims) - 1
+    for order in (0, 1):
+        a = oracle.train_step(G, p.cfg.dims, p.X, p.y, [w.copy() for w in p.W], [x.copy() for x in p.b], order=order)
+        c = oracle.train_step_composed(G, p.cfg.dims, p.X, p.y, p.W, p.b, order=order)
+        masks = [c["Z%d" % l] > 0 for l in range(1, L)]
+        d = oracle.train_step_composed(G, p.cfg.dims, p.X, p.y, p.W, p.b, order=order, masks=masks)
+        for k, v in a.items():
+            if k == "loss":
+                assert v == c[k] == d[k]
+            else:
+                assert np.array_equal(v, c[k]) and np.array_equal(v, d[k]), k
