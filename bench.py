@@ -163,6 +163,8 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")          # the image's default prints a banner on stdout; keep stdout = one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = synth.CONFIGS[args.config]
     L = len(cfg.dims) - 1
@@ -172,6 +174,9 @@ def run_ours(args):
         log("[bench] generated %s: N=%d E=%d in %.1fs" % (cfg.name, cfg.N, cfg.E, time.time() - t0))
 
     ctx = host.Context(local_rank)
+    if args.spmm_variant:
+        from gnn_cpp_b200 import capi
+        capi.call("gnn_set_spmm_variant", ctx.h, args.spmm_variant)
     if world > 1:
         ctx.init_comm_from_torch()
     t0 = time.time()
@@ -292,7 +297,7 @@ def run_ours(args):
             cms, info = cpu_step_ms(args.config)
             cpu = dict(info, value=cms, unit="ms")
         cfgd = workload_desc(cfg, nnz)
-        cfgd.update({"parallelism": "1-D row partition x%d, NCCL all-gather of aggregation inputs + grad all-reduce" % world if world > 1 else "single GPU",
+        cfgd.update({"parallelism": "1-D row partition x%d, %s of aggregation inputs + NCCL grad all-reduce" % (world, "ncclAllGather" if os.environ.get("GNN_COMM") == "nccl" else "copy-engine peer pushes over NVLink (IPC arena)") if world > 1 else "single GPU",
                      "l2_policy": "working set (feature matrices %.1f GB) larger than L2; no flush needed" % (cfg.N * max(cfg.dims) * 4 / 1e9)
                      if cfg.N * max(cfg.dims) * 4 > 2.5e8 else "small working set (L2-resident): launch-bound config",
                      "gemm_precision": "fp32 FMA" if args.precision == 0 else "3xTF32 tcgen05",
@@ -325,6 +330,7 @@ def main():
     ap.add_argument("--config", default="products", choices=sorted(synth.CONFIGS))
     ap.add_argument("--precision", type=int, default=1, help="dense transforms: 1 = 3xTF32 on tcgen05 (default), 0 = FP32 FMA")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--spmm-variant", type=int, default=0, help="0 auto (by degree skew), 1 rows kernel, 2 merge kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

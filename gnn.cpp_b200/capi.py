@@ -81,6 +81,11 @@ SIGNATURES = {
     "gnn_comm_destroy": (C.c_int, [vp]),
     "gnn_allgather_rows": (C.c_int, [vp, vp, vp, i64, i32]),
     "gnn_allreduce_sum": (C.c_int, [vp, vp, i64]),
+    "gnn_peer_arena_create": (C.c_int, [vp, sz, pp]),
+    "gnn_peer_arena_destroy": (C.c_int, [vp, vp]),
+    "gnn_peer_arena_local": (vp, [vp]),
+    "gnn_peer_gather_begin": (C.c_int, [vp, vp, C.c_int, sz, sz]),
+    "gnn_peer_gather_wait": (C.c_int, [vp, vp, C.c_int]),
 }
 # int-returning functions that are NOT status codes
 _PLAIN_INT = {"gnn_version", "gnn_ctx_sm_count", "gnn_graph_is_symmetric"}

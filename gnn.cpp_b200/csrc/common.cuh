@@ -57,7 +57,7 @@ struct gnn_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t launches = 0;
-    int spmm_variant = 0;
+    int spmm_variant = 0, spmm_tune_u = 0, spmm_tune_pf = 1, spmm_chunk = 0;
     // grow-only scratch (sort double buffers, scan levels, split-K partials ...)
     void *ws = nullptr;
     size_t ws_bytes = 0;
@@ -87,11 +87,7 @@ struct gnn_graph {
     int32_t *deg = nullptr;
     float *dinv = nullptr;
     // degree statistics (host) for SpMM variant selection
-    int32_t max_row_nnz = 0, max_col_nnz = 0;
-    // row-split work lists (built lazily by spmm.cu): items of (row, begin, end) for rows cut into chunks
-    int32_t *split_items_csr = nullptr, *split_items_csc = nullptr;
-    int64_t n_split_csr = 0, n_split_csc = 0;
-    int32_t split_chunk = 0;
+    int32_t max_row_nnz = 0, max_col_nnz = 0, min_row_nnz = 0, min_col_nnz = 0;
 };
 
 namespace gnn {
@@ -102,7 +98,8 @@ int exclusive_scan_u32(gnn_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t 
 // keys/vals are overwritten with the sorted sequence (scratch comes from ctx->workspace).
 int radix_sort_u64(gnn_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int bit_lo, int bit_hi);
 // spmm.cu -----------------------------------------------------------------------------------------
-int spmm_launch(gnn_ctx *ctx, int32_t n_out, const int32_t *ptr, const int32_t *idx, const float *val,
-                int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias,
-                int relu, const float *mask, int64_t ldm);
+// nnz = ptr[n_out] (host copy); min/max_nnz_row steer the variant choice (see spmm.cu)
+int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t nnz, const int32_t *ptr, const int32_t *idx, const float *val,
+                int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy,
+                const float *bias, int relu, const float *mask, int64_t ldm);
 } // namespace gnn

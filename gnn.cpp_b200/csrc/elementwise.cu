@@ -202,6 +202,32 @@ __global__ void gather_cols_kernel(int64_t rows, int64_t cols, const float *__re
     if (i < rows) out[i] = a[i * cols + idx[i]];
 }
 
+// dst[r, 0:cols] = src[r, 0:cols] for two row-major views (a strided cudaMemcpy2DAsync of sub-kilobyte rows runs far
+// below HBM speed; this moves 128-bit vectors when the views allow it)
+__global__ void copy2d_kernel(float *__restrict__ dst, int64_t ldd, const float *__restrict__ src, int64_t lds,
+                              int64_t rows, int32_t cols, int vec) {
+    const int32_t cpr = vec ? cols / 4 : cols; // elements per row in units of the access width
+    const int64_t total = rows * cpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cpr;
+        const int32_t c = (int32_t)(i - r * cpr);
+        if (vec) reinterpret_cast<float4 *>(dst + r * ldd)[c] = __ldg(reinterpret_cast<const float4 *>(src + r * lds) + c);
+        else dst[r * ldd + c] = src[r * lds + c];
+    }
+}
+
+int copy2d(gnn_ctx *ctx, float *dst, int64_t ldd, const float *src, int64_t lds, int64_t rows, int32_t cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    if (ldd == cols && lds == cols) {
+        GNN_CHECK_CUDA(cudaMemcpyAsync(dst, src, (size_t)rows * cols * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    }
+    const int vec = (cols % 4 == 0) && (ldd % 4 == 0) && (lds % 4 == 0) && ((uintptr_t)dst % 16 == 0) && ((uintptr_t)src % 16 == 0);
+    copy2d_kernel<<<stream_grid(ctx, rows * (vec ? cols / 4 : cols), 256), 256, 0, ctx->stream>>>(dst, ldd, src, lds, rows, cols, vec);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
 int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out) {
     int64_t nblocks = (int64_t)ctx->sm_count * 4;
     int64_t rows_per_block = ceil_div(N, nblocks);

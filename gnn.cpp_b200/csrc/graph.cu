@@ -67,12 +67,20 @@ __global__ void lower_bound_kernel(const uint64_t *__restrict__ ukeys, int64_t n
     ptr[r] = (int32_t)lo;
 }
 
+// out[0] = max row length, out[1] = min row length (out[1] preset to INT_MAX)
 __global__ void max_diff_kernel(const int32_t *__restrict__ ptr, int32_t n, int32_t *__restrict__ out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int32_t d = (r < n) ? ptr[r + 1] - ptr[r] : 0;
+    int32_t m = (r < n) ? d : 0x7fffffff;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
-    if ((threadIdx.x & 31) == 0 && d > 0) atomicMax(out, d);
+    for (int o = 16; o > 0; o >>= 1) {
+        d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
+        m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (d > 0) atomicMax(out, d);
+        atomicMin(out + 1, m);
+    }
 }
 
 // one warp per row: keys[k] = row << cb | col, vals[k] = k
@@ -170,20 +178,25 @@ static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)ceil_
 
 static int finish_stats(gnn_ctx *ctx, gnn_graph *g) {
     int32_t *d_max = nullptr;
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&d_max, 8, ctx->stream));
-    GNN_CHECK_CUDA(cudaMemsetAsync(d_max, 0, 8, ctx->stream));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&d_max, 16, ctx->stream));
+    const int32_t init[4] = {0, 0x7fffffff, 0, 0x7fffffff};
+    GNN_CHECK_CUDA(cudaMemcpyAsync(d_max, init, 16, cudaMemcpyHostToDevice, ctx->stream));
     max_diff_kernel<<<grid_for(g->n_rows, 256), 256, 0, ctx->stream>>>(g->rowptr, g->n_rows, d_max);
     GNN_LAUNCHED(ctx);
     if (g->colptr) {
-        max_diff_kernel<<<grid_for(g->t_rows, 256), 256, 0, ctx->stream>>>(g->colptr, g->t_rows, d_max + 1);
+        max_diff_kernel<<<grid_for(g->t_rows, 256), 256, 0, ctx->stream>>>(g->colptr, g->t_rows, d_max + 2);
         GNN_LAUNCHED(ctx);
     }
-    int32_t h[2] = {0, 0};
-    GNN_CHECK_CUDA(cudaMemcpyAsync(h, d_max, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t h[4] = {0, 0, 0, 0};
+    GNN_CHECK_CUDA(cudaMemcpyAsync(h, d_max, 16, cudaMemcpyDeviceToHost, ctx->stream));
     GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     GNN_CHECK_CUDA(cudaFreeAsync(d_max, ctx->stream));
     g->max_row_nnz = h[0];
-    if (g->colptr) g->max_col_nnz = h[1];
+    g->min_row_nnz = g->n_rows > 0 ? h[1] : 0;
+    if (g->colptr) {
+        g->max_col_nnz = h[2];
+        g->min_col_nnz = g->t_rows > 0 ? h[3] : 0;
+    }
     return 0;
 }
 
@@ -375,7 +388,6 @@ int gnn_graph_destroy(gnn_ctx_t *ctx, gnn_graph_t *g) {
     cudaFree(g->rowptr); cudaFree(g->colidx); cudaFree(g->val);
     cudaFree(g->colptr); cudaFree(g->rowidx); cudaFree(g->perm); cudaFree(g->valT);
     cudaFree(g->deg); cudaFree(g->dinv);
-    cudaFree(g->split_items_csr); cudaFree(g->split_items_csc);
     delete g;
     return 0;
 }
@@ -474,6 +486,7 @@ int gnn_graph_slice_rows(gnn_ctx_t *ctx, const gnn_graph_t *g, int64_t lo, int64
         GNN_TRY(gnn_graph_from_csr(ctx, (int32_t)(hi - lo), g->n_rows, tptr + lo, tidx, tval, &t));
         l->colptr = t->rowptr; l->rowidx = t->colidx; l->valT = t->val;
         l->max_col_nnz = t->max_row_nnz;
+        l->min_col_nnz = t->min_row_nnz;
         l->t_rows = t->n_rows;
         l->nnz_t = t->nnz;
         t->rowptr = nullptr; t->colidx = nullptr; t->val = nullptr;

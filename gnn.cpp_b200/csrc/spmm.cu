@@ -8,7 +8,8 @@
 //   - the group's lanes load LPR (column, value) pairs at a time, coalesced, and broadcast them with
 //     shuffles; feature rows are gathered with U independent 128-bit loads in flight per lane;
 //   - index/value streams use the no-allocate path (read once), feature rows the default path (L2 reuse);
-//   - rows are distributed over a 1-D grid sized to whole waves of 148 SMs x resident CTAs.
+//   - two work distributions, chosen by degree skew (use_merge): one row per lane group, or equal nonzero chunks
+//     per lane group with a fixed-order fix-up of the rows cut by chunk boundaries (hub rows).
 #include "common.cuh"
 
 namespace gnn {
@@ -54,44 +55,50 @@ __device__ __forceinline__ float epilogue1(float v, int col, int F, const float 
 }
 
 constexpr int SPMM_THREADS = 256;
-constexpr int SPMM_U = 4; // independent feature-row loads in flight per lane and vector slot
+// Loads in flight per lane (U nonzeros x VEC vectors) and whether the next (column, value) batch is requested
+// before the current one is consumed.  Measured on B200 (tools/spmm_probe.py, products-shaped, merge kernel):
+// 16 B/lane/nonzero: U=4 + prefetch best (F=100: 5.31 ms vs 6.05 without prefetch, 6.32 with U=8);
+// 32 B/lane/nonzero (F=256): U=4 without prefetch best (10.6-10.8 ms vs 11.3 with, 13.4 with U=8).
+template <typename V, int VEC> struct Tune {
+    static constexpr int BYTES = (int)sizeof(V) * VEC;
+    static constexpr int U = BYTES >= 64 ? 2 : 4;
+    static constexpr bool PF = BYTES <= 16;
+};
 
-// V = float4: requires P/Y 16-byte aligned and ldp/ldy multiples of 4 (padding columns may be touched).
-// V = float : no alignment requirement.
-template <typename V, int LPR, int VEC, bool USE_VAL>
-__global__ void __launch_bounds__(SPMM_THREADS)
-    spmm_rows_kernel(int32_t n_out, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
-                     const float *__restrict__ val, const float *__restrict__ P, int64_t ldp, int32_t F,
-                     float *__restrict__ Y, int64_t ldy, const float *__restrict__ bias, int relu,
-                     const float *__restrict__ mask, int64_t ldm) {
+// acc += sum over k in [begin, end) of val[k] * P[idx[k], :]   for the LPR-lane group this thread belongs to.
+// The group's lanes fetch LPR (column, value) pairs at a time (coalesced, streaming) — the NEXT batch is requested
+// before the current one is consumed — and broadcast them with shuffles; every lane keeps U x VEC 128-bit gathers
+// in flight.  Accumulation order = stored order (ascending k): deterministic.
+template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF>
+__device__ __forceinline__ void accumulate_range(V (&acc)[VEC], const int32_t *__restrict__ idx,
+                                                 const float *__restrict__ val, int32_t begin, int32_t end,
+                                                 const float *__restrict__ P, int64_t ldp, int nvec, int sub,
+                                                 unsigned gmask) {
     using T = VecTraits<V>;
-    constexpr int W = T::W;
-    constexpr int GROUPS = SPMM_THREADS / LPR;
-    const int sub = threadIdx.x % LPR;
-    const int64_t row = (int64_t)blockIdx.x * GROUPS + threadIdx.x / LPR;
-    if (row >= n_out) return; // whole group exits together (LPR divides 32, group-uniform)
-    // active-lane mask of this group inside its warp
-    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
-    const int nvec = (F + W - 1) / W; // vectors per row
-
-    V acc[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; v++) acc[v] = T::zero();
-
-    const int32_t begin = ptr[row], end = ptr[row + 1];
+    int32_t nx_c = 0;
+    float nx_a = 0.f;
+    if (PF && begin + sub < end) {
+        nx_c = ld_stream_i32(idx + begin + sub);
+        if (USE_VAL) nx_a = ld_stream_f32(val + begin + sub);
+    }
     for (int32_t k = begin; k < end; k += LPR) {
-        int32_t my_c = 0;
-        float my_a = 0.f;
-        if (k + sub < end) {
+        int32_t my_c = nx_c;
+        float my_a = nx_a;
+        if (PF) {
+            if (k + LPR + sub < end) {
+                nx_c = ld_stream_i32(idx + k + LPR + sub);
+                if (USE_VAL) nx_a = ld_stream_f32(val + k + LPR + sub);
+            }
+        } else if (k + sub < end) {
             my_c = ld_stream_i32(idx + k + sub);
             if (USE_VAL) my_a = ld_stream_f32(val + k + sub);
         }
         const int cnt = min(LPR, end - k);
-        for (int j = 0; j < cnt; j += SPMM_U) {
-            V p[SPMM_U][VEC];
-            float a[SPMM_U];
+        for (int j = 0; j < cnt; j += U) {
+            V p[U][VEC];
+            float a[U];
 #pragma unroll
-            for (int u = 0; u < SPMM_U; u++) {
+            for (int u = 0; u < U; u++) {
                 const int jj = j + u;                       // group-uniform
                 const int src_lane = jj < LPR ? jj : LPR - 1;
                 const int32_t c = __shfl_sync(gmask, my_c, src_lane, LPR);
@@ -106,7 +113,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
                 if (jj >= cnt) a[u] = 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < SPMM_U; u++) {
+            for (int u = 0; u < U; u++) {
 #pragma unroll
                 for (int v = 0; v < VEC; v++) {
                     if (USE_VAL) T::fma(acc[v], a[u], p[u][v]);
@@ -115,9 +122,12 @@ __global__ void __launch_bounds__(SPMM_THREADS)
             }
         }
     }
+}
 
-    const float *mrow = mask ? mask + row * ldm : nullptr;
-    float *yrow = Y + row * ldy;
+template <typename V, int LPR, int VEC>
+__device__ __forceinline__ void store_row(const V (&acc)[VEC], float *__restrict__ yrow, int nvec, int sub, int32_t F,
+                                          const float *__restrict__ bias, int relu, const float *__restrict__ mrow) {
+    constexpr int W = VecTraits<V>::W;
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
         const int vi = sub + v * LPR;
@@ -136,27 +146,188 @@ __global__ void __launch_bounds__(SPMM_THREADS)
     }
 }
 
-template <typename V, int LPR, int VEC>
+// ---- variant 1: one output row per lane group ------------------------------------------------------------------
+// V = float4: requires P/Y 16-byte aligned and ldp/ldy multiples of 4 (padding columns may be touched).
+// V = float : no alignment requirement.
+template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF>
+__global__ void __launch_bounds__(SPMM_THREADS)
+    spmm_rows_kernel(int32_t n_out, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                     const float *__restrict__ val, const float *__restrict__ P, int64_t ldp, int32_t F,
+                     float *__restrict__ Y, int64_t ldy, const float *__restrict__ bias, int relu,
+                     const float *__restrict__ mask, int64_t ldm) {
+    using T = VecTraits<V>;
+    constexpr int GROUPS = SPMM_THREADS / LPR;
+    const int sub = threadIdx.x % LPR;
+    const int64_t row = (int64_t)blockIdx.x * GROUPS + threadIdx.x / LPR;
+    if (row >= n_out) return; // whole group exits together (LPR divides 32, group-uniform)
+    // active-lane mask of this group inside its warp
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
+    const int nvec = (F + T::W - 1) / T::W; // vectors per row
+
+    V acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) acc[v] = T::zero();
+    accumulate_range<V, LPR, VEC, USE_VAL, U, PF>(acc, idx, val, ptr[row], ptr[row + 1], P, ldp, nvec, sub, gmask);
+    store_row<V, LPR, VEC>(acc, Y + row * ldy, nvec, sub, F, bias, relu, mask ? mask + row * ldm : nullptr);
+}
+
+// ---- variant 2: nonzero-balanced (merge-path style) ------------------------------------------------------------
+// The nonzero range [0, nnz) is cut into chunks of MERGE_CHUNK; a lane group owns one chunk and walks the rows that
+// intersect it (start row by binary search on ptr).  Rows entirely inside the chunk are finished in place.  A row
+// cut by a chunk boundary leaves partial sums in a workspace: `tail[g]` when the row continues past chunk g,
+// `head[g]` when it started before chunk g and ends inside it.  spmm_merge_fixup_kernel then adds, for every head,
+// the tails of the preceding chunks of the same row in ascending chunk order, applies the epilogue and writes the
+// row — fixed order, no atomics.  Hub rows are thus spread over as many groups as they have chunks.
+// Requires every row to hold at least one nonzero (the dispatcher checks min_nnz_row >= 1).
+constexpr int MERGE_CHUNK_MIN = 256;
+
+template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF>
+__global__ void __launch_bounds__(SPMM_THREADS)
+    spmm_merge_kernel(int32_t n_out, int32_t nnz, int32_t n_chunks, int32_t MERGE_CHUNK, const int32_t *__restrict__ ptr,
+                      const int32_t *__restrict__ idx, const float *__restrict__ val, const float *__restrict__ P,
+                      int64_t ldp, int32_t F, float *__restrict__ Y, int64_t ldy, const float *__restrict__ bias,
+                      int relu, const float *__restrict__ mask, int64_t ldm, float *__restrict__ head,
+                      float *__restrict__ tail, int32_t *__restrict__ head_row, int32_t *__restrict__ tail_row,
+                      int32_t ldw) {
+    using T = VecTraits<V>;
+    constexpr int GROUPS = SPMM_THREADS / LPR;
+    const int sub = threadIdx.x % LPR;
+    const int32_t g = blockIdx.x * GROUPS + threadIdx.x / LPR;
+    if (g >= n_chunks) return;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
+    const int nvec = (F + T::W - 1) / T::W;
+    const int32_t k0 = g * MERGE_CHUNK, k1 = min(nnz, k0 + MERGE_CHUNK);
+
+    // last row r with ptr[r] <= k0 (rows are non-empty, so it is the row that holds nonzero k0)
+    int32_t lo = 0, hi = n_out; // invariant: ptr[lo] <= k0 < ptr[hi]
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (__ldg(ptr + mid) <= k0) lo = mid;
+        else hi = mid;
+    }
+    int32_t row = lo, k = k0;
+    int32_t hrow = -1, trow = -1;
+    int32_t rb = __ldg(ptr + row), re = __ldg(ptr + row + 1);
+    while (k < k1) {
+        const int32_t seg_end = min(re, k1);
+        const int32_t re_next = (seg_end == re && row + 2 <= n_out) ? __ldg(ptr + row + 2) : re; // prefetch
+        V acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[v] = T::zero();
+        accumulate_range<V, LPR, VEC, USE_VAL, U, PF>(acc, idx, val, k, seg_end, P, ldp, nvec, sub, gmask);
+        const bool starts = (k == rb), ends = (seg_end == re);
+        if (starts && ends) {
+            store_row<V, LPR, VEC>(acc, Y + (int64_t)row * ldy, nvec, sub, F, bias, relu,
+                                   mask ? mask + (int64_t)row * ldm : nullptr);
+        } else {
+            float *dst = (ends ? head : tail) + (int64_t)g * ldw;
+            if (ends) hrow = row;
+            else trow = row;
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                const int vi = sub + v * LPR;
+                if (vi < nvec) reinterpret_cast<V *>(dst)[vi] = acc[v];
+            }
+        }
+        k = seg_end;
+        row++;
+        rb = re;
+        re = re_next;
+    }
+    if (sub == 0) {
+        head_row[g] = hrow;
+        tail_row[g] = trow;
+    }
+}
+
+// one warp per chunk that finishes a cut row
+__global__ void __launch_bounds__(256)
+    spmm_merge_fixup_kernel(int32_t n_chunks, int32_t F, const float *__restrict__ head, const float *__restrict__ tail,
+                            const int32_t *__restrict__ head_row, const int32_t *__restrict__ tail_row, int32_t ldw,
+                            float *__restrict__ Y, int64_t ldy, const float *__restrict__ bias, int relu,
+                            const float *__restrict__ mask, int64_t ldm) {
+    const int32_t g = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= n_chunks) return;
+    const int32_t row = head_row[g];
+    if (row < 0) return;
+    int32_t first = g;
+    while (first > 0 && tail_row[first - 1] == row) first--;
+    const float *mrow = mask ? mask + (int64_t)row * ldm : nullptr;
+    for (int32_t c = lane; c < F; c += 32) {
+        float s = 0.f;
+        for (int32_t t = first; t < g; t++) s += tail[(int64_t)t * ldw + c];
+        s += head[(int64_t)g * ldw + c];
+        Y[(int64_t)row * ldy + c] = epilogue1(s, c, F, bias, relu, mrow);
+    }
+}
+
+// nonzeros per lane group of the merge kernel: narrow rows (two or more groups per warp) prefer shorter chunks
+static inline int32_t merge_chunk(const gnn_ctx *ctx, int lpr) {
+    return ctx->spmm_chunk > 0 ? ctx->spmm_chunk : (lpr <= 16 ? 512 : 1024);
+}
+
+template <typename V, int LPR, int VEC, int U, bool PF>
 static int launch_rows(gnn_ctx *ctx, int32_t n_out, const int32_t *ptr, const int32_t *idx, const float *val,
                        const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
                        const float *mask, int64_t ldm) {
     constexpr int GROUPS = SPMM_THREADS / LPR;
     const unsigned grid = (unsigned)ceil_div(n_out, GROUPS);
     if (val)
-        spmm_rows_kernel<V, LPR, VEC, true><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n_out, ptr, idx, val, P, ldp, F, Y,
+        spmm_rows_kernel<V, LPR, VEC, true, U, PF><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n_out, ptr, idx, val, P, ldp, F, Y,
                                                                                    ldy, bias, relu, mask, ldm);
     else
-        spmm_rows_kernel<V, LPR, VEC, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n_out, ptr, idx, val, P, ldp, F,
+        spmm_rows_kernel<V, LPR, VEC, false, U, PF><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n_out, ptr, idx, val, P, ldp, F,
                                                                                     Y, ldy, bias, relu, mask, ldm);
     GNN_LAUNCHED(ctx);
     return 0;
 }
 
-// Dispatch on width.  Wide rows are processed in column blocks (separate launches on shifted pointers).
-int spmm_launch(gnn_ctx *ctx, int32_t n_out, const int32_t *ptr, const int32_t *idx, const float *val,
-                int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias,
-                int relu, const float *mask, int64_t ldm) {
+template <typename V, int LPR, int VEC, int U, bool PF>
+static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t nnz, const int32_t *ptr, const int32_t *idx,
+                        const float *val, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy,
+                        const float *bias, int relu, const float *mask, int64_t ldm) {
+    constexpr int GROUPS = SPMM_THREADS / LPR;
+    const int32_t MERGE_CHUNK = merge_chunk(ctx, LPR);
+    const int32_t n_chunks = (int32_t)ceil_div(nnz, MERGE_CHUNK);
+    const int32_t ldw = (int32_t)round_up(F, 4);
+    void *ws = nullptr;
+    const size_t part = (size_t)n_chunks * ldw * 4;
+    GNN_TRY(ctx->workspace(2 * part + (size_t)n_chunks * 8 + 64, &ws));
+    float *head = (float *)ws, *tail = head + (size_t)n_chunks * ldw;
+    int32_t *head_row = (int32_t *)(tail + (size_t)n_chunks * ldw), *tail_row = head_row + n_chunks;
+    const unsigned grid = (unsigned)ceil_div(n_chunks, GROUPS);
+    if (val)
+        spmm_merge_kernel<V, LPR, VEC, true, U, PF><<<grid, SPMM_THREADS, 0, ctx->stream>>>(
+            n_out, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, val, P, ldp, F, Y, ldy, bias, relu, mask, ldm, head, tail, head_row,
+            tail_row, ldw);
+    else
+        spmm_merge_kernel<V, LPR, VEC, false, U, PF><<<grid, SPMM_THREADS, 0, ctx->stream>>>(
+            n_out, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, val, P, ldp, F, Y, ldy, bias, relu, mask, ldm, head, tail, head_row,
+            tail_row, ldw);
+    GNN_LAUNCHED(ctx);
+    spmm_merge_fixup_kernel<<<(unsigned)ceil_div((int64_t)n_chunks * 32, 256), 256, 0, ctx->stream>>>(
+        n_chunks, F, head, tail, head_row, tail_row, ldw, Y, ldy, bias, relu, mask, ldm);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+// Variant choice (ctx->spmm_variant: 0 auto, 1 rows, 2 merge).  The nonzero-balanced kernel is the default: it is
+// never slower than one-row-per-group on B200 (products-shaped, mild skew: 33.0 vs 36.3 ms per step; Reddit-shaped,
+// hub rows of 60 K nonzeros: 7.7 vs 15.3 ms) because a lane group streams one row sequentially, so with the rows
+// kernel every hub row is a serial tail, and short rows leave CTA slots idle until the slowest row of the CTA ends.
+// The rows kernel remains for matrices with empty rows (the merge walk needs every row to own a nonzero) and for
+// tiny inputs.
+static bool use_merge(const gnn_ctx *ctx, int64_t nnz, int32_t min_nnz_row, int32_t max_nnz_row, int lpr) {
     (void)max_nnz_row;
+    if (min_nnz_row < 1 || nnz >= (1ll << 31) || nnz < 4 * (int64_t)merge_chunk(ctx, lpr)) return false;
+    return ctx->spmm_variant != 1;
+}
+
+// Dispatch on width.  Wide rows are processed in column blocks (separate launches on shifted pointers).
+int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t nnz, const int32_t *ptr, const int32_t *idx, const float *val,
+                int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy,
+                const float *bias, int relu, const float *mask, int64_t ldm) {
     if (n_out <= 0 || F <= 0) return 0;
     const bool vec_ok = ((uintptr_t)P % 16 == 0) && ((uintptr_t)Y % 16 == 0) && (ldp % 4 == 0) && (ldy % 4 == 0) &&
                         ldp >= round_up(F, 4) && ldy >= round_up(F, 4);
@@ -167,7 +338,28 @@ int spmm_launch(gnn_ctx *ctx, int32_t n_out, const int32_t *ptr, const int32_t *
         float *Yc = Y + c0;
         const float *bc = bias ? bias + c0 : nullptr;
         const float *mc = mask ? mask + c0 : nullptr;
-#define GO(V, LPR, VEC) GNN_TRY((launch_rows<V, LPR, VEC>(ctx, n_out, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm)))
+#define GO2(V, LPR, VEC, U, PF)                                                                                      \
+    do {                                                                                                             \
+        if (use_merge(ctx, nnz, min_nnz_row, max_nnz_row, LPR))                                                      \
+            GNN_TRY((launch_merge<V, LPR, VEC, U, PF>(ctx, n_out, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \
+        else                                                                                                         \
+            GNN_TRY((launch_rows<V, LPR, VEC, U, PF>(ctx, n_out, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm)));  \
+    } while (0)
+#ifdef GNN_SPMM_TUNE /* experiment build: (U, prefetch) selectable at run time for the float4 kernels */
+#define GO(V, LPR, VEC)                                                                                              \
+    do {                                                                                                             \
+        const int tu = ctx->spmm_tune_u, tp = ctx->spmm_tune_pf;                                                     \
+        if (sizeof(V) == 16 && tu == 2 && tp == 0) GO2(V, LPR, VEC, 2, false);                                       \
+        else if (sizeof(V) == 16 && tu == 2 && tp == 1) GO2(V, LPR, VEC, 2, true);                                   \
+        else if (sizeof(V) == 16 && tu == 4 && tp == 0) GO2(V, LPR, VEC, 4, false);                                  \
+        else if (sizeof(V) == 16 && tu == 4 && tp == 1) GO2(V, LPR, VEC, 4, true);                                   \
+        else if (sizeof(V) == 16 && tu == 8 && tp == 0) GO2(V, LPR, VEC, 8, false);                                  \
+        else if (sizeof(V) == 16 && tu == 8 && tp == 1) GO2(V, LPR, VEC, 8, true);                                   \
+        else GO2(V, LPR, VEC, (Tune<V, VEC>::U), (Tune<V, VEC>::PF));                                                               \
+    } while (0)
+#else
+#define GO(V, LPR, VEC) GO2(V, LPR, VEC, (Tune<V, VEC>::U), (Tune<V, VEC>::PF))
+#endif
         if (vec_ok) {
             const int nv = (f + 3) / 4;
             if (nv <= 4) GO(float4, 4, 1);
@@ -185,6 +377,7 @@ int spmm_launch(gnn_ctx *ctx, int32_t n_out, const int32_t *ptr, const int32_t *
             else GO(float, 32, 8);
         }
 #undef GO
+#undef GO2
     }
     return 0;
 }
@@ -196,8 +389,15 @@ using namespace gnn;
 extern "C" {
 
 int gnn_set_spmm_variant(gnn_ctx_t *ctx, int variant) {
-    GNN_REQUIRE(ctx && variant >= 0 && variant <= 2, "gnn_set_spmm_variant: bad argument");
-    ctx->spmm_variant = variant;
+    // variant % 10: 0 auto / 1 rows / 2 merge.  Tuning digits (experiments): (variant / 10) % 10 = loads in flight
+    // U (only in GNN_SPMM_TUNE builds), (variant / 100) % 10 = 1 disables the index prefetch (same builds),
+    // variant / 1000 = merge chunk in units of 256 nonzeros (0 keeps the default).
+    GNN_REQUIRE(ctx && variant >= 0 && variant % 10 <= 2, "gnn_set_spmm_variant: bad argument");
+    ctx->spmm_variant = variant % 10;
+    ctx->spmm_tune_u = (variant / 10) % 10;
+    ctx->spmm_tune_pf = ((variant / 100) % 10) ? 0 : 1;
+    const int ch = variant / 1000;
+    ctx->spmm_chunk = ch > 0 ? ch * MERGE_CHUNK_MIN : 0;
     return 0;
 }
 
@@ -207,8 +407,8 @@ int gnn_spmm_fwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *P, int64_t l
     GNN_REQUIRE(F > 0 && ldp >= F && ldy >= F, "tensors are not compatible, tensors should of shape [...,A,B] and [...,B,A]");
     GNN_REQUIRE(!use_values || g->val, "gnn_spmm_fwd: edge values not built (call gnn_graph_normalize)");
     GNN_REQUIRE(P != Y, "gnn_spmm_fwd: in-place aggregation is not supported");
-    return spmm_launch(ctx, g->n_rows, g->rowptr, g->colidx, use_values ? g->val : nullptr, g->max_row_nnz, P, ldp, F,
-                       Y, ldy, bias, relu, mask, ldm);
+    return spmm_launch(ctx, g->n_rows, g->nnz, g->rowptr, g->colidx, use_values ? g->val : nullptr, g->min_row_nnz,
+                       g->max_row_nnz, P, ldp, F, Y, ldy, bias, relu, mask, ldm);
 }
 
 int gnn_spmm_bwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *dZ, int64_t ldz, int32_t F, float *dP, int64_t ldp,
@@ -223,8 +423,9 @@ int gnn_spmm_bwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *dZ, int64_t 
         v = alias ? g->val : g->valT;
         GNN_REQUIRE(v, "gnn_spmm_bwd: edge values not built (call gnn_graph_normalize after gnn_graph_build_csc)");
     }
-    return spmm_launch(ctx, g->t_rows, alias ? g->rowptr : g->colptr, alias ? g->colidx : g->rowidx, v, g->max_col_nnz,
-                       dZ, ldz, F, dP, ldp, nullptr, 0, mask, ldm);
+    return spmm_launch(ctx, g->t_rows, alias ? g->nnz : g->nnz_t, alias ? g->rowptr : g->colptr,
+                       alias ? g->colidx : g->rowidx, v, alias ? g->min_row_nnz : g->min_col_nnz,
+                       alias ? g->max_row_nnz : g->max_col_nnz, dZ, ldz, F, dP, ldp, nullptr, 0, mask, ldm);
 }
 
 } // extern "C"

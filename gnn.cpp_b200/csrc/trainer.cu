@@ -9,12 +9,16 @@
 //   AF (aggregate first, F_{l-1} < F_l):   M = A_hat H_{l-1} ;    H_l = relu(M W^T + b)        [SpMM, GEMM+epilogue]
 //       backward: dW = dZ^T M ; dM = dZ W ; dZ_{l-1} = (A_hat^T dM) . [H_{l-1} > 0]
 //       (for l = 1 no input gradient is needed, so an AF first layer has NO backward aggregation)
-// Row-partitioned multi-GPU (graph with n_rows < n_cols): every aggregation input is all-gathered into a
-// global-row-order buffer first; weight/bias gradients and the loss are all-reduced in one slab.
+// Row-partitioned multi-GPU (graph with n_rows < n_cols): every aggregation input is gathered into a
+// global-row-order buffer first; weight/bias gradients and the loss are all-reduced in one slab.  The gather is a
+// copy-engine push of the rank's block into every peer's arena over NVLink (comm.cu), started as soon as the
+// block is produced and awaited right before the aggregation, so the bias-gradient column sums and the dW GEMMs
+// of the backward run while the next aggregation input is in flight (NN GEMM before TN GEMM for that reason).
 #include "common.cuh"
 
 namespace gnn {
 int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out);
+int copy2d(gnn_ctx *ctx, float *dst, int64_t ldd, const float *src, int64_t lds, int64_t rows, int32_t cols);
 }
 
 struct gnn_gcn {
@@ -32,7 +36,13 @@ struct gnn_gcn {
     std::vector<float *> H;  // H[l], l = 1..L  [n_loc, ld[l]]
     std::vector<float *> M;  // aggregated inputs of AF layers [n_loc, ld[l-1]]
     float *S1 = nullptr, *G0 = nullptr, *G1 = nullptr; // scratch [n_loc, maxld]
-    float *AG = nullptr;                                 // all-gather buffer [world*chunk, maxld] (dist)
+    float *AG = nullptr;                                 // all-gather buffer [world*chunk, maxld] (dist, NCCL mode)
+    // dist, peer mode: one gather region [world][chunk, ldw] per aggregation of a step inside the peer arena;
+    // slot(l, dir) = 2*(l-1) + dir (dir 0 forward, 1 backward); the rank produces its own block in place
+    gnn_peer_arena_t *arena = nullptr;
+    std::vector<size_t> slot_off;
+    int comm_mode = 1; // 1 = peer arena pushes (falls back to 0 when IPC is unavailable), 0 = ncclAllGather
+    int32_t panel_cols = 128; // peer mode: column panel width of a gathered matrix (pipelines transfer and SpMM)
     float *Xs[2] = {nullptr, nullptr};                   // double-buffered staged inputs for *_h entry points
     int32_t *ys[2] = {nullptr, nullptr};
     int cur_slot = 0;
@@ -105,7 +115,7 @@ static void recompute_stats(gnn_gcn *m) {
     }
 }
 
-// aggregation input must be visible in global row order: all-gather under row partitioning
+// aggregation input must be visible in global row order: all-gather under row partitioning (NCCL mode)
 static int gather_input(gnn_ctx *ctx, gnn_gcn *m, const float *local, int32_t ldw, const float **global_out) {
     if (!m->dist) {
         *global_out = local;
@@ -117,6 +127,60 @@ static int gather_input(gnn_ctx *ctx, gnn_gcn *m, const float *local, int32_t ld
     return 0;
 }
 
+// ---- peer mode helpers -----------------------------------------------------------------------------------------
+// A gathered matrix of padded width ldw is cut into column panels of at most m->panel_cols columns; panel p of a
+// region is [world][chunk, w_p] (panel-major), so one panel of one rank is a contiguous block the copy engines push
+// in one go, and the aggregation of panel p (SpMM acts on columns independently) starts as soon as panel p landed
+// while panel p+1 is still in flight.  Outside peer mode there is a single panel and every view is row-major.
+constexpr int MAX_PANELS = 8;
+struct Panels {
+    int n = 1;
+    int32_t c0[MAX_PANELS] = {0}, w[MAX_PANELS] = {0};
+};
+static Panels panels_of(const gnn_gcn *m, int32_t ldw) {
+    Panels P;
+    int32_t pc = m->arena ? m->panel_cols : ldw;
+    if (pc <= 0 || (int64_t)pc * MAX_PANELS < ldw) pc = (int32_t)round_up(ceil_div(ldw, MAX_PANELS), 4);
+    P.n = 0;
+    for (int32_t c = 0; c < ldw; c += pc) {
+        P.c0[P.n] = c;
+        P.w[P.n] = ldw - c < pc ? ldw - c : pc;
+        P.n++;
+    }
+    return P;
+}
+// columns [c0, c0+f) of a logical [n_loc, F] matrix: pointer to (row 0, column c0) and leading dimension
+struct View {
+    float *ptr;
+    int64_t ld;
+};
+static inline int op_of(int32_t l, int dir) { return 2 * (l - 1) + dir; }
+static inline float *panel_region(gnn_ctx *ctx, gnn_gcn *m, int op, const Panels &P, int p) {
+    return reinterpret_cast<float *>((char *)gnn_peer_arena_local(m->arena) + m->slot_off[op]) +
+           (size_t)ctx->world * m->chunk * P.c0[p];
+}
+static inline View own_view(gnn_ctx *ctx, gnn_gcn *m, int op, const Panels &P, int p) {
+    return {panel_region(ctx, m, op, P, p) + (size_t)ctx->rank * m->chunk * P.w[p], P.w[p]};
+}
+static inline View rowmajor_view(float *base, int64_t ld, const Panels &P, int p) { return {base + P.c0[p], ld}; }
+static inline int32_t panel_f(const Panels &P, int p, int32_t F) { return F - P.c0[p] < P.w[p] ? F - P.c0[p] : P.w[p]; }
+
+static int peer_begin(gnn_ctx *ctx, gnn_gcn *m, int op, const Panels &P, int p) {
+    return gnn_peer_gather_begin(ctx, m->arena, op * MAX_PANELS + p,
+                                 m->slot_off[op] + (size_t)ctx->world * m->chunk * P.c0[p] * 4,
+                                 (size_t)m->chunk * P.w[p] * 4);
+}
+static int peer_wait(gnn_ctx *ctx, gnn_gcn *m, int op, int p) {
+    Prof pr(ctx, m, CLS_OTHER);
+    return gnn_peer_gather_wait(ctx, m->arena, op * MAX_PANELS + p);
+}
+// where panel p of dZ_l is written: a transform-first layer aggregates dZ_l itself, so in peer mode it is produced
+// straight into the rank's block of that aggregation's gather region; otherwise a row-major ping-pong buffer
+static inline View dz_view(gnn_ctx *ctx, gnn_gcn *m, int32_t l, const Panels &P, int p) {
+    if (m->arena && !m->agg_first[l]) return own_view(ctx, m, op_of(l, 1), P, p);
+    return rowmajor_view(((m->L - l) & 1) ? m->G1 : m->G0, m->ld[l], P, p);
+}
+
 static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
     const gnn_graph *g = m->g;
     const float *Hin = X;
@@ -125,27 +189,58 @@ static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
         const int32_t Fi = m->dims[l - 1], Fo = m->dims[l];
         const float *W = m->params + m->w_off[l], *b = m->params + m->b_off[l];
         const int relu = l < m->L;
+        const int op = op_of(l, 0);
         if (m->agg_first[l]) {
-            const float *src = nullptr;
-            // the gather needs a dense [chunk, ld] block; X may have ldx != ld[0] only in single-GPU mode
-            GNN_TRY(gather_input(ctx, m, Hin, (int32_t)ld_in, &src));
-            {
-                Prof p(ctx, m, CLS_SPMM);
-                GNN_TRY(gnn_spmm_fwd(ctx, g, src, ld_in, Fi, m->M[l], m->ld[l - 1], nullptr, 0, nullptr, 0, 1));
+            const Panels P = panels_of(m, m->ld[l - 1]);
+            if (m->arena)
+                for (int p = 0; p < P.n; p++) { // stage the input panels and start their transfer
+                    const View own = own_view(ctx, m, op, P, p);
+                    GNN_TRY(copy2d(ctx, own.ptr, own.ld, Hin + P.c0[p], ld_in, m->n_loc, panel_f(P, p, Fi)));
+                    GNN_TRY(peer_begin(ctx, m, op, P, p));
+                }
+            for (int p = 0; p < P.n; p++) {
+                const float *src = nullptr;
+                int64_t ld_src = ld_in;
+                if (m->arena) {
+                    GNN_TRY(peer_wait(ctx, m, op, p));
+                    src = panel_region(ctx, m, op, P, p);
+                    ld_src = P.w[p];
+                } else {
+                    // the gather needs a dense [chunk, ld] block; X may have ldx != ld[0] only in single-GPU mode
+                    GNN_TRY(gather_input(ctx, m, Hin, (int32_t)ld_in, &src));
+                }
+                Prof pr(ctx, m, CLS_SPMM);
+                GNN_TRY(gnn_spmm_fwd(ctx, g, src, ld_src, panel_f(P, p, Fi), m->M[l] + P.c0[p], m->ld[l - 1], nullptr, 0,
+                                     nullptr, 0, 1));
             }
-            Prof p(ctx, m, CLS_GEMM);
+            Prof pr(ctx, m, CLS_GEMM);
             GNN_TRY(gnn_gemm_nt(ctx, m->n_loc, Fo, Fi, m->M[l], m->ld[l - 1], W, Fi, m->H[l], m->ld[l], b, relu,
                                 m->precision));
         } else {
-            {
-                Prof p(ctx, m, CLS_GEMM);
-                GNN_TRY(gnn_gemm_nt(ctx, m->n_loc, Fo, Fi, Hin, ld_in, W, Fi, m->S1, m->ld[l], nullptr, 0,
-                                    m->precision));
+            const Panels P = panels_of(m, m->ld[l]);
+            for (int p = 0; p < P.n; p++) { // P[:, panel] = H W[panel rows]^T, pushed as soon as it is produced
+                const View out = m->arena ? own_view(ctx, m, op, P, p) : rowmajor_view(m->S1, m->ld[l], P, p);
+                {
+                    Prof pr(ctx, m, CLS_GEMM);
+                    GNN_TRY(gnn_gemm_nt(ctx, m->n_loc, panel_f(P, p, Fo), Fi, Hin, ld_in, W + (int64_t)P.c0[p] * Fi, Fi,
+                                        out.ptr, out.ld, nullptr, 0, m->precision));
+                }
+                if (m->arena) GNN_TRY(peer_begin(ctx, m, op, P, p));
             }
-            const float *src = nullptr;
-            GNN_TRY(gather_input(ctx, m, m->S1, m->ld[l], &src));
-            Prof p(ctx, m, CLS_SPMM);
-            GNN_TRY(gnn_spmm_fwd(ctx, g, src, m->ld[l], Fo, m->H[l], m->ld[l], b, relu, nullptr, 0, 1));
+            for (int p = 0; p < P.n; p++) {
+                const float *src = nullptr;
+                int64_t ld_src = m->ld[l];
+                if (m->arena) {
+                    GNN_TRY(peer_wait(ctx, m, op, p));
+                    src = panel_region(ctx, m, op, P, p);
+                    ld_src = P.w[p];
+                } else {
+                    GNN_TRY(gather_input(ctx, m, m->S1, m->ld[l], &src));
+                }
+                Prof pr(ctx, m, CLS_SPMM);
+                GNN_TRY(gnn_spmm_fwd(ctx, g, src, ld_src, panel_f(P, p, Fo), m->H[l] + P.c0[p], m->ld[l], b + P.c0[p],
+                                     relu, nullptr, 0, 1));
+            }
         }
         Hin = m->H[l];
         ld_in = m->ld[l];
@@ -153,53 +248,94 @@ static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
     return 0;
 }
 
+// dZ_L has been written to dz_view(L, .) (and, in peer mode with a transform-first last layer, its gather begun)
 static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
     const gnn_graph *g = m->g;
-    float *dZ = m->G0, *dNext = m->G1;
     for (int32_t l = m->L; l >= 1; l--) {
         const int32_t Fi = m->dims[l - 1], Fo = m->dims[l];
         const float *W = m->params + m->w_off[l];
         float *dW = m->grads + m->w_off[l], *db = m->grads + m->b_off[l];
         const float *Hin = l > 1 ? m->H[l - 1] : X;
         const int64_t ld_in = l > 1 ? m->ld[l - 1] : ldx;
-        {
-            Prof p(ctx, m, CLS_BIAS);
-            GNN_TRY(colsum(ctx, m->n_loc, Fo, dZ, m->ld[l], db));
+        const int op = op_of(l, 1);
+        const Panels Po = panels_of(m, m->ld[l]);                 // panels of dZ_l (width F_l)
+        const Panels Pi = panels_of(m, m->ld[l > 1 ? l - 1 : l]); // panels of dZ_{l-1} (width F_{l-1})
+        // in peer mode the gather of a transform-first layer's dZ is started by whoever produces dZ
+        const bool next_begins = m->arena && l > 1 && !m->agg_first[l - 1];
+        const bool dz_panel_major = m->arena && !m->agg_first[l];
+        for (int p = 0; p < (dz_panel_major ? Po.n : 1); p++) {
+            Prof pr(ctx, m, CLS_BIAS);
+            const View dz = dz_view(ctx, m, l, Po, p);
+            GNN_TRY(colsum(ctx, m->n_loc, dz_panel_major ? panel_f(Po, p, Fo) : Fo, dz.ptr, dz.ld, db + (dz_panel_major ? Po.c0[p] : 0)));
         }
         if (m->agg_first[l]) {
+            const View dZ = dz_view(ctx, m, l, Po, 0); // row-major (an aggregate-first layer does not gather dZ)
+            if (l > 1)
+                for (int p = 0; p < Pi.n; p++) { // dM[:, panel] = dZ W[:, panel]
+                    const View dM = m->arena ? own_view(ctx, m, op, Pi, p) : rowmajor_view(m->S1, m->ld[l - 1], Pi, p);
+                    {
+                        Prof pr(ctx, m, CLS_GEMM);
+                        GNN_TRY(gnn_gemm_nn(ctx, m->n_loc, m->arena ? panel_f(Pi, p, Fi) : Fi, Fo, dZ.ptr, dZ.ld,
+                                            W + Pi.c0[p], Fi, dM.ptr, dM.ld, nullptr, 0, m->precision));
+                    }
+                    if (m->arena) GNN_TRY(peer_begin(ctx, m, op, Pi, p));
+                    else break; // single row-major launch
+                }
             {
-                Prof p(ctx, m, CLS_GEMM);
-                GNN_TRY(gnn_gemm_tn(ctx, m->n_loc, Fo, Fi, dZ, m->ld[l], m->M[l], m->ld[l - 1], dW, Fi, m->precision));
+                Prof pr(ctx, m, CLS_GEMM); // overlaps the transfer of dM
+                GNN_TRY(gnn_gemm_tn(ctx, m->n_loc, Fo, Fi, dZ.ptr, dZ.ld, m->M[l], m->ld[l - 1], dW, Fi, m->precision));
             }
             if (l > 1) {
-                {
-                    Prof p(ctx, m, CLS_GEMM);
-                    GNN_TRY(gnn_gemm_nn(ctx, m->n_loc, Fi, Fo, dZ, m->ld[l], W, Fi, m->S1, m->ld[l - 1], nullptr, 0,
-                                        m->precision));
+                for (int p = 0; p < Pi.n; p++) {
+                    const float *src = nullptr;
+                    int64_t ld_src = m->ld[l - 1];
+                    if (m->arena) {
+                        GNN_TRY(peer_wait(ctx, m, op, p));
+                        src = panel_region(ctx, m, op, Pi, p);
+                        ld_src = Pi.w[p];
+                    } else {
+                        GNN_TRY(gather_input(ctx, m, m->S1, m->ld[l - 1], &src));
+                    }
+                    const View dn = dz_view(ctx, m, l - 1, Pi, p);
+                    {
+                        Prof pr(ctx, m, CLS_SPMM);
+                        GNN_TRY(gnn_spmm_bwd(ctx, g, src, ld_src, m->arena ? panel_f(Pi, p, Fi) : Fi, dn.ptr, dn.ld,
+                                             Hin + Pi.c0[p], ld_in, 1));
+                    }
+                    if (next_begins) GNN_TRY(peer_begin(ctx, m, op_of(l - 1, 1), Pi, p));
+                    if (!m->arena) break;
                 }
-                const float *src = nullptr;
-                GNN_TRY(gather_input(ctx, m, m->S1, m->ld[l - 1], &src));
-                Prof p(ctx, m, CLS_SPMM);
-                GNN_TRY(gnn_spmm_bwd(ctx, g, src, m->ld[l - 1], Fi, dNext, m->ld[l - 1], Hin, ld_in, 1));
             }
         } else {
-            const float *src = nullptr;
-            GNN_TRY(gather_input(ctx, m, dZ, m->ld[l], &src));
-            {
-                Prof p(ctx, m, CLS_SPMM);
-                GNN_TRY(gnn_spmm_bwd(ctx, g, src, m->ld[l], Fo, m->S1, m->ld[l], nullptr, 0, 1));
+            for (int p = 0; p < Po.n; p++) { // dP[:, panel] = A_hat^T dZ[:, panel]
+                const float *src = nullptr;
+                int64_t ld_src = m->ld[l];
+                if (m->arena) {
+                    GNN_TRY(peer_wait(ctx, m, op, p));
+                    src = panel_region(ctx, m, op, Po, p);
+                    ld_src = Po.w[p];
+                } else {
+                    GNN_TRY(gather_input(ctx, m, dz_view(ctx, m, l, Po, 0).ptr, m->ld[l], &src));
+                }
+                Prof pr(ctx, m, CLS_SPMM);
+                GNN_TRY(gnn_spmm_bwd(ctx, g, src, ld_src, panel_f(Po, p, Fo), m->S1 + Po.c0[p], m->ld[l], nullptr, 0, 1));
             }
-            {
-                Prof p(ctx, m, CLS_GEMM);
-                GNN_TRY(gnn_gemm_tn(ctx, m->n_loc, Fo, Fi, m->S1, m->ld[l], Hin, ld_in, dW, Fi, m->precision));
+            if (l > 1) { // dZ_{l-1} first, so its transfer runs under the dW GEMM below
+                const bool pm = m->arena && !m->agg_first[l - 1];
+                for (int p = 0; p < (pm ? Pi.n : 1); p++) {
+                    const View dn = dz_view(ctx, m, l - 1, Pi, p);
+                    {
+                        Prof pr(ctx, m, CLS_GEMM);
+                        GNN_TRY(gnn_gemm_nn(ctx, m->n_loc, pm ? panel_f(Pi, p, Fi) : Fi, Fo, m->S1, m->ld[l],
+                                            W + (pm ? Pi.c0[p] : 0), Fi, dn.ptr, dn.ld, Hin + (pm ? Pi.c0[p] : 0), ld_in,
+                                            m->precision));
+                    }
+                    if (next_begins) GNN_TRY(peer_begin(ctx, m, op_of(l - 1, 1), Pi, p));
+                }
             }
-            if (l > 1) {
-                Prof p(ctx, m, CLS_GEMM);
-                GNN_TRY(gnn_gemm_nn(ctx, m->n_loc, Fi, Fo, m->S1, m->ld[l], W, Fi, dNext, m->ld[l - 1], Hin, ld_in,
-                                    m->precision));
-            }
+            Prof pr(ctx, m, CLS_GEMM);
+            GNN_TRY(gnn_gemm_tn(ctx, m->n_loc, Fo, Fi, m->S1, m->ld[l], Hin, ld_in, dW, Fi, m->precision));
         }
-        float *t = dZ; dZ = dNext; dNext = t;
     }
     return 0;
 }
@@ -260,7 +396,21 @@ int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_
     GNN_TRY(alloc(&m->S1, rows_alloc * m->maxld));
     GNN_TRY(alloc(&m->G0, rows_alloc * m->maxld));
     GNN_TRY(alloc(&m->G1, rows_alloc * m->maxld));
-    if (m->dist) GNN_TRY(alloc(&m->AG, (int64_t)ctx->world * m->chunk * m->maxld));
+    if (const char *e = getenv("GNN_COMM")) m->comm_mode = strcmp(e, "nccl") ? 1 : 0; // ablation switches
+    if (const char *e = getenv("GNN_PANEL_COLS")) m->panel_cols = (int32_t)round_up(atoi(e) > 0 ? atoi(e) : 1 << 20, 4);
+    if (m->dist && ctx->world > 1 && m->comm_mode == 1) {
+        // one region per aggregation of a step, wide enough for either layer order
+        size_t off = 0;
+        m->slot_off.assign(2 * L, 0);
+        for (int32_t l = 1; l <= L; l++)
+            for (int dir = 0; dir < 2; dir++) {
+                const int32_t w = m->ld[l - 1] > m->ld[l] ? m->ld[l - 1] : m->ld[l];
+                m->slot_off[2 * (l - 1) + dir] = off;
+                off += (size_t)round_up((int64_t)ctx->world * m->chunk * w * 4, 256);
+            }
+        if (gnn_peer_arena_create(ctx, off, &m->arena) != 0) m->arena = nullptr; // collective; falls back to NCCL
+    }
+    if (m->dist && !m->arena) GNN_TRY(alloc(&m->AG, (int64_t)ctx->world * m->chunk * m->maxld));
     GNN_TRY(alloc(&m->loss_d, 4));
     recompute_stats(m);
     *out = m;
@@ -274,6 +424,7 @@ int gnn_gcn_destroy(gnn_ctx_t *ctx, gnn_gcn_t *m) {
     for (auto p : m->H) cudaFree(p);
     for (auto p : m->M) cudaFree(p);
     cudaFree(m->S1); cudaFree(m->G0); cudaFree(m->G1); cudaFree(m->AG);
+    if (m->arena) gnn_peer_arena_destroy(ctx, m->arena);
     for (int i = 0; i < 2; i++) { cudaFree(m->Xs[i]); cudaFree(m->ys[i]); }
     if (m->copy_stream) { cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_uploaded); cudaEventDestroy(m->ev_consumed); }
     cudaFree(m->loss_d);
@@ -345,6 +496,7 @@ int gnn_gcn_set_option(gnn_gcn_t *m, const char *key, double value) {
     else if (!strcmp(key, "dampening")) m->dampening = (float)value;
     else if (!strcmp(key, "weight_decay")) m->weight_decay = (float)value;
     else if (!strcmp(key, "nesterov")) m->nesterov = (int)value;
+
     else if (!strcmp(key, "agg_first_mask")) { // bit l-1 set -> layer l aggregates first (tests / ablation)
         for (int32_t l = 1; l <= m->L; l++) m->agg_first[l] = (((int64_t)value) >> (l - 1)) & 1;
         recompute_stats(m);
@@ -369,7 +521,11 @@ int gnn_gcn_forward(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx) {
     GNN_REQUIRE(ctx && m && X && ldx >= m->dims[0], "gnn_gcn_forward: bad argument");
     GNN_TRY(ensure_buffers(ctx, m));
     GNN_REQUIRE(!m->dist || ldx == m->ld[0], "gnn_gcn_forward: row-partitioned mode needs ldx == round_up(F0,4)");
-    return forward(ctx, m, X, ldx);
+    GNN_TRY(forward(ctx, m, X, ldx));
+    // peer mode: a gather region may only be rewritten once every rank is done reading it; the train step gets
+    // that ordering from its gradient all-reduce, a forward-only call from this one-word all-reduce
+    if (m->arena) GNN_TRY(gnn_allreduce_sum(ctx, m->grads + m->n_params + 1, 1));
+    return 0;
 }
 
 int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx, const int32_t *y, float lr,
@@ -384,7 +540,20 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
     float *loss_slot = m->grads + m->n_params; // rides along with the gradient all-reduce
     {
         Prof p(ctx, m, CLS_LOSS);
-        GNN_TRY(gnn_softmax_xent(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], y, m->n_glob, loss_slot, m->G0, m->ld[m->L]));
+        // dZ_L goes where the backward expects it; a panel-major destination with more than one panel is staged
+        // through the row-major buffer
+        const Panels PL = panels_of(m, m->ld[m->L]);
+        const bool pm = m->arena && !m->agg_first[m->L];
+        const View dz = (pm && PL.n > 1) ? View{m->G0, m->ld[m->L]} : dz_view(ctx, m, m->L, PL, 0);
+        GNN_TRY(gnn_softmax_xent(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], y, m->n_glob, loss_slot, dz.ptr, dz.ld));
+        if (pm)
+            for (int p = 0; p < PL.n; p++) {
+                if (PL.n > 1) {
+                    const View own = own_view(ctx, m, op_of(m->L, 1), PL, p);
+                    GNN_TRY(copy2d(ctx, own.ptr, own.ld, m->G0 + PL.c0[p], m->ld[m->L], m->n_loc, panel_f(PL, p, C)));
+                }
+                GNN_TRY(peer_begin(ctx, m, op_of(m->L, 1), PL, p));
+            }
     }
     GNN_TRY(backward(ctx, m, X, ldx));
     if (m->dist) {

@@ -176,6 +176,74 @@ def test_spmm_epilogues(ctx, oracle):
     g.close()
 
 
+def _hub_problem(N=6000, E=40000, hubs=(0, 17), seed=7):
+    """power-law-free random graph plus a few hub nodes adjacent to (almost) every node: max degree >> mean."""
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, N, E).astype(np.int32); dst = rng.integers(0, N, E).astype(np.int32)
+    hs, hd = [], []
+    for h in hubs:
+        others = np.arange(N, dtype=np.int32)[::1 if h == hubs[0] else 2]
+        hs += [np.full(len(others), h, np.int32), others]; hd += [others, np.full(len(others), h, np.int32)]
+    return np.concatenate([src, dst] + hs), np.concatenate([dst, src] + hd), N
+
+
+@pytest.mark.parametrize("F", [7, 47, 100, 256, 300])
+@pytest.mark.parametrize("variant", [1, 2])
+def test_spmm_variants_vs_oracle(ctx, oracle, F, variant):
+    """rows kernel (1) and nonzero-balanced merge kernel (2) forced in turn, on a mildly skewed graph and on a hub
+    graph whose longest rows span several chunks; epilogues included; the two must also agree within rounding."""
+    from gnn_cpp_b200 import capi, host
+    cases = [(load_problem("tiny_pl").src, load_problem("tiny_pl").dst, 3000), _hub_problem()]
+    try:
+        capi.call("gnn_set_spmm_variant", ctx.h, variant)
+        for src, dst, N in cases:
+            G = oracle.Graph(src, dst, N)
+            g = host.Graph.build(ctx, src, dst, N)
+            rng = np.random.default_rng(F + N)
+            P = rng.uniform(-1, 1, (N, F)).astype(np.float32)
+            bias = rng.uniform(-1, 1, F).astype(np.float32)
+            mask = rng.uniform(-1, 1, (N, F)).astype(np.float32)
+            Y = oracle.spmm(N, G.rowptr, G.colidx, G.val, P, order=1)
+            Z, H = oracle.bias_relu(Y, bias)
+            l0 = ctx.launches
+            got = g.spmm_fwd(_dev(P, ctx)).cpu().numpy()
+            n_launch = ctx.launches - l0
+            assert n_launch == (2 if variant == 2 else 1) * ((F + 255) // 256 if F % 4 else (F + 511) // 512)
+            assert rel_err(got, Y) <= TOL
+            assert rel_err(g.spmm_fwd(_dev(P, ctx), bias=_dev(bias, ctx), relu=True).cpu().numpy(), H) <= TOL
+            ref_b = oracle.relu_bwd(oracle.spmm(N, G.colptr, G.rowidx, G.valT, P, order=1), mask)
+            assert rel_err(g.spmm_bwd(_dev(P, ctx), mask=_dev(mask, ctx)).cpu().numpy(), ref_b) <= TOL
+            a = g.spmm_fwd(_dev(P, ctx)); b = g.spmm_fwd(_dev(P, ctx))   # deterministic: fixed-order fix-up
+            assert np.array_equal(a.cpu().numpy(), b.cpu().numpy())
+            g.close()
+    finally:
+        capi.call("gnn_set_spmm_variant", ctx.h, 0)
+
+
+def test_spmm_variant_auto_choice(ctx, oracle):
+    """auto (0): graphs whose rows all own a nonzero go to the nonzero-balanced merge kernel (2 launches: kernel +
+    fix-up) whatever the skew; a matrix with an empty row is routed to the rows kernel (1 launch)."""
+    from gnn_cpp_b200 import host
+    F = 64
+    for (src, dst, N), want in [((load_problem("tiny_pl").src, load_problem("tiny_pl").dst, 3000), 2), (_hub_problem(), 2)]:
+        g = host.Graph.build(ctx, src, dst, N)
+        P = _dev(np.ones((N, F), np.float32), ctx)
+        l0 = ctx.launches
+        g.spmm_fwd(P)
+        assert ctx.launches - l0 == want
+        g.close()
+    src, dst, N = _hub_problem()
+    g = host.Graph.build(ctx, src[src != 5], dst[src != 5], N, fill_mode=0)   # row 5 empty, no diagonal
+    G_rowptr, G_colidx = oracle.csr_build(src[src != 5], dst[src != 5], N, 0)
+    P = np.random.default_rng(3).uniform(-1, 1, (N, F)).astype(np.float32)
+    l0 = ctx.launches
+    got = g.spmm_fwd(_dev(P, ctx), use_values=False).cpu().numpy()
+    assert ctx.launches - l0 == 1
+    ref = oracle.spmm(N, G_rowptr, G_colidx, np.ones(len(G_colidx), np.float32), P, order=1)
+    assert rel_err(got, ref) <= TOL
+    g.close()
+
+
 # ------------------------------------------------------------------------------------------------ GEMMs, epilogues
 @pytest.mark.parametrize("M,N,K", [(5, 4, 20), (200, 16, 24), (2708, 16, 1433), (3001, 47, 256), (4099, 256, 100),
                                    (1000, 130, 257), (777, 3, 64)])
