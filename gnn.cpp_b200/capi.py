@@ -85,7 +85,7 @@ SIGNATURES = {
     "gnn_peer_arena_destroy": (C.c_int, [vp, vp]),
     "gnn_peer_arena_local": (vp, [vp]),
     "gnn_peer_gather_begin": (C.c_int, [vp, vp, C.c_int, sz, sz]),
-    "gnn_peer_gather_wait": (C.c_int, [vp, vp, C.c_int]),
+    "gnn_peer_gather_wait": (C.c_int, [vp, vp, C.c_int, C.c_int]),
 }
 # int-returning functions that are NOT status codes
 _PLAIN_INT = {"gnn_version", "gnn_ctx_sm_count", "gnn_graph_is_symmetric"}

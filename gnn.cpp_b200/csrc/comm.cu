@@ -65,7 +65,7 @@ static NcclApi *nccl_api() {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------------- peer arena
-constexpr int PEER_MAX_WORLD = 16, PEER_MAX_SLOTS = 256;
+constexpr int PEER_MAX_WORLD = 16, PEER_MAX_SLOTS = 1024;
 
 __global__ void peer_set_flag_kernel(uint32_t *flag, uint32_t seq) {
     __threadfence_system();
@@ -112,15 +112,21 @@ __global__ void __launch_bounds__(512)
     }
 }
 
-// one warp: lane q polls the flag of peer q until it reaches seq (bounded: a lost peer traps instead of hanging)
-__global__ void peer_wait_flags_kernel(const uint32_t *flags, int world, int rank, uint32_t seq) {
+// one warp: lane q polls the flags of peer q for `count` consecutive slots until each reached its sequence number
+// (bounded: a lost peer traps instead of hanging)
+struct PeerWaitArgs {
+    uint32_t seq[32];
+};
+__global__ void peer_wait_flags_kernel(const uint32_t *flags, int world, int rank, int count, const PeerWaitArgs w) {
     const int q = threadIdx.x;
     if (q < world && q != rank) {
-        const volatile uint32_t *f = flags + q;
         const long long t0 = clock64();
-        while ((int32_t)(*f - seq) < 0) {
-            __nanosleep(200);
-            if (clock64() - t0 > 60000000000LL) __trap(); // ~30 s
+        for (int s = 0; s < count; s++) {
+            const volatile uint32_t *f = flags + s * PEER_MAX_WORLD + q;
+            while ((int32_t)(*f - w.seq[s]) < 0) {
+                __nanosleep(200);
+                if (clock64() - t0 > 60000000000LL) __trap(); // ~30 s
+            }
         }
     }
     __threadfence_system();
@@ -137,7 +143,7 @@ struct gnn_peer_arena {
     unsigned *done = nullptr;                   // SM mode: CTA completion counter
     int sm_mode = 1, sm_ctas = 32;
     cudaEvent_t ev_ready = nullptr;
-    uint32_t seq[gnn::PEER_MAX_SLOTS] = {};
+    uint32_t seq[gnn::PEER_MAX_SLOTS] = {};      // last sequence number begun per slot (identical on every rank)
     uint32_t *flags(int r) const { return reinterpret_cast<uint32_t *>(base[r] + bytes); }
 };
 
@@ -301,44 +307,48 @@ int gnn_peer_arena_destroy(gnn_ctx_t *ctx, gnn_peer_arena_t *a) {
 
 void *gnn_peer_arena_local(gnn_peer_arena_t *a) { return a ? (void *)a->base[a->rank] : nullptr; }
 
-int gnn_peer_gather_begin(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot, size_t region_offset, size_t block_bytes) {
+int gnn_peer_gather_begin(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot, size_t offset, size_t bytes) {
     GNN_REQUIRE(ctx && a && slot >= 0 && slot < PEER_MAX_SLOTS - 1, "gnn_peer_gather_begin: bad argument");
-    GNN_REQUIRE(region_offset + (size_t)a->world * block_bytes <= a->bytes && block_bytes % 16 == 0,
-                "gnn_peer_gather_begin: region [%zu, +%d x %zu) outside the arena (%zu bytes)", region_offset, a->world,
-                block_bytes, a->bytes);
+    GNN_REQUIRE(offset + bytes <= a->bytes && bytes % 16 == 0 && offset % 16 == 0,
+                "gnn_peer_gather_begin: range [%zu, +%zu) outside the arena (%zu bytes) or not 16-byte aligned", offset,
+                bytes, a->bytes);
     const uint32_t seq = ++a->seq[slot];
-    const size_t own = region_offset + (size_t)a->rank * block_bytes;
     GNN_CHECK_CUDA(cudaEventRecord(a->ev_ready, ctx->stream));
     if (a->sm_mode) {
         PeerPushArgs pa;
         pa.n_dst = 0;
         for (int i = 1; i < a->world; i++) {
-            const int r = (a->rank + i) % a->world;
-            pa.dst[pa.n_dst] = reinterpret_cast<uint4 *>(a->base[r] + own);
+            const int r = (a->rank + i) % a->world; // staggered so the ranks do not all hit the same peer first
+            pa.dst[pa.n_dst] = reinterpret_cast<uint4 *>(a->base[r] + offset);
             pa.flag[pa.n_dst] = a->flags(r) + slot * PEER_MAX_WORLD + a->rank;
             pa.n_dst++;
         }
         GNN_CHECK_CUDA(cudaStreamWaitEvent(a->push_sm, a->ev_ready, 0));
-        peer_push_kernel<<<a->sm_ctas, 512, 0, a->push_sm>>>(pa, reinterpret_cast<const uint4 *>(a->base[a->rank] + own),
-                                                            block_bytes / 16, seq, a->done);
+        peer_push_kernel<<<a->sm_ctas, 512, 0, a->push_sm>>>(pa, reinterpret_cast<const uint4 *>(a->base[a->rank] + offset),
+                                                            bytes / 16, seq, a->done);
         GNN_LAUNCHED(ctx);
         return 0;
     }
     for (int i = 1; i < a->world; i++) {
-        const int r = (a->rank + i) % a->world; // staggered so the ranks do not all hit the same peer first
+        const int r = (a->rank + i) % a->world;
         GNN_CHECK_CUDA(cudaStreamWaitEvent(a->push[r], a->ev_ready, 0));
-        GNN_CHECK_CUDA(cudaMemcpyAsync(a->base[r] + own, a->base[a->rank] + own, block_bytes, cudaMemcpyDefault, a->push[r]));
+        GNN_CHECK_CUDA(cudaMemcpyAsync(a->base[r] + offset, a->base[a->rank] + offset, bytes, cudaMemcpyDefault, a->push[r]));
         peer_set_flag_kernel<<<1, 1, 0, a->push[r]>>>(a->flags(r) + slot * PEER_MAX_WORLD + a->rank, seq);
         GNN_LAUNCHED(ctx);
     }
     return 0;
 }
 
-int gnn_peer_gather_wait(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot) {
-    GNN_REQUIRE(ctx && a && slot >= 0 && slot < PEER_MAX_SLOTS, "gnn_peer_gather_wait: bad argument");
-    peer_wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(a->flags(a->rank) + slot * PEER_MAX_WORLD, a->world, a->rank,
-                                                     a->seq[slot]);
-    GNN_LAUNCHED(ctx);
+int gnn_peer_gather_wait(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot, int count) {
+    GNN_REQUIRE(ctx && a && slot >= 0 && count >= 1 && slot + count < PEER_MAX_SLOTS, "gnn_peer_gather_wait: bad argument");
+    for (int s0 = 0; s0 < count; s0 += 32) {
+        PeerWaitArgs w;
+        const int n = count - s0 < 32 ? count - s0 : 32;
+        for (int s = 0; s < n; s++) w.seq[s] = a->seq[slot + s0 + s];
+        peer_wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(a->flags(a->rank) + (slot + s0) * PEER_MAX_WORLD, a->world,
+                                                         a->rank, n, w);
+        GNN_LAUNCHED(ctx);
+    }
     return 0;
 }
 

@@ -98,8 +98,10 @@ int exclusive_scan_u32(gnn_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t 
 // keys/vals are overwritten with the sorted sequence (scratch comes from ctx->workspace).
 int radix_sort_u64(gnn_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int bit_lo, int bit_hi);
 // spmm.cu -----------------------------------------------------------------------------------------
-// nnz = ptr[n_out] (host copy); min/max_nnz_row steer the variant choice (see spmm.cu)
-int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t nnz, const int32_t *ptr, const int32_t *idx, const float *val,
-                int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy,
-                const float *bias, int relu, const float *mask, int64_t ldm);
+int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
+                const float *val, int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F,
+                float *Y, int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm);
+int spmm_rows_range(gnn_ctx *ctx, const gnn_graph *g, int transpose, int32_t r0, int32_t r1, int64_t k0, int64_t k1,
+                    const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
+                    const float *mask, int64_t ldm);
 } // namespace gnn

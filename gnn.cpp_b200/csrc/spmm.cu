@@ -183,7 +183,8 @@ constexpr int MERGE_CHUNK_MIN = 256;
 
 template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF>
 __global__ void __launch_bounds__(SPMM_THREADS)
-    spmm_merge_kernel(int32_t n_out, int32_t nnz, int32_t n_chunks, int32_t MERGE_CHUNK, const int32_t *__restrict__ ptr,
+    spmm_merge_kernel(int32_t n_out, int32_t k_base, int32_t nnz, int32_t n_chunks, int32_t MERGE_CHUNK,
+                      const int32_t *__restrict__ ptr,
                       const int32_t *__restrict__ idx, const float *__restrict__ val, const float *__restrict__ P,
                       int64_t ldp, int32_t F, float *__restrict__ Y, int64_t ldy, const float *__restrict__ bias,
                       int relu, const float *__restrict__ mask, int64_t ldm, float *__restrict__ head,
@@ -196,7 +197,8 @@ __global__ void __launch_bounds__(SPMM_THREADS)
     if (g >= n_chunks) return;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
     const int nvec = (F + T::W - 1) / T::W;
-    const int32_t k0 = g * MERGE_CHUNK, k1 = min(nnz, k0 + MERGE_CHUNK);
+    // nonzeros [k_base, nnz) belong to rows [0, n_out) of `ptr` (a row range of a larger matrix keeps absolute offsets)
+    const int32_t k0 = k_base + g * MERGE_CHUNK, k1 = min(nnz, k0 + MERGE_CHUNK);
 
     // last row r with ptr[r] <= k0 (rows are non-empty, so it is the row that holds nonzero k0)
     int32_t lo = 0, hi = n_out; // invariant: ptr[lo] <= k0 < ptr[hi]
@@ -284,12 +286,12 @@ static int launch_rows(gnn_ctx *ctx, int32_t n_out, const int32_t *ptr, const in
 }
 
 template <typename V, int LPR, int VEC, int U, bool PF>
-static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t nnz, const int32_t *ptr, const int32_t *idx,
+static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
                         const float *val, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy,
                         const float *bias, int relu, const float *mask, int64_t ldm) {
     constexpr int GROUPS = SPMM_THREADS / LPR;
     const int32_t MERGE_CHUNK = merge_chunk(ctx, LPR);
-    const int32_t n_chunks = (int32_t)ceil_div(nnz, MERGE_CHUNK);
+    const int32_t n_chunks = (int32_t)ceil_div(nnz - k_base, MERGE_CHUNK);
     const int32_t ldw = (int32_t)round_up(F, 4);
     void *ws = nullptr;
     const size_t part = (size_t)n_chunks * ldw * 4;
@@ -299,11 +301,11 @@ static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t nnz, const int32_t 
     const unsigned grid = (unsigned)ceil_div(n_chunks, GROUPS);
     if (val)
         spmm_merge_kernel<V, LPR, VEC, true, U, PF><<<grid, SPMM_THREADS, 0, ctx->stream>>>(
-            n_out, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, val, P, ldp, F, Y, ldy, bias, relu, mask, ldm, head, tail, head_row,
+            n_out, (int32_t)k_base, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, val, P, ldp, F, Y, ldy, bias, relu, mask, ldm, head, tail, head_row,
             tail_row, ldw);
     else
         spmm_merge_kernel<V, LPR, VEC, false, U, PF><<<grid, SPMM_THREADS, 0, ctx->stream>>>(
-            n_out, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, val, P, ldp, F, Y, ldy, bias, relu, mask, ldm, head, tail, head_row,
+            n_out, (int32_t)k_base, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, val, P, ldp, F, Y, ldy, bias, relu, mask, ldm, head, tail, head_row,
             tail_row, ldw);
     GNN_LAUNCHED(ctx);
     spmm_merge_fixup_kernel<<<(unsigned)ceil_div((int64_t)n_chunks * 32, 256), 256, 0, ctx->stream>>>(
@@ -318,16 +320,19 @@ static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t nnz, const int32_t 
 // kernel every hub row is a serial tail, and short rows leave CTA slots idle until the slowest row of the CTA ends.
 // The rows kernel remains for matrices with empty rows (the merge walk needs every row to own a nonzero) and for
 // tiny inputs.
-static bool use_merge(const gnn_ctx *ctx, int64_t nnz, int32_t min_nnz_row, int32_t max_nnz_row, int lpr) {
+static bool use_merge(const gnn_ctx *ctx, int64_t nnz, int64_t k_end, int32_t min_nnz_row, int32_t max_nnz_row,
+                      int lpr) {
     (void)max_nnz_row;
-    if (min_nnz_row < 1 || nnz >= (1ll << 31) || nnz < 4 * (int64_t)merge_chunk(ctx, lpr)) return false;
+    if (min_nnz_row < 1 || k_end >= (1ll << 31) || nnz < 4 * (int64_t)merge_chunk(ctx, lpr)) return false;
     return ctx->spmm_variant != 1;
 }
 
 // Dispatch on width.  Wide rows are processed in column blocks (separate launches on shifted pointers).
-int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t nnz, const int32_t *ptr, const int32_t *idx, const float *val,
-                int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy,
-                const float *bias, int relu, const float *mask, int64_t ldm) {
+// Rows [0, n_out) of `ptr` hold the nonzeros [k_base, nnz) of idx/val (k_base = 0 for a whole matrix; a row range of
+// a larger matrix passes ptr + r0 with the absolute offsets ptr[r0], ptr[r1]).
+int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
+                const float *val, int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F,
+                float *Y, int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm) {
     if (n_out <= 0 || F <= 0) return 0;
     const bool vec_ok = ((uintptr_t)P % 16 == 0) && ((uintptr_t)Y % 16 == 0) && (ldp % 4 == 0) && (ldy % 4 == 0) &&
                         ldp >= round_up(F, 4) && ldy >= round_up(F, 4);
@@ -340,8 +345,8 @@ int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t nnz, const int32_t *ptr, co
         const float *mc = mask ? mask + c0 : nullptr;
 #define GO2(V, LPR, VEC, U, PF)                                                                                      \
     do {                                                                                                             \
-        if (use_merge(ctx, nnz, min_nnz_row, max_nnz_row, LPR))                                                      \
-            GNN_TRY((launch_merge<V, LPR, VEC, U, PF>(ctx, n_out, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \
+        if (use_merge(ctx, nnz - k_base, nnz, min_nnz_row, max_nnz_row, LPR))                                       \
+            GNN_TRY((launch_merge<V, LPR, VEC, U, PF>(ctx, n_out, k_base, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \
         else                                                                                                         \
             GNN_TRY((launch_rows<V, LPR, VEC, U, PF>(ctx, n_out, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm)));  \
     } while (0)
@@ -382,6 +387,21 @@ int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t nnz, const int32_t *ptr, co
     return 0;
 }
 
+// Aggregation restricted to output rows [r0, r1) (the trainer's row blocks).  transpose = 0: A_hat (CSR),
+// 1: A_hat^T (CSC, or the CSR arrays again for a symmetric graph).  k0/k1 = ptr[r0]/ptr[r1] (host copies).
+// Y and mask point at row r0.
+int spmm_rows_range(gnn_ctx *ctx, const gnn_graph *g, int transpose, int32_t r0, int32_t r1, int64_t k0, int64_t k1,
+                    const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
+                    const float *mask, int64_t ldm) {
+    const bool alias = transpose && g->symmetric;
+    const int32_t *ptr = (!transpose || alias) ? g->rowptr : g->colptr;
+    const int32_t *idx = (!transpose || alias) ? g->colidx : g->rowidx;
+    const float *val = (!transpose || alias) ? g->val : g->valT;
+    const int32_t mn = (!transpose || alias) ? g->min_row_nnz : g->min_col_nnz;
+    const int32_t mx = (!transpose || alias) ? g->max_row_nnz : g->max_col_nnz;
+    return spmm_launch(ctx, r1 - r0, k0, k1, ptr + r0, idx, val, mn, mx, P, ldp, F, Y, ldy, bias, relu, mask, ldm);
+}
+
 } // namespace gnn
 
 using namespace gnn;
@@ -407,7 +427,7 @@ int gnn_spmm_fwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *P, int64_t l
     GNN_REQUIRE(F > 0 && ldp >= F && ldy >= F, "tensors are not compatible, tensors should of shape [...,A,B] and [...,B,A]");
     GNN_REQUIRE(!use_values || g->val, "gnn_spmm_fwd: edge values not built (call gnn_graph_normalize)");
     GNN_REQUIRE(P != Y, "gnn_spmm_fwd: in-place aggregation is not supported");
-    return spmm_launch(ctx, g->n_rows, g->nnz, g->rowptr, g->colidx, use_values ? g->val : nullptr, g->min_row_nnz,
+    return spmm_launch(ctx, g->n_rows, 0, g->nnz, g->rowptr, g->colidx, use_values ? g->val : nullptr, g->min_row_nnz,
                        g->max_row_nnz, P, ldp, F, Y, ldy, bias, relu, mask, ldm);
 }
 
@@ -423,7 +443,7 @@ int gnn_spmm_bwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *dZ, int64_t 
         v = alias ? g->val : g->valT;
         GNN_REQUIRE(v, "gnn_spmm_bwd: edge values not built (call gnn_graph_normalize after gnn_graph_build_csc)");
     }
-    return spmm_launch(ctx, g->t_rows, alias ? g->nnz : g->nnz_t, alias ? g->rowptr : g->colptr,
+    return spmm_launch(ctx, g->t_rows, 0, alias ? g->nnz : g->nnz_t, alias ? g->rowptr : g->colptr,
                        alias ? g->colidx : g->rowidx, v, alias ? g->min_row_nnz : g->min_col_nnz,
                        alias ? g->max_row_nnz : g->max_col_nnz, dZ, ldz, F, dP, ldp, nullptr, 0, mask, ldm);
 }

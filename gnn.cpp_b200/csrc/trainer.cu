@@ -19,6 +19,9 @@
 namespace gnn {
 int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out);
 int copy2d(gnn_ctx *ctx, float *dst, int64_t ldd, const float *src, int64_t lds, int64_t rows, int32_t cols);
+int spmm_rows_range(gnn_ctx *ctx, const gnn_graph *g, int transpose, int32_t r0, int32_t r1, int64_t k0, int64_t k1,
+                    const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
+                    const float *mask, int64_t ldm);
 }
 
 struct gnn_gcn {
@@ -43,6 +46,10 @@ struct gnn_gcn {
     std::vector<size_t> slot_off;
     int comm_mode = 1; // 1 = peer arena pushes (falls back to 0 when IPC is unavailable), 0 = ncclAllGather
     int32_t panel_cols = 128; // peer mode: column panel width of a gathered matrix (pipelines transfer and SpMM)
+    // row blocks of the rank's rows (peer mode; one block otherwise): rows rb_row[i]..rb_row[i+1], with the matching
+    // nonzero offsets of the forward (CSR) and backward (CSC) structure
+    int n_rb = 1;
+    int64_t rb_row[9] = {0}, rb_kf[9] = {0}, rb_kb[9] = {0};
     float *Xs[2] = {nullptr, nullptr};                   // double-buffered staged inputs for *_h entry points
     int32_t *ys[2] = {nullptr, nullptr};
     int cur_slot = 0;
@@ -127,12 +134,19 @@ static int gather_input(gnn_ctx *ctx, gnn_gcn *m, const float *local, int32_t ld
     return 0;
 }
 
-// ---- peer mode helpers -----------------------------------------------------------------------------------------
-// A gathered matrix of padded width ldw is cut into column panels of at most m->panel_cols columns; panel p of a
-// region is [world][chunk, w_p] (panel-major), so one panel of one rank is a contiguous block the copy engines push
-// in one go, and the aggregation of panel p (SpMM acts on columns independently) starts as soon as panel p landed
-// while panel p+1 is still in flight.  Outside peer mode there is a single panel and every view is row-major.
-constexpr int MAX_PANELS = 8;
+// ---- tiling of a gathered matrix ---------------------------------------------------------------------------------
+// Peer mode cuts every gathered matrix (padded width ldw, the rank's n_loc rows) into column panels of at most
+// m->panel_cols columns and row blocks of the rank's rows.  Panel p of a region is stored panel-major,
+// [world][chunk, w_p], so a tile (row block, panel) of one rank is one contiguous byte range: it is pushed into the
+// peers' arenas (comm.cu) the moment it is produced, with its own flag slot.
+//   * column panels pipeline a transfer with ITS OWN aggregation: SpMM acts on columns independently, so panel p
+//     is aggregated as soon as every rank's panel p has landed while panel p+1 is still in flight;
+//   * row blocks pipeline a transfer with the PREVIOUS aggregation: everything between the output of one
+//     aggregation and the input of the next (bias/ReLU epilogue, dense transform, ReLU mask) is row-local, so the
+//     rows of block rb are transformed and pushed while the aggregation still works on block rb+1.
+// Outside peer mode there is one panel and one row block and every view is row-major: the schedule degenerates to
+// the plain sequence (NCCL mode inserts an all-gather where peer mode waits).
+constexpr int MAX_PANELS = 4, MAX_RB = 8;
 struct Panels {
     int n = 1;
     int32_t c0[MAX_PANELS] = {0}, w[MAX_PANELS] = {0};
@@ -153,8 +167,10 @@ static Panels panels_of(const gnn_gcn *m, int32_t ldw) {
 struct View {
     float *ptr;
     int64_t ld;
+    float *row(int64_t r) const { return ptr + r * ld; }
 };
 static inline int op_of(int32_t l, int dir) { return 2 * (l - 1) + dir; }
+static inline int slot_of(int op, int p, int rb) { return (op * MAX_PANELS + p) * MAX_RB + rb; }
 static inline float *panel_region(gnn_ctx *ctx, gnn_gcn *m, int op, const Panels &P, int p) {
     return reinterpret_cast<float *>((char *)gnn_peer_arena_local(m->arena) + m->slot_off[op]) +
            (size_t)ctx->world * m->chunk * P.c0[p];
@@ -165,14 +181,18 @@ static inline View own_view(gnn_ctx *ctx, gnn_gcn *m, int op, const Panels &P, i
 static inline View rowmajor_view(float *base, int64_t ld, const Panels &P, int p) { return {base + P.c0[p], ld}; }
 static inline int32_t panel_f(const Panels &P, int p, int32_t F) { return F - P.c0[p] < P.w[p] ? F - P.c0[p] : P.w[p]; }
 
-static int peer_begin(gnn_ctx *ctx, gnn_gcn *m, int op, const Panels &P, int p) {
-    return gnn_peer_gather_begin(ctx, m->arena, op * MAX_PANELS + p,
-                                 m->slot_off[op] + (size_t)ctx->world * m->chunk * P.c0[p] * 4,
-                                 (size_t)m->chunk * P.w[p] * 4);
+// push tile (row block rb, panel p) of the rank's block of gather region `op` to every peer
+static int push_tile(gnn_ctx *ctx, gnn_gcn *m, int op, const Panels &P, int p, int rb) {
+    const int64_t r0 = m->rb_row[rb], r1 = m->rb_row[rb + 1];
+    const size_t off = m->slot_off[op] +
+                       ((size_t)ctx->world * m->chunk * P.c0[p] + (size_t)ctx->rank * m->chunk * P.w[p] + (size_t)r0 * P.w[p]) * 4;
+    // an empty row block still publishes its sequence number (16 bytes of padding keep the range valid)
+    const size_t bytes = r1 > r0 ? (size_t)(r1 - r0) * P.w[p] * 4 : 0;
+    return gnn_peer_gather_begin(ctx, m->arena, slot_of(op, p, rb), off, bytes);
 }
-static int peer_wait(gnn_ctx *ctx, gnn_gcn *m, int op, int p) {
+static int wait_panel(gnn_ctx *ctx, gnn_gcn *m, int op, int p) {
     Prof pr(ctx, m, CLS_OTHER);
-    return gnn_peer_gather_wait(ctx, m->arena, op * MAX_PANELS + p);
+    return gnn_peer_gather_wait(ctx, m->arena, slot_of(op, p, 0), m->n_rb);
 }
 // where panel p of dZ_l is written: a transform-first layer aggregates dZ_l itself, so in peer mode it is produced
 // straight into the rank's block of that aggregation's gather region; otherwise a row-major ping-pong buffer
@@ -181,65 +201,80 @@ static inline View dz_view(gnn_ctx *ctx, gnn_gcn *m, int32_t l, const Panels &P,
     return rowmajor_view(((m->L - l) & 1) ? m->G1 : m->G0, m->ld[l], P, p);
 }
 
+// rows of block rb of the aggregation input of layer l: the transformed features P_l = H_{l-1} W_l^T (transform
+// first) or H_{l-1} itself (aggregate first); in peer mode written into the gather region and pushed
+static int produce_fwd(gnn_ctx *ctx, gnn_gcn *m, int32_t l, int rb, const float *Hin, int64_t ld_in) {
+    const int64_t r0 = m->rb_row[rb], rows = m->rb_row[rb + 1] - r0;
+    const int32_t Fi = m->dims[l - 1], Fo = m->dims[l];
+    const int op = op_of(l, 0);
+    if (m->agg_first[l]) {
+        if (!m->arena) return 0;
+        const Panels P = panels_of(m, m->ld[l - 1]);
+        for (int p = 0; p < P.n; p++) {
+            const View own = own_view(ctx, m, op, P, p);
+            GNN_TRY(copy2d(ctx, own.row(r0), own.ld, Hin + r0 * ld_in + P.c0[p], ld_in, rows, panel_f(P, p, Fi)));
+            GNN_TRY(push_tile(ctx, m, op, P, p, rb));
+        }
+        return 0;
+    }
+    const float *W = m->params + m->w_off[l];
+    const Panels P = panels_of(m, m->ld[l]);
+    for (int p = 0; p < P.n; p++) {
+        const View out = m->arena ? own_view(ctx, m, op, P, p) : rowmajor_view(m->S1, m->ld[l], P, p);
+        if (rows > 0) {
+            Prof pr(ctx, m, CLS_GEMM);
+            GNN_TRY(gnn_gemm_nt(ctx, rows, panel_f(P, p, Fo), Fi, Hin + r0 * ld_in, ld_in, W + (int64_t)P.c0[p] * Fi, Fi,
+                                out.row(r0), out.ld, nullptr, 0, m->precision));
+        }
+        if (m->arena) GNN_TRY(push_tile(ctx, m, op, P, p, rb));
+    }
+    return 0;
+}
+
 static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
     const gnn_graph *g = m->g;
     const float *Hin = X;
     int64_t ld_in = ldx;
+    for (int rb = 0; rb < m->n_rb; rb++) GNN_TRY(produce_fwd(ctx, m, 1, rb, X, ldx));
     for (int32_t l = 1; l <= m->L; l++) {
         const int32_t Fi = m->dims[l - 1], Fo = m->dims[l];
         const float *W = m->params + m->w_off[l], *b = m->params + m->b_off[l];
         const int relu = l < m->L;
         const int op = op_of(l, 0);
-        if (m->agg_first[l]) {
-            const Panels P = panels_of(m, m->ld[l - 1]);
-            if (m->arena)
-                for (int p = 0; p < P.n; p++) { // stage the input panels and start their transfer
-                    const View own = own_view(ctx, m, op, P, p);
-                    GNN_TRY(copy2d(ctx, own.ptr, own.ld, Hin + P.c0[p], ld_in, m->n_loc, panel_f(P, p, Fi)));
-                    GNN_TRY(peer_begin(ctx, m, op, P, p));
-                }
-            for (int p = 0; p < P.n; p++) {
-                const float *src = nullptr;
-                int64_t ld_src = ld_in;
-                if (m->arena) {
-                    GNN_TRY(peer_wait(ctx, m, op, p));
-                    src = panel_region(ctx, m, op, P, p);
-                    ld_src = P.w[p];
-                } else {
-                    // the gather needs a dense [chunk, ld] block; X may have ldx != ld[0] only in single-GPU mode
-                    GNN_TRY(gather_input(ctx, m, Hin, (int32_t)ld_in, &src));
-                }
-                Prof pr(ctx, m, CLS_SPMM);
-                GNN_TRY(gnn_spmm_fwd(ctx, g, src, ld_src, panel_f(P, p, Fi), m->M[l] + P.c0[p], m->ld[l - 1], nullptr, 0,
-                                     nullptr, 0, 1));
+        const bool af = m->agg_first[l];
+        const int32_t Fagg = af ? Fi : Fo, ld_agg = af ? m->ld[l - 1] : m->ld[l];
+        float *Yout = af ? m->M[l] : m->H[l]; // aggregation output, leading dimension ld_agg
+        const Panels P = panels_of(m, ld_agg);
+        for (int p = 0; p < P.n; p++) {
+            const float *src = nullptr;
+            int64_t ld_src = ld_agg;
+            if (m->arena) {
+                GNN_TRY(wait_panel(ctx, m, op, p));
+                src = panel_region(ctx, m, op, P, p);
+                ld_src = P.w[p];
+            } else if (af) {
+                // the gather needs a dense [chunk, ld] block; X may have ldx != ld[0] only in single-GPU mode
+                GNN_TRY(gather_input(ctx, m, Hin, (int32_t)ld_in, &src));
+                ld_src = ld_in;
+            } else {
+                GNN_TRY(gather_input(ctx, m, m->S1, m->ld[l], &src));
             }
-            Prof pr(ctx, m, CLS_GEMM);
-            GNN_TRY(gnn_gemm_nt(ctx, m->n_loc, Fo, Fi, m->M[l], m->ld[l - 1], W, Fi, m->H[l], m->ld[l], b, relu,
-                                m->precision));
-        } else {
-            const Panels P = panels_of(m, m->ld[l]);
-            for (int p = 0; p < P.n; p++) { // P[:, panel] = H W[panel rows]^T, pushed as soon as it is produced
-                const View out = m->arena ? own_view(ctx, m, op, P, p) : rowmajor_view(m->S1, m->ld[l], P, p);
-                {
+            for (int rb = 0; rb < m->n_rb; rb++) {
+                const int64_t r0 = m->rb_row[rb], r1 = m->rb_row[rb + 1];
+                if (r1 > r0) {
+                    Prof pr(ctx, m, CLS_SPMM);
+                    GNN_TRY(spmm_rows_range(ctx, g, 0, (int32_t)r0, (int32_t)r1, m->rb_kf[rb], m->rb_kf[rb + 1], src, ld_src,
+                                            panel_f(P, p, Fagg), Yout + r0 * ld_agg + P.c0[p], ld_agg,
+                                            af ? nullptr : b + P.c0[p], af ? 0 : relu, nullptr, 0));
+                }
+                if (p + 1 < P.n) continue;
+                // the row block is complete: finish the layer for these rows and feed the next layer's exchange
+                if (af && r1 > r0) {
                     Prof pr(ctx, m, CLS_GEMM);
-                    GNN_TRY(gnn_gemm_nt(ctx, m->n_loc, panel_f(P, p, Fo), Fi, Hin, ld_in, W + (int64_t)P.c0[p] * Fi, Fi,
-                                        out.ptr, out.ld, nullptr, 0, m->precision));
+                    GNN_TRY(gnn_gemm_nt(ctx, r1 - r0, Fo, Fi, m->M[l] + r0 * m->ld[l - 1], m->ld[l - 1], W, Fi,
+                                        m->H[l] + r0 * m->ld[l], m->ld[l], b, relu, m->precision));
                 }
-                if (m->arena) GNN_TRY(peer_begin(ctx, m, op, P, p));
-            }
-            for (int p = 0; p < P.n; p++) {
-                const float *src = nullptr;
-                int64_t ld_src = m->ld[l];
-                if (m->arena) {
-                    GNN_TRY(peer_wait(ctx, m, op, p));
-                    src = panel_region(ctx, m, op, P, p);
-                    ld_src = P.w[p];
-                } else {
-                    GNN_TRY(gather_input(ctx, m, m->S1, m->ld[l], &src));
-                }
-                Prof pr(ctx, m, CLS_SPMM);
-                GNN_TRY(gnn_spmm_fwd(ctx, g, src, ld_src, panel_f(P, p, Fo), m->H[l] + P.c0[p], m->ld[l], b + P.c0[p],
-                                     relu, nullptr, 0, 1));
+                if (l < m->L) GNN_TRY(produce_fwd(ctx, m, l + 1, rb, m->H[l], m->ld[l]));
             }
         }
         Hin = m->H[l];
@@ -248,7 +283,7 @@ static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
     return 0;
 }
 
-// dZ_L has been written to dz_view(L, .) (and, in peer mode with a transform-first last layer, its gather begun)
+// dZ_L has been written to dz_view(L, .) (and, in peer mode with a transform-first last layer, its tiles pushed)
 static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
     const gnn_graph *g = m->g;
     for (int32_t l = m->L; l >= 1; l--) {
@@ -260,77 +295,90 @@ static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
         const int op = op_of(l, 1);
         const Panels Po = panels_of(m, m->ld[l]);                 // panels of dZ_l (width F_l)
         const Panels Pi = panels_of(m, m->ld[l > 1 ? l - 1 : l]); // panels of dZ_{l-1} (width F_{l-1})
-        // in peer mode the gather of a transform-first layer's dZ is started by whoever produces dZ
-        const bool next_begins = m->arena && l > 1 && !m->agg_first[l - 1];
-        const bool dz_panel_major = m->arena && !m->agg_first[l];
-        for (int p = 0; p < (dz_panel_major ? Po.n : 1); p++) {
+        // dZ_{l-1} feeds a transform-first layer's aggregation: produced panel-major and pushed tile by tile
+        const bool next_pm = m->arena && l > 1 && !m->agg_first[l - 1];
+        const bool dz_pm = m->arena && !m->agg_first[l];
+        for (int p = 0; p < (dz_pm ? Po.n : 1); p++) {
             Prof pr(ctx, m, CLS_BIAS);
             const View dz = dz_view(ctx, m, l, Po, p);
-            GNN_TRY(colsum(ctx, m->n_loc, dz_panel_major ? panel_f(Po, p, Fo) : Fo, dz.ptr, dz.ld, db + (dz_panel_major ? Po.c0[p] : 0)));
+            GNN_TRY(colsum(ctx, m->n_loc, dz_pm ? panel_f(Po, p, Fo) : Fo, dz.ptr, dz.ld, db + (dz_pm ? Po.c0[p] : 0)));
         }
         if (m->agg_first[l]) {
             const View dZ = dz_view(ctx, m, l, Po, 0); // row-major (an aggregate-first layer does not gather dZ)
             if (l > 1)
-                for (int p = 0; p < Pi.n; p++) { // dM[:, panel] = dZ W[:, panel]
-                    const View dM = m->arena ? own_view(ctx, m, op, Pi, p) : rowmajor_view(m->S1, m->ld[l - 1], Pi, p);
-                    {
-                        Prof pr(ctx, m, CLS_GEMM);
-                        GNN_TRY(gnn_gemm_nn(ctx, m->n_loc, m->arena ? panel_f(Pi, p, Fi) : Fi, Fo, dZ.ptr, dZ.ld,
-                                            W + Pi.c0[p], Fi, dM.ptr, dM.ld, nullptr, 0, m->precision));
+                for (int rb = 0; rb < m->n_rb; rb++) { // dM[rows, panel] = dZ[rows] W[:, panel]
+                    const int64_t r0 = m->rb_row[rb], rows = m->rb_row[rb + 1] - r0;
+                    for (int p = 0; p < Pi.n; p++) {
+                        const View dM = m->arena ? own_view(ctx, m, op, Pi, p) : rowmajor_view(m->S1, m->ld[l - 1], Pi, p);
+                        if (rows > 0) {
+                            Prof pr(ctx, m, CLS_GEMM);
+                            GNN_TRY(gnn_gemm_nn(ctx, rows, m->arena ? panel_f(Pi, p, Fi) : Fi, Fo, dZ.row(r0), dZ.ld,
+                                                W + Pi.c0[p], Fi, dM.row(r0), dM.ld, nullptr, 0, m->precision));
+                        }
+                        if (!m->arena) break; // single row-major launch
+                        GNN_TRY(push_tile(ctx, m, op, Pi, p, rb));
                     }
-                    if (m->arena) GNN_TRY(peer_begin(ctx, m, op, Pi, p));
-                    else break; // single row-major launch
                 }
             {
                 Prof pr(ctx, m, CLS_GEMM); // overlaps the transfer of dM
                 GNN_TRY(gnn_gemm_tn(ctx, m->n_loc, Fo, Fi, dZ.ptr, dZ.ld, m->M[l], m->ld[l - 1], dW, Fi, m->precision));
             }
-            if (l > 1) {
+            if (l > 1)
                 for (int p = 0; p < Pi.n; p++) {
                     const float *src = nullptr;
                     int64_t ld_src = m->ld[l - 1];
                     if (m->arena) {
-                        GNN_TRY(peer_wait(ctx, m, op, p));
+                        GNN_TRY(wait_panel(ctx, m, op, p));
                         src = panel_region(ctx, m, op, Pi, p);
                         ld_src = Pi.w[p];
                     } else {
                         GNN_TRY(gather_input(ctx, m, m->S1, m->ld[l - 1], &src));
                     }
                     const View dn = dz_view(ctx, m, l - 1, Pi, p);
-                    {
-                        Prof pr(ctx, m, CLS_SPMM);
-                        GNN_TRY(gnn_spmm_bwd(ctx, g, src, ld_src, m->arena ? panel_f(Pi, p, Fi) : Fi, dn.ptr, dn.ld,
-                                             Hin + Pi.c0[p], ld_in, 1));
+                    for (int rb = 0; rb < m->n_rb; rb++) {
+                        const int64_t r0 = m->rb_row[rb], r1 = m->rb_row[rb + 1];
+                        if (r1 > r0) {
+                            Prof pr(ctx, m, CLS_SPMM);
+                            GNN_TRY(spmm_rows_range(ctx, g, 1, (int32_t)r0, (int32_t)r1, m->rb_kb[rb], m->rb_kb[rb + 1], src,
+                                                    ld_src, m->arena ? panel_f(Pi, p, Fi) : Fi, dn.row(r0), dn.ld, nullptr, 0,
+                                                    Hin + r0 * ld_in + Pi.c0[p], ld_in));
+                        }
+                        if (next_pm) GNN_TRY(push_tile(ctx, m, op_of(l - 1, 1), Pi, p, rb));
                     }
-                    if (next_begins) GNN_TRY(peer_begin(ctx, m, op_of(l - 1, 1), Pi, p));
                     if (!m->arena) break;
                 }
-            }
         } else {
             for (int p = 0; p < Po.n; p++) { // dP[:, panel] = A_hat^T dZ[:, panel]
                 const float *src = nullptr;
                 int64_t ld_src = m->ld[l];
                 if (m->arena) {
-                    GNN_TRY(peer_wait(ctx, m, op, p));
+                    GNN_TRY(wait_panel(ctx, m, op, p));
                     src = panel_region(ctx, m, op, Po, p);
                     ld_src = Po.w[p];
                 } else {
                     GNN_TRY(gather_input(ctx, m, dz_view(ctx, m, l, Po, 0).ptr, m->ld[l], &src));
                 }
-                Prof pr(ctx, m, CLS_SPMM);
-                GNN_TRY(gnn_spmm_bwd(ctx, g, src, ld_src, panel_f(Po, p, Fo), m->S1 + Po.c0[p], m->ld[l], nullptr, 0, 1));
-            }
-            if (l > 1) { // dZ_{l-1} first, so its transfer runs under the dW GEMM below
-                const bool pm = m->arena && !m->agg_first[l - 1];
-                for (int p = 0; p < (pm ? Pi.n : 1); p++) {
-                    const View dn = dz_view(ctx, m, l - 1, Pi, p);
-                    {
-                        Prof pr(ctx, m, CLS_GEMM);
-                        GNN_TRY(gnn_gemm_nn(ctx, m->n_loc, pm ? panel_f(Pi, p, Fi) : Fi, Fo, m->S1, m->ld[l],
-                                            W + (pm ? Pi.c0[p] : 0), Fi, dn.ptr, dn.ld, Hin + (pm ? Pi.c0[p] : 0), ld_in,
-                                            m->precision));
+                for (int rb = 0; rb < m->n_rb; rb++) {
+                    const int64_t r0 = m->rb_row[rb], r1 = m->rb_row[rb + 1];
+                    if (r1 > r0) {
+                        Prof pr(ctx, m, CLS_SPMM);
+                        GNN_TRY(spmm_rows_range(ctx, g, 1, (int32_t)r0, (int32_t)r1, m->rb_kb[rb], m->rb_kb[rb + 1], src, ld_src,
+                                                panel_f(Po, p, Fo), m->S1 + r0 * m->ld[l] + Po.c0[p], m->ld[l], nullptr, 0,
+                                                nullptr, 0));
                     }
-                    if (next_begins) GNN_TRY(peer_begin(ctx, m, op_of(l - 1, 1), Pi, p));
+                    if (p + 1 < Po.n || l == 1) continue;
+                    // dP rows of this block are complete: dZ_{l-1} for these rows first (its transfer then runs under
+                    // the remaining row blocks and the dW GEMM below)
+                    for (int p2 = 0; p2 < (next_pm ? Pi.n : 1); p2++) {
+                        const View dn = dz_view(ctx, m, l - 1, Pi, p2);
+                        if (r1 > r0) {
+                            Prof pr(ctx, m, CLS_GEMM);
+                            GNN_TRY(gnn_gemm_nn(ctx, r1 - r0, next_pm ? panel_f(Pi, p2, Fi) : Fi, Fo, m->S1 + r0 * m->ld[l],
+                                                m->ld[l], W + (next_pm ? Pi.c0[p2] : 0), Fi, dn.row(r0), dn.ld,
+                                                Hin + r0 * ld_in + (next_pm ? Pi.c0[p2] : 0), ld_in, m->precision));
+                        }
+                        if (next_pm) GNN_TRY(push_tile(ctx, m, op_of(l - 1, 1), Pi, p2, rb));
+                    }
                 }
             }
             Prof pr(ctx, m, CLS_GEMM);
@@ -398,7 +446,7 @@ int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_
     GNN_TRY(alloc(&m->G1, rows_alloc * m->maxld));
     if (const char *e = getenv("GNN_COMM")) m->comm_mode = strcmp(e, "nccl") ? 1 : 0; // ablation switches
     if (const char *e = getenv("GNN_PANEL_COLS")) m->panel_cols = (int32_t)round_up(atoi(e) > 0 ? atoi(e) : 1 << 20, 4);
-    if (m->dist && ctx->world > 1 && m->comm_mode == 1) {
+    if (m->dist && ctx->world > 1 && m->comm_mode == 1 && 2 * L * MAX_PANELS * MAX_RB < 1000) {
         // one region per aggregation of a step, wide enough for either layer order
         size_t off = 0;
         m->slot_off.assign(2 * L, 0);
@@ -409,6 +457,23 @@ int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_
                 off += (size_t)round_up((int64_t)ctx->world * m->chunk * w * 4, 256);
             }
         if (gnn_peer_arena_create(ctx, off, &m->arena) != 0) m->arena = nullptr; // collective; falls back to NCCL
+    }
+    {
+        int want = 4;
+        if (const char *e = getenv("GNN_ROW_BLOCKS")) want = atoi(e);
+        m->n_rb = m->arena ? (want < 1 ? 1 : (want > MAX_RB ? MAX_RB : want)) : 1;
+        const int64_t per = round_up(ceil_div(m->n_loc > 0 ? m->n_loc : 1, m->n_rb), 128);
+        const bool alias = g->symmetric;
+        const int32_t *tptr = alias ? g->rowptr : g->colptr;
+        for (int i = 0; i <= m->n_rb; i++) {
+            m->rb_row[i] = per * i < m->n_loc ? per * i : m->n_loc;
+            int32_t kf = 0, kb = 0;
+            GNN_CHECK_CUDA(cudaMemcpyAsync(&kf, g->rowptr + m->rb_row[i], 4, cudaMemcpyDeviceToHost, ctx->stream));
+            GNN_CHECK_CUDA(cudaMemcpyAsync(&kb, tptr + m->rb_row[i], 4, cudaMemcpyDeviceToHost, ctx->stream));
+            GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+            m->rb_kf[i] = kf;
+            m->rb_kb[i] = kb;
+        }
     }
     if (m->dist && !m->arena) GNN_TRY(alloc(&m->AG, (int64_t)ctx->world * m->chunk * m->maxld));
     GNN_TRY(alloc(&m->loss_d, 4));
@@ -552,7 +617,7 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
                     const View own = own_view(ctx, m, op_of(m->L, 1), PL, p);
                     GNN_TRY(copy2d(ctx, own.ptr, own.ld, m->G0 + PL.c0[p], m->ld[m->L], m->n_loc, panel_f(PL, p, C)));
                 }
-                GNN_TRY(peer_begin(ctx, m, op_of(m->L, 1), PL, p));
+                for (int rb = 0; rb < m->n_rb; rb++) GNN_TRY(push_tile(ctx, m, op_of(m->L, 1), PL, p, rb));
             }
     }
     GNN_TRY(backward(ctx, m, X, ldx));

@@ -230,21 +230,21 @@ GNN_API int gnn_allreduce_sum(gnn_ctx_t *ctx, float *buf, int64_t n);
 /* Peer arena: the exchange the fused trainer uses instead of ncclAllGather.  Every rank allocates `bytes` of
  * device memory, the ranks swap CUDA IPC handles through the communicator and map each other's arenas (collective
  * call; returns 5 when IPC peer mapping is unavailable and the caller stays on gnn_allgather_rows).
- * A gather region is [world][block_bytes] at the same `region_offset` in every arena; a rank produces its own block
- * in place (gnn_peer_arena_local + region_offset + rank*block_bytes), then
- *   gnn_peer_gather_begin: after the work already enqueued on the context's stream, push the own block into the
- *       same position of every peer's arena with the copy engines over NVLink (one stream per peer) and publish a
- *       per-(slot, rank) sequence number in the peer's flag words;
- *   gnn_peer_gather_wait:  make the context's stream wait until every peer's block of the latest begin on `slot`
- *       has landed.  Work enqueued between the two calls overlaps the transfer.
- * A slot's region may be rewritten only after a collective that orders all ranks (the trainer's gradient
- * all-reduce) — the trainer gives every aggregation of a step its own slot and region. */
+ * Ranks exchange byte ranges of their arenas: a rank produces data in place in its own arena, then
+ *   gnn_peer_gather_begin: after the work already enqueued on the context's stream, push [offset, offset+bytes) of
+ *       the own arena to the same offset of every peer's arena over NVLink (SM store kernel on a high-priority side
+ *       stream; GNN_PEER_COPY=ce selects copy engines) and publish the slot's next sequence number in every peer's
+ *       flag word for (slot, this rank);
+ *   gnn_peer_gather_wait:  make the context's stream wait until, for each of the `count` slots starting at `slot`,
+ *       every peer's latest push on that slot has landed.  Work enqueued between the two calls overlaps the
+ *       transfer.  Every rank must issue the same sequence of begin calls per slot.
+ * A range may be rewritten only after a collective that orders all ranks (the trainer's gradient all-reduce) —
+ * the trainer gives every aggregation of a step its own slots and region. */
 GNN_API int gnn_peer_arena_create(gnn_ctx_t *ctx, size_t bytes, gnn_peer_arena_t **out);
 GNN_API int gnn_peer_arena_destroy(gnn_ctx_t *ctx, gnn_peer_arena_t *a);
 GNN_API void *gnn_peer_arena_local(gnn_peer_arena_t *a);
-GNN_API int gnn_peer_gather_begin(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot, size_t region_offset,
-                                  size_t block_bytes);
-GNN_API int gnn_peer_gather_wait(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot);
+GNN_API int gnn_peer_gather_begin(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot, size_t offset, size_t bytes);
+GNN_API int gnn_peer_gather_wait(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot, int count);
 
 #ifdef __cplusplus
 }

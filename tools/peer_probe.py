@@ -29,8 +29,8 @@ for F in (256, 128, 48):
         dist.all_reduce(bar)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        capi.call("gnn_peer_gather_begin", ctx.h, arena, 0, 0, block)
-        capi.call("gnn_peer_gather_wait", ctx.h, arena, 0)
+        capi.call("gnn_peer_gather_begin", ctx.h, arena, 0, rank * block, block)
+        capi.call("gnn_peer_gather_wait", ctx.h, arena, 0, 1)
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
