@@ -141,7 +141,7 @@ struct gnn_peer_arena {
     cudaStream_t push[gnn::PEER_MAX_WORLD] = {}; // copy-engine mode: one stream per peer
     cudaStream_t push_sm = nullptr;             // SM mode: one high-priority stream
     unsigned *done = nullptr;                   // SM mode: CTA completion counter
-    int sm_mode = 1, sm_ctas = 32;
+    int sm_mode = 1, sm_ctas = 64; // 64 CTAs: 649 GB/s between two B200s (32: 617, 16: 458; ncclAllGather: 467)
     cudaEvent_t ev_ready = nullptr;
     uint32_t seq[gnn::PEER_MAX_SLOTS] = {};      // last sequence number begun per slot (identical on every rank)
     uint32_t *flags(int r) const { return reinterpret_cast<uint32_t *>(base[r] + bytes); }

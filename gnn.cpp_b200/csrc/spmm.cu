@@ -264,9 +264,14 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// nonzeros per lane group of the merge kernel: narrow rows (two or more groups per warp) prefer shorter chunks
-static inline int32_t merge_chunk(const gnn_ctx *ctx, int lpr) {
-    return ctx->spmm_chunk > 0 ? ctx->spmm_chunk : (lpr <= 16 ? 512 : 1024);
+// nonzeros per lane group of the merge kernel: narrow rows (two or more groups per warp) prefer shorter chunks, and
+// a small launch (a row block of a partition) is cut finer so that it still spans >= 4 waves of resident groups
+static inline int32_t merge_chunk(const gnn_ctx *ctx, int lpr, int64_t nnz) {
+    if (ctx->spmm_chunk > 0) return ctx->spmm_chunk;
+    int64_t chunk = lpr <= 16 ? 512 : 1024;
+    const int64_t want_chunks = 4ll * ctx->sm_count * (2048 / lpr);
+    if (nnz / chunk < want_chunks) chunk = nnz / want_chunks / 64 * 64;
+    return (int32_t)(chunk < 128 ? 128 : chunk);
 }
 
 template <typename V, int LPR, int VEC, int U, bool PF>
@@ -290,7 +295,7 @@ static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz
                         const float *val, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy,
                         const float *bias, int relu, const float *mask, int64_t ldm) {
     constexpr int GROUPS = SPMM_THREADS / LPR;
-    const int32_t MERGE_CHUNK = merge_chunk(ctx, LPR);
+    const int32_t MERGE_CHUNK = merge_chunk(ctx, LPR, nnz - k_base);
     const int32_t n_chunks = (int32_t)ceil_div(nnz - k_base, MERGE_CHUNK);
     const int32_t ldw = (int32_t)round_up(F, 4);
     void *ws = nullptr;
@@ -323,7 +328,7 @@ static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz
 static bool use_merge(const gnn_ctx *ctx, int64_t nnz, int64_t k_end, int32_t min_nnz_row, int32_t max_nnz_row,
                       int lpr) {
     (void)max_nnz_row;
-    if (min_nnz_row < 1 || k_end >= (1ll << 31) || nnz < 4 * (int64_t)merge_chunk(ctx, lpr)) return false;
+    if (min_nnz_row < 1 || k_end >= (1ll << 31) || nnz < 4 * (int64_t)merge_chunk(ctx, lpr, nnz)) return false;
     return ctx->spmm_variant != 1;
 }
 

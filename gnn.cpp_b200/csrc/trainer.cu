@@ -445,6 +445,9 @@ int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_
     GNN_TRY(alloc(&m->G0, rows_alloc * m->maxld));
     GNN_TRY(alloc(&m->G1, rows_alloc * m->maxld));
     if (const char *e = getenv("GNN_COMM")) m->comm_mode = strcmp(e, "nccl") ? 1 : 0; // ablation switches
+    // 8 ranks are exchange-bound (6 GB received per rank and step vs 6 ms of compute): narrower panels shorten the
+    // link-idle gap between the last panel's aggregation and the first push of the next exchange
+    if (ctx->world >= 8) m->panel_cols = 64;
     if (const char *e = getenv("GNN_PANEL_COLS")) m->panel_cols = (int32_t)round_up(atoi(e) > 0 ? atoi(e) : 1 << 20, 4);
     if (m->dist && ctx->world > 1 && m->comm_mode == 1 && 2 * L * MAX_PANELS * MAX_RB < 1000) {
         // one region per aggregation of a step, wide enough for either layer order
@@ -459,7 +462,10 @@ int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_
         if (gnn_peer_arena_create(ctx, off, &m->arena) != 0) m->arena = nullptr; // collective; falls back to NCCL
     }
     {
-        int want = 4;
+        // Measured on 2 and 4 B200s (products-shaped): splitting the aggregation into row blocks costs more SpMM
+        // efficiency (smaller launches, more tails) than the earlier start of the next exchange wins back
+        // (4 GPUs: 19.1 ms with 1 block, 19.8 with 2, 20.5 with 4), so one block is the default.
+        int want = 1;
         if (const char *e = getenv("GNN_ROW_BLOCKS")) want = atoi(e);
         m->n_rb = m->arena ? (want < 1 ? 1 : (want > MAX_RB ? MAX_RB : want)) : 1;
         const int64_t per = round_up(ceil_div(m->n_loc > 0 ? m->n_loc : 1, m->n_rb), 128);
