@@ -66,11 +66,50 @@ __global__ void __launch_bounds__(CS_THREADS) colsum_partial_kernel(int64_t N, i
         __syncthreads();
     }
 }
-__global__ void colsum_final_kernel(int32_t F, int nblocks, const float *__restrict__ partial, float *__restrict__ out) {
+// vector variant (F % 4 == 0, 16-byte aligned rows): a thread owns one float4 column group, 4 independent row loads
+// in flight; rows are combined over the thread's row lanes in fixed order through shared memory
+template <int TX> // threads across a row (F/4 <= TX), CS_THREADS/TX row lanes
+__global__ void __launch_bounds__(CS_THREADS)
+    colsum_partial_vec_kernel(int64_t N, int32_t nvec, const float *__restrict__ A, int64_t lda, int64_t rows_per_block,
+                              float *__restrict__ partial) {
+    constexpr int TY = CS_THREADS / TX;
+    __shared__ float4 red[TY][TX];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(N, r0 + rows_per_block);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tx < nvec) {
+        int64_t r = r0 + ty;
+        for (; r + 3 * TY < r1; r += 4 * TY) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(A + r * lda) + tx);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(A + (r + TY) * lda) + tx);
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(A + (r + 2 * TY) * lda) + tx);
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(A + (r + 3 * TY) * lda) + tx);
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+            s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+            s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+        }
+        for (; r < r1; r += TY) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(A + r * lda) + tx);
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && tx < nvec) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < TY; j++) { t.x += red[j][tx].x; t.y += red[j][tx].y; t.z += red[j][tx].z; t.w += red[j][tx].w; }
+        reinterpret_cast<float4 *>(partial + (int64_t)blockIdx.x * nvec * 4)[tx] = t;
+    }
+}
+__global__ void colsum_final_kernel(int32_t F, int nblocks, const float *__restrict__ partial, float *__restrict__ out,
+                                    int32_t ldp) {
     const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= F) return;
     float s = 0.f;
-    for (int b = 0; b < nblocks; b++) s += partial[(int64_t)b * F + c];
+    for (int b = 0; b < nblocks; b++) s += partial[(int64_t)b * ldp + c];
     out[c] = s;
 }
 
@@ -117,6 +156,74 @@ __global__ void __launch_bounds__(XE_THREADS)
         for (int w = 0; w < XE_THREADS / 32; w++) t += wsum[w];
         partial[blockIdx.x] = t;
     }
+}
+// Tiled variant for C <= 64: persistent CTAs stage 128 rows at a time through shared memory with coalesced 128-bit
+// loads, one thread then owns one row (max, sum of exp, loss term, dZ written back into the tile), the tile leaves
+// with coalesced stores, and thread c < C adds column c of the tile to its running bias-gradient sum.  Per-CTA
+// loss and column-sum partials are combined by fixed-order final kernels.
+constexpr int XT_ROWS = 128, XT_THREADS = 128;
+__global__ void __launch_bounds__(XT_THREADS)
+    softmax_xent_tile_kernel(int64_t N, int32_t C, const float *__restrict__ Z, int64_t ldz, const int32_t *__restrict__ y,
+                             float inv_n, float *__restrict__ dZ, int64_t ldd, float *__restrict__ loss_partial,
+                             float *__restrict__ db_partial, int32_t ldw /* padded C, multiple of 4 */) {
+    extern __shared__ float tile[]; // [XT_ROWS][ldw + 1]
+    const int32_t lds = ldw + 1;
+    const int32_t nvec = ldw / 4;
+    float loss_acc = 0.f, db_acc = 0.f;
+    const int64_t n_tiles = (N + XT_ROWS - 1) / XT_ROWS;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t r0 = t * XT_ROWS;
+        const int32_t rows = (int32_t)min((int64_t)XT_ROWS, N - r0);
+        for (int32_t i = threadIdx.x; i < rows * nvec; i += XT_THREADS) {
+            const int32_t r = i / nvec, v = i - r * nvec;
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(Z + (r0 + r) * ldz) + v);
+            float *d = tile + r * lds + v * 4;
+            d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+        }
+        __syncthreads();
+        if ((int32_t)threadIdx.x < rows) {
+            float *z = tile + threadIdx.x * lds;
+            float mx = -INFINITY;
+            for (int32_t c = 0; c < C; c++) mx = fmaxf(mx, z[c]);
+            float s = 0.f;
+            for (int32_t c = 0; c < C; c++) s += expf(z[c] - mx);
+            const int32_t yi = y[r0 + threadIdx.x];
+            const float zy = z[yi];
+            // same evaluation as softmax_xent_kernel (reference formula, src/nn.cpp:446-450, max factored out)
+            const float eps = (mx > -60.f) ? 1e-20f * expf(-mx) : INFINITY;
+            loss_acc += -logf(expf(zy - mx) / (s + eps));
+            const float inv_s = 1.f / s;
+            for (int32_t c = 0; c < C; c++) {
+                float pr = expf(z[c] - mx) * inv_s;
+                if (c == yi) pr -= 1.f;
+                z[c] = pr * inv_n;
+            }
+            for (int32_t c = C; c < ldw; c++) z[c] = 0.f;
+        }
+        __syncthreads();
+        if (dZ)
+            for (int32_t i = threadIdx.x; i < rows * nvec; i += XT_THREADS) {
+                const int32_t r = i / nvec, v = i - r * nvec;
+                const float *d = tile + r * lds + v * 4;
+                reinterpret_cast<float4 *>(dZ + (r0 + r) * ldd)[v] = make_float4(d[0], d[1], d[2], d[3]);
+            }
+        if (db_partial && (int32_t)threadIdx.x < C) {
+            float cs = 0.f;
+            for (int32_t r = 0; r < rows; r++) cs += tile[r * lds + threadIdx.x];
+            db_acc += cs;
+        }
+        __syncthreads();
+    }
+    // loss: fixed-order sum over the CTA's threads
+    __shared__ float red[XT_THREADS];
+    red[threadIdx.x] = loss_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tsum = 0.f;
+        for (int i = 0; i < XT_THREADS; i++) tsum += red[i];
+        loss_partial[blockIdx.x] = tsum;
+    }
+    if (db_partial && (int32_t)threadIdx.x < C) db_partial[(int64_t)blockIdx.x * C + threadIdx.x] = db_acc;
 }
 __global__ void xent_final_kernel(int nblocks, const float *__restrict__ partial, float inv_n, float *__restrict__ loss) {
     // one warp, fixed order: lane-strided partial sums then a shuffle tree
@@ -235,11 +342,70 @@ int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, floa
     rows_per_block = round_up(rows_per_block, 8);
     nblocks = ceil_div(N, rows_per_block);
     void *ws = nullptr;
-    GNN_TRY(ctx->workspace((size_t)nblocks * F * 4, &ws));
+    const int32_t Fp = (int32_t)round_up(F, 4);
+    GNN_TRY(ctx->workspace((size_t)nblocks * Fp * 4, &ws));
+    // vector path: the padding columns of a row (up to lda) are read and summed into unused partial slots
+    const bool vec = ((uintptr_t)A % 16 == 0) && (lda % 4 == 0) && lda >= Fp && Fp <= 512;
+    if (vec) {
+        const int32_t nvec = Fp / 4;
+        if (nvec <= 16)
+            colsum_partial_vec_kernel<16><<<(unsigned)nblocks, CS_THREADS, 0, ctx->stream>>>(N, nvec, A, lda, rows_per_block, (float *)ws);
+        else if (nvec <= 32)
+            colsum_partial_vec_kernel<32><<<(unsigned)nblocks, CS_THREADS, 0, ctx->stream>>>(N, nvec, A, lda, rows_per_block, (float *)ws);
+        else if (nvec <= 64)
+            colsum_partial_vec_kernel<64><<<(unsigned)nblocks, CS_THREADS, 0, ctx->stream>>>(N, nvec, A, lda, rows_per_block, (float *)ws);
+        else
+            colsum_partial_vec_kernel<128><<<(unsigned)nblocks, CS_THREADS, 0, ctx->stream>>>(N, nvec, A, lda, rows_per_block, (float *)ws);
+        GNN_LAUNCHED(ctx);
+        colsum_final_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, ctx->stream>>>(F, (int)nblocks, (const float *)ws, out, Fp);
+        GNN_LAUNCHED(ctx);
+        return 0;
+    }
     colsum_partial_kernel<<<(unsigned)nblocks, CS_THREADS, 0, ctx->stream>>>(N, F, A, lda, rows_per_block, (float *)ws);
     GNN_LAUNCHED(ctx);
-    colsum_final_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, ctx->stream>>>(F, (int)nblocks, (const float *)ws, out);
+    colsum_final_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, ctx->stream>>>(F, (int)nblocks, (const float *)ws, out, F);
     GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+// loss + dZ (+ db = column sums of dZ when db != NULL, which needs the tiled kernel: returns through *db_done)
+int softmax_xent_launch(gnn_ctx *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
+                        int64_t n_total, float *loss, float *dZ, int64_t ldd, float *db) {
+    GNN_REQUIRE(ctx && Z && y && loss, "gnn_softmax_xent: NULL argument");
+    GNN_REQUIRE(N > 0 && C > 0 && ldz >= C, "invalid input, logits must be of rank 2 and targets must be 1D tensor");
+    if (n_total <= 0) n_total = N;
+    const float inv_n = 1.0f / (float)n_total;
+    const int32_t ldw = (int32_t)round_up(C, 4);
+    const bool tiled = C <= 64 && ((uintptr_t)Z % 16 == 0) && (ldz % 4 == 0) && ldz >= ldw &&
+                       (!dZ || (((uintptr_t)dZ % 16 == 0) && (ldd % 4 == 0) && ldd >= ldw));
+    void *ws = nullptr;
+    if (tiled) {
+        int64_t nblocks = ceil_div(N, XT_ROWS);
+        const int64_t cap = (int64_t)ctx->sm_count * 8;
+        if (nblocks > cap) nblocks = cap;
+        GNN_TRY(ctx->workspace((size_t)nblocks * (C + 1) * 4, &ws));
+        float *lp = (float *)ws, *dbp = db ? lp + nblocks : nullptr;
+        const size_t smem = (size_t)XT_ROWS * (ldw + 1) * 4;
+        softmax_xent_tile_kernel<<<(unsigned)nblocks, XT_THREADS, smem, ctx->stream>>>(N, C, Z, ldz, y, inv_n, dZ, ldd, lp,
+                                                                                      dbp, ldw);
+        GNN_LAUNCHED(ctx);
+        xent_final_kernel<<<1, 32, 0, ctx->stream>>>((int)nblocks, lp, inv_n, loss);
+        GNN_LAUNCHED(ctx);
+        if (db) {
+            colsum_final_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, ctx->stream>>>(C, (int)nblocks, dbp, db, C);
+            GNN_LAUNCHED(ctx);
+        }
+        return 0;
+    }
+    int64_t nblocks = ceil_div(N, XE_THREADS / 32);
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (nblocks > cap) nblocks = cap;
+    GNN_TRY(ctx->workspace((size_t)nblocks * 4, &ws));
+    softmax_xent_kernel<<<(unsigned)nblocks, XE_THREADS, 0, ctx->stream>>>(N, C, Z, ldz, y, inv_n, dZ, ldd, (float *)ws);
+    GNN_LAUNCHED(ctx);
+    xent_final_kernel<<<1, 32, 0, ctx->stream>>>((int)nblocks, (const float *)ws, inv_n, loss);
+    GNN_LAUNCHED(ctx);
+    if (db && dZ) GNN_TRY(colsum(ctx, N, C, dZ, ldd, db));
     return 0;
 }
 
@@ -280,20 +446,7 @@ int gnn_bias_grad(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *dZ, int64_t
 
 int gnn_softmax_xent(gnn_ctx_t *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
                      int64_t n_total, float *loss, float *dZ, int64_t ldd) {
-    GNN_REQUIRE(ctx && Z && y && loss, "gnn_softmax_xent: NULL argument");
-    GNN_REQUIRE(N > 0 && C > 0 && ldz >= C, "invalid input, logits must be of rank 2 and targets must be 1D tensor");
-    if (n_total <= 0) n_total = N;
-    int64_t nblocks = ceil_div(N, XE_THREADS / 32);
-    const int64_t cap = (int64_t)ctx->sm_count * 8;
-    if (nblocks > cap) nblocks = cap;
-    void *ws = nullptr;
-    GNN_TRY(ctx->workspace((size_t)nblocks * 4, &ws));
-    const float inv_n = 1.0f / (float)n_total;
-    softmax_xent_kernel<<<(unsigned)nblocks, XE_THREADS, 0, ctx->stream>>>(N, C, Z, ldz, y, inv_n, dZ, ldd, (float *)ws);
-    GNN_LAUNCHED(ctx);
-    xent_final_kernel<<<1, 32, 0, ctx->stream>>>((int)nblocks, (const float *)ws, inv_n, loss);
-    GNN_LAUNCHED(ctx);
-    return 0;
+    return softmax_xent_launch(ctx, N, C, Z, ldz, y, n_total, loss, dZ, ldd, nullptr);
 }
 
 int gnn_sgd_step(gnn_ctx_t *ctx, int64_t n, float *p, const float *g, float *vel, float lr, float momentum,

@@ -59,6 +59,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
                  : "r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
 }
+// smem -> global tile store through the async proxy (no LSU instructions, completion tracked by bulk groups)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, uint32_t src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :
+                 : "l"((uint64_t)tm), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most one committed store group may still be reading its shared-memory source
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
 }
@@ -114,7 +125,7 @@ __device__ __forceinline__ void split4(float4 *hi_ptr, float4 *lo_ptr) {
 // shared-memory matrix descriptor, descriptor version 1 (sm_100).  layout 2 = 128-byte swizzle of 16-byte chunks
 // (TMA SWIZZLE_128B), layout 1 = 128-byte swizzle of 32-byte chunks (TMA SWIZZLE_128B_ATOM_32B) — the only layout
 // the tensor core accepts for MN-major 32-bit operands.
-constexpr uint64_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+constexpr uint64_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1, LAYOUT_SW64 = 4;
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                               uint64_t layout = LAYOUT_SW128) {
     uint64_t d = 0;
@@ -135,13 +146,17 @@ constexpr int ROWS_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2-5 converter
 constexpr int TILE_M = 128;
 constexpr int BK = 32;                      // floats per k-block = one 128-byte swizzle row
 constexpr uint32_t A_TILE_BYTES = TILE_M * BK * 4; // 16 KB
-constexpr uint32_t CTRL_BYTES = 1024;
-constexpr uint32_t STAGING_BYTES = 4 * 32 * 128; // 4 epilogue warps x 32 rows x 32 columns
+constexpr uint32_t CTRL_BYTES = 2048;            // [0,1024) mbarriers + TMEM slot, [1024,2048) bias copy (256 floats)
+constexpr uint32_t STAGING_BYTES = 4 * 32 * 128; // 4 epilogue warps x 32 rows x 32 columns (x2 buffers, x2 with a mask, in TMA-epilogue mode)
 
 struct RowsArgs {
     int64_t M;
-    int32_t N, Npad, kblocks, num_tiles, stages;
-    uint32_t tmem_cols, acc_stride, stage_bytes, b_bytes;
+    int32_t N, Npad, kblocks, num_tiles, stages, bk; // bk = floats per k-block: 32 (128-byte swizzle) or 16 (64-byte)
+    uint32_t tmem_cols, acc_stride, stage_bytes, a_bytes, b_bytes;
+    uint32_t epi_bytes;  // shared memory of the epilogue: staging (+ mask tiles)
+    int tma_epi;         // 1: output tiles leave (and mask tiles arrive) through TMA; 0: per-lane global stores/loads
+    uint32_t debug;      // timing experiments only (GNN_GEMM_DEBUG): 1 skip global stores, 2 skip the hi/lo split, 4 skip mask loads
+    uint32_t b_resident; // bytes of the whole split weight matrix kept in shared memory for the kernel's lifetime (0 = streamed per k-block)
     float *C;
     int64_t ldc;
     const float *bias;
@@ -151,22 +166,31 @@ struct RowsArgs {
 };
 
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
-    tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const RowsArgs a) {
+    tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmM, const RowsArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
     uint8_t *gbase = smem_raw + (base - raw_u32);
 
     const uint32_t bar_full = base, bar_conv = base + 64, bar_empty = base + 128;
-    const uint32_t bar_tfull = base + 192, bar_tempty = base + 208, tmem_slot = base + 224;
+    const uint32_t bar_tfull = base + 192, bar_tempty = base + 208, tmem_slot = base + 224, bar_bres = base + 232;
+    const uint32_t bar_mask = base + 256; // 4 epilogue warps x 2 mask buffers
     const uint32_t staging = base + CTRL_BYTES;
-    const uint32_t stage0 = staging + STAGING_BYTES;
+    const uint32_t bres = staging + a.epi_bytes;          // resident weights (when a.b_resident != 0)
+    const uint32_t stage0 = bres + a.b_resident;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        mbar_init(bar_bres, 1);
+        for (int i = 0; i < 8; i++) mbar_init(bar_mask + 8 * i, 1);
+        if (a.tma_epi) {
+            tma_prefetch_desc(&tmC);
+            if (a.mask) tma_prefetch_desc(&tmM);
+        }
         for (int s = 0; s < a.stages; s++) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_conv + 8 * s, 4);
@@ -177,6 +201,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
             mbar_init(bar_tempty + 8 * i, 4);
         }
         fence_barrier_init();
+    }
+    if (warp >= 6) { // bias copy for the TMA epilogue (zero when there is no bias / beyond N)
+        float *bias_s = reinterpret_cast<float *>(gbase + 1024);
+        for (int i = threadIdx.x - 192; i < 256; i += 128) bias_s[i] = (a.bias && i < a.N) ? __ldg(a.bias + i) : 0.f;
     }
     if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
     tc_fence_before();
@@ -189,16 +217,25 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            const uint32_t tx = A_TILE_BYTES + 2 * a.b_bytes;
+            if (a.b_resident) { // the whole split weight matrix, once: [k-block][hi | lo]
+                mbar_arrive_expect_tx(bar_bres, a.b_resident);
+                for (int32_t kb = 0; kb < a.kblocks; kb++) {
+                    tma_load_2d(bres + kb * 2 * a.b_bytes, &tmB, bar_bres, kb * a.bk, 0);
+                    tma_load_2d(bres + kb * 2 * a.b_bytes + a.b_bytes, &tmB, bar_bres, kb * a.bk, a.Npad);
+                }
+            }
+            const uint32_t tx = a.a_bytes + (a.b_resident ? 0 : 2 * a.b_bytes);
             for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step) {
                 for (int32_t kb = 0; kb < a.kblocks; kb++, it++) {
                     const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     const uint32_t st = stage0 + s * a.stage_bytes;
                     mbar_arrive_expect_tx(bar_full + 8 * s, tx);
-                    tma_load_2d(st, &tmA, bar_full + 8 * s, kb * BK, tile * TILE_M);
-                    tma_load_2d(st + 2 * A_TILE_BYTES, &tmB, bar_full + 8 * s, kb * BK, 0);
-                    tma_load_2d(st + 2 * A_TILE_BYTES + a.b_bytes, &tmB, bar_full + 8 * s, kb * BK, a.Npad);
+                    tma_load_2d(st, &tmA, bar_full + 8 * s, kb * a.bk, tile * TILE_M);
+                    if (!a.b_resident) {
+                        tma_load_2d(st + 2 * a.a_bytes, &tmB, bar_full + 8 * s, kb * a.bk, 0);
+                        tma_load_2d(st + 2 * a.a_bytes + a.b_bytes, &tmB, bar_full + 8 * s, kb * a.bk, a.Npad);
+                    }
                 }
             }
         }
@@ -206,6 +243,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
         if (lane == 0) {
             const uint32_t idesc = instr_desc(TILE_M, (uint32_t)a.Npad, 0, 0);
             uint32_t it = 0, tile_it = 0;
+            if (a.b_resident) mbar_wait(bar_bres, 0);
             for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step, tile_it++) {
                 const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
@@ -217,11 +255,14 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                     mbar_wait(bar_conv + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t st = stage0 + s * a.stage_bytes;
-                    const uint64_t a_hi = smem_desc(st, 16, 1024), a_lo = smem_desc(st + A_TILE_BYTES, 16, 1024);
-                    const uint64_t b_hi = smem_desc(st + 2 * A_TILE_BYTES, 16, 1024);
-                    const uint64_t b_lo = smem_desc(st + 2 * A_TILE_BYTES + a.b_bytes, 16, 1024);
-#pragma unroll
-                    for (uint32_t k = 0; k < BK / 8; k++) {
+                    // K-major operands: 8-row groups are sbo bytes apart (8 rows x one swizzle row of bk floats)
+                    const uint32_t sbo = 32u * a.bk;
+                    const uint64_t lay = a.bk == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
+                    const uint64_t a_hi = smem_desc(st, 16, sbo, lay), a_lo = smem_desc(st + a.a_bytes, 16, sbo, lay);
+                    const uint32_t bst = a.b_resident ? bres + kb * 2 * a.b_bytes : st + 2 * a.a_bytes;
+                    const uint64_t b_hi = smem_desc(bst, 16, sbo, lay);
+                    const uint64_t b_lo = smem_desc(bst + a.b_bytes, 16, sbo, lay);
+                    for (uint32_t k = 0; k < (uint32_t)a.bk / 8; k++) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4); // 8 tf32 = 32 bytes along the swizzled row
                         mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
                         mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
@@ -239,17 +280,99 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
             for (int32_t kb = 0; kb < a.kblocks; kb++, it++) {
                 const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
                 mbar_wait(bar_full + 8 * s, ph);
-                uint8_t *st = gbase + CTRL_BYTES + STAGING_BYTES + (size_t)s * a.stage_bytes;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
+                uint8_t *st = gbase + CTRL_BYTES + a.epi_bytes + a.b_resident + (size_t)s * a.stage_bytes;
+                const int nit = (a.debug & 2) ? 0 : a.bk / 4; // 128 x bk floats = 32 bk float4 over 128 threads
+#pragma unroll 4
+                for (int i = 0; i < nit; i++) {
                     float4 *hp = reinterpret_cast<float4 *>(st) + (i * 128 + t);
-                    split4(hp, hp + A_TILE_BYTES / 16);
+                    split4(hp, hp + a.a_bytes / 16);
                 }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_conv + 8 * s);
             }
         }
+    } else if (a.tma_epi) {
+        // Epilogue through the async proxy: a warp owns the 32 accumulator rows of its TMEM lane quadrant; per chunk
+        // of 32 columns every lane (= one row) applies bias / ReLU / mask in registers, writes the row into a
+        // 128-byte-swizzled staging tile, and one lane hands the tile to a TMA store.  Mask tiles are fetched two
+        // chunks ahead by TMA loads.  No global load/store instruction is issued here, so the LSU queue the
+        // converter warps share stays free (per-lane STG/LDG made the epilogue additive to the MMA time).
+        const int q = warp & 3;
+        const uint32_t stg0 = staging + q * 8192;                          // two 4 KB staging tiles
+        const uint32_t msk0 = staging + 32768 + q * 8192;                  // two 4 KB mask tiles (only with a mask)
+        uint8_t *g_stg = gbase + CTRL_BYTES + q * 8192, *g_msk = gbase + CTRL_BYTES + 32768 + q * 8192;
+        const float *bias_s = reinterpret_cast<const float *>(gbase + 1024);
+        const uint32_t mbar = bar_mask + 16 * q;
+        const int32_t nch = (a.Npad + 31) / 32;                            // chunks per tile
+        const int32_t my_tiles = first_tile < a.num_tiles ? (a.num_tiles - first_tile + tile_step - 1) / tile_step : 0;
+        const int64_t total_ch = (int64_t)my_tiles * nch;
+        auto issue_mask = [&](int64_t ci) { // lane 0: TMA load of the mask tile of chunk ci into buffer ci & 1
+            const int32_t tile = first_tile + (int32_t)(ci / nch) * tile_step;
+            const int32_t c0 = (int32_t)(ci % nch) * 32;
+            mbar_arrive_expect_tx(mbar + 8 * (ci & 1), 4096);
+            tma_load_2d(msk0 + (uint32_t)(ci & 1) * 4096, &tmM, mbar + 8 * (ci & 1), c0, tile * TILE_M + q * 32);
+        };
+        if (a.mask && lane == 0)
+            for (int64_t ci = 0; ci < 2 && ci < total_ch; ci++) issue_mask(ci);
+        int64_t ci = 0;
+        uint32_t tile_it = 0;
+        for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step, tile_it++) {
+            const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * acc, acc_ph);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * a.acc_stride;
+            const int32_t row0 = tile * TILE_M + q * 32;
+            for (int32_t c0 = 0; c0 < a.Npad; c0 += 32, ci++) {
+                const uint32_t b = (uint32_t)(ci & 1);
+                uint32_t r[32];
+                const bool two = c0 + 16 < a.Npad;
+                tmem_ld16(t_row + c0, r);
+                if (two) tmem_ld16(t_row + c0 + 16, r + 16);
+                else {
+#pragma unroll
+                    for (int i = 16; i < 32; i++) r[i] = 0u;
+                }
+                tmem_ld_wait();
+                if (c0 + 32 >= a.Npad) { // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                }
+                // the TMA store issued two chunks ago must have finished reading staging tile b
+                if (lane == 0) bulk_wait_read1();
+                if (a.mask) mbar_wait(mbar + 8 * b, (uint32_t)(ci >> 1) & 1);
+                __syncwarp();
+                uint8_t *srow = g_stg + b * 4096 + lane * 128;
+                const uint8_t *mrow = g_msk + b * 4096 + lane * 128;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    float4 v = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                           __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
+                    const float4 bv = *reinterpret_cast<const float4 *>(bias_s + c0 + 4 * c);
+                    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                    if (a.relu) {
+                        v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+                        v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+                    }
+                    const int sw = (c ^ (lane & 7)) << 4;
+                    if (a.mask) {
+                        const float4 mk = *reinterpret_cast<const float4 *>(mrow + sw);
+                        v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
+                        v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+                    }
+                    *reinterpret_cast<float4 *>(srow + sw) = v;
+                }
+                fence_proxy_async(); // staging writes (generic proxy) -> visible to the TMA store (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    if (!(a.debug & 1)) tma_store_2d(&tmC, stg0 + b * 4096, c0, row0);
+                    bulk_commit();
+                    if (a.mask && ci + 2 < total_ch) issue_mask(ci + 2); // mask tile b has been consumed by every lane
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_all();
     } else {
         const int q = warp & 3; // TMEM lane quadrant this warp may read
         uint8_t *stg = gbase + CTRL_BYTES + q * 4096;
@@ -295,7 +418,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                     }
                     // all mask vectors of this chunk are fetched before the first store so the loads overlap
                     float4 mk[8];
-                    if (a.mask && full) {
+                    if (a.mask && full && !(a.debug & 4)) {
 #pragma unroll
                         for (int itr = 0; itr < 8; itr++) {
                             const int64_t grow = row0 + itr * 4 + rsub;
@@ -307,7 +430,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                     for (int itr = 0; itr < 8; itr++) {
                         const int rr = itr * 4 + rsub;
                         const int64_t grow = row0 + rr;
-                        if (grow >= a.M) continue;
+                        if (grow >= a.M || (a.debug & 1)) continue;
                         float4 v = *reinterpret_cast<const float4 *>(stg + rr * 128 + ((j ^ (rr & 7)) << 4));
                         v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                         if (a.relu) {
@@ -575,12 +698,12 @@ static EncodeTiledFn encode_fn() {
 // 2-D FP32 row-major view [rows, cols] with leading dimension ld; box = {32 floats, box_rows}, 128-byte swizzle,
 // out-of-bounds elements read as zero
 static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows,
-                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, uint32_t box_cols = 32) {
     EncodeTiledFn fn = encode_fn();
     GNN_REQUIRE(fn, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -611,31 +734,56 @@ static int rows_gemm(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float 
         prep_weights_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(B, ldb, N, K, transpose, Bs, Npad, Kpad);
         GNN_LAUNCHED(ctx);
     }
-    CUtensorMap tmA, tmB;
-    GNN_TRY(make_map(&tmA, A, M, K, lda, TILE_M));
-    GNN_TRY(make_map(&tmB, Bs, 2 * (int64_t)Npad, Kpad, Kpad, (uint32_t)Npad));
-
+    // A stage holds the A tile twice (hi, lo) and both halves of the weight k-block.  With 32-float k-blocks a
+    // 256-wide output leaves room for only 2 stages (96 KB each) and the TMA -> convert -> MMA chain of a stage
+    // cannot overlap enough; 16-float k-blocks (64-byte swizzle) halve the stage and double the depth.
     RowsArgs a;
-    a.M = M; a.N = N; a.Npad = Npad; a.kblocks = Kpad / BK;
+    // TMA stores clip the tensor edge in 16-byte units (observed: column 47 of a 47-wide, ld 48 output was written),
+    // so an output whose width is not a multiple of 4 keeps the per-lane store epilogue with its exact guards
+    a.tma_epi = (N % 4 != 0) || (getenv("GNN_GEMM_EPI") && !strcmp(getenv("GNN_GEMM_EPI"), "lsu")) ? 0 : 1;
+    a.epi_bytes = a.tma_epi ? (mask ? 65536u : 32768u) : STAGING_BYTES;
+    const uint32_t fixed = 1024 /*align slack*/ + CTRL_BYTES + a.epi_bytes;
+    a.bk = BK;
+    // Short reductions: the whole split weight matrix (2 * Npad * Kpad floats) stays resident in shared memory and
+    // only A is streamed (otherwise every k-block of every tile re-fetches 2 * Npad * bk weights from L2).
+    const uint32_t b_all = 2u * (uint32_t)Npad * (uint32_t)Kpad * 4u;
+    const bool resident = Kpad <= 64 && b_all + 3 * (2 * A_TILE_BYTES) <= SMEM_MAX - fixed && !getenv("GNN_GEMM_NO_RESIDENT");
+    // 32-float k-blocks unless that leaves fewer than 3 pipeline stages (measured: N=47, K=256 runs 1.06 ms with
+    // four 32-float stages and 1.50 ms with 16-float ones; a 256-wide output only fits 16-float stages)
+    const uint32_t stage32 = 2 * A_TILE_BYTES + (resident ? 0 : 2 * (uint32_t)Npad * 128);
+    if ((SMEM_MAX - fixed - (resident ? b_all : 0)) / stage32 < 3) a.bk = 16;
+    if (getenv("GNN_GEMM_BK")) a.bk = atoi(getenv("GNN_GEMM_BK")) == 16 ? 16 : 32;
+    a.a_bytes = (uint32_t)TILE_M * a.bk * 4;
+    a.b_bytes = (uint32_t)Npad * a.bk * 4;
+    a.b_resident = resident ? b_all : 0;
+    a.debug = getenv("GNN_GEMM_DEBUG") ? (uint32_t)atoi(getenv("GNN_GEMM_DEBUG")) : 0;
+    a.stage_bytes = 2 * a.a_bytes + (resident ? 0 : 2 * a.b_bytes);
+    CUtensorMap tmA, tmB;
+    const CUtensorMapSwizzle sw = a.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    GNN_TRY(make_map(&tmA, A, M, K, lda, TILE_M, sw, (uint32_t)a.bk));
+    GNN_TRY(make_map(&tmB, Bs, 2 * (int64_t)Npad, Kpad, Kpad, (uint32_t)Npad, sw, (uint32_t)a.bk));
+
+    a.M = M; a.N = N; a.Npad = Npad; a.kblocks = Kpad / a.bk;
     a.num_tiles = (int32_t)ceil_div(M, TILE_M);
-    a.b_bytes = (uint32_t)Npad * 128;
-    a.stage_bytes = 2 * A_TILE_BYTES + 2 * a.b_bytes;
-    const uint32_t fixed = 1024 /*align slack*/ + CTRL_BYTES + STAGING_BYTES;
-    int stages = (int)((SMEM_MAX - fixed) / a.stage_bytes);
-    if (stages > 6) stages = 6;
+    int stages = (int)((SMEM_MAX - fixed - a.b_resident) / a.stage_bytes);
+    if (stages > 8) stages = 8;
     GNN_REQUIRE(stages >= 2, "gemm_tc: tile does not fit shared memory");
     a.stages = stages;
     a.acc_stride = pow2_cols((uint32_t)Npad);
     a.tmem_cols = 2 * a.acc_stride;
     a.C = C; a.ldc = ldc; a.bias = bias; a.relu = relu; a.mask = mask; a.ldm = ldm;
-    const uint32_t smem = fixed + (uint32_t)stages * a.stage_bytes;
+    const uint32_t smem = fixed + a.b_resident + (uint32_t)stages * a.stage_bytes;
     static bool attr_set = false;
     if (!attr_set) {
         GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         attr_set = true;
     }
     const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
-    tc_rows_kernel<<<grid, ROWS_THREADS, smem, ctx->stream>>>(tmA, tmB, a);
+    CUtensorMap tmC, tmM;
+    GNN_TRY(make_map(&tmC, C, M, N, ldc, 32));
+    if (mask) GNN_TRY(make_map(&tmM, mask, M, N, ldm, 32));
+    else tmM = tmC;
+    tc_rows_kernel<<<grid, ROWS_THREADS, smem, ctx->stream>>>(tmA, tmB, tmC, tmM, a);
     GNN_LAUNCHED(ctx);
     return 0;
 }

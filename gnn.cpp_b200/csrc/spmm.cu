@@ -65,44 +65,50 @@ template <typename V, int VEC> struct Tune {
     static constexpr bool PF = BYTES <= 16;
 };
 
-// acc += sum over k in [begin, end) of val[k] * P[idx[k], :]   for the LPR-lane group this thread belongs to.
-// The group's lanes fetch LPR (column, value) pairs at a time (coalesced, streaming) — the NEXT batch is requested
-// before the current one is consumed — and broadcast them with shuffles; every lane keeps U x VEC 128-bit gathers
-// in flight.  Accumulation order = stored order (ascending k): deterministic.
-template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF>
+// acc += sum over k in [begin, end) of val[k] * P[idx[k], :]   for the lane group this thread belongs to.
+// A group is S slots of LPR lanes (G = S*LPR lanes, `lig` = lane index inside the group): the LPR lanes of a slot
+// cover one feature row, and the S slots work on S consecutive nonzeros at once — narrow rows (F <= 64) keep the
+// whole warp on one row range that way instead of running two or more divergent groups per warp.
+// The group's lanes fetch G (column, value) pairs at a time (coalesced, streaming; with PF the NEXT batch is
+// requested before the current one is consumed) and broadcast them with shuffles; every lane keeps U x VEC 128-bit
+// gathers in flight.  A slot accumulates its nonzeros in stored (ascending k) order; the caller combines the slots
+// with reduce_slots (fixed tree): deterministic.
+template <typename V, int LPR, int S, int VEC, bool USE_VAL, int U, bool PF>
 __device__ __forceinline__ void accumulate_range(V (&acc)[VEC], const int32_t *__restrict__ idx,
                                                  const float *__restrict__ val, int32_t begin, int32_t end,
-                                                 const float *__restrict__ P, int64_t ldp, int nvec, int sub,
+                                                 const float *__restrict__ P, int64_t ldp, int nvec, int lig,
                                                  unsigned gmask) {
     using T = VecTraits<V>;
+    constexpr int G = LPR * S;
+    const int sub = lig % LPR, slot = lig / LPR;
     int32_t nx_c = 0;
     float nx_a = 0.f;
-    if (PF && begin + sub < end) {
-        nx_c = ld_stream_i32(idx + begin + sub);
-        if (USE_VAL) nx_a = ld_stream_f32(val + begin + sub);
+    if (PF && begin + lig < end) {
+        nx_c = ld_stream_i32(idx + begin + lig);
+        if (USE_VAL) nx_a = ld_stream_f32(val + begin + lig);
     }
-    for (int32_t k = begin; k < end; k += LPR) {
+    for (int32_t k = begin; k < end; k += G) {
         int32_t my_c = nx_c;
         float my_a = nx_a;
         if (PF) {
-            if (k + LPR + sub < end) {
-                nx_c = ld_stream_i32(idx + k + LPR + sub);
-                if (USE_VAL) nx_a = ld_stream_f32(val + k + LPR + sub);
+            if (k + G + lig < end) {
+                nx_c = ld_stream_i32(idx + k + G + lig);
+                if (USE_VAL) nx_a = ld_stream_f32(val + k + G + lig);
             }
-        } else if (k + sub < end) {
-            my_c = ld_stream_i32(idx + k + sub);
-            if (USE_VAL) my_a = ld_stream_f32(val + k + sub);
+        } else if (k + lig < end) {
+            my_c = ld_stream_i32(idx + k + lig);
+            if (USE_VAL) my_a = ld_stream_f32(val + k + lig);
         }
-        const int cnt = min(LPR, end - k);
-        for (int j = 0; j < cnt; j += U) {
+        const int cnt = min(G, end - k);
+        for (int j = 0; j < cnt; j += S * U) {
             V p[U][VEC];
             float a[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const int jj = j + u;                       // group-uniform
-                const int src_lane = jj < LPR ? jj : LPR - 1;
-                const int32_t c = __shfl_sync(gmask, my_c, src_lane, LPR);
-                a[u] = USE_VAL ? __shfl_sync(gmask, my_a, src_lane, LPR) : 1.f;
+                const int jj = j + u * S + slot;            // uniform inside a slot
+                const int src_lane = jj < G ? jj : G - 1;
+                const int32_t c = __shfl_sync(gmask, my_c, src_lane, G);
+                a[u] = USE_VAL ? __shfl_sync(gmask, my_a, src_lane, G) : 1.f;
                 const V *prow = reinterpret_cast<const V *>(P + (int64_t)c * ldp);
 #pragma unroll
                 for (int v = 0; v < VEC; v++) {
@@ -118,6 +124,27 @@ __device__ __forceinline__ void accumulate_range(V (&acc)[VEC], const int32_t *_
                 for (int v = 0; v < VEC; v++) {
                     if (USE_VAL) T::fma(acc[v], a[u], p[u][v]);
                     else T::add(acc[v], p[u][v]);
+                }
+            }
+        }
+    }
+}
+
+// sum the S slots of a group (butterfly over lane offsets LPR, 2 LPR, ...): every lane ends with the total
+template <typename V, int LPR, int S, int VEC>
+__device__ __forceinline__ void reduce_slots(V (&acc)[VEC], unsigned gmask) {
+    if constexpr (S > 1) {
+#pragma unroll
+        for (int off = LPR; off < LPR * S; off <<= 1) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                if constexpr (VecTraits<V>::W == 4) {
+                    acc[v].x += __shfl_xor_sync(gmask, acc[v].x, off, LPR * S);
+                    acc[v].y += __shfl_xor_sync(gmask, acc[v].y, off, LPR * S);
+                    acc[v].z += __shfl_xor_sync(gmask, acc[v].z, off, LPR * S);
+                    acc[v].w += __shfl_xor_sync(gmask, acc[v].w, off, LPR * S);
+                } else {
+                    acc[v] += __shfl_xor_sync(gmask, acc[v], off, LPR * S);
                 }
             }
         }
@@ -167,7 +194,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
     V acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; v++) acc[v] = T::zero();
-    accumulate_range<V, LPR, VEC, USE_VAL, U, PF>(acc, idx, val, ptr[row], ptr[row + 1], P, ldp, nvec, sub, gmask);
+    accumulate_range<V, LPR, 1, VEC, USE_VAL, U, PF>(acc, idx, val, ptr[row], ptr[row + 1], P, ldp, nvec, sub, gmask);
     store_row<V, LPR, VEC>(acc, Y + row * ldy, nvec, sub, F, bias, relu, mask ? mask + row * ldm : nullptr);
 }
 
@@ -184,19 +211,20 @@ constexpr int MERGE_CHUNK_MIN = 256;
 template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF>
 __global__ void __launch_bounds__(SPMM_THREADS)
     spmm_merge_kernel(int32_t n_out, int32_t k_base, int32_t nnz, int32_t n_chunks, int32_t MERGE_CHUNK,
-                      const int32_t *__restrict__ ptr,
-                      const int32_t *__restrict__ idx, const float *__restrict__ val, const float *__restrict__ P,
-                      int64_t ldp, int32_t F, float *__restrict__ Y, int64_t ldy, const float *__restrict__ bias,
-                      int relu, const float *__restrict__ mask, int64_t ldm, float *__restrict__ head,
-                      float *__restrict__ tail, int32_t *__restrict__ head_row, int32_t *__restrict__ tail_row,
-                      int32_t ldw) {
+                      const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx, const float *__restrict__ val,
+                      const float *__restrict__ P, int64_t ldp, int32_t F, float *__restrict__ Y, int64_t ldy,
+                      const float *__restrict__ bias, int relu, const float *__restrict__ mask, int64_t ldm,
+                      float *__restrict__ head, float *__restrict__ tail, int32_t *__restrict__ head_row,
+                      int32_t *__restrict__ tail_row, int32_t ldw) {
     using T = VecTraits<V>;
-    constexpr int GROUPS = SPMM_THREADS / LPR;
-    const int sub = threadIdx.x % LPR;
-    const int32_t g = blockIdx.x * GROUPS + threadIdx.x / LPR;
+    constexpr int S = 32 / LPR;                  // the whole warp owns one chunk: S nonzeros in flight side by side
+    constexpr int GROUPS = SPMM_THREADS / 32;
+    const int lig = threadIdx.x & 31, sub = lig % LPR, slot = lig / LPR;
+    const int32_t g = blockIdx.x * GROUPS + (threadIdx.x >> 5);
     if (g >= n_chunks) return;
-    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
+    const unsigned gmask = 0xffffffffu;
     const int nvec = (F + T::W - 1) / T::W;
+    const int nvec_st = slot == 0 ? nvec : 0;    // after reduce_slots every slot holds the sum; slot 0 stores it
     // nonzeros [k_base, nnz) belong to rows [0, n_out) of `ptr` (a row range of a larger matrix keeps absolute offsets)
     const int32_t k0 = k_base + g * MERGE_CHUNK, k1 = min(nnz, k0 + MERGE_CHUNK);
 
@@ -216,10 +244,11 @@ __global__ void __launch_bounds__(SPMM_THREADS)
         V acc[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; v++) acc[v] = T::zero();
-        accumulate_range<V, LPR, VEC, USE_VAL, U, PF>(acc, idx, val, k, seg_end, P, ldp, nvec, sub, gmask);
+        accumulate_range<V, LPR, S, VEC, USE_VAL, U, PF>(acc, idx, val, k, seg_end, P, ldp, nvec, lig, gmask);
+        reduce_slots<V, LPR, S, VEC>(acc, gmask);
         const bool starts = (k == rb), ends = (seg_end == re);
         if (starts && ends) {
-            store_row<V, LPR, VEC>(acc, Y + (int64_t)row * ldy, nvec, sub, F, bias, relu,
+            store_row<V, LPR, VEC>(acc, Y + (int64_t)row * ldy, nvec_st, sub, F, bias, relu,
                                    mask ? mask + (int64_t)row * ldm : nullptr);
         } else {
             float *dst = (ends ? head : tail) + (int64_t)g * ldw;
@@ -228,7 +257,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
                 const int vi = sub + v * LPR;
-                if (vi < nvec) reinterpret_cast<V *>(dst)[vi] = acc[v];
+                if (vi < nvec_st) reinterpret_cast<V *>(dst)[vi] = acc[v];
             }
         }
         k = seg_end;
@@ -236,7 +265,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
         rb = re;
         re = re_next;
     }
-    if (sub == 0) {
+    if (lig == 0) {
         head_row[g] = hrow;
         tail_row[g] = trow;
     }
@@ -264,12 +293,13 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// nonzeros per lane group of the merge kernel: narrow rows (two or more groups per warp) prefer shorter chunks, and
-// a small launch (a row block of a partition) is cut finer so that it still spans >= 4 waves of resident groups
+// nonzeros per warp of the merge kernel; a small launch (e.g. a row block of a partition) is cut finer so that it
+// still spans >= 4 waves of resident warps
 static inline int32_t merge_chunk(const gnn_ctx *ctx, int lpr, int64_t nnz) {
+    (void)lpr;
     if (ctx->spmm_chunk > 0) return ctx->spmm_chunk;
-    int64_t chunk = lpr <= 16 ? 512 : 1024;
-    const int64_t want_chunks = 4ll * ctx->sm_count * (2048 / lpr);
+    int64_t chunk = 1024;
+    const int64_t want_chunks = 4ll * ctx->sm_count * 64;
     if (nnz / chunk < want_chunks) chunk = nnz / want_chunks / 64 * 64;
     return (int32_t)(chunk < 128 ? 128 : chunk);
 }
@@ -294,7 +324,7 @@ template <typename V, int LPR, int VEC, int U, bool PF>
 static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
                         const float *val, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy,
                         const float *bias, int relu, const float *mask, int64_t ldm) {
-    constexpr int GROUPS = SPMM_THREADS / LPR;
+    constexpr int GROUPS = SPMM_THREADS / 32; // one warp per chunk
     const int32_t MERGE_CHUNK = merge_chunk(ctx, LPR, nnz - k_base);
     const int32_t n_chunks = (int32_t)ceil_div(nnz - k_base, MERGE_CHUNK);
     const int32_t ldw = (int32_t)round_up(F, 4);

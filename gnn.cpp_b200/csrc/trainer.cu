@@ -18,6 +18,8 @@
 
 namespace gnn {
 int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out);
+int softmax_xent_launch(gnn_ctx *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
+                        int64_t n_total, float *loss, float *dZ, int64_t ldd, float *db);
 int copy2d(gnn_ctx *ctx, float *dst, int64_t ldd, const float *src, int64_t lds, int64_t rows, int32_t cols);
 int spmm_rows_range(gnn_ctx *ctx, const gnn_graph *g, int transpose, int32_t r0, int32_t r1, int64_t k0, int64_t k1,
                     const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
@@ -298,7 +300,7 @@ static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
         // dZ_{l-1} feeds a transform-first layer's aggregation: produced panel-major and pushed tile by tile
         const bool next_pm = m->arena && l > 1 && !m->agg_first[l - 1];
         const bool dz_pm = m->arena && !m->agg_first[l];
-        for (int p = 0; p < (dz_pm ? Po.n : 1); p++) {
+        for (int p = 0; l < m->L && p < (dz_pm ? Po.n : 1); p++) { // db_L comes out of the loss kernel
             Prof pr(ctx, m, CLS_BIAS);
             const View dz = dz_view(ctx, m, l, Po, p);
             GNN_TRY(colsum(ctx, m->n_loc, dz_pm ? panel_f(Po, p, Fo) : Fo, dz.ptr, dz.ld, db + (dz_pm ? Po.c0[p] : 0)));
@@ -616,7 +618,9 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
         const Panels PL = panels_of(m, m->ld[m->L]);
         const bool pm = m->arena && !m->agg_first[m->L];
         const View dz = (pm && PL.n > 1) ? View{m->G0, m->ld[m->L]} : dz_view(ctx, m, m->L, PL, 0);
-        GNN_TRY(gnn_softmax_xent(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], y, m->n_glob, loss_slot, dz.ptr, dz.ld));
+        // db_L (column sums of dZ_L) is produced by the same kernel from the tiles it already holds
+        GNN_TRY(softmax_xent_launch(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], y, m->n_glob, loss_slot, dz.ptr, dz.ld,
+                                    m->grads + m->b_off[m->L]));
         if (pm)
             for (int p = 0; p < PL.n; p++) {
                 if (PL.n > 1) {
