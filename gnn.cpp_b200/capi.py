@@ -54,6 +54,9 @@ SIGNATURES = {
     "gnn_bias_grad": (C.c_int, [vp, i64, i32, vp, i64, vp]),
     "gnn_softmax_xent": (C.c_int, [vp, i64, i32, vp, i64, vp, i64, vp, vp, i64]),
     "gnn_sgd_step": (C.c_int, [vp, i64, vp, vp, vp, f32, f32, f32, f32, C.c_int, C.c_int]),
+    "gnn_adam_step": (C.c_int, [vp, i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, i64]),
+    "gnn_softmax_xent_masked": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, i64, vp, vp, i64]),
+    "gnn_argmax_correct": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, vp]),
     "gnn_binary_f32": (C.c_int, [vp, C.c_int, i64, i64, vp, i64, i64, vp, i64, i64, vp]),
     "gnn_unary_f32": (C.c_int, [vp, C.c_int, i64, vp, vp]),
     "gnn_where_f32": (C.c_int, [vp, i64, vp, vp, vp, vp]),
@@ -72,7 +75,10 @@ SIGNATURES = {
     "gnn_gcn_forward": (C.c_int, [vp, vp, vp, i64]),
     "gnn_gcn_train_step_h": (C.c_int, [vp, vp, vp, vp, f32, vp]),
     "gnn_gcn_prefetch_h": (C.c_int, [vp, vp, vp, vp]),
+    "gnn_gcn_set_train_mask": (C.c_int, [vp, vp, vp, i64]),
+    "gnn_gcn_accuracy": (C.c_int, [vp, vp, vp, vp, vp]),
     "gnn_gcn_last_breakdown": (C.c_int, [vp, vp, C.c_int]),
+    "gnn_gcn_last_spmm_spans": (C.c_int, [vp, vp, vp, vp, C.c_int, vp]),
     "gnn_gcn_spmm_stats": (C.c_int, [vp, vp, vp, vp]),
     "gnn_partition_ptr_h": (C.c_int, [i64, i32, vp]),
     "gnn_graph_slice_rows": (C.c_int, [vp, vp, i64, i64, pp]),

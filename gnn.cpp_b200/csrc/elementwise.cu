@@ -1,6 +1,8 @@
 // elementwise.cu — epilogue, loss, optimiser and cyg::tensor-surface kernels (K7, K8, K9).
 // All HBM-bound streaming kernels: grid-stride over whole waves of the SMs, fixed-order reductions
 // (per-block partials combined by one block) so results are deterministic run to run.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace gnn {
@@ -249,6 +251,113 @@ __global__ void sgd_kernel(int64_t n, float *__restrict__ p, const float *__rest
     }
 }
 
+// torch.optim.Adam semantics (the intent of nn::Adam, reference include/nn.h:180-188; the body, src/nn.cpp:419-441,
+// divides by sqrt(v)*eps and uses the parameter index as the step count).  bc1 = 1 - b1^t, bc2 = 1 - b2^t.
+__global__ void adam_kernel(int64_t n, float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                            float *__restrict__ v, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float pi = p[i];
+        float d = g[i];
+        if (wd != 0.f) d = d + wd * pi;
+        const float mi = b1 * m[i] + (1.f - b1) * d;
+        const float vi = b2 * v[i] + (1.f - b2) * d * d;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+// masked softmax cross-entropy: one warp per row like softmax_xent_kernel, rows with mask[r] == 0 contribute neither
+// to the loss nor to dZ (their dZ row is zero); the mean is over n_sel (selected rows of the whole graph)
+__global__ void __launch_bounds__(256)
+    softmax_xent_masked_kernel(int64_t N, int32_t C, const float *__restrict__ Z, int64_t ldz, const int32_t *__restrict__ y,
+                               const uint8_t *__restrict__ mask, float inv_n, float *__restrict__ dZ, int64_t ldd,
+                               float *__restrict__ partial) {
+    __shared__ float wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    float local = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < N; r += nwarps) {
+        if (!mask[r]) {
+            if (dZ)
+                for (int32_t c = lane; c < C; c += 32) dZ[r * ldd + c] = 0.f;
+            continue;
+        }
+        const float *z = Z + r * ldz;
+        float mx = -INFINITY;
+        for (int32_t c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float s = 0.f;
+        for (int32_t c = lane; c < C; c += 32) s += expf(z[c] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const int32_t yi = y[r];
+        const float eps = (mx > -60.f) ? 1e-20f * expf(-mx) : INFINITY;
+        const float li = -logf(expf(z[yi] - mx) / (s + eps));
+        if (lane == 0) local += li;
+        if (dZ) {
+            const float inv_s = 1.f / s;
+            for (int32_t c = lane; c < C; c += 32) {
+                float pr = expf(z[c] - mx) * inv_s;
+                if (c == yi) pr -= 1.f;
+                dZ[r * ldd + c] = pr * inv_n;
+            }
+        }
+    }
+    if (lane == 0) wsum[warp] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += wsum[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+// rows whose arg-max logit (first maximum, like tensor::argmax, reference include/tensor.h:645-648) equals the label,
+// counted over the rows selected by mask (all rows when mask == NULL): exact integer partials, fixed-order sum
+__global__ void __launch_bounds__(256)
+    argmax_correct_kernel(int64_t N, int32_t C, const float *__restrict__ Z, int64_t ldz, const int32_t *__restrict__ y,
+                          const uint8_t *__restrict__ mask, int32_t *__restrict__ partial) {
+    __shared__ int32_t wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    int32_t local = 0;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < N; r += nwarps) {
+        if (mask && !mask[r]) continue;
+        const float *z = Z + r * ldz;
+        float best = -INFINITY;
+        int32_t bi = 0x7fffffff;
+        for (int32_t c = lane; c < C; c += 32) {
+            const float v = z[c];
+            if (v > best) { best = v; bi = c; } // strict: keeps the first maximum of this lane's columns
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0 && bi == y[r]) local++;
+    }
+    if (lane == 0) wsum[warp] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t t = 0;
+        for (int w = 0; w < 8; w++) t += wsum[w];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void count_final_kernel(int nblocks, const int32_t *__restrict__ partial, int64_t *__restrict__ out) {
+    int64_t s = 0;
+    for (int b = threadIdx.x; b < nblocks; b += 32) s += partial[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *out = s;
+}
+
 __global__ void binary_kernel(int op, int64_t rows, int64_t cols, const float *__restrict__ a, int64_t a_rs,
                               int64_t a_cs, const float *__restrict__ b, int64_t b_rs, int64_t b_cs,
                               float *__restrict__ out) {
@@ -455,6 +564,49 @@ int gnn_sgd_step(gnn_ctx_t *ctx, int64_t n, float *p, const float *g, float *vel
     GNN_REQUIRE(momentum == 0.f || vel, "gnn_sgd_step: momentum needs a velocity buffer");
     sgd_kernel<<<stream_grid(ctx, n, 256, 1), 256, 0, ctx->stream>>>(n, p, g, vel, lr, momentum, dampening, weight_decay,
                                                                    nesterov, first);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_adam_step(gnn_ctx_t *ctx, int64_t n, float *p, const float *g, float *m, float *v, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step) {
+    GNN_REQUIRE(ctx && p && g && m && v && n > 0 && step >= 1, "gnn_adam_step: bad argument (step counts from 1)");
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)), bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+    adam_kernel<<<stream_grid(ctx, n, 256, 1), 256, 0, ctx->stream>>>(n, p, g, m, v, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                                     bc2);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_softmax_xent_masked(gnn_ctx_t *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
+                            const uint8_t *mask, int64_t n_selected, float *loss, float *dZ, int64_t ldd) {
+    GNN_REQUIRE(ctx && Z && y && mask && loss, "gnn_softmax_xent_masked: NULL argument");
+    GNN_REQUIRE(N > 0 && C > 0 && ldz >= C && n_selected > 0,
+                "invalid input, logits must be of rank 2 and targets must be 1D tensor");
+    int64_t nblocks = ceil_div(N, 8);
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (nblocks > cap) nblocks = cap;
+    void *ws = nullptr;
+    GNN_TRY(ctx->workspace((size_t)nblocks * 4, &ws));
+    const float inv_n = 1.0f / (float)n_selected;
+    softmax_xent_masked_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(N, C, Z, ldz, y, mask, inv_n, dZ, ldd, (float *)ws);
+    GNN_LAUNCHED(ctx);
+    xent_final_kernel<<<1, 32, 0, ctx->stream>>>((int)nblocks, (const float *)ws, inv_n, loss);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_argmax_correct(gnn_ctx_t *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
+                       const uint8_t *mask, int64_t *count) {
+    GNN_REQUIRE(ctx && Z && y && count && N > 0 && C > 0 && ldz >= C, "gnn_argmax_correct: bad argument");
+    int64_t nblocks = ceil_div(N, 8);
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (nblocks > cap) nblocks = cap;
+    void *ws = nullptr;
+    GNN_TRY(ctx->workspace((size_t)nblocks * 4, &ws));
+    argmax_correct_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(N, C, Z, ldz, y, mask, (int32_t *)ws);
+    GNN_LAUNCHED(ctx);
+    count_final_kernel<<<1, 32, 0, ctx->stream>>>((int)nblocks, (const int32_t *)ws, count);
     GNN_LAUNCHED(ctx);
     return 0;
 }

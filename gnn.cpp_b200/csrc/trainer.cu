@@ -65,12 +65,17 @@ struct gnn_gcn {
     int precision = 1, profile = 0; // dense transforms: 1 = 3xTF32 on tcgen05 (falls back per shape), 0 = FP32 FMA
     float momentum = 0.f, dampening = 0.f, weight_decay = 0.f;
     int nesterov = 0;
+    int optimizer = 0; // 0 = SGD (nn::SGD), 1 = Adam (nn::Adam)
+    float beta1 = 0.9f, beta2 = 0.999f, adam_eps = 1e-8f;
+    float *adam_m = nullptr, *adam_v = nullptr;
+    const uint8_t *train_mask = nullptr; // device uint8[n_loc]: rows that enter the loss (Data::set_mask TRAIN)
+    int64_t n_train = 0;                 // selected rows over the whole graph
     int64_t steps = 0;
     // stats
     double alg_bytes = 0, gemm_flops = 0;
     int32_t n_spmm = 0;
     // profiling
-    struct Span { int cls; cudaEvent_t a, b; };
+    struct Span { int cls; cudaEvent_t a, b; int32_t F; double bytes; float ms; };
     std::vector<Span> spans;
     size_t span_used = 0;
     double breakdown[6] = {0, 0, 0, 0, 0, 0};
@@ -84,17 +89,20 @@ struct Prof {
     gnn_ctx *ctx;
     gnn_gcn *m;
     int idx = -1;
-    Prof(gnn_ctx *c, gnn_gcn *mm, int cls) : ctx(c), m(mm) {
+    Prof(gnn_ctx *c, gnn_gcn *mm, int cls, int32_t F = 0, double bytes = 0) : ctx(c), m(mm) {
         if (!m->profile) return;
         if (m->span_used == m->spans.size()) {
             gnn_gcn::Span s;
             s.cls = cls;
+            s.F = 0; s.bytes = 0; s.ms = 0;
             cudaEventCreate(&s.a);
             cudaEventCreate(&s.b);
             m->spans.push_back(s);
         }
         idx = (int)m->span_used++;
         m->spans[idx].cls = cls;
+        m->spans[idx].F = F;
+        m->spans[idx].bytes = bytes;
         cudaEventRecord(m->spans[idx].a, ctx->stream);
     }
     ~Prof() {
@@ -264,7 +272,8 @@ static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
             for (int rb = 0; rb < m->n_rb; rb++) {
                 const int64_t r0 = m->rb_row[rb], r1 = m->rb_row[rb + 1];
                 if (r1 > r0) {
-                    Prof pr(ctx, m, CLS_SPMM);
+                    Prof pr(ctx, m, CLS_SPMM, panel_f(P, p, Fagg),
+                            spmm_alg_bytes(r1 - r0, m->rb_kf[rb + 1] - m->rb_kf[rb], panel_f(P, p, Fagg)));
                     GNN_TRY(spmm_rows_range(ctx, g, 0, (int32_t)r0, (int32_t)r1, m->rb_kf[rb], m->rb_kf[rb + 1], src, ld_src,
                                             panel_f(P, p, Fagg), Yout + r0 * ld_agg + P.c0[p], ld_agg,
                                             af ? nullptr : b + P.c0[p], af ? 0 : relu, nullptr, 0));
@@ -340,7 +349,8 @@ static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
                     for (int rb = 0; rb < m->n_rb; rb++) {
                         const int64_t r0 = m->rb_row[rb], r1 = m->rb_row[rb + 1];
                         if (r1 > r0) {
-                            Prof pr(ctx, m, CLS_SPMM);
+                            const int32_t fw = m->arena ? panel_f(Pi, p, Fi) : Fi;
+                            Prof pr(ctx, m, CLS_SPMM, fw, spmm_alg_bytes(r1 - r0, m->rb_kb[rb + 1] - m->rb_kb[rb], fw));
                             GNN_TRY(spmm_rows_range(ctx, g, 1, (int32_t)r0, (int32_t)r1, m->rb_kb[rb], m->rb_kb[rb + 1], src,
                                                     ld_src, m->arena ? panel_f(Pi, p, Fi) : Fi, dn.row(r0), dn.ld, nullptr, 0,
                                                     Hin + r0 * ld_in + Pi.c0[p], ld_in));
@@ -363,7 +373,8 @@ static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
                 for (int rb = 0; rb < m->n_rb; rb++) {
                     const int64_t r0 = m->rb_row[rb], r1 = m->rb_row[rb + 1];
                     if (r1 > r0) {
-                        Prof pr(ctx, m, CLS_SPMM);
+                        Prof pr(ctx, m, CLS_SPMM, panel_f(Po, p, Fo),
+                                spmm_alg_bytes(r1 - r0, m->rb_kb[rb + 1] - m->rb_kb[rb], panel_f(Po, p, Fo)));
                         GNN_TRY(spmm_rows_range(ctx, g, 1, (int32_t)r0, (int32_t)r1, m->rb_kb[rb], m->rb_kb[rb + 1], src, ld_src,
                                                 panel_f(Po, p, Fo), m->S1 + r0 * m->ld[l] + Po.c0[p], m->ld[l], nullptr, 0,
                                                 nullptr, 0));
@@ -493,7 +504,7 @@ int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_
 int gnn_gcn_destroy(gnn_ctx_t *ctx, gnn_gcn_t *m) {
     if (!m) return 0;
     if (ctx) cudaStreamSynchronize(ctx->stream);
-    cudaFree(m->params); cudaFree(m->grads); cudaFree(m->vel);
+    cudaFree(m->params); cudaFree(m->grads); cudaFree(m->vel); cudaFree(m->adam_m); cudaFree(m->adam_v);
     for (auto p : m->H) cudaFree(p);
     for (auto p : m->M) cudaFree(p);
     cudaFree(m->S1); cudaFree(m->G0); cudaFree(m->G1); cudaFree(m->AG);
@@ -569,6 +580,10 @@ int gnn_gcn_set_option(gnn_gcn_t *m, const char *key, double value) {
     else if (!strcmp(key, "dampening")) m->dampening = (float)value;
     else if (!strcmp(key, "weight_decay")) m->weight_decay = (float)value;
     else if (!strcmp(key, "nesterov")) m->nesterov = (int)value;
+    else if (!strcmp(key, "optimizer")) m->optimizer = (int)value;
+    else if (!strcmp(key, "beta1")) m->beta1 = (float)value;
+    else if (!strcmp(key, "beta2")) m->beta2 = (float)value;
+    else if (!strcmp(key, "eps")) m->adam_eps = (float)value;
 
     else if (!strcmp(key, "agg_first_mask")) { // bit l-1 set -> layer l aggregates first (tests / ablation)
         for (int32_t l = 1; l <= m->L; l++) m->agg_first[l] = (((int64_t)value) >> (l - 1)) & 1;
@@ -618,9 +633,15 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
         const Panels PL = panels_of(m, m->ld[m->L]);
         const bool pm = m->arena && !m->agg_first[m->L];
         const View dz = (pm && PL.n > 1) ? View{m->G0, m->ld[m->L]} : dz_view(ctx, m, m->L, PL, 0);
-        // db_L (column sums of dZ_L) is produced by the same kernel from the tiles it already holds
-        GNN_TRY(softmax_xent_launch(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], y, m->n_glob, loss_slot, dz.ptr, dz.ld,
-                                    m->grads + m->b_off[m->L]));
+        if (m->train_mask) { // loss over the training nodes only
+            GNN_TRY(gnn_softmax_xent_masked(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], y, m->train_mask, m->n_train,
+                                            loss_slot, dz.ptr, dz.ld));
+            GNN_TRY(colsum(ctx, m->n_loc, C, dz.ptr, dz.ld, m->grads + m->b_off[m->L]));
+        } else {
+            // db_L (column sums of dZ_L) is produced by the same kernel from the tiles it already holds
+            GNN_TRY(softmax_xent_launch(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], y, m->n_glob, loss_slot, dz.ptr, dz.ld,
+                                        m->grads + m->b_off[m->L]));
+        }
         if (pm)
             for (int p = 0; p < PL.n; p++) {
                 if (PL.n > 1) {
@@ -639,7 +660,17 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
         GNN_CHECK_CUDA(cudaMalloc((void **)&m->vel, (size_t)m->n_params * 4));
         GNN_CHECK_CUDA(cudaMemsetAsync(m->vel, 0, (size_t)m->n_params * 4, ctx->stream));
     }
-    if (lr != 0.f) {
+    if (lr != 0.f && m->optimizer == 1) {
+        Prof p(ctx, m, CLS_SGD);
+        if (!m->adam_m) {
+            GNN_CHECK_CUDA(cudaMalloc((void **)&m->adam_m, (size_t)m->n_params * 4));
+            GNN_CHECK_CUDA(cudaMalloc((void **)&m->adam_v, (size_t)m->n_params * 4));
+            GNN_CHECK_CUDA(cudaMemsetAsync(m->adam_m, 0, (size_t)m->n_params * 4, ctx->stream));
+            GNN_CHECK_CUDA(cudaMemsetAsync(m->adam_v, 0, (size_t)m->n_params * 4, ctx->stream));
+        }
+        GNN_TRY(gnn_adam_step(ctx, m->n_params, m->params, m->grads, m->adam_m, m->adam_v, lr, m->beta1, m->beta2,
+                              m->adam_eps, m->weight_decay, m->steps + 1));
+    } else if (lr != 0.f) {
         Prof p(ctx, m, CLS_SGD);
         GNN_TRY(gnn_sgd_step(ctx, m->n_params, m->params, m->grads, m->vel, lr, m->momentum, m->dampening,
                              m->weight_decay, m->nesterov, m->steps == 0));
@@ -652,6 +683,7 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
         for (size_t i = 0; i < m->span_used; i++) {
             float ms = 0;
             cudaEventElapsedTime(&ms, m->spans[i].a, m->spans[i].b);
+            m->spans[i].ms = ms;
             m->breakdown[m->spans[i].cls] += ms;
         }
     }
@@ -721,9 +753,37 @@ int gnn_gcn_train_step_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const i
     return 0;
 }
 
+int gnn_gcn_set_train_mask(gnn_ctx_t *ctx, gnn_gcn_t *m, const uint8_t *mask, int64_t n_selected_total) {
+    GNN_REQUIRE(ctx && m && (!mask || n_selected_total > 0), "invalid input, mask must be 1D and of same size with num of nodes in graph");
+    m->train_mask = mask;
+    m->n_train = n_selected_total;
+    return 0;
+}
+
+int gnn_gcn_accuracy(gnn_ctx_t *ctx, gnn_gcn_t *m, const int32_t *y, const uint8_t *mask, int64_t *count) {
+    GNN_REQUIRE(ctx && m && y && count, "gnn_gcn_accuracy: NULL argument");
+    return gnn_argmax_correct(ctx, m->n_loc, m->dims[m->L], m->H[m->L], m->ld[m->L], y, mask, count);
+}
+
 int gnn_gcn_last_breakdown(gnn_gcn_t *m, double *ms, int n) {
     GNN_REQUIRE(m && ms, "gnn_gcn_last_breakdown: NULL argument");
     for (int i = 0; i < n && i < 6; i++) ms[i] = m->breakdown[i];
+    return 0;
+}
+
+int gnn_gcn_last_spmm_spans(gnn_gcn_t *m, double *ms, double *alg_bytes, int32_t *F, int cap, int *n) {
+    GNN_REQUIRE(m && n, "gnn_gcn_last_spmm_spans: NULL argument");
+    int k = 0;
+    for (size_t i = 0; i < m->span_used; i++) {
+        if (m->spans[i].cls != CLS_SPMM) continue;
+        if (k < cap) {
+            if (ms) ms[k] = m->spans[i].ms;
+            if (alg_bytes) alg_bytes[k] = m->spans[i].bytes;
+            if (F) F[k] = m->spans[i].F;
+        }
+        k++;
+    }
+    *n = k;
     return 0;
 }
 

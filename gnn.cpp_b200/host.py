@@ -218,8 +218,46 @@ def sgd_step(ctx, p, g, vel=None, lr=0.01, momentum=0.0, dampening=0.0, weight_d
               int(nesterov), int(first))
 
 
+def adam_step(ctx, p, g, m, v, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1):
+    capi.call("gnn_adam_step", ctx.h, p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), lr, beta1, beta2, eps, weight_decay, int(step))
+
+
+def softmax_xent_masked(ctx, Z, y, mask, n_selected=None):
+    """mask: torch uint8/bool [N] on the device; returns (loss tensor[1], dZ)."""
+    N, Cn = Z.shape
+    mask = mask.to(torch.uint8)
+    loss = torch.zeros(1, dtype=torch.float32, device=Z.device)
+    dZ = torch.empty((N, Cn), dtype=torch.float32, device=Z.device)
+    n_sel = int(mask.sum().item()) if n_selected is None else int(n_selected)
+    capi.call("gnn_softmax_xent_masked", ctx.h, N, Cn, _ptr(Z), Z.stride(0), _ptr(y), _ptr(mask), n_sel, _ptr(loss), _ptr(dZ), Cn)
+    return loss, dZ
+
+
+def argmax_correct(ctx, Z, y, mask=None):
+    cnt = torch.zeros(1, dtype=torch.int64, device=Z.device)
+    m8 = None if mask is None else mask.to(torch.uint8)
+    capi.call("gnn_argmax_correct", ctx.h, Z.shape[0], Z.shape[1], _ptr(Z), Z.stride(0), _ptr(y), _ptr(m8), _ptr(cnt))
+    return int(cnt.item())
+
+
 class GCN:
     """Fused trainer (gnn_gcn_* entry points)."""
+
+    def set_train_mask(self, mask, n_selected_total=None):
+        """mask: torch uint8/bool [local rows] on the device, or None for all nodes."""
+        if mask is None:
+            self._mask = None
+            capi.call("gnn_gcn_set_train_mask", self.ctx.h, self.h, None, 0)
+            return
+        self._mask = mask.to(torch.uint8).contiguous()   # keep alive: the library stores the pointer
+        n = int(self._mask.sum().item()) if n_selected_total is None else int(n_selected_total)
+        capi.call("gnn_gcn_set_train_mask", self.ctx.h, self.h, _ptr(self._mask), n)
+
+    def accuracy(self, y, mask=None):
+        cnt = torch.zeros(1, dtype=torch.int64, device=y.device)
+        m8 = None if mask is None else mask.to(torch.uint8).contiguous()
+        capi.call("gnn_gcn_accuracy", self.ctx.h, self.h, _ptr(y), _ptr(m8), _ptr(cnt))
+        return int(cnt.item())
 
     def __init__(self, ctx, graph, dims):
         self.ctx, self.graph, self.dims = ctx, graph, list(dims)
@@ -286,6 +324,13 @@ class GCN:
         ms = np.zeros(6, np.float64)
         capi.call("gnn_gcn_last_breakdown", self.h, _ptr(ms), 6)
         return dict(zip(["spmm", "gemm", "loss", "bias_grad", "sgd", "other"], ms.tolist()))
+
+    def spmm_spans(self, cap=256):
+        """[(ms, algorithmic bytes, F)] of every aggregation launch of the last profiled step."""
+        ms = np.zeros(cap, np.float64); by = np.zeros(cap, np.float64); F = np.zeros(cap, np.int32); n = C.c_int(0)
+        capi.call("gnn_gcn_last_spmm_spans", self.h, _ptr(ms), _ptr(by), _ptr(F), cap, C.byref(n))
+        k = min(n.value, cap)
+        return [(float(ms[i]), float(by[i]), int(F[i])) for i in range(k)]
 
     def stats(self):
         b, n, f = C.c_double(), C.c_int32(), C.c_double()

@@ -155,6 +155,21 @@ GNN_API int gnn_softmax_xent(gnn_ctx_t *ctx, int64_t N, int32_t C, const float *
 GNN_API int gnn_sgd_step(gnn_ctx_t *ctx, int64_t n, float *p, const float *g, float *vel, float lr, float momentum,
                          float dampening, float weight_decay, int nesterov, int first);
 
+/* torch.optim.Adam semantics — the intent of nn::Adam (include/nn.h:180-188); the reference body (src/nn.cpp:419-441)
+ * divides by sqrt(v)*eps and uses the parameter index as step count.  m, v: first/second moment buffers (zeroed by
+ * the caller before step 1); step counts from 1. */
+GNN_API int gnn_adam_step(gnn_ctx_t *ctx, int64_t n, float *p, const float *g, float *m, float *v, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, int64_t step);
+/* Loss over the rows selected by a node mask (graph::Data::set_mask train/val/test masks, src/graph.cpp:130-151):
+ * mean over n_selected of the same per-row term as gnn_softmax_xent; dZ rows of unselected nodes are zero.
+ * mask: device uint8[N] (the reference's tensor<bool>). */
+GNN_API int gnn_softmax_xent_masked(gnn_ctx_t *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
+                                    const uint8_t *mask, int64_t n_selected, float *loss, float *dZ, int64_t ldd);
+/* Number of rows (selected by mask, or all when mask is NULL) whose arg-max logit (first maximum, tensor::argmax,
+ * include/tensor.h:645-648) equals the label; *count is a device int64. */
+GNN_API int gnn_argmax_correct(gnn_ctx_t *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
+                               const uint8_t *mask, int64_t *count);
+
 /* ---------------------------------------------------------------- elementwise / reductions for the
  * cyg::tensor surface (functional::add/mul/div/exp/log/sum/transpose/mask, include/functional.h:162-471) */
 enum { GNN_OP_ADD = 0, GNN_OP_MUL = 1, GNN_OP_DIV = 2, GNN_OP_POW = 3, GNN_OP_GT = 4 };
@@ -188,7 +203,8 @@ GNN_API int gnn_gcn_get_grads_h(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, flo
 /* activations of layer l (pre-ReLU Z_l is not kept for l < L; this returns H_l = ReLU(Z_l), logits for l = L) */
 GNN_API int gnn_gcn_get_activation_h(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, float *out_h);
 GNN_API int gnn_gcn_get_dlogits_h(gnn_ctx_t *ctx, gnn_gcn_t *m, float *out_h);
-/* options: precision (0 fp32 / 1 3xTF32), keep_preact (store Z_l for parity tests), lr etc. */
+/* options: precision (0 fp32 / 1 3xTF32), agg_first_mask, profile, momentum, dampening, weight_decay, nesterov,
+ * optimizer (0 SGD / 1 Adam), beta1, beta2, eps */
 GNN_API int gnn_gcn_set_option(gnn_gcn_t *m, const char *key, double value);
 /* X[N,F0] (ld = ldx) and y[N] on the device.  loss_d: device float written by the step. */
 GNN_API int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx, const int32_t *y,
@@ -205,9 +221,18 @@ GNN_API int gnn_gcn_train_step_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h,
  * pipelining).  So a loop `prefetch(b0); for k: train_step_h(b[k+1])` uploads every step's inputs exactly once,
  * hidden behind the previous step.  Host buffers must be pinned and stay valid until consumed. */
 GNN_API int gnn_gcn_prefetch_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const int32_t *y_h);
+/* Training-node mask (graph::Data::set_mask(mask, TRAIN), src/graph.cpp:130-151): device uint8[local rows]; the
+ * loss becomes the mean over the n_selected_total selected nodes of the whole graph (all ranks).  NULL = all nodes. */
+GNN_API int gnn_gcn_set_train_mask(gnn_ctx_t *ctx, gnn_gcn_t *m, const uint8_t *mask, int64_t n_selected_total);
+/* correct predictions (arg-max of the logits of the last forward) among the rows selected by mask (val/test mask;
+ * NULL = all local rows); *count is a device int64 (per rank: sum over ranks on the host side). */
+GNN_API int gnn_gcn_accuracy(gnn_ctx_t *ctx, gnn_gcn_t *m, const int32_t *y, const uint8_t *mask, int64_t *count);
 /* per-kernel-class device time of the last profiled step, ms: fills up to n entries of
  * {spmm, gemm, loss, bias_grad, sgd, other}.  Enabled by option "profile" = 1 (adds event records). */
 GNN_API int gnn_gcn_last_breakdown(gnn_gcn_t *m, double *ms, int n);
+/* every aggregation launch of the last profiled step, in execution order: device time (ms), algorithmic bytes
+ * (4(rows+1) + nnz(8+4F) + 4 rows F) and width F; *n = number of launches (may exceed cap) */
+GNN_API int gnn_gcn_last_spmm_spans(gnn_gcn_t *m, double *ms, double *alg_bytes, int32_t *F, int cap, int *n);
 /* algorithmic SpMM bytes / number of SpMM launches in one train step (for the roofline line) */
 GNN_API int gnn_gcn_spmm_stats(gnn_gcn_t *m, double *alg_bytes, int32_t *n_spmm, double *gemm_flops);
 

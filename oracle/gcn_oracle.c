@@ -408,6 +408,67 @@ ORC_API void orc_sgd_step(int64_t n, float *p, const float *g, float *vel, float
     }
 }
 
+/* Adam with torch.optim.Adam semantics — the documented intent of nn::Adam (include/nn.h:180-188); the reference
+ * body (src/nn.cpp:419-441) divides by sqrt(v)*eps and uses the parameter index as step: parity unpinned in the
+ * reference, pinned against torch in tests/test_oracle_vs_reference.py.  step counts from 1. */
+ORC_API void orc_adam_step(int64_t n, float *p, const float *g, float *m, float *v, float lr, float b1, float b2,
+                           float eps, float weight_decay, int64_t step) {
+    const float bc1 = (float)(1.0 - pow((double)b1, (double)step)), bc2 = (float)(1.0 - pow((double)b2, (double)step));
+    for (int64_t i = 0; i < n; i++) {
+        float d = g[i];
+        if (weight_decay != 0.0f) d = d + weight_decay * p[i];
+        m[i] = b1 * m[i] + (1.0f - b1) * d;
+        v[i] = b2 * v[i] + (1.0f - b2) * d * d;
+        const float denom = sqrtf(v[i]) / sqrtf(bc2) + eps;
+        p[i] = p[i] - (lr / bc1) * (m[i] / denom);
+    }
+}
+
+/* Loss over the rows selected by a node mask (Data::set_mask, src/graph.cpp:130-151): the reference would slice
+ * logits/targets by the mask and call cross_entropy_loss (src/nn.cpp:442-453) on the slice: mean over the selected
+ * rows of -log(exp(z_y)/(sum exp(z)+1e-20)), ascending row order.  dZ (optional): (softmax - onehot)/n_sel on selected
+ * rows, 0 elsewhere.  Returns the loss; *n_sel_out = number of selected rows. */
+ORC_API float orc_softmax_xent_masked(int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
+                                      const uint8_t *mask, float *dZ, int64_t ldd, int64_t *n_sel_out) {
+    int64_t n_sel = 0;
+    for (int64_t r = 0; r < N; r++) n_sel += mask[r] ? 1 : 0;
+    if (n_sel_out) *n_sel_out = n_sel;
+    double acc = 0.0;
+    const float inv_n = 1.0f / (float)n_sel;
+    for (int64_t r = 0; r < N; r++) {
+        if (!mask[r]) {
+            if (dZ) for (int32_t c = 0; c < C; c++) dZ[r * ldd + c] = 0.0f;
+            continue;
+        }
+        const float *z = Z + r * ldz;
+        double s = 0.0;
+        for (int32_t c = 0; c < C; c++) s += exp((double)z[c]);
+        acc += -log(exp((double)z[y[r]]) / (s + 1e-20));
+        if (dZ)
+            for (int32_t c = 0; c < C; c++) {
+                float pr = (float)(exp((double)z[c]) / s);
+                if (c == y[r]) pr -= 1.0f;
+                dZ[r * ldd + c] = pr * inv_n;
+            }
+    }
+    return (float)(acc / (double)n_sel);
+}
+
+/* rows (selected by mask, all when NULL) whose first-maximum column equals the label (tensor::argmax,
+ * include/tensor.h:645-648 uses std::max_element: first maximum) */
+ORC_API int64_t orc_argmax_correct(int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y, const uint8_t *mask) {
+    int64_t n = 0;
+    for (int64_t r = 0; r < N; r++) {
+        if (mask && !mask[r]) continue;
+        const float *z = Z + r * ldz;
+        int32_t bi = 0;
+        for (int32_t c = 1; c < C; c++)
+            if (z[c] > z[bi]) bi = c;
+        n += bi == y[r];
+    }
+    return n;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * 1-D row partition.  No counterpart in the reference.
  *   part_ptr[p] = min(N, p * ceil(N/P)),  p = 0..P

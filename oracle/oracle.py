@@ -50,6 +50,11 @@ def lib():
         L.orc_softmax_xent.restype = C.c_float
         L.orc_softmax_xent.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _i32p, C.c_void_p, C.c_int64, C.c_int]
         L.orc_sgd_step.argtypes = [C.c_int64, _f32p, _f32p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.orc_adam_step.argtypes = [C.c_int64, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64]
+        L.orc_softmax_xent_masked.restype = C.c_float
+        L.orc_softmax_xent_masked.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _i32p, _u8p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_argmax_correct.restype = C.c_int64
+        L.orc_argmax_correct.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _i32p, C.c_void_p]
         L.orc_partition_ptr.argtypes = [C.c_int64, C.c_int32, _i64p]
         L.orc_partition_rows.restype = C.c_int64
         L.orc_partition_rows.argtypes = [_i64p, _i32p, C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, C.c_void_p]
@@ -200,6 +205,27 @@ def softmax_xent(Z, y, order=0, want_grad=True):
 def sgd_step(p, g, vel=None, lr=0.01, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, first=True):
     lib().orc_sgd_step(p.size, p.reshape(-1), np.ascontiguousarray(g, dtype=np.float32).reshape(-1), _ptr(vel), lr,
                        momentum, dampening, weight_decay, int(nesterov), int(first))
+
+
+def adam_step(p, g, m, v, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1):
+    lib().orc_adam_step(p.size, p.reshape(-1), np.ascontiguousarray(g, dtype=np.float32).reshape(-1), m.reshape(-1),
+                        v.reshape(-1), lr, beta1, beta2, eps, weight_decay, int(step))
+
+
+def softmax_xent_masked(Z, y, mask, want_grad=True):
+    Z = np.ascontiguousarray(Z, dtype=np.float32)
+    N, Cn = Z.shape
+    dZ = np.empty_like(Z) if want_grad else None
+    nsel = C.c_int64(0)
+    loss = lib().orc_softmax_xent_masked(N, Cn, Z, Cn, np.ascontiguousarray(y, dtype=np.int32),
+                                         np.ascontiguousarray(mask, dtype=np.uint8), _ptr(dZ), Cn, C.byref(nsel))
+    return float(loss), dZ, int(nsel.value)
+
+
+def argmax_correct(Z, y, mask=None):
+    Z = np.ascontiguousarray(Z, dtype=np.float32)
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+    return int(lib().orc_argmax_correct(Z.shape[0], Z.shape[1], Z, Z.shape[1], np.ascontiguousarray(y, dtype=np.int32), _ptr(m)))
 
 
 def partition_ptr(N, P):

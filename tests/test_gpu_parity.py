@@ -377,6 +377,81 @@ def test_bias_relu_sgd_vs_oracle(ctx, oracle):
         np.testing.assert_allclose(pd.cpu().numpy(), pc, rtol=2e-6, atol=1e-7)
 
 
+def test_adam_masked_loss_accuracy_vs_oracle(ctx, oracle):
+    """Adam (torch semantics), loss over a node mask, arg-max accuracy."""
+    import torch
+    from gnn_cpp_b200 import host
+    rng = np.random.default_rng(11)
+    for kw in [dict(), dict(weight_decay=1e-2), dict(beta1=0.8, beta2=0.95, eps=1e-6)]:
+        p0 = rng.standard_normal(5000).astype(np.float32)
+        pd = _dev(p0, ctx); md = _dev(np.zeros_like(p0), ctx); vd = _dev(np.zeros_like(p0), ctx)
+        pc = p0.copy(); mc = np.zeros_like(p0); vc = np.zeros_like(p0)
+        for it in range(4):
+            g = rng.standard_normal(5000).astype(np.float32)
+            host.adam_step(ctx, pd, _dev(g, ctx), md, vd, lr=0.01, step=it + 1, **kw)
+            oracle.adam_step(pc, g, mc, vc, lr=0.01, step=it + 1, **kw)
+        np.testing.assert_allclose(pd.cpu().numpy(), pc, rtol=3e-6, atol=2e-7)
+    N, Cn = 3001, 47
+    Z = rng.uniform(-3, 3, (N, Cn)).astype(np.float32); y = rng.integers(0, Cn, N).astype(np.int32)
+    Z[5, 2] = Z[5, 9] = 4.0; y[5] = 2                      # tie -> first maximum
+    mask = rng.random(N) < 0.25; mask[5] = True
+    loss_ref, dZ_ref, nsel = oracle.softmax_xent_masked(Z, y, mask)
+    Zd, yd, mk = _dev(Z, ctx), _dev(y, ctx), torch.from_numpy(mask).to(ctx.device)
+    loss, dZ = host.softmax_xent_masked(ctx, Zd, yd, mk)
+    assert abs(float(loss.cpu()[0]) - loss_ref) <= TOL * abs(loss_ref)
+    assert rel_err(dZ.cpu().numpy(), dZ_ref) <= TOL
+    assert bool((dZ.cpu().numpy()[~mask] == 0).all())
+    assert host.argmax_correct(ctx, Zd, yd, mk) == oracle.argmax_correct(Z, y, mask)       # integer: exact
+    assert host.argmax_correct(ctx, Zd, yd) == oracle.argmax_correct(Z, y)
+
+
+def test_trainer_adam_and_train_mask(ctx, oracle):
+    """fused trainer with a training-node mask and Adam: 3 steps track the oracle composition
+    (forward/backward primitives + masked loss + Adam on the parameter slab)."""
+    import torch
+    from gnn_cpp_b200 import host
+    p = load_problem("tiny_pl")
+    cfg = p.cfg
+    G = oracle.Graph(p.src, p.dst, cfg.N)
+    mask = np.random.default_rng(3).random(cfg.N) < 0.4
+    g = host.Graph.build(ctx, p.src, p.dst, cfg.N)
+    m = host.GCN(ctx, g, cfg.dims)
+    m.set_params(p.W, p.b)
+    m.set_option("optimizer", 1)
+    m.set_train_mask(torch.from_numpy(mask).to(ctx.device))
+    X, yd = _dev(p.X, ctx), _dev(p.y, ctx)
+    W = [w.copy() for w in p.W]; b = [x.copy() for x in p.b]
+    L = len(cfg.dims) - 1
+    mom = [[np.zeros_like(w), np.zeros_like(x)] for w, x in zip(W, b)]
+    vel = [[np.zeros_like(w), np.zeros_like(x)] for w, x in zip(W, b)]
+    for it in range(3):
+        # oracle: forward with primitives, masked loss, backward with primitives, Adam
+        H = [p.X]; Zs = []
+        for l in range(L):
+            Z, Hn = oracle.bias_relu(oracle.spmm(G.N, G.rowptr, G.colidx, G.val, oracle.gemm_nt(H[l], W[l], 1), 1), b[l])
+            Zs.append(Z); H.append(Hn)
+        loss_ref, dZ, _ = oracle.softmax_xent_masked(Zs[-1], p.y, mask)
+        grads = []
+        for l in range(L - 1, -1, -1):
+            db = oracle.bias_grad(dZ, 1)
+            dP = oracle.spmm(G.N, G.colptr, G.rowidx, G.valT, dZ, 1)
+            grads.append((oracle.gemm_tn(dP, H[l], 1), db))
+            if l > 0:
+                dZ = oracle.relu_bwd(oracle.gemm_nn(dP, W[l], 1), Zs[l - 1])
+        grads = grads[::-1]
+        loss = float(m.train_step(X, yd, 0.01).cpu()[0])
+        assert abs(loss - loss_ref) <= 2 * TOL * abs(loss_ref), it
+        for l in range(L):
+            oracle.adam_step(W[l], grads[l][0], mom[l][0], vel[l][0], lr=0.01, step=it + 1)
+            oracle.adam_step(b[l], grads[l][1], mom[l][1], vel[l][1], lr=0.01, step=it + 1)
+    for l in range(L):
+        Wg, bg = m.params(l + 1)
+        assert rel_err(Wg, W[l]) <= 1e-4 and rel_err(bg, b[l]) <= 1e-4   # Adam divides by sqrt(v): amplifies rounding
+    acc = m.accuracy(yd, torch.from_numpy(~mask).to(ctx.device))
+    assert 0 <= acc <= int((~mask).sum())
+    m.close(); g.close()
+
+
 # ------------------------------------------------------------------------------------------------ whole train step
 def _run_trainer(ctx, p, lr=0.0, agg_mask=None, precision=1):
     from gnn_cpp_b200 import host

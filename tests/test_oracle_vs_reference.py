@@ -126,3 +126,45 @@ def test_composed_step_equals_c_step(oracle, name):
                 assert v == c[k] == d[k]
             else:
                 assert np.array_equal(v, c[k]) and np.array_equal(v, d[k]), k
+
+
+def test_adam_matches_torch(oracle):
+    """nn::Adam's intent is torch.optim.Adam (include/nn.h:180-188); the reference body (nn.cpp:419-441) is broken."""
+    import torch
+    rng = np.random.default_rng(1)
+    for kw in [dict(), dict(weight_decay=1e-2), dict(betas=(0.8, 0.95), eps=1e-6)]:
+        p0 = rng.standard_normal(301).astype(np.float32)
+        tp = torch.tensor(p0.copy(), requires_grad=True)
+        opt = torch.optim.Adam([tp], lr=0.01, **kw)
+        mine = p0.copy(); m = np.zeros_like(mine); v = np.zeros_like(mine)
+        b1, b2 = kw.get("betas", (0.9, 0.999))
+        for it in range(5):
+            g = rng.standard_normal(301).astype(np.float32)
+            tp.grad = torch.tensor(g)
+            opt.step()
+            oracle.adam_step(mine, g, m, v, lr=0.01, beta1=b1, beta2=b2, eps=kw.get("eps", 1e-8),
+                             weight_decay=kw.get("weight_decay", 0.0), step=it + 1)
+            np.testing.assert_allclose(mine, tp.detach().numpy(), rtol=3e-6, atol=2e-7)
+
+
+def test_masked_loss_and_accuracy_match_torch(oracle):
+    """masked loss == cross_entropy over the sliced rows (how Data::set_mask masks are meant to be used); argmax
+    accuracy with first-maximum tie breaking (tensor::argmax, tensor.h:645-648)."""
+    import torch
+    rng = np.random.default_rng(2)
+    N, C = 500, 7
+    Z = rng.standard_normal((N, C)).astype(np.float32); y = rng.integers(0, C, N).astype(np.int32)
+    Z[3, 1] = Z[3, 4] = Z[3].max() + 1.0; y[3] = 1                    # tie: the first maximum wins
+    mask = rng.random(N) < 0.3; mask[3] = True
+    loss, dZ, nsel = oracle.softmax_xent_masked(Z, y, mask)
+    zt = torch.tensor(Z, requires_grad=True)
+    lt = torch.nn.functional.cross_entropy(zt[torch.tensor(mask)], torch.tensor(y[mask]).long())
+    lt.backward()
+    assert nsel == int(mask.sum())
+    assert abs(loss - float(lt)) <= 1e-6 * abs(float(lt))
+    np.testing.assert_allclose(dZ, zt.grad.numpy(), rtol=1e-5, atol=1e-8)
+    assert oracle.argmax_correct(Z, y, mask) == int((torch.tensor(Z).argmax(1).numpy() == y)[mask].sum())
+    assert oracle.argmax_correct(Z, y) == int((torch.tensor(Z).argmax(1).numpy() == y).sum())
+    # with an all-true mask it is the plain loss of the restatement
+    full, _ = oracle.softmax_xent(Z, y, order=1)
+    assert abs(oracle.softmax_xent_masked(Z, y, np.ones(N, bool))[0] - full) <= 1e-6 * abs(full)
