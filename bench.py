@@ -322,6 +322,8 @@ def run_ours(args):
                              "achieved": dom_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                              "frac": dom_gbs / peak, "traffic": traffic,
                              "alg_bytes_per_launch": dom_bytes / dom_n, "ms_per_launch": dom_ms / dom_n,
+                             # when frac > 1 on B_alg (L2 serves reuse) quote the touch-once bound too
+                             "b_min_bytes_per_launch": 4.0 * (n_loc + 1) + 8.0 * nnz / world + 8.0 * n_loc * dom_F,
                              "all_aggregations_of_a_step": {"achieved": spmm_gbs, "frac": spmm_gbs / peak,
                                                             "alg_bytes": st["spmm_alg_bytes"], "ms": bd["spmm"],
                                                             "by_width": launches_detail}},
