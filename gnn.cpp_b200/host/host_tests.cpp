@@ -172,6 +172,29 @@ static void test_loss_and_sgd() { // reference nn.cpp:442-453 (forward), nn.h:16
     CHECK(all_close(*p->data(), std::valarray<float>{0.42f, 0.42f}));
 }
 
+static void test_adam_masks_accuracy() { // nn::Adam intent (nn.h:180-188), Data::set_mask use
+    auto p = T({2}, {1, 1}, true);
+    Adam opt({p}, 0.1f);
+    for (int i = 0; i < 2; i++) { opt.zero_grad(); (p * 2.0f)->sum()->backward(); opt.step(); }
+    // torch.optim.Adam, constant gradient 2: every step moves by lr * 1/(1 + eps/2) -> 0.9, 0.8
+    CHECK(all_close(*p->data(), std::valarray<float>{0.8f, 0.8f}));
+    auto Z = T({3, 3}, {1, 2, 3, 1, 1, 1, 5, 0, 5}, true);
+    auto y = std::make_shared<tensor<int>>(std::vector<size_t>{3}, new std::valarray<int>{2, 0, 0}, false);
+    tensor<bool> mask(std::vector<size_t>{3}, new std::valarray<bool>{true, false, true}, false);
+    auto loss = cross_entropy_loss(Z, y, mask);
+    const float e1 = std::exp(1.f), e2 = std::exp(2.f), e3 = std::exp(3.f), e5 = std::exp(5.f);
+    const float expect = 0.5f * (-std::log(e3 / (e1 + e2 + e3)) - std::log(e5 / (2 * e5 + 1)));
+    CHECK(close(loss->item(), expect));
+    loss->backward();
+    std::valarray<float> g = *Z->grad();
+    CHECK(g[3] == 0.0f && g[4] == 0.0f && g[5] == 0.0f); // unselected row
+    CHECK(close(g[2], (e3 / (e1 + e2 + e3) - 1) / 2));
+    CHECK(count_correct(Z, y) == 3);        // rows: argmax 2 (==2), 0 (first max of a tie, ==0), 0 (first of the 5,5 tie, ==0)
+    CHECK(count_correct(Z, y, &mask) == 2);
+    tensor<bool> bad(std::vector<size_t>{2}, new std::valarray<bool>{true, false}, false);
+    CHECK_THROWS_WITH(cross_entropy_loss(Z, y, bad), "mask must be 1D and of same size");
+}
+
 static void test_graph_structure() { // reference tests/graph.test.cpp:16-43 (its toy graph; it asserts nothing)
     auto edge_list = vec_to_edge_list({1, 2, 3, 0, 4, 1, 2, 3}, {1, 2, 0, 1, 2, 2, 1, 1});
     CHECK(edge_list->shape() == (std::vector<size_t>{2, 8}));
@@ -237,6 +260,7 @@ int main() {
         {"tensor_basics", test_tensor_basics},       {"elementwise_ops", test_elementwise_ops},
         {"fan_out_accumulates", test_fan_out_accumulates}, {"matmul_and_relu", test_matmul_and_relu},
         {"module_and_linear", test_module_and_linear}, {"loss_and_sgd", test_loss_and_sgd},
+        {"adam_masks_accuracy", test_adam_masks_accuracy},
         {"graph_structure", test_graph_structure},
         {"gcn_vs_dense_transform_first", [] { check_gcn_against_dense(12, 5); }},
         {"gcn_vs_dense_aggregate_first", [] { check_gcn_against_dense(6, 17); }},

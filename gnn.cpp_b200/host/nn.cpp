@@ -161,6 +161,49 @@ tptr<float> cross_entropy_loss(const tptr<float> logits, const tptr<int> target)
     return out;
 }
 
+// node mask (0/1) -> device uint8 array + number of selected nodes
+static device::buffer_ptr mask_to_u8(const tensor<bool> &mask, int64_t n_rows, int64_t *n_selected) {
+    if ((int64_t)mask.numel() != n_rows)
+        throw std::runtime_error("invalid input, mask must be 1D and of same size with num of nodes in graph");
+    const std::valarray<bool> *h = mask.data();
+    std::vector<uint8_t> u8(mask.numel());
+    int64_t n = 0;
+    for (size_t i = 0; i < u8.size(); i++) {
+        u8[i] = (*h)[i] ? 1 : 0;
+        n += u8[i];
+    }
+    auto buf = device::alloc(u8.size() ? u8.size() : 1);
+    device::check(gnn_memcpy_h2d(device::ctx(), buf->ptr, u8.data(), u8.size()));
+    device::check(gnn_ctx_sync(device::ctx())); // u8 is a stack-local staging buffer
+    *n_selected = n;
+    return buf;
+}
+
+tptr<float> cross_entropy_loss(const tptr<float> logits, const tptr<int> target, const tensor<bool> &mask) {
+    int64_t n_sel = 0;
+    auto m8 = mask_to_u8(mask, (int64_t)logits->shape()[0], &n_sel);
+    if (n_sel == 0) throw std::runtime_error("invalid input, mask selects no node");
+    auto op = std::make_unique<MaskedSoftmaxCrossEntropy<tensor<float>>>();
+    auto out = op->forward(logits, target, m8, n_sel);
+    if (out->requires_grad()) out->grad_fn = std::move(op);
+    return out;
+}
+
+size_t count_correct(const tptr<float> logits, const tptr<int> target, const tensor<bool> *mask) {
+    if (logits->rank() != 2 || target->rank() != 1 || target->numel() != logits->shape()[0])
+        throw std::runtime_error("invalid input, logits must be of rank 2 and targets must be 1D tensor");
+    device::buffer_ptr m8;
+    int64_t n_sel = 0;
+    if (mask) m8 = mask_to_u8(*mask, (int64_t)logits->shape()[0], &n_sel);
+    auto cnt = device::alloc(8);
+    device::check(gnn_argmax_correct(device::ctx(), (int64_t)logits->shape()[0], (int32_t)logits->shape()[1], logits->dptr(),
+                                     (int64_t)logits->shape()[1], target->dptr(), m8 ? static_cast<const uint8_t *>(m8->ptr) : nullptr,
+                                     static_cast<int64_t *>(cnt->ptr)));
+    int64_t h = 0;
+    device::check(gnn_memcpy_d2h(device::ctx(), &h, cnt->ptr, 8));
+    return (size_t)h;
+}
+
 void Optimizer::zero_grad() {
     for (auto &p : _parameters) p->zero_grad();
 }
@@ -178,6 +221,26 @@ void SGD::step() {
                                    _weight_decay, _nestorov, _steps == 0));
     }
     _steps++;
+}
+
+Adam::Adam(std::vector<tptr<float>> parameters, float lr, float b1, float b2, float eps, float weight_decay)
+    : Optimizer(std::move(parameters)), _lr(lr), _b1(b1), _b2(b2), _eps(eps), _weight_decay(weight_decay) {
+    for (const auto &p : _parameters) { // zero-initialised moments like the reference constructor (nn.cpp:419-426)
+        _velocity.push_back(device::alloc(p->numel() * 4));
+        _momentum.push_back(device::alloc(p->numel() * 4));
+        device::check(gnn_memset(device::ctx(), _velocity.back()->ptr, 0, p->numel() * 4));
+        device::check(gnn_memset(device::ctx(), _momentum.back()->ptr, 0, p->numel() * 4));
+    }
+}
+
+void Adam::step() {
+    _steps++;
+    for (size_t i = 0; i < _parameters.size(); i++) {
+        auto &p = _parameters[i];
+        device::check(gnn_adam_step(device::ctx(), (int64_t)p->numel(), p->dptr(), p->grad_dptr(),
+                                    static_cast<float *>(_momentum[i]->ptr), static_cast<float *>(_velocity[i]->ptr), _lr, _b1,
+                                    _b2, _eps, _weight_decay, (int64_t)_steps));
+    }
 }
 
 } // namespace nn

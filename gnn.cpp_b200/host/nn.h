@@ -1,6 +1,6 @@
 // nn.h — Module tree, Linear, ReLU, Sequential, softmax, cross-entropy loss and the optimisers of the GCN
 // training loop (counterpart of reference include/nn.h:28-91,155-191).  Out of scope here: BatchNorm,
-// LayerNorm, Dropout, Sigmoid, tanh, Adam, MLP, Embedding.
+// LayerNorm, Dropout, Sigmoid, tanh, MLP, Embedding.
 #ifndef GNNB200_NN_H
 #define GNNB200_NN_H
 
@@ -94,6 +94,26 @@ class SGD : public Optimizer {
     std::vector<cyg::device::buffer_ptr> _velocity;
     size_t _steps = 0;
 };
+
+/** torch.optim.Adam semantics — the intent of reference nn.h:180-188.  The reference body (nn.cpp:419-441) divides
+ *  by sqrt(v)*eps, uses the parameter INDEX as the step count and its default `eps = 10 - 8` evaluates to 2; here
+ *  eps defaults to 1e-8 and the step count is the number of step() calls. */
+class Adam : public Optimizer {
+  public:
+    Adam(std::vector<cyg::tptr<float>> parameters, float lr, float b1 = 0.9f, float b2 = 0.999f, float eps = 1e-8f,
+         float weight_decay = 0);
+    void step();
+    float _lr, _b1, _b2, _eps, _weight_decay;
+    std::vector<cyg::device::buffer_ptr> _velocity, _momentum; // second / first moment (reference member names)
+    size_t _steps = 0;
+};
+
+/** cross-entropy over the nodes selected by a mask (graph::Data::set_mask TRAIN/VAL/TEST, reference graph.cpp:130-151):
+ *  mean over the selected rows; the gradient of unselected rows is zero. */
+cyg::tptr<float> cross_entropy_loss(const cyg::tptr<float> logits, const cyg::tptr<int> target, const cyg::tensor<bool> &mask);
+/** number of selected rows (all rows when mask == nullptr) whose arg-max logit equals the target
+ *  (tensor::argmax semantics, reference tensor.h:645-648: first maximum) */
+size_t count_correct(const cyg::tptr<float> logits, const cyg::tptr<int> target, const cyg::tensor<bool> *mask = nullptr);
 
 } // namespace nn
 #endif

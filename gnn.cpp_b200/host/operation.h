@@ -449,6 +449,36 @@ template <class T> class SoftmaxCrossEntropy : public Operation<T> {
     }
 };
 
+/** cross-entropy over the rows selected by a node mask (graph::Data::set_mask): gnn_softmax_xent_masked */
+template <class T> class MaskedSoftmaxCrossEntropy : public Operation<T> {
+    std::shared_ptr<T> dZ_;
+
+  public:
+    MaskedSoftmaxCrossEntropy() { this->name = "MaskedCrossEntropy"; }
+    std::shared_ptr<T> forward(const std::shared_ptr<T> &logits, const std::shared_ptr<tensor<int>> &target,
+                               const device::buffer_ptr &mask_u8, int64_t n_selected) {
+        if (logits->rank() != 2 || target->rank() != 1 || target->numel() != logits->shape()[0])
+            throw std::runtime_error("invalid input, logits must be of rank 2 and targets must be 1D tensor");
+        const int64_t N = logits->shape()[0], C = logits->shape()[1];
+        auto out = functional::detail::make<float>({1}, logits->requires_grad());
+        if (logits->requires_grad()) {
+            dZ_ = functional::detail::make<float>(logits->shape(), false);
+            this->context->save_for_backward({logits});
+        }
+        device::check(gnn_softmax_xent_masked(device::ctx(), N, (int32_t)C, logits->dptr(), C, target->dptr(),
+                                              static_cast<const uint8_t *>(mask_u8->ptr), n_selected, out->dptr(),
+                                              dZ_ ? dZ_->dptr() : nullptr, C));
+        return out;
+    }
+    void _backward(std::shared_ptr<T> g) override {
+        auto var = this->context->get_variables();
+        check_backward(var, 1);
+        if (var[0]->requires_grad()) var[0]->backward(functional::binary(GNN_OP_MUL, *dZ_, *g, false));
+        dZ_.reset();
+        this->_done = true;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // engine implementation (needs the complete tensor type)
 // ---------------------------------------------------------------------------------------------------------
