@@ -66,6 +66,16 @@ struct gnn_gcn {
     float momentum = 0.f, dampening = 0.f, weight_decay = 0.f;
     int nesterov = 0;
     int optimizer = 0; // 0 = SGD (nn::SGD), 1 = Adam (nn::Adam)
+    // CUDA graph of the whole step for launch-bound (small) problems: -1 auto, 0 off, 1 on.  The step is a fixed
+    // launch sequence over preallocated buffers, so it is captured once (after an eager warm-up step that sizes the
+    // workspace) and replayed while the arguments stay the same.
+    int use_graph = -1;
+    cudaGraphExec_t graph_exec = nullptr, graph_exec2 = nullptr; // two entries: the host-buffer path alternates slots
+    int64_t graph_launches = 0;
+    struct GraphKey {
+        const float *X; int64_t ldx; const int32_t *y; float lr; float *loss_d;
+        bool operator==(const GraphKey &o) const { return X == o.X && ldx == o.ldx && y == o.y && lr == o.lr && loss_d == o.loss_d; }
+    } graph_key = {nullptr, 0, nullptr, 0.f, nullptr}, graph_key2 = {nullptr, 0, nullptr, 0.f, nullptr};
     float beta1 = 0.9f, beta2 = 0.999f, adam_eps = 1e-8f;
     float *adam_m = nullptr, *adam_v = nullptr;
     const uint8_t *train_mask = nullptr; // device uint8[n_loc]: rows that enter the loss (Data::set_mask TRAIN)
@@ -405,6 +415,12 @@ static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
 
 using namespace gnn;
 
+static void drop_graph(gnn_gcn_t *m) {
+    if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+    if (m->graph_exec2) cudaGraphExecDestroy(m->graph_exec2);
+    m->graph_exec = m->graph_exec2 = nullptr;
+}
+
 extern "C" {
 
 int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_t *dims, gnn_gcn_t **out) {
@@ -504,6 +520,7 @@ int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_
 int gnn_gcn_destroy(gnn_ctx_t *ctx, gnn_gcn_t *m) {
     if (!m) return 0;
     if (ctx) cudaStreamSynchronize(ctx->stream);
+    drop_graph(m);
     cudaFree(m->params); cudaFree(m->grads); cudaFree(m->vel); cudaFree(m->adam_m); cudaFree(m->adam_v);
     for (auto p : m->H) cudaFree(p);
     for (auto p : m->M) cudaFree(p);
@@ -574,6 +591,7 @@ int gnn_gcn_get_dlogits_h(gnn_ctx_t *ctx, gnn_gcn_t *m, float *out_h) {
 
 int gnn_gcn_set_option(gnn_gcn_t *m, const char *key, double value) {
     GNN_REQUIRE(m && key, "gnn_gcn_set_option: NULL argument");
+    drop_graph(m); // a captured step bakes the options in
     if (!strcmp(key, "precision")) m->precision = (int)value;
     else if (!strcmp(key, "profile")) m->profile = (int)value;
     else if (!strcmp(key, "momentum")) m->momentum = (float)value;
@@ -581,6 +599,7 @@ int gnn_gcn_set_option(gnn_gcn_t *m, const char *key, double value) {
     else if (!strcmp(key, "weight_decay")) m->weight_decay = (float)value;
     else if (!strcmp(key, "nesterov")) m->nesterov = (int)value;
     else if (!strcmp(key, "optimizer")) m->optimizer = (int)value;
+    else if (!strcmp(key, "cuda_graph")) m->use_graph = (int)value;
     else if (!strcmp(key, "beta1")) m->beta1 = (float)value;
     else if (!strcmp(key, "beta2")) m->beta2 = (float)value;
     else if (!strcmp(key, "eps")) m->adam_eps = (float)value;
@@ -616,13 +635,9 @@ int gnn_gcn_forward(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx) {
     return 0;
 }
 
-int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx, const int32_t *y, float lr,
-                       float *loss_d) {
-    GNN_REQUIRE(ctx && m && X && y && ldx >= m->dims[0], "gnn_gcn_train_step: bad argument");
-    GNN_REQUIRE(!m->dist || ldx == m->ld[0], "gnn_gcn_train_step: row-partitioned mode needs ldx == round_up(F0,4)");
-    GNN_TRY(ensure_buffers(ctx, m));
-    m->last_y = y;
-    m->span_used = 0;
+// the launch sequence of one step (forward, loss, backward, gradient exchange, optimiser, loss copy)
+static int train_step_body(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx, const int32_t *y, float lr,
+                           float *loss_d) {
     GNN_TRY(forward(ctx, m, X, ldx));
     const int32_t C = m->dims[m->L];
     float *loss_slot = m->grads + m->n_params; // rides along with the gradient all-reduce
@@ -676,6 +691,49 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
                              m->weight_decay, m->nesterov, m->steps == 0));
     }
     if (loss_d) GNN_CHECK_CUDA(cudaMemcpyAsync(loss_d, loss_slot, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx, const int32_t *y, float lr,
+                       float *loss_d) {
+    GNN_REQUIRE(ctx && m && X && y && ldx >= m->dims[0], "gnn_gcn_train_step: bad argument");
+    GNN_REQUIRE(!m->dist || ldx == m->ld[0], "gnn_gcn_train_step: row-partitioned mode needs ldx == round_up(F0,4)");
+    GNN_TRY(ensure_buffers(ctx, m));
+    m->last_y = y;
+    m->span_used = 0;
+    // Graph replay: single GPU, SGD (Adam's bias correction is a per-step kernel argument), no profiling.  Auto mode
+    // turns it on for launch-bound sizes only (activations up to 32 M floats, i.e. steps of about a millisecond).
+    const bool want_graph = !m->dist && !m->profile && m->optimizer == 0 && m->steps >= 1 &&
+                            (m->use_graph == 1 || (m->use_graph < 0 && (int64_t)m->n_loc * m->maxld <= (1ll << 25)));
+    const gnn_gcn::GraphKey key = {X, ldx, y, lr, loss_d};
+    if (want_graph) {
+        if (m->graph_exec && !(m->graph_key == key)) { // keep the previous graph as the second entry (swap)
+            std::swap(m->graph_exec, m->graph_exec2);
+            std::swap(m->graph_key, m->graph_key2);
+            if (m->graph_exec && !(m->graph_key == key)) {
+                cudaGraphExecDestroy(m->graph_exec);
+                m->graph_exec = nullptr;
+            }
+        }
+        if (!m->graph_exec) {
+            const int64_t l0 = ctx->launches;
+            cudaGraph_t graph = nullptr;
+            GNN_CHECK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = train_step_body(ctx, m, X, ldx, y, lr, loss_d);
+            const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc) return rc;
+            GNN_CHECK_CUDA(ce);
+            GNN_CHECK_CUDA(cudaGraphInstantiate(&m->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            m->graph_launches = ctx->launches - l0;
+            ctx->launches = l0;
+            m->graph_key = key;
+        }
+        GNN_CHECK_CUDA(cudaGraphLaunch(m->graph_exec, ctx->stream));
+        ctx->launches += m->graph_launches;
+    } else {
+        GNN_TRY(train_step_body(ctx, m, X, ldx, y, lr, loss_d));
+    }
     m->steps++;
     if (m->profile) {
         GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -755,6 +813,7 @@ int gnn_gcn_train_step_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const i
 
 int gnn_gcn_set_train_mask(gnn_ctx_t *ctx, gnn_gcn_t *m, const uint8_t *mask, int64_t n_selected_total) {
     GNN_REQUIRE(ctx && m && (!mask || n_selected_total > 0), "invalid input, mask must be 1D and of same size with num of nodes in graph");
+    drop_graph(m);
     m->train_mask = mask;
     m->n_train = n_selected_total;
     return 0;

@@ -541,6 +541,36 @@ def test_sgd_training_tracks_oracle(ctx, oracle, name):
     m.close(); g.close()
 
 
+@pytest.mark.parametrize("name", ["tiny_pl", "cora"])
+def test_cuda_graph_replay_matches_eager(ctx, name):
+    """the captured-and-replayed step (launch-bound sizes) is the same launch sequence as the eager step: identical
+    bits for losses and parameters, identical launch accounting, with momentum, and through the host-buffer path
+    whose double-buffered inputs alternate between two cached graphs."""
+    from gnn_cpp_b200 import host
+    p = load_problem(name)
+    X, y = _dev(p.X, ctx), _dev(p.y, ctx)
+    Xh, yh = np.ascontiguousarray(p.X), np.ascontiguousarray(p.y)
+    res = {}
+    for mode in (0, 1):
+        g = host.Graph.build(ctx, p.src, p.dst, p.cfg.N)
+        m = host.GCN(ctx, g, p.cfg.dims)
+        m.set_option("cuda_graph", mode)
+        m.set_option("momentum", 0.9)
+        m.set_params(p.W, p.b)
+        l0 = ctx.launches
+        losses = [float(m.train_step(X, y, 0.05).cpu()[0]) for _ in range(5)]
+        losses += [m.train_step_host(Xh, yh, 0.05) for _ in range(3)]
+        m.prefetch_host(Xh, yh)
+        losses += [m.train_step_host(Xh, yh, 0.05) for _ in range(4)]
+        losses.append(m.train_step_host(None, None, 0.05))
+        res[mode] = (losses, [m.params(l) for l in range(1, len(p.cfg.dims))], ctx.launches - l0)
+        m.close(); g.close()
+    assert res[0][0] == res[1][0]
+    for (W0, b0), (W1, b1) in zip(res[0][1], res[1][1]):
+        assert np.array_equal(W0, W1) and np.array_equal(b0, b1)
+    assert res[0][2] == res[1][2]
+
+
 def test_train_step_host_entry_point(ctx, oracle):
     """gnn_gcn_train_step_h: host buffers in, loss out (the e2e call bench.py times)."""
     from gnn_cpp_b200 import host
