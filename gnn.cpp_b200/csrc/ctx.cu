@@ -46,6 +46,15 @@ int gnn_ctx_create(int device, void *stream, gnn_ctx_t **out) {
     GNN_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
     GNN_REQUIRE(prop.major >= 10, "gnn_ctx_create: device %d is sm_%d%d; kernels are built for sm_100a only", device,
                 prop.major, prop.minor);
+    {   // keep stream-ordered temporaries (sort buffers, workspace) cached in the pool instead of returning them to
+        // the driver at every synchronisation: a second structure build then costs kernel time only
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     gnn_ctx *c = new gnn_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;

@@ -408,6 +408,83 @@ ORC_API void orc_sgd_step(int64_t n, float *p, const float *g, float *vel, float
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm over the node dimension, training statistics (nn::BatchNorm::forward, src/nn.cpp:301-330):
+ *   mean_c = sum_r x[r,c] / N                        x->mean(-2,true): ascending fp32 sum (functional.h:266-307)
+ *   var_c  = sum_r (x[r,c]-mean_c)^2 / max(0, N-0)   x->var(-2, 0, true): two passes, std::pow(.,2) (functional.h:383-387)
+ *   y      = (x - mean) / pow(var + eps, 0.5) * gamma + beta     (nn.cpp:314-318), optional ReLU (nn.cpp:229-237)
+ * order=1: fp64 statistics.  mean/var are returned for the backward.
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API void orc_batchnorm_fwd(int64_t N, int32_t F, const float *X, int64_t ldx, const float *gamma, const float *beta,
+                               float eps, int relu, float *Y, int64_t ldy, float *mean, float *var, int order) {
+    for (int32_t c = 0; c < F; c++) {
+        if (order == 0) {
+            float s = 0.0f;
+            for (int64_t r = 0; r < N; r++) s = s + X[r * ldx + c];
+            const float m = s / (float)N;
+            float q = 0.0f;
+            for (int64_t r = 0; r < N; r++) { float d = X[r * ldx + c] - m; q = q + powf(d, 2.0f); }
+            mean[c] = m;
+            var[c] = q / (float)(N > 0 ? N : 0);
+        } else {
+            double s = 0.0;
+            for (int64_t r = 0; r < N; r++) s += X[r * ldx + c];
+            const double m = s / (double)N;
+            double q = 0.0;
+            for (int64_t r = 0; r < N; r++) { double d = X[r * ldx + c] - m; q += d * d; }
+            mean[c] = (float)m;
+            var[c] = (float)(q / (double)N);
+        }
+    }
+    for (int64_t r = 0; r < N; r++)
+        for (int32_t c = 0; c < F; c++) {
+            float v = (X[r * ldx + c] - mean[c]) / powf(var[c] + eps, 0.5f);
+            v = v * gamma[c];
+            if (beta) v = v + beta[c];
+            if (relu) v = v > 0.0f ? v : 0.0f;
+            Y[r * ldy + c] = v;
+        }
+}
+
+/* Gradient of y = relu?(BN(x)) w.r.t. x, gamma, beta — the standard batch-norm backward (the reference's autograd
+ * loses the fan-out contributions of x here, bug B2: parity unpinned in the reference, pinned against torch autograd in
+ * tests/test_oracle_vs_reference.py).  Yout = the forward output (ReLU mask), may be NULL when relu == 0. */
+ORC_API void orc_batchnorm_bwd(int64_t N, int32_t F, const float *X, int64_t ldx, const float *mean, const float *var,
+                               const float *gamma, float eps, int relu, const float *Yout, int64_t ldy, const float *dY,
+                               int64_t ldd, float *dX, int64_t ldo, float *dgamma, float *dbeta) {
+    for (int32_t c = 0; c < F; c++) {
+        const double istd = 1.0 / sqrt((double)var[c] + (double)eps);
+        double sg = 0.0, sgx = 0.0;
+        for (int64_t r = 0; r < N; r++) {
+            double g = dY[r * ldd + c];
+            if (relu && !(Yout[r * ldy + c] > 0.0f)) g = 0.0;
+            const double xh = ((double)X[r * ldx + c] - (double)mean[c]) * istd;
+            sg += g;
+            sgx += g * xh;
+        }
+        if (dbeta) dbeta[c] = (float)sg;
+        if (dgamma) dgamma[c] = (float)sgx;
+        for (int64_t r = 0; r < N; r++) {
+            double g = dY[r * ldd + c];
+            if (relu && !(Yout[r * ldy + c] > 0.0f)) g = 0.0;
+            const double xh = ((double)X[r * ldx + c] - (double)mean[c]) * istd;
+            dX[r * ldo + c] = (float)((double)gamma[c] * istd * (g - sg / (double)N - xh * sgx / (double)N));
+        }
+    }
+}
+
+/* The factorised normalisation of graph::GCNConv::forward as written (src/graph.cpp:176-185) on the loop-free
+ * adjacency A0 (CSR without diagonal):  deg = rowsum(A0)+1, dinv = pow(deg,-0.5), norm = (A0 dinv) * dinv, where the
+ * matrix-vector product is the reference's descending-k fp32 dot product. */
+ORC_API void orc_aswritten_norm(int32_t N, const int64_t *rowptr, const int32_t *colidx, float *dinv, float *norm) {
+    for (int32_t r = 0; r < N; r++) dinv[r] = powf((float)(rowptr[r + 1] - rowptr[r]) + 1.0f, -0.5f);
+    for (int32_t r = 0; r < N; r++) {
+        float s = 0.0f;
+        for (int64_t k = rowptr[r + 1] - 1; k >= rowptr[r]; k--) { float t = dinv[colidx[k]] * 1.0f; s = s + t; }
+        norm[r] = s * dinv[r];
+    }
+}
+
 /* Adam with torch.optim.Adam semantics — the documented intent of nn::Adam (include/nn.h:180-188); the reference
  * body (src/nn.cpp:419-441) divides by sqrt(v)*eps and uses the parameter index as step: parity unpinned in the
  * reference, pinned against torch in tests/test_oracle_vs_reference.py.  step counts from 1. */

@@ -55,6 +55,11 @@ def lib():
         L.orc_softmax_xent_masked.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _i32p, _u8p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_argmax_correct.restype = C.c_int64
         L.orc_argmax_correct.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _i32p, C.c_void_p]
+        L.orc_batchnorm_fwd.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _f32p, C.c_void_p, C.c_float, C.c_int, _f32p,
+                                        C.c_int64, _f32p, _f32p, C.c_int]
+        L.orc_batchnorm_bwd.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _f32p, _f32p, _f32p, C.c_float, C.c_int,
+                                        C.c_void_p, C.c_int64, _f32p, C.c_int64, _f32p, C.c_int64, _f32p, _f32p]
+        L.orc_aswritten_norm.argtypes = [C.c_int32, _i64p, _i32p, _f32p, _f32p]
         L.orc_partition_ptr.argtypes = [C.c_int64, C.c_int32, _i64p]
         L.orc_partition_rows.restype = C.c_int64
         L.orc_partition_rows.argtypes = [_i64p, _i32p, C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, C.c_void_p]
@@ -226,6 +231,41 @@ def argmax_correct(Z, y, mask=None):
     Z = np.ascontiguousarray(Z, dtype=np.float32)
     m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
     return int(lib().orc_argmax_correct(Z.shape[0], Z.shape[1], Z, Z.shape[1], np.ascontiguousarray(y, dtype=np.int32), _ptr(m)))
+
+
+def batchnorm_fwd(X, gamma, beta, eps=1e-5, relu=False, order=0):
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    N, F = X.shape
+    Y = np.empty_like(X); mean = np.empty(F, np.float32); var = np.empty(F, np.float32)
+    lib().orc_batchnorm_fwd(N, F, X, F, np.ascontiguousarray(gamma, dtype=np.float32), _ptr(beta), eps, int(relu), Y, F, mean,
+                            var, order)
+    return Y, mean, var
+
+
+def batchnorm_bwd(X, mean, var, gamma, dY, eps=1e-5, relu_out=None):
+    X = np.ascontiguousarray(X, dtype=np.float32); dY = np.ascontiguousarray(dY, dtype=np.float32)
+    N, F = X.shape
+    dX = np.empty_like(X); dg = np.empty(F, np.float32); db = np.empty(F, np.float32)
+    lib().orc_batchnorm_bwd(N, F, X, F, mean, var, np.ascontiguousarray(gamma, dtype=np.float32), eps,
+                            int(relu_out is not None), _ptr(relu_out), F, dY, F, dX, F, dg, db)
+    return dX, dg, db
+
+
+def gcnconv_as_written(src, dst, N, X, W, bias, gamma, beta, eps=1e-5, order=0):
+    """graph::GCNConv::forward exactly as written (reference src/graph.cpp:170-212): loops removed, Linear (no bias) ->
+    BatchNorm (training statistics) -> ReLU, then (A0 h) * norm + bias with norm = (A0 dinv) * dinv, deg = rowsum(A0)+1.
+    Returns a dict with every intermediate (lin, bn, h, norm, Z) and the loop-free CSR."""
+    rowptr, colidx = csr_build(src, dst, N, 0)
+    lin = gemm_nt(X, W, order)
+    bn, mean, var = batchnorm_fwd(lin, gamma, beta, eps, relu=False, order=order)
+    h = np.maximum(bn, np.float32(0)).astype(np.float32)
+    dinv = np.empty(N, np.float32); norm = np.empty(N, np.float32)
+    lib().orc_aswritten_norm(N, rowptr, colidx, dinv, norm)
+    ones = np.ones(max(len(colidx), 1), np.float32)
+    agg = spmm(N, rowptr, colidx, ones, h, order)
+    Z = (agg * norm[:, None] + np.asarray(bias, np.float32)[None, :]).astype(np.float32)
+    return {"lin": lin, "bn": bn, "h": h, "mean": mean, "var": var, "dinv": dinv, "norm": norm, "Z": Z, "rowptr": rowptr,
+            "colidx": colidx}
 
 
 def partition_ptr(N, P):

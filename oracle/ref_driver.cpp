@@ -19,6 +19,7 @@
 // usage:
 //   ref_gcn structure <problem.gcnp> <out.gcno>
 //   ref_gcn step      <problem.gcnp> <out.gcno>
+//   ref_gcn aswritten <problem.gcnp> <out.gcno>      (one graph::GCNConv::forward exactly as written)
 //   ref_gcn time      <problem.gcnp> <steps>         (prints one JSON line with per-stage ms)
 #include "graph.h"
 #include "nn.h"
@@ -187,6 +188,34 @@ int run_step(const Problem &p, Writer *w, StepTimes *tm) {
     return 0;
 }
 
+// The reference's graph::GCNConv layer EXACTLY AS WRITTEN (src/graph.cpp:160-212), run through its own forward():
+//   add_self_loops(..., 0)  -> loops removed;  lin (no bias) -> BatchNorm (training statistics) -> ReLU;
+//   deg = rowsum(A0) + 1; dinv = deg^-0.5; norm = (A0 dinv) * dinv;  out = (A0 h) * norm + bias
+// Parameters injected: lin.weight = W1, conv bias = b1, BatchNorm gammas = 1 + b1/2, betas = b1/4 (so the affine part
+// is exercised).  The registered Dropout module is not called by forward().  Only the forward is a valid oracle:
+// BatchNorm uses its input several times and the reference autograd loses fan-out gradients (SURVEY.md bug B2).
+int cmd_aswritten(const Problem &p, const char *out) {
+    Writer w(out);
+    const size_t N = p.N, Fi = p.dims[0], Fo = p.dims[1];
+    auto ei = graph::vec_to_edge_list(p.src, p.dst);
+    auto *ei_raw = new tensor<int>(ei->shape(), new std::valarray<int>(*ei->data()), false); // Data keeps the raw pointer
+    auto x = make_f(p.X, {N, Fi}, false);
+    graph::GCNConv conv(Fi, Fo, 0.0f);
+    std::valarray<float> wv(p.W[0].data(), p.W[0].size()), bv(p.b[0].data(), p.b[0].size());
+    std::valarray<float> gam = 1.0f + 0.5f * bv, bet = 0.25f * bv;
+    conv.get_module("lin")->get_parameter("weight")->set_data(&wv);
+    conv.get_parameter("bias")->set_data(&bv);
+    conv.get_module("bnorm")->get_parameter("gammas")->set_data(&gam);
+    conv.get_module("bnorm")->get_parameter("betas")->set_data(&bet);
+    auto lin = (*conv.get_module("lin"))(x);
+    w.f32("aw_lin", *lin->data(), lin->shape());
+    auto bn = (*conv.get_module("bnorm"))(lin);
+    w.f32("aw_bn", *bn->data(), bn->shape());
+    auto Z = conv.forward(graph::Data(x, ei_raw));
+    w.f32("aw_Z", *Z->data(), Z->shape());
+    return 0;
+}
+
 } // namespace
 
 int main(int argc, char **argv) {
@@ -198,6 +227,7 @@ int main(int argc, char **argv) {
     Problem p = load(argv[2]);
     if (cmd == "structure") return cmd_structure(p, argv[3]);
     if (cmd == "step") { Writer w(argv[3]); return run_step(p, &w, nullptr); }
+    if (cmd == "aswritten") return cmd_aswritten(p, argv[3]);
     if (cmd == "time") {
         int steps = atoi(argv[3]);
         StepTimes tm;

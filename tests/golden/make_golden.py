@@ -60,6 +60,22 @@ def run(prob, name, step=True, structure=True, subsample=None):
     print(name, {k: v.shape for k, v in res.items()})
 
 
+def run_aswritten(prob, name, subsample=256):
+    """one graph::GCNConv::forward exactly as written (ref_gcn aswritten): lin / BatchNorm / layer output"""
+    with tempfile.TemporaryDirectory() as td:
+        pin = os.path.join(td, "p.gcnp")
+        problem_io.write_problem(pin, prob)
+        subprocess.check_call([REF, "aswritten", pin, os.path.join(td, "o.gcno")])
+        res = problem_io.read_results(os.path.join(td, "o.gcno"))
+    n = res["aw_Z"].shape[0]
+    if n > subsample:
+        rows = np.arange(0, n, n // subsample, dtype=np.int64)
+        res = {k: v[rows].copy() for k, v in res.items()}
+        res["rows"] = rows
+    np.savez_compressed(os.path.join(OUT, "aswritten_" + name + ".npz"), **res)
+    print("aswritten", name, {k: v.shape for k, v in res.items()})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pubmed", action="store_true")
@@ -76,8 +92,11 @@ def main():
     }
     if a.pubmed:
         jobs["pubmed"] = lambda: run(synth.make_problem(synth.CONFIGS["pubmed"]), "pubmed", structure=False, subsample=512)
+    for k in ("toy", "tiny", "directed", "tiny_pl", "cora"):
+        prob = directed_problem() if k == "directed" else synth.make_problem(synth.CONFIGS[k])
+        jobs["aswritten_" + k] = (lambda prob=prob, k=k: run_aswritten(prob, k))
     for k, fn in jobs.items():
-        if a.only is None or a.only == k:
+        if a.only is None or a.only == k or (a.only == "aswritten" and k.startswith("aswritten_")):
             fn()
 
 

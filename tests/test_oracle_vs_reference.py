@@ -6,7 +6,9 @@ The restatement follows the reference's accumulation order, so everything is req
 import numpy as np
 import pytest
 
-from conftest import load_golden, load_problem
+import os
+
+from conftest import GOLDEN, load_golden, load_problem
 
 SMALL = ["toy", "tiny", "directed", "tiny_pl", "cora"]
 
@@ -168,3 +170,45 @@ def test_masked_loss_and_accuracy_match_torch(oracle):
     # with an all-true mask it is the plain loss of the restatement
     full, _ = oracle.softmax_xent(Z, y, order=1)
     assert abs(oracle.softmax_xent_masked(Z, y, np.ones(N, bool))[0] - full) <= 1e-6 * abs(full)
+
+
+AW_TOL = 5e-6   # the as-written layer is pinned to the real reference within this (valarray-internal summation order)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_gcnconv_as_written_matches_reference(oracle, name):
+    """SURVEY §8f row 1: graph::GCNConv::forward exactly as written (loops removed, Linear -> BatchNorm -> ReLU,
+    factorised norm, bias) restated from primitives vs outputs of the REAL reference (`ref_gcn aswritten`)."""
+    p = load_problem(name)
+    g = np.load(os.path.join(GOLDEN, "aswritten_%s.npz" % name))
+    b = p.b[0]
+    o = oracle.gcnconv_as_written(p.src, p.dst, p.cfg.N, p.X, p.W[0], b, 1 + 0.5 * b, 0.25 * b, order=0)
+    rows = g["rows"] if "rows" in g.files else slice(None)
+    assert np.array_equal(o["lin"][rows], g["aw_lin"])
+    for k, ko in [("aw_bn", "bn"), ("aw_Z", "Z")]:
+        assert np.abs(o[ko][rows] - g[k]).max() <= AW_TOL * np.abs(g[k]).max(), k
+    o1 = oracle.gcnconv_as_written(p.src, p.dst, p.cfg.N, p.X, p.W[0], b, 1 + 0.5 * b, 0.25 * b, order=1)
+    assert np.abs(o1["Z"][rows] - g["aw_Z"]).max() <= 1e-5 * np.abs(g["aw_Z"]).max()
+
+
+def test_batchnorm_backward_matches_torch(oracle):
+    """the reference autograd loses BatchNorm's fan-out gradients (bug B2); the restated backward is pinned to torch"""
+    import torch
+    rng = np.random.default_rng(4)
+    N, F = 300, 9
+    X = rng.standard_normal((N, F)).astype(np.float32) * 2 + 1
+    gamma = rng.uniform(0.5, 1.5, F).astype(np.float32); beta = rng.uniform(-0.5, 0.5, F).astype(np.float32)
+    dY = rng.standard_normal((N, F)).astype(np.float32)
+    for relu in (False, True):
+        Y, mean, var = oracle.batchnorm_fwd(X, gamma, beta, relu=relu, order=1)
+        xt = torch.tensor(X, dtype=torch.float64, requires_grad=True)
+        gt = torch.tensor(gamma, dtype=torch.float64, requires_grad=True); bt = torch.tensor(beta, dtype=torch.float64, requires_grad=True)
+        yt = torch.nn.functional.batch_norm(xt, None, None, gt, bt, training=True, eps=1e-5)
+        if relu:
+            yt = torch.relu(yt)
+        np.testing.assert_allclose(Y, yt.detach().numpy(), rtol=2e-5, atol=2e-6)
+        yt.backward(torch.tensor(dY, dtype=torch.float64))
+        dX, dg, db = oracle.batchnorm_bwd(X, mean, var, gamma, dY, relu_out=Y if relu else None)
+        np.testing.assert_allclose(dX, xt.grad.numpy(), rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(dg, gt.grad.numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(db, bt.grad.numpy(), rtol=1e-5, atol=1e-5)
