@@ -35,6 +35,7 @@ SIGNATURES = {
     "gnn_graph_from_csr": (C.c_int, [vp, i32, i32, vp, vp, vp, pp]),
     "gnn_graph_build_csc": (C.c_int, [vp, vp]),
     "gnn_graph_normalize": (C.c_int, [vp, vp]),
+    "gnn_graph_normalize_as_written": (C.c_int, [vp, vp, vp]),
     "gnn_graph_destroy": (C.c_int, [vp, vp]),
     "gnn_graph_nnz": (i64, [vp]),
     "gnn_graph_rows": (i32, [vp]),
@@ -54,6 +55,8 @@ SIGNATURES = {
     "gnn_bias_grad": (C.c_int, [vp, i64, i32, vp, i64, vp]),
     "gnn_softmax_xent": (C.c_int, [vp, i64, i32, vp, i64, vp, i64, vp, vp, i64]),
     "gnn_sgd_step": (C.c_int, [vp, i64, vp, vp, vp, f32, f32, f32, f32, C.c_int, C.c_int]),
+    "gnn_batchnorm_fwd": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, f32, C.c_int, vp, i64, vp, vp]),
+    "gnn_batchnorm_bwd": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, vp, f32, vp, i64, vp, i64, vp, i64, vp, vp]),
     "gnn_adam_step": (C.c_int, [vp, i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, i64]),
     "gnn_softmax_xent_masked": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, i64, vp, vp, i64]),
     "gnn_argmax_correct": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, vp]),

@@ -444,6 +444,102 @@ int copy2d(gnn_ctx *ctx, float *dst, int64_t ldd, const float *src, int64_t lds,
     return 0;
 }
 
+// ---- BatchNorm over the node dimension (nn::BatchNorm, reference src/nn.cpp:285-330) ----------------------------
+// column statistics: block b reduces rows [b*rows_per_block, ...) of up to three per-column quantities
+//   MODE 0: sum x                                   (mean)
+//   MODE 1: sum (x - mean)^2                        (two-pass variance like functional::var, functional.h:383-387)
+//   MODE 2: sum g and sum g * xhat, g = dY masked by the forward output (backward reductions)
+template <int MODE>
+__global__ void __launch_bounds__(CS_THREADS)
+    bn_partial_kernel(int64_t N, int32_t F, const float *__restrict__ X, int64_t ldx, const float *__restrict__ mean,
+                      const float *__restrict__ var, float eps, const float *__restrict__ dY, int64_t ldd,
+                      const float *__restrict__ Yout, int64_t ldy, int64_t rows_per_block, float *__restrict__ partial) {
+    __shared__ float red[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(N, r0 + rows_per_block);
+    for (int32_t c0 = 0; c0 < F; c0 += 32) {
+        const int32_t c = c0 + tx;
+        float s0 = 0.f, s1 = 0.f;
+        if (c < F) {
+            const float m = MODE >= 1 ? mean[c] : 0.f;
+            const float istd = MODE == 2 ? rsqrtf(var[c] + eps) : 0.f;
+            for (int64_t r = r0 + ty; r < r1; r += 8) {
+                const float x = X[r * ldx + c];
+                if (MODE == 0) s0 += x;
+                else if (MODE == 1) s0 += (x - m) * (x - m);
+                else {
+                    float g = dY[r * ldd + c];
+                    if (Yout && !(Yout[r * ldy + c] > 0.f)) g = 0.f;
+                    s0 += g;
+                    s1 += g * ((x - m) * istd);
+                }
+            }
+        }
+        red[0][ty][tx] = s0;
+        red[1][ty][tx] = s1;
+        __syncthreads();
+        if (ty == 0 && c < F) {
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { t0 += red[0][j][tx]; t1 += red[1][j][tx]; }
+            partial[(int64_t)blockIdx.x * 2 * F + c] = t0;
+            partial[(int64_t)blockIdx.x * 2 * F + F + c] = t1;
+        }
+        __syncthreads();
+    }
+}
+// out[c] = scale * sum_b partial[b][which][c]   (fixed block order)
+__global__ void bn_final_kernel(int32_t F, int nblocks, const float *__restrict__ partial, int which, float scale,
+                                float *__restrict__ out) {
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= F) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; b++) s += partial[(int64_t)b * 2 * F + which * F + c];
+    out[c] = s * scale;
+}
+__global__ void bn_apply_kernel(int64_t N, int32_t F, const float *__restrict__ X, int64_t ldx, const float *__restrict__ mean,
+                                const float *__restrict__ var, float eps, const float *__restrict__ gamma,
+                                const float *__restrict__ beta, int relu, float *__restrict__ Y, int64_t ldy) {
+    const int64_t total = N * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / F;
+        const int32_t c = (int32_t)(i - r * F);
+        float v = (X[r * ldx + c] - mean[c]) / sqrtf(var[c] + eps);
+        v = v * gamma[c];
+        if (beta) v += beta[c];
+        if (relu) v = v > 0.f ? v : 0.f;
+        Y[r * ldy + c] = v;
+    }
+}
+// dX = gamma * istd * (g - mean(g) - xhat * mean(g xhat))
+__global__ void bn_bwd_apply_kernel(int64_t N, int32_t F, const float *__restrict__ X, int64_t ldx,
+                                    const float *__restrict__ mean, const float *__restrict__ var, float eps,
+                                    const float *__restrict__ gamma, const float *__restrict__ dY, int64_t ldd,
+                                    const float *__restrict__ Yout, int64_t ldy, const float *__restrict__ sum_g,
+                                    const float *__restrict__ sum_gx, float *__restrict__ dX, int64_t ldo) {
+    const int64_t total = N * F;
+    const float inv_n = 1.f / (float)N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / F;
+        const int32_t c = (int32_t)(i - r * F);
+        const float istd = rsqrtf(var[c] + eps);
+        float g = dY[r * ldd + c];
+        if (Yout && !(Yout[r * ldy + c] > 0.f)) g = 0.f;
+        const float xh = (X[r * ldx + c] - mean[c]) * istd;
+        dX[r * ldo + c] = gamma[c] * istd * (g - sum_g[c] * inv_n - xh * sum_gx[c] * inv_n);
+    }
+}
+
+static int bn_blocks(gnn_ctx *ctx, int64_t N, int64_t *rows_per_block) {
+    int64_t nblocks = (int64_t)ctx->sm_count * 4;
+    int64_t rpb = ceil_div(N, nblocks);
+    if (rpb < 64) rpb = 64;
+    rpb = round_up(rpb, 8);
+    *rows_per_block = rpb;
+    return (int)ceil_div(N, rpb);
+}
+
 int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out) {
     int64_t nblocks = (int64_t)ctx->sm_count * 4;
     int64_t rows_per_block = ceil_div(N, nblocks);
@@ -564,6 +660,48 @@ int gnn_sgd_step(gnn_ctx_t *ctx, int64_t n, float *p, const float *g, float *vel
     GNN_REQUIRE(momentum == 0.f || vel, "gnn_sgd_step: momentum needs a velocity buffer");
     sgd_kernel<<<stream_grid(ctx, n, 256, 1), 256, 0, ctx->stream>>>(n, p, g, vel, lr, momentum, dampening, weight_decay,
                                                                    nesterov, first);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_batchnorm_fwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *X, int64_t ldx, const float *gamma,
+                      const float *beta, float eps, int relu, float *Y, int64_t ldy, float *mean, float *var) {
+    GNN_REQUIRE(ctx && X && gamma && Y && mean && var && N > 0 && F > 0 && ldx >= F && ldy >= F, "gnn_batchnorm_fwd: bad argument");
+    int64_t rpb = 0;
+    const int nb = bn_blocks(ctx, N, &rpb);
+    void *ws = nullptr;
+    GNN_TRY(ctx->workspace((size_t)nb * 2 * F * 4, &ws));
+    float *part = (float *)ws;
+    bn_partial_kernel<0><<<nb, CS_THREADS, 0, ctx->stream>>>(N, F, X, ldx, nullptr, nullptr, eps, nullptr, 0, nullptr, 0, rpb, part);
+    GNN_LAUNCHED(ctx);
+    bn_final_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, ctx->stream>>>(F, nb, part, 0, 1.0f / (float)N, mean);
+    GNN_LAUNCHED(ctx);
+    bn_partial_kernel<1><<<nb, CS_THREADS, 0, ctx->stream>>>(N, F, X, ldx, mean, nullptr, eps, nullptr, 0, nullptr, 0, rpb, part);
+    GNN_LAUNCHED(ctx);
+    bn_final_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, ctx->stream>>>(F, nb, part, 0, 1.0f / (float)N, var);
+    GNN_LAUNCHED(ctx);
+    bn_apply_kernel<<<stream_grid(ctx, N * F, 256), 256, 0, ctx->stream>>>(N, F, X, ldx, mean, var, eps, gamma, beta, relu, Y, ldy);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_batchnorm_bwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *X, int64_t ldx, const float *mean, const float *var,
+                      const float *gamma, float eps, const float *relu_out, int64_t ldy, const float *dY, int64_t ldd,
+                      float *dX, int64_t ldo, float *dgamma, float *dbeta) {
+    GNN_REQUIRE(ctx && X && mean && var && gamma && dY && dX && dgamma && dbeta && N > 0 && F > 0, "gnn_batchnorm_bwd: bad argument");
+    int64_t rpb = 0;
+    const int nb = bn_blocks(ctx, N, &rpb);
+    void *ws = nullptr;
+    GNN_TRY(ctx->workspace((size_t)nb * 2 * F * 4, &ws));
+    float *part = (float *)ws;
+    bn_partial_kernel<2><<<nb, CS_THREADS, 0, ctx->stream>>>(N, F, X, ldx, mean, var, eps, dY, ldd, relu_out, ldy, rpb, part);
+    GNN_LAUNCHED(ctx);
+    bn_final_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, ctx->stream>>>(F, nb, part, 0, 1.0f, dbeta);
+    GNN_LAUNCHED(ctx);
+    bn_final_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, ctx->stream>>>(F, nb, part, 1, 1.0f, dgamma);
+    GNN_LAUNCHED(ctx);
+    bn_bwd_apply_kernel<<<stream_grid(ctx, N * F, 256), 256, 0, ctx->stream>>>(N, F, X, ldx, mean, var, eps, gamma, dY, ldd,
+                                                                              relu_out, ldy, dbeta, dgamma, dX, ldo);
     GNN_LAUNCHED(ctx);
     return 0;
 }

@@ -131,6 +131,41 @@ __global__ void edge_val_kernel(const int32_t *__restrict__ rowptr, const int32_
     for (int32_t k = b + lane; k < e; k += 32) val[k] = dr * dinv[colidx[k]];
 }
 
+// graph::GCNConv::forward as written (reference src/graph.cpp:176-185) on the loop-free adjacency A0:
+//   dinv = (rowsum(A0) + 1)^-1/2 ;  norm[r] = dinv[r] * sum_{c in row r} dinv[c]     (one warp per row, fixed order)
+__global__ void aswritten_dinv_kernel(const int32_t *__restrict__ rowptr, int32_t n, int32_t *__restrict__ deg,
+                                      float *__restrict__ dinv) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int32_t d = rowptr[r + 1] - rowptr[r] + 1;
+    deg[r] = d;
+    dinv[r] = (float)(1.0 / sqrt((double)d));
+}
+__global__ void aswritten_norm_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                      const float *__restrict__ dinv, int32_t n_rows, float *__restrict__ norm) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    float s = 0.f;
+    for (int32_t k = rowptr[w] + lane; k < rowptr[w + 1]; k += 32) s += dinv[colidx[k]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) norm[w] = s * dinv[w];
+}
+// val[k] = norm[row(k)] (forward: (A0 h) * norm) ; valT in CSR order for the aliased transpose: norm[colidx[k]]
+__global__ void aswritten_val_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                     const float *__restrict__ norm, int32_t n_rows, float *__restrict__ val,
+                                     float *__restrict__ valT_alias) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    const float nr = norm[w];
+    for (int32_t k = rowptr[w] + lane; k < rowptr[w + 1]; k += 32) {
+        val[k] = nr;
+        if (valT_alias) valT_alias[k] = norm[colidx[k]];
+    }
+}
+
 __global__ void gather_f32_kernel(const float *__restrict__ src, const int32_t *__restrict__ idx, int64_t n,
                                   float *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -379,6 +414,36 @@ int gnn_graph_normalize(gnn_ctx_t *ctx, gnn_graph_t *g) {
         gather_f32_kernel<<<grid_for(g->nnz, 256), 256, 0, s>>>(g->val, g->perm, g->nnz, g->valT);
         GNN_LAUNCHED(ctx);
     }
+    return 0;
+}
+
+int gnn_graph_normalize_as_written(gnn_ctx_t *ctx, gnn_graph_t *g, float *norm_out) {
+    GNN_REQUIRE(ctx && g, "gnn_graph_normalize_as_written: NULL argument");
+    GNN_REQUIRE(g->n_rows == g->n_cols, "gnn_graph_normalize_as_written: needs the square (global) graph");
+    GNN_REQUIRE(g->fill_mode == 0, "gnn_graph_normalize_as_written: build the graph with fill_mode 0 (add_self_loops(.., 0))");
+    cudaStream_t s = ctx->stream;
+    const int64_t nnz = g->nnz ? g->nnz : 1;
+    if (!g->deg) GNN_CHECK_CUDA(cudaMalloc((void **)&g->deg, (size_t)g->n_rows * 4));
+    if (!g->dinv) GNN_CHECK_CUDA(cudaMalloc((void **)&g->dinv, (size_t)g->n_rows * 4));
+    if (!g->val) GNN_CHECK_CUDA(cudaMalloc((void **)&g->val, (size_t)nnz * 4));
+    if (g->colptr && !g->valT) GNN_CHECK_CUDA(cudaMalloc((void **)&g->valT, (size_t)nnz * 4));
+    float *norm = nullptr;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&norm, (size_t)g->n_rows * 4, s));
+    aswritten_dinv_kernel<<<grid_for(g->n_rows, 256), 256, 0, s>>>(g->rowptr, g->n_rows, g->deg, g->dinv);
+    GNN_LAUNCHED(ctx);
+    aswritten_norm_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, s>>>(g->rowptr, g->colidx, g->dinv, g->n_rows, norm);
+    GNN_LAUNCHED(ctx);
+    // the values are constant along a row, so the transpose differs from the matrix even when the structure is
+    // symmetric: the aliased (CSR-as-CSC) backward gets its own value array in CSR order
+    aswritten_val_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, s>>>(g->rowptr, g->colidx, norm, g->n_rows, g->val,
+                                                                            (g->colptr && g->symmetric) ? g->valT : nullptr);
+    GNN_LAUNCHED(ctx);
+    if (g->colptr && !g->symmetric) {
+        gather_f32_kernel<<<grid_for(g->nnz, 256), 256, 0, s>>>(g->val, g->perm, g->nnz, g->valT);
+        GNN_LAUNCHED(ctx);
+    }
+    if (norm_out) GNN_CHECK_CUDA(cudaMemcpyAsync(norm_out, norm, (size_t)g->n_rows * 4, cudaMemcpyDeviceToDevice, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(norm, s));
     return 0;
 }
 

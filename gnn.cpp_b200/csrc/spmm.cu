@@ -431,7 +431,7 @@ int spmm_rows_range(gnn_ctx *ctx, const gnn_graph *g, int transpose, int32_t r0,
     const bool alias = transpose && g->symmetric;
     const int32_t *ptr = (!transpose || alias) ? g->rowptr : g->colptr;
     const int32_t *idx = (!transpose || alias) ? g->colidx : g->rowidx;
-    const float *val = (!transpose || alias) ? g->val : g->valT;
+    const float *val = !transpose ? g->val : (alias ? (g->valT ? g->valT : g->val) : g->valT);
     const int32_t mn = (!transpose || alias) ? g->min_row_nnz : g->min_col_nnz;
     const int32_t mx = (!transpose || alias) ? g->max_row_nnz : g->max_col_nnz;
     return spmm_launch(ctx, r1 - r0, k0, k1, ptr + r0, idx, val, mn, mx, P, ldp, F, Y, ldy, bias, relu, mask, ldm);
@@ -475,7 +475,7 @@ int gnn_spmm_bwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *dZ, int64_t 
     const bool alias = g->symmetric; // A_hat^T == A_hat structurally and in value: reuse the CSR arrays
     const float *v = nullptr;
     if (use_values) {
-        v = alias ? g->val : g->valT;
+        v = alias ? (g->valT ? g->valT : g->val) : g->valT; // as-written normalisation keeps a transposed value array
         GNN_REQUIRE(v, "gnn_spmm_bwd: edge values not built (call gnn_graph_normalize after gnn_graph_build_csc)");
     }
     return spmm_launch(ctx, g->t_rows, 0, alias ? g->nnz : g->nnz_t, alias ? g->rowptr : g->colptr,

@@ -137,6 +137,12 @@ class Graph:
         capi.call("gnn_graph_to_dense", self.ctx.h, self.h, int(weighted), _ptr(out), self.n_cols)
         return out
 
+    def normalize_as_written(self):
+        """graph::GCNConv::forward's factorised normalisation (graph built with fill_mode=0); returns norm[N]."""
+        norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.ctx.device)
+        capi.call("gnn_graph_normalize_as_written", self.ctx.h, self.h, _ptr(norm))
+        return norm
+
     def spmm_fwd(self, P, bias=None, relu=False, mask=None, use_values=True, out=None):
         n, F = self.n_rows, P.shape[1]
         Y = out if out is not None else torch.empty((n, F), dtype=torch.float32, device=P.device)
@@ -216,6 +222,24 @@ def softmax_xent(ctx, Z, y, n_total=0, want_grad=True):
 def sgd_step(ctx, p, g, vel=None, lr=0.01, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, first=True):
     capi.call("gnn_sgd_step", ctx.h, p.numel(), _ptr(p), _ptr(g), _ptr(vel), lr, momentum, dampening, weight_decay,
               int(nesterov), int(first))
+
+
+def batchnorm_fwd(ctx, X, gamma, beta=None, eps=1e-5, relu=False):
+    N, F = X.shape
+    Y = torch.empty((N, F), dtype=torch.float32, device=X.device)
+    mean = torch.empty(F, dtype=torch.float32, device=X.device); var = torch.empty(F, dtype=torch.float32, device=X.device)
+    capi.call("gnn_batchnorm_fwd", ctx.h, N, F, _ptr(X), X.stride(0), _ptr(gamma), _ptr(beta), eps, int(relu), _ptr(Y), F,
+              _ptr(mean), _ptr(var))
+    return Y, mean, var
+
+
+def batchnorm_bwd(ctx, X, mean, var, gamma, dY, eps=1e-5, relu_out=None):
+    N, F = X.shape
+    dX = torch.empty((N, F), dtype=torch.float32, device=X.device)
+    dg = torch.empty(F, dtype=torch.float32, device=X.device); db = torch.empty(F, dtype=torch.float32, device=X.device)
+    capi.call("gnn_batchnorm_bwd", ctx.h, N, F, _ptr(X), X.stride(0), _ptr(mean), _ptr(var), _ptr(gamma), eps, _ptr(relu_out),
+              relu_out.stride(0) if relu_out is not None else 0, _ptr(dY), dY.stride(0), _ptr(dX), F, _ptr(dg), _ptr(db))
+    return dX, dg, db
 
 
 def adam_step(ctx, p, g, m, v, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1):

@@ -84,6 +84,12 @@ GNN_API int gnn_graph_build_csc(gnn_ctx_t *ctx, gnn_graph_t *g);
  * val[r,c] = dinv[r]*dinv[c] (mode-B composition of functional::mul, include/functional.h:189-213);
  * also valT when the CSC exists. */
 GNN_API int gnn_graph_normalize(gnn_ctx_t *ctx, gnn_graph_t *g);
+/* Normalisation of graph::GCNConv::forward AS WRITTEN (reference src/graph.cpp:176-185) for a graph built with
+ * fill_mode 0 (its add_self_loops(.., 0) removes the loops): deg = rowsum(A0)+1, dinv = deg^-1/2,
+ * norm = (A0 dinv) * dinv, and the stored values become val[r,c] = norm[r], so that gnn_spmm_fwd(use_values=1) computes
+ * aggregate_and_update's (A0 h) * norm (src/graph.cpp:204-212) and gnn_spmm_bwd its transpose.  norm_out: optional
+ * device float[N]. */
+GNN_API int gnn_graph_normalize_as_written(gnn_ctx_t *ctx, gnn_graph_t *g, float *norm_out);
 GNN_API int gnn_graph_destroy(gnn_ctx_t *ctx, gnn_graph_t *g);
 GNN_API int64_t gnn_graph_nnz(const gnn_graph_t *g);
 GNN_API int32_t gnn_graph_rows(const gnn_graph_t *g);
@@ -155,6 +161,17 @@ GNN_API int gnn_softmax_xent(gnn_ctx_t *ctx, int64_t N, int32_t C, const float *
 GNN_API int gnn_sgd_step(gnn_ctx_t *ctx, int64_t n, float *p, const float *g, float *vel, float lr, float momentum,
                          float dampening, float weight_decay, int nesterov, int first);
 
+/* nn::BatchNorm over the node dimension with training statistics (reference src/nn.cpp:301-330): per feature
+ * mean = sum x / N, var = sum (x-mean)^2 / N (two passes, functional::var with correction 0),
+ * Y = (X - mean) / sqrt(var + eps) * gamma (+ beta) (ReLU optional: GCNConv applies nn::ReLU right after).
+ * mean/var (device float[F]) are outputs, kept by the caller for the backward and the running statistics.
+ * Backward: the standard batch-norm gradient with the ReLU mask taken from relu_out (the forward output; NULL = no
+ * ReLU); dgamma/dbeta are device float[F].  (The reference's own autograd loses fan-out gradients here, bug B2.) */
+GNN_API int gnn_batchnorm_fwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *X, int64_t ldx, const float *gamma,
+                              const float *beta, float eps, int relu, float *Y, int64_t ldy, float *mean, float *var);
+GNN_API int gnn_batchnorm_bwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *X, int64_t ldx, const float *mean,
+                              const float *var, const float *gamma, float eps, const float *relu_out, int64_t ldy,
+                              const float *dY, int64_t ldd, float *dX, int64_t ldo, float *dgamma, float *dbeta);
 /* torch.optim.Adam semantics — the intent of nn::Adam (include/nn.h:180-188); the reference body (src/nn.cpp:419-441)
  * divides by sqrt(v)*eps and uses the parameter index as step count.  m, v: first/second moment buffers (zeroed by
  * the caller before step 1); step counts from 1. */
