@@ -115,6 +115,7 @@ void Data::set_edge_index(tensor<int> *edge_index, tptr<float> edge_attr) {
     _edge_attr = edge_attr;
     _num_edges = edge_index ? edge_index->shape()[1] : 0;
     _structure.reset();
+    _structure_as_written.reset();
 }
 tptr<float> Data::to_adj() {
     if (_edge_index == nullptr) throw std::runtime_error("pls provide adj matr or edge");
@@ -132,6 +133,15 @@ device::graph_ptr Data::structure() const {
     if (_edge_index == nullptr) throw std::runtime_error("pls provide adj matr or edge");
     if (!_structure) _structure = build_structure(*_edge_index, _num_nodes, /*fill_mode=*/1, /*normalize=*/true);
     return _structure;
+}
+
+device::graph_ptr Data::structure_as_written() const {
+    if (_edge_index == nullptr) throw std::runtime_error("pls provide adj matr or edge");
+    if (!_structure_as_written) {
+        _structure_as_written = build_structure(*_edge_index, _num_nodes, /*fill_mode=*/0, /*normalize=*/false);
+        device::check(gnn_graph_normalize_as_written(device::ctx(), _structure_as_written->g, nullptr));
+    }
+    return _structure_as_written;
 }
 
 tptr<float> MessagePassing::propagate(const tensor<int> &edge_index, const tptr<float> &x, const tptr<float> *norm) {
@@ -165,6 +175,24 @@ tptr<float> GCNConv::forward(Data &&input) {
     auto out = agg->forward(structure, P, b, _fused_relu);
     if (out->requires_grad()) out->grad_fn = std::move(agg);
     return out;
+}
+
+GCNConvAsWritten::GCNConvAsWritten(size_t in_channels, size_t out_channels, float dropout)
+    : MessagePassing(), _in_channels(in_channels), _out_channels(out_channels), _dropout(dropout) {
+    register_module("lin", new nn::Linear(in_channels, out_channels, false));
+    register_module("bnorm", new nn::BatchNorm(out_channels));
+    register_module("relu", new nn::ReLU());
+    register_parameter("bias", std::make_shared<tensor<float>>(std::vector<size_t>{out_channels}, 0.0f, true));
+}
+
+tptr<float> GCNConvAsWritten::forward(Data &&input) {
+    auto structure = input.structure_as_written();
+    auto out = (*get_module("lin"))(input.x());
+    out = std::static_pointer_cast<nn::BatchNorm>(get_module("bnorm"))->forward_relu(out, true); // bnorm + relu, one kernel
+    auto agg = std::make_unique<SpMM<tensor<float>>>();
+    auto Z = agg->forward(structure, out, _parameters["bias"], false); // (A0 h) * norm + bias: values hold norm[row]
+    if (Z->requires_grad()) Z->grad_fn = std::move(agg);
+    return Z;
 }
 
 tptr<float> GCNConv::propagate(const tensor<int> &edge_index, const tptr<float> &x, const tptr<float> *others) {

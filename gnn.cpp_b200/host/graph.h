@@ -64,7 +64,11 @@ class Data {
     cyg::tensor<int> *_edge_index = nullptr;
     cyg::tensor<float> *_y = nullptr;
     cyg::tptr<float> _x, _edge_attr;
-    mutable cyg::device::graph_ptr _structure;
+    mutable cyg::device::graph_ptr _structure, _structure_as_written;
+  public:
+    /** loop-free structure with the factorised normalisation of the reference's GCNConv::forward as written
+     *  (values norm[row], graph.cpp:172-185), cached like structure() */
+    cyg::device::graph_ptr structure_as_written() const;
 };
 
 class MessagePassing : public nn::Module { // reference graph.h:110-120
@@ -93,6 +97,18 @@ class GCNConv : public MessagePassing {
     size_t _in_channels, _out_channels;
     float _dropout;
     bool _fused_relu;
+};
+
+/** graph::GCNConv EXACTLY AS WRITTEN in the reference (graph.cpp:160-212): self loops removed, Linear without bias ->
+ *  BatchNorm (training statistics) -> ReLU, then (A0 h) * norm + bias with deg = rowsum(A0)+1, norm = (A0 dinv) * dinv.
+ *  Same registered children as the reference ("lin", "bnorm", "drop", "relu", parameter "bias"); like the reference's
+ *  forward, the Dropout child is registered but not applied.  The north-star layer is graph::GCNConv above. */
+class GCNConvAsWritten : public MessagePassing {
+  public:
+    GCNConvAsWritten(size_t in_channels, size_t out_channels, float dropout = 0.0);
+    cyg::tptr<float> forward(Data &&input) override;
+    size_t _in_channels, _out_channels;
+    float _dropout;
 };
 
 } // namespace graph

@@ -255,6 +255,58 @@ static void check_gcn_against_dense(size_t in, size_t out_ch) {
     CHECK(all_close(db, *b2->grad(), 2e-5f));
 }
 
+// graph::GCNConv exactly as written in the reference (graph.cpp:160-212) vs the same layer composed from dense tensor
+// ops, gradients included (the composed graph exercises the fan-out accumulation the reference loses, bug B2)
+static void check_gcn_as_written_against_dense() {
+    seed_rng(23);
+    const size_t N = 40, in = 9, out_ch = 6;
+    std::vector<int> src, dst;
+    for (size_t i = 0; i < N; i++)
+        for (size_t j : {(i * 7 + 3) % N, (i * 13 + 5) % N, i}) { src.push_back((int)i); dst.push_back((int)j); src.push_back((int)j); dst.push_back((int)i); }
+    auto ei = vec_to_edge_list(src, dst);
+    auto x = randn<float>({N, in}, -1.0f, 1.0f, false);
+    Data data(x, ei.get());
+    GCNConvAsWritten conv(in, out_ch);
+    auto W = conv.get_module("lin")->_parameters["weight"];
+    auto b = conv._parameters["bias"];
+    auto bn = conv.get_module("bnorm");
+    auto gam = bn->_parameters["gammas"], bet = bn->_parameters["betas"];
+    b->uniform(-0.5f, 0.5f);
+    gam->uniform(0.5f, 1.5f);
+    bet->uniform(-0.3f, 0.3f);
+    auto Z = conv.forward(data.with_x(x));
+    auto G = randn<float>({N, out_ch}, -1.0f, 1.0f, false);
+    Z->backward(G);
+    std::valarray<float> dW = *W->grad(), db = *b->grad(), dgam = *gam->grad(), dbet = *bet->grad();
+    // dense composition with the reference's formulas
+    auto A = edge_to_adj_mat(*ei, nullptr, N);
+    A->fill_diagonal_(0); // add_self_loops(.., 0) removes the loops (graph.cpp:172)
+    auto deg = A->sum(-1, true) + 1.0f;
+    cyg::tensor<float> mhalf(std::vector<size_t>{1}, -0.5f, false);
+    auto dinv = functional::pow(*deg, mhalf);
+    auto norm = A->mm(dinv) * dinv;
+    auto W2 = W->clone(true), b2 = b->clone(true), g2 = gam->clone(true), be2 = bet->clone(true);
+    auto lin = x->mm(W2->t());
+    auto mean = lin->mean(-2, true);
+    auto cen = lin - mean;
+    auto var = (cen * cen)->mean(-2, true);
+    auto stdv = ((var + 1e-5f)->log() * 0.5f)->exp();
+    auto y = (cen / stdv) * g2 + be2;
+    auto h = y->where(y > 0.0f, 0.0f);
+    auto Zd = A->mm(h) * norm + b2;
+    Zd->backward(G);
+    CHECK(all_close(*Z->data(), *Zd->data(), 5e-5f));
+    CHECK(all_close(dW, *W2->grad(), 5e-5f));
+    CHECK(all_close(db, *b2->grad(), 5e-5f));
+    CHECK(all_close(dgam, *g2->grad(), 5e-5f));
+    CHECK(all_close(dbet, *be2->grad(), 5e-5f));
+    // running statistics moved towards the batch statistics (nn.cpp:321-327), evaluation mode uses them
+    CHECK(std::abs(bn->_buffers["running_mean"]->data()->sum()) > 0.0f);
+    conv.eval();
+    auto Ze = conv.forward(data.with_x(x));
+    CHECK(Ze->shape() == Z->shape());
+}
+
 int main() {
     const std::pair<const char *, std::function<void()>> tests[] = {
         {"tensor_basics", test_tensor_basics},       {"elementwise_ops", test_elementwise_ops},
@@ -264,6 +316,7 @@ int main() {
         {"graph_structure", test_graph_structure},
         {"gcn_vs_dense_transform_first", [] { check_gcn_against_dense(12, 5); }},
         {"gcn_vs_dense_aggregate_first", [] { check_gcn_against_dense(6, 17); }},
+        {"gcn_as_written_vs_dense", check_gcn_as_written_against_dense},
     };
     for (auto &t : tests) {
         const int before = g_failed;

@@ -154,6 +154,44 @@ tptr<float> softmax(const tptr<float> &x, int dim) {
     return out;
 }
 
+BatchNorm::BatchNorm(const size_t &num_features, const float &eps, const float &momentum, const bool &affine,
+                     const bool &track_running_stats, const std::string &n)
+    : Module(n), _num_features((int)num_features), _eps(eps), _momentum(momentum), _affine(affine), _tracking_running_stats(track_running_stats) {
+    std::vector<size_t> dims = {1, num_features};
+    register_parameter("gammas", std::make_shared<tensor<float>>(dims, 1.0f, true));
+    if (affine) register_parameter("betas", std::make_shared<tensor<float>>(dims, 0.0f, true));
+    if (_tracking_running_stats) {
+        register_buffer("running_mean", std::make_shared<tensor<float>>(dims, 0.0f, false));
+        register_buffer("running_var", std::make_shared<tensor<float>>(dims, 0.0f, false));
+    }
+    training = true;
+}
+
+tptr<float> BatchNorm::forward_relu(const tptr<float> &x, bool relu) {
+    if (x->rank() != 2 || (int)x->shape()[1] != _num_features) throw std::runtime_error(err::size_mismatch());
+    auto gamma = _parameters["gammas"];
+    auto beta = _affine ? _parameters["betas"] : nullptr;
+    if (!training && _tracking_running_stats) { // evaluation: running statistics, composed from tensor ops (nn.cpp:307-309)
+        auto stdv = ((_buffers["running_var"] + _eps)->log() * 0.5f)->exp(); // (var + eps)^0.5 from the ops this surface has
+        auto scaled = (x - _buffers["running_mean"]) / stdv;
+        auto out = scaled * gamma;
+        if (beta) out = out + beta;
+        return relu ? out->where(out > 0.0f, 0.0f) : out;
+    }
+    auto op = std::make_unique<BatchNormOp<tensor<float>>>();
+    auto out = op->forward(x, gamma, beta, _eps, relu);
+    if (_tracking_running_stats) { // nn.cpp:321-327: running = running*momentum + stat*(1-momentum), unbiased variance
+        const size_t F = (size_t)_num_features, N = x->shape()[0];
+        auto mean = std::make_shared<tensor<float>>(std::vector<size_t>{1, F}, op->mean(), false);
+        auto var = std::make_shared<tensor<float>>(std::vector<size_t>{1, F}, op->var(), false);
+        const float unbias = N > 1 ? (float)N / (float)(N - 1) : 0.0f;
+        _buffers["running_mean"] = (_buffers["running_mean"] * _momentum) + mean * (1.0f - _momentum);
+        _buffers["running_var"] = (_buffers["running_var"] * _momentum) + var * (unbias * (1.0f - _momentum));
+    }
+    if (out->requires_grad()) out->grad_fn = std::move(op);
+    return out;
+}
+
 tptr<float> cross_entropy_loss(const tptr<float> logits, const tptr<int> target) {
     auto op = std::make_unique<SoftmaxCrossEntropy<tensor<float>>>();
     auto out = op->forward(logits, target);

@@ -1,5 +1,5 @@
-// nn.h — Module tree, Linear, ReLU, Sequential, softmax, cross-entropy loss and the optimisers of the GCN
-// training loop (counterpart of reference include/nn.h:28-91,155-191).  Out of scope here: BatchNorm,
+// nn.h — Module tree, Linear, ReLU, Sequential, BatchNorm, softmax, cross-entropy loss and the optimisers of the GCN
+// training loop (counterpart of reference include/nn.h:28-123,155-191).  Out of scope here:
 // LayerNorm, Dropout, Sigmoid, tanh, MLP, Embedding.
 #ifndef GNNB200_NN_H
 #define GNNB200_NN_H
@@ -66,6 +66,22 @@ class ReLU : public Module { // reference nn.h:84-91, nn.cpp:229-237
   public:
     explicit ReLU(const std::string &n = "ReLU") : Module(n) {}
     cyg::tptr<float> forward(const cyg::tptr<float> &input_tensor) override;
+};
+
+/** batch normalisation over the node dimension — reference nn.h:114-123, nn.cpp:285-330: parameters "gammas" (1) and
+ *  "betas" (0) of shape {1, F}, buffers "running_mean"/"running_var"; training mode normalises with the batch
+ *  statistics (biased variance) and updates the running statistics as running = running*momentum + stat*(1-momentum)
+ *  (unbiased variance for running_var), evaluation mode uses the running statistics.  forward_relu fuses the ReLU
+ *  that graph::GCNConv applies right after (graph.cpp:174-175). */
+class BatchNorm : public Module {
+  public:
+    BatchNorm(const size_t &num_features, const float &eps = 1e-05, const float &momentum = 0.1, const bool &affine = true,
+              const bool &track_running_stats = true, const std::string &n = "BatchNorm");
+    cyg::tptr<float> forward(const cyg::tptr<float> &x) override { return forward_relu(x, false); }
+    cyg::tptr<float> forward_relu(const cyg::tptr<float> &x, bool relu);
+    int _num_features;
+    float _eps, _momentum;
+    bool _affine, _tracking_running_stats;
 };
 
 /** softmax(x) = exp(x - log(sum(exp(x)))) composed from tensor ops like the reference (nn.cpp:270-278) */

@@ -449,6 +449,54 @@ template <class T> class SoftmaxCrossEntropy : public Operation<T> {
     }
 };
 
+/** y = relu?((x - mean) / sqrt(var + eps) * gamma + beta) with batch statistics over the node dimension — one fused node
+ *  for nn::BatchNorm (+ the nn::ReLU GCNConv applies next); the backward is the standard batch-norm gradient
+ *  (gnn_batchnorm_bwd), which the reference's own autograd cannot produce (fan-out, bug B2). */
+template <class T> class BatchNormOp : public Operation<T> {
+    device::buffer_ptr mean_, var_, out_;
+    float eps_ = 1e-5f;
+    bool relu_ = false;
+
+  public:
+    BatchNormOp() { this->name = "BatchNorm"; }
+    const device::buffer_ptr &mean() const { return mean_; }
+    const device::buffer_ptr &var() const { return var_; }
+    std::shared_ptr<T> forward(const std::shared_ptr<T> &x, const std::shared_ptr<T> &gamma, const std::shared_ptr<T> &beta, float eps, bool relu) {
+        if (x->rank() != 2 || gamma->numel() != x->shape()[1]) throw std::runtime_error(err::size_mismatch());
+        const int64_t N = x->shape()[0], F = x->shape()[1];
+        const bool rg = x->requires_grad() || gamma->requires_grad() || (beta && beta->requires_grad());
+        auto out = functional::detail::make<float>(x->shape(), rg);
+        mean_ = device::alloc(F * 4);
+        var_ = device::alloc(F * 4);
+        device::check(gnn_batchnorm_fwd(device::ctx(), N, (int32_t)F, x->dptr(), F, gamma->dptr(), beta ? beta->dptr() : nullptr, eps, relu,
+                                        out->dptr(), F, static_cast<float *>(mean_->ptr), static_cast<float *>(var_->ptr)));
+        if (rg) {
+            this->context->save_for_backward(beta ? std::vector<std::shared_ptr<T>>{x, gamma, beta} : std::vector<std::shared_ptr<T>>{x, gamma});
+            eps_ = eps;
+            relu_ = relu;
+            if (relu) out_ = out->buffer();
+        }
+        return out;
+    }
+    void _backward(std::shared_ptr<T> g) override {
+        auto var = this->context->get_variables();
+        if (var.size() < 2) throw std::runtime_error("cant backprop without executing a forward computation first");
+        auto x = var[0], gamma = var[1];
+        const int64_t N = x->shape()[0], F = x->shape()[1];
+        auto dx = functional::detail::make<float>(x->shape(), false);
+        auto dg = functional::detail::make<float>(gamma->shape(), false);
+        auto db = functional::detail::make<float>(gamma->shape(), false);
+        device::check(gnn_batchnorm_bwd(device::ctx(), N, (int32_t)F, x->dptr(), F, static_cast<const float *>(mean_->ptr),
+                                        static_cast<const float *>(var_->ptr), gamma->dptr(), eps_,
+                                        relu_ ? static_cast<const float *>(out_->ptr) : nullptr, F, g->dptr(), F, dx->dptr(), F, dg->dptr(), db->dptr()));
+        if (x->requires_grad()) x->backward(dx);
+        if (gamma->requires_grad()) gamma->backward(dg);
+        if (var.size() == 3 && var[2]->requires_grad()) var[2]->backward(db);
+        out_.reset();
+        this->_done = true;
+    }
+};
+
 /** cross-entropy over the rows selected by a node mask (graph::Data::set_mask): gnn_softmax_xent_masked */
 template <class T> class MaskedSoftmaxCrossEntropy : public Operation<T> {
     std::shared_ptr<T> dZ_;
