@@ -141,6 +141,9 @@ struct gnn_peer_arena {
     cudaStream_t push[gnn::PEER_MAX_WORLD] = {}; // copy-engine mode: one stream per peer
     cudaStream_t push_sm = nullptr;             // SM mode: one high-priority stream
     unsigned *done = nullptr;                   // SM mode: CTA completion counter
+    // transport of a tile: 1 = SM store kernel (default), 0 = copy engines, 2 = in-place ncclAllGather of the panel
+    // on the side stream (the pipelined schedule with NCCL's transport, e.g. NVLS multicast on 8 ranks)
+    std::vector<cudaEvent_t> ev_slot;          // transport 2: completion event per slot
     int sm_mode = 1, sm_ctas = 64; // 64 CTAs: 649 GB/s between two B200s (32: 617, 16: 458; ncclAllGather: 467)
     cudaEvent_t ev_ready = nullptr;
     uint32_t seq[gnn::PEER_MAX_SLOTS] = {};      // last sequence number begun per slot (identical on every rank)
@@ -275,7 +278,7 @@ int gnn_peer_arena_create(gnn_ctx_t *ctx, size_t bytes, gnn_peer_arena_t **out) 
         GNN_CHECK_CUDA(cudaStreamCreateWithPriority(&a->push_sm, cudaStreamNonBlocking, hi));
         GNN_CHECK_CUDA(cudaMalloc((void **)&a->done, 4));
         GNN_CHECK_CUDA(cudaMemsetAsync(a->done, 0, 4, ctx->stream));
-        if (const char *e = getenv("GNN_PEER_COPY")) a->sm_mode = strcmp(e, "ce") ? 1 : 0;
+        if (const char *e = getenv("GNN_PEER_COPY")) a->sm_mode = !strcmp(e, "ce") ? 0 : (!strcmp(e, "nccl") ? 2 : 1);
         if (const char *e = getenv("GNN_PEER_CTAS")) a->sm_ctas = atoi(e) > 0 ? atoi(e) : a->sm_ctas;
     }
     GNN_CHECK_CUDA(cudaEventCreateWithFlags(&a->ev_ready, cudaEventDisableTiming));
@@ -293,6 +296,8 @@ int gnn_peer_arena_destroy(gnn_ctx_t *ctx, gnn_peer_arena_t *a) {
     if (a->push_sm) { cudaStreamSynchronize(a->push_sm); cudaStreamDestroy(a->push_sm); }
     if (a->done) cudaFree(a->done);
     if (a->ev_ready) cudaEventDestroy(a->ev_ready);
+    for (auto e : a->ev_slot)
+        if (e) cudaEventDestroy(e);
     // an exporter must not free memory a peer still has mapped: order all ranks (collective) before the free
     NcclApi *api = nccl_api();
     if (ctx && ctx->nccl_comm && api && a->base[a->rank]) {
@@ -314,6 +319,19 @@ int gnn_peer_gather_begin(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot, size_t 
                 bytes, a->bytes);
     const uint32_t seq = ++a->seq[slot];
     GNN_CHECK_CUDA(cudaEventRecord(a->ev_ready, ctx->stream));
+    if (a->sm_mode == 2) { // the tile must be the rank's whole block of a [world][bytes] region (one row block)
+        GNN_REQUIRE(offset >= (size_t)a->rank * bytes && offset - (size_t)a->rank * bytes + (size_t)a->world * bytes <= a->bytes,
+                    "gnn_peer_gather_begin: nccl transport needs whole-panel tiles");
+        NcclApi *api = nccl_api();
+        if ((int)a->ev_slot.size() <= slot) a->ev_slot.resize(slot + 1, nullptr);
+        if (!a->ev_slot[slot]) GNN_CHECK_CUDA(cudaEventCreateWithFlags(&a->ev_slot[slot], cudaEventDisableTiming));
+        GNN_CHECK_CUDA(cudaStreamWaitEvent(a->push_sm, a->ev_ready, 0));
+        if (bytes)
+            GNN_CHECK_NCCL(api, api->AllGather(a->base[a->rank] + offset, a->base[a->rank] + offset - (size_t)a->rank * bytes,
+                                              bytes / 4, NCCL_FLOAT32, (ncclComm_t_)ctx->nccl_comm, a->push_sm));
+        GNN_CHECK_CUDA(cudaEventRecord(a->ev_slot[slot], a->push_sm));
+        return 0;
+    }
     if (a->sm_mode) {
         PeerPushArgs pa;
         pa.n_dst = 0;
@@ -341,6 +359,11 @@ int gnn_peer_gather_begin(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot, size_t 
 
 int gnn_peer_gather_wait(gnn_ctx_t *ctx, gnn_peer_arena_t *a, int slot, int count) {
     GNN_REQUIRE(ctx && a && slot >= 0 && count >= 1 && slot + count < PEER_MAX_SLOTS, "gnn_peer_gather_wait: bad argument");
+    if (a->sm_mode == 2) {
+        for (int s = slot; s < slot + count; s++)
+            if (s < (int)a->ev_slot.size() && a->ev_slot[s]) GNN_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, a->ev_slot[s], 0));
+        return 0;
+    }
     for (int s0 = 0; s0 < count; s0 += 32) {
         PeerWaitArgs w;
         const int n = count - s0 < 32 ? count - s0 : 32;

@@ -47,6 +47,7 @@ struct gnn_gcn {
     gnn_peer_arena_t *arena = nullptr;
     std::vector<size_t> slot_off;
     int comm_mode = 1; // 1 = peer arena pushes (falls back to 0 when IPC is unavailable), 0 = ncclAllGather
+    bool nccl_transport = false; // GNN_PEER_COPY=nccl: tiles travel by in-place ncclAllGather on the side stream
     int32_t panel_cols = 128; // peer mode: column panel width of a gathered matrix (pipelines transfer and SpMM)
     // row blocks of the rank's rows (peer mode; one block otherwise): rows rb_row[i]..rb_row[i+1], with the matching
     // nonzero offsets of the forward (CSR) and backward (CSC) structure
@@ -207,7 +208,8 @@ static int push_tile(gnn_ctx *ctx, gnn_gcn *m, int op, const Panels &P, int p, i
     const size_t off = m->slot_off[op] +
                        ((size_t)ctx->world * m->chunk * P.c0[p] + (size_t)ctx->rank * m->chunk * P.w[p] + (size_t)r0 * P.w[p]) * 4;
     // an empty row block still publishes its sequence number (16 bytes of padding keep the range valid)
-    const size_t bytes = r1 > r0 ? (size_t)(r1 - r0) * P.w[p] * 4 : 0;
+    size_t bytes = r1 > r0 ? (size_t)(r1 - r0) * P.w[p] * 4 : 0;
+    if (m->nccl_transport) bytes = (size_t)m->chunk * P.w[p] * 4; // a collective: every rank contributes a whole chunk block
     return gnn_peer_gather_begin(ctx, m->arena, slot_of(op, p, rb), off, bytes);
 }
 static int wait_panel(gnn_ctx *ctx, gnn_gcn *m, int op, int p) {
@@ -496,6 +498,8 @@ int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_
         // (4 GPUs: 19.1 ms with 1 block, 19.8 with 2, 20.5 with 4), so one block is the default.
         int want = 1;
         if (const char *e = getenv("GNN_ROW_BLOCKS")) want = atoi(e);
+        if (const char *e = getenv("GNN_PEER_COPY"))
+            if (!strcmp(e, "nccl")) { want = 1; m->nccl_transport = true; } // an in-place all-gather moves whole panels
         m->n_rb = m->arena ? (want < 1 ? 1 : (want > MAX_RB ? MAX_RB : want)) : 1;
         const int64_t per = round_up(ceil_div(m->n_loc > 0 ? m->n_loc : 1, m->n_rb), 128);
         const bool alias = g->symmetric;
