@@ -476,9 +476,7 @@ int gnn_gcn_create(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_
     GNN_TRY(alloc(&m->G0, rows_alloc * m->maxld));
     GNN_TRY(alloc(&m->G1, rows_alloc * m->maxld));
     if (const char *e = getenv("GNN_COMM")) m->comm_mode = strcmp(e, "nccl") ? 1 : 0; // ablation switches
-    // 8 ranks are exchange-bound (6 GB received per rank and step vs 6 ms of compute): narrower panels shorten the
-    // link-idle gap between the last panel's aggregation and the first push of the next exchange
-    if (ctx->world >= 8) m->panel_cols = 64;
+    // (8 ranks: panels of 32 / 64 / 128 columns all give 14.8-14.9 ms per step, so one width serves every world size)
     if (const char *e = getenv("GNN_PANEL_COLS")) m->panel_cols = (int32_t)round_up(atoi(e) > 0 ? atoi(e) : 1 << 20, 4);
     if (m->dist && ctx->world > 1 && m->comm_mode == 1 && 2 * L * MAX_PANELS * MAX_RB < 1000) {
         // one region per aggregation of a step, wide enough for either layer order
