@@ -160,6 +160,52 @@ ORC_API int64_t orc_csr_build(const int32_t *src, const int32_t *dst, int64_t E,
     return nnz;
 }
 
+/* Weighted adjacency (graph::edge_to_adj_mat with edge_attr, src/graph.cpp:21-44): A[src][dst] = w by ASSIGNMENT in
+ * edge order, so for duplicate (src, dst) pairs the LAST weight wins; fill_mode 1 then forces the diagonal to 1
+ * (tensor::fill_diagonal_(1), include/tensor.h:806-817: the A + I of mode B), fill_mode 2 leaves it as given.
+ * Output: CSR (rows ascending, columns ascending) with the raw weights val0.  Entries whose final weight is exactly 0
+ * stay as explicit zeros (they are zeros of the dense matrix and contribute nothing). */
+typedef struct { uint64_t key; int64_t idx; } orc_item;
+static int orc_item_cmp(const void *a, const void *b) {
+    const orc_item *x = (const orc_item *)a, *y = (const orc_item *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+ORC_API int64_t orc_csr_build_weighted(const int32_t *src, const int32_t *dst, const float *w, int64_t E, int32_t N,
+                                       int fill_mode, int64_t *rowptr, int32_t *colidx, float *val0) {
+    const int64_t m = E + (fill_mode == 1 ? N : 0);
+    orc_item *it = (orc_item *)malloc((size_t)(m > 0 ? m : 1) * sizeof(orc_item));
+    for (int64_t e = 0; e < E; e++) { it[e].key = ((uint64_t)(uint32_t)src[e] << 32) | (uint32_t)dst[e]; it[e].idx = e; }
+    if (fill_mode == 1)
+        for (int32_t i = 0; i < N; i++) { it[E + i].key = ((uint64_t)(uint32_t)i << 32) | (uint32_t)i; it[E + i].idx = E + i; }
+    qsort(it, (size_t)m, sizeof(orc_item), orc_item_cmp);
+    int64_t nnz = 0;
+    memset(rowptr, 0, (size_t)(N + 1) * 8);
+    for (int64_t i = 0; i < m; i++) {
+        if (i + 1 < m && it[i + 1].key == it[i].key) continue; /* not the last write to this position */
+        colidx[nnz] = (int32_t)(it[i].key & 0xFFFFFFFFu);
+        val0[nnz] = it[i].idx < E ? w[it[i].idx] : 1.0f;
+        rowptr[(int32_t)(it[i].key >> 32) + 1]++;
+        nnz++;
+    }
+    for (int32_t r = 0; r < N; r++) rowptr[r + 1] += rowptr[r];
+    free(it);
+    return nnz;
+}
+/* Weighted mode B: deg = A->sum(-1,true) (ascending fp32 row sum, src/graph.cpp:178 / functional.h:266-296),
+ * dinv = pow(deg,-0.5), val = (A*dinv)*dinv^T (functional.h:189-213). */
+ORC_API void orc_degree_norm_weighted(int32_t N, const int64_t *rowptr, const int32_t *colidx, const float *val0,
+                                      float *degf, float *dinv, float *val) {
+    for (int32_t r = 0; r < N; r++) {
+        float s = 0.0f;
+        for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++) s = s + val0[k];
+        degf[r] = s;
+        dinv[r] = powf(s, -0.5f);
+    }
+    for (int32_t r = 0; r < N; r++)
+        for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++) val[k] = (val0[k] * dinv[r]) * dinv[colidx[k]];
+}
+
 /* CSR -> CSC (= CSR of the transpose), rows ascending inside each column, and the permutation
  * perm[k] = CSR position of CSC entry k.  No counterpart in the reference (it transposes the dense
  * matrix, include/functional.h:330-357; include/operation.h:526-528). */

@@ -60,6 +60,9 @@ def lib():
         L.orc_batchnorm_bwd.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _f32p, _f32p, _f32p, C.c_float, C.c_int,
                                         C.c_void_p, C.c_int64, _f32p, C.c_int64, _f32p, C.c_int64, _f32p, _f32p]
         L.orc_aswritten_norm.argtypes = [C.c_int32, _i64p, _i32p, _f32p, _f32p]
+        L.orc_csr_build_weighted.restype = C.c_int64
+        L.orc_csr_build_weighted.argtypes = [_i32p, _i32p, _f32p, C.c_int64, C.c_int32, C.c_int, _i64p, _i32p, _f32p]
+        L.orc_degree_norm_weighted.argtypes = [C.c_int32, _i64p, _i32p, _f32p, _f32p, _f32p, _f32p]
         L.orc_partition_ptr.argtypes = [C.c_int64, C.c_int32, _i64p]
         L.orc_partition_rows.restype = C.c_int64
         L.orc_partition_rows.argtypes = [_i64p, _i32p, C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, C.c_void_p]
@@ -130,11 +133,41 @@ def degree_norm(N, rowptr, colidx):
     return deg, dinv, val[: int(rowptr[N])]
 
 
-class Graph:
-    """CSR/CSC/normalisation of A_hat = D^-1/2 (A0 + I) D^-1/2 built by the oracle."""
+def edge_weights(E):
+    """deterministic positive test weights, exact in fp32 on every platform: w_i = 0.25 + ((7919 i) mod 1024) / 512"""
+    i = np.arange(E, dtype=np.int64)
+    return (np.float32(0.25) + ((i * 7919) % 1024).astype(np.float32) / np.float32(512.0)).astype(np.float32)
 
-    def __init__(self, src, dst, N):
+
+def csr_build_weighted(src, dst, w, N, fill_mode=1):
+    src = np.ascontiguousarray(src, dtype=np.int32); dst = np.ascontiguousarray(dst, dtype=np.int32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    E = len(src)
+    rowptr = np.zeros(N + 1, dtype=np.int64)
+    colidx = np.empty(max(E + N, 1), dtype=np.int32); val0 = np.empty(max(E + N, 1), dtype=np.float32)
+    nnz = lib().orc_csr_build_weighted(src, dst, w, E, N, fill_mode, rowptr, colidx, val0)
+    return rowptr, colidx[:nnz].copy(), val0[:nnz].copy()
+
+
+def degree_norm_weighted(N, rowptr, colidx, val0):
+    degf = np.empty(N, np.float32); dinv = np.empty(N, np.float32); val = np.empty(max(len(val0), 1), np.float32)
+    lib().orc_degree_norm_weighted(N, rowptr, np.ascontiguousarray(colidx), np.ascontiguousarray(val0), degf, dinv, val)
+    return degf, dinv, val[: len(val0)]
+
+
+class Graph:
+    """CSR/CSC/normalisation of A_hat = D^-1/2 (A0 + I) D^-1/2 built by the oracle (A0 weighted when w is given)."""
+
+    def __init__(self, src, dst, N, w=None):
         self.N = N
+        if w is not None:
+            self.rowptr, self.colidx, self.val0 = csr_build_weighted(src, dst, w, N, 1)
+            self.nnz = int(self.rowptr[N])
+            self.degf, self.dinv, self.val = degree_norm_weighted(N, self.rowptr, self.colidx, self.val0)
+            self.deg = np.diff(self.rowptr).astype(np.int32)
+            self.colptr, self.rowidx, self.perm = csc_from_csr(N, self.rowptr, self.colidx)
+            self.valT = self.val[self.perm].copy()
+            return
         self.rowptr, self.colidx = csr_build(src, dst, N, 1)
         self.nnz = int(self.rowptr[N])
         self.deg, self.dinv, self.val = degree_norm(N, self.rowptr, self.colidx)

@@ -19,6 +19,7 @@
 // usage:
 //   ref_gcn structure <problem.gcnp> <out.gcno>
 //   ref_gcn step      <problem.gcnp> <out.gcno>
+//   ref_gcn structure_w <problem.gcnp> <out.gcno>    (weighted adjacency + normalisation, mode B with edge_attr)
 //   ref_gcn aswritten <problem.gcnp> <out.gcno>      (one graph::GCNConv::forward exactly as written)
 //   ref_gcn time      <problem.gcnp> <steps>         (prints one JSON line with per-stage ms)
 #include "graph.h"
@@ -188,6 +189,37 @@ int run_step(const Problem &p, Writer *w, StepTimes *tm) {
     return 0;
 }
 
+// Weighted adjacency through the reference's own code: edge_to_adj_mat with edge_attr (src/graph.cpp:21-44, last write
+// wins), fill_diagonal_(1), deg = rowsum, dinv = pow(deg,-0.5), Ahat = (A*dinv)*dinv^T (mode B with weights).
+// Weights: w_i = 0.25 + ((7919 i) mod 1024)/512 (positive, exact in fp32; same formula as oracle.edge_weights).
+int cmd_structure_w(const Problem &p, const char *out) {
+    Writer w(out);
+    auto ei = graph::vec_to_edge_list(p.src, p.dst);
+    auto *wv = new std::valarray<float>(p.E);
+    for (int64_t i = 0; i < p.E; i++) (*wv)[i] = 0.25f + (float)((i * 7919) % 1024) / 512.0f;
+    tensor<float> attr(std::vector<size_t>{(size_t)p.E}, wv, false);
+    auto A = graph::edge_to_adj_mat(*ei, &attr, p.N);
+    A->fill_diagonal_(1);
+    auto deg = A->sum(-1, true);
+    auto dinv = deg->pow(-0.5);
+    auto Ahat = (A * dinv) * dinv->t(-1, -2);
+    w.f32("w_deg", *deg->data(), {(size_t)p.N});
+    w.f32("w_dinv", *dinv->data(), {(size_t)p.N});
+    auto &a0 = *A->data();
+    auto &ad = *Ahat->data();
+    std::vector<float> nz, raw;
+    std::vector<int> rows, cols;
+    for (size_t i = 0; i < ad.size(); i++)
+        if (a0[i] != 0.0f) { nz.push_back(ad[i]); raw.push_back(a0[i]); rows.push_back((int)(i / p.N)); cols.push_back((int)(i % p.N)); }
+    std::valarray<float> nzv(nz.data(), nz.size()), rawv(raw.data(), raw.size());
+    std::valarray<int> rv(rows.data(), rows.size()), cv(cols.data(), cols.size());
+    w.f32("w_ahat_val", nzv, {nz.size()});
+    w.f32("w_raw_val", rawv, {raw.size()});
+    w.i32("w_rows", rv, {rows.size()});
+    w.i32("w_cols", cv, {cols.size()});
+    return 0;
+}
+
 // The reference's graph::GCNConv layer EXACTLY AS WRITTEN (src/graph.cpp:160-212), run through its own forward():
 //   add_self_loops(..., 0)  -> loops removed;  lin (no bias) -> BatchNorm (training statistics) -> ReLU;
 //   deg = rowsum(A0) + 1; dinv = deg^-0.5; norm = (A0 dinv) * dinv;  out = (A0 h) * norm + bias
@@ -228,6 +260,7 @@ int main(int argc, char **argv) {
     if (cmd == "structure") return cmd_structure(p, argv[3]);
     if (cmd == "step") { Writer w(argv[3]); return run_step(p, &w, nullptr); }
     if (cmd == "aswritten") return cmd_aswritten(p, argv[3]);
+    if (cmd == "structure_w") return cmd_structure_w(p, argv[3]);
     if (cmd == "time") {
         int steps = atoi(argv[3]);
         StepTimes tm;

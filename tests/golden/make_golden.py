@@ -76,6 +76,17 @@ def run_aswritten(prob, name, subsample=256):
     print("aswritten", name, {k: v.shape for k, v in res.items()})
 
 
+def run_weighted(prob, name):
+    """weighted adjacency + normalisation through the reference (ref_gcn structure_w)"""
+    with tempfile.TemporaryDirectory() as td:
+        pin = os.path.join(td, "p.gcnp")
+        problem_io.write_problem(pin, prob)
+        subprocess.check_call([REF, "structure_w", pin, os.path.join(td, "o.gcno")])
+        res = problem_io.read_results(os.path.join(td, "o.gcno"))
+    np.savez_compressed(os.path.join(OUT, "weighted_" + name + ".npz"), **res)
+    print("weighted", name, {k: v.shape for k, v in res.items()})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pubmed", action="store_true")
@@ -95,8 +106,11 @@ def main():
     for k in ("toy", "tiny", "directed", "tiny_pl", "cora"):
         prob = directed_problem() if k == "directed" else synth.make_problem(synth.CONFIGS[k])
         jobs["aswritten_" + k] = (lambda prob=prob, k=k: run_aswritten(prob, k))
+    for k in ("toy", "tiny", "directed", "tiny_pl"):
+        prob = directed_problem() if k == "directed" else synth.make_problem(synth.CONFIGS[k])
+        jobs["weighted_" + k] = (lambda prob=prob, k=k: run_weighted(prob, k))
     for k, fn in jobs.items():
-        if a.only is None or a.only == k or (a.only == "aswritten" and k.startswith("aswritten_")):
+        if a.only is None or a.only == k or (a.only in ("aswritten", "weighted") and k.startswith(a.only + "_")):
             fn()
 
 

@@ -212,3 +212,22 @@ def test_batchnorm_backward_matches_torch(oracle):
         np.testing.assert_allclose(dX, xt.grad.numpy(), rtol=1e-4, atol=2e-6)
         np.testing.assert_allclose(dg, gt.grad.numpy(), rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(db, bt.grad.numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["toy", "tiny", "directed", "tiny_pl"])
+def test_weighted_adjacency_bit_exact(oracle, name):
+    """edge_attr weights through edge_to_adj_mat (last write wins, graph.cpp:38-40) into the CSR
+    values, diagonal forced to 1, weighted degree / D^-1/2 / A_hat — every array BIT-EXACT against the real reference
+    (tests/golden/weighted_*.npz from `ref_gcn structure_w`)."""
+    p = load_problem(name)
+    g = np.load(os.path.join(GOLDEN, "weighted_%s.npz" % name))
+    w = oracle.edge_weights(len(p.src))
+    G = oracle.Graph(p.src, p.dst, p.cfg.N, w=w)
+    rows = np.repeat(np.arange(p.cfg.N, dtype=np.int32), np.diff(G.rowptr))
+    assert np.array_equal(rows, g["w_rows"]) and np.array_equal(G.colidx, g["w_cols"])
+    assert np.array_equal(G.val0, g["w_raw_val"])
+    assert np.array_equal(G.degf, g["w_deg"]) and np.array_equal(G.dinv, g["w_dinv"])
+    assert np.array_equal(G.val, g["w_ahat_val"])
+    # structure equals the unweighted build (weights never change which entries exist)
+    G1 = oracle.Graph(p.src, p.dst, p.cfg.N)
+    assert np.array_equal(G.rowptr, G1.rowptr) and np.array_equal(G.colidx, G1.colidx)
