@@ -32,6 +32,8 @@ SIGNATURES = {
     "gnn_fill_f32": (C.c_int, [vp, vp, f32, i64]),
     "gnn_graph_build": (C.c_int, [vp, vp, vp, i64, i32, C.c_int, pp]),
     "gnn_graph_build_h": (C.c_int, [vp, vp, vp, i64, i32, C.c_int, pp]),
+    "gnn_graph_build_weighted": (C.c_int, [vp, vp, vp, vp, i64, i32, C.c_int, pp]),
+    "gnn_graph_export_weights_h": (C.c_int, [vp, vp, vp]),
     "gnn_graph_from_csr": (C.c_int, [vp, i32, i32, vp, vp, vp, pp]),
     "gnn_graph_build_csc": (C.c_int, [vp, vp]),
     "gnn_graph_normalize": (C.c_int, [vp, vp]),

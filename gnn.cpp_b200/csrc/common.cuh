@@ -79,6 +79,7 @@ struct gnn_graph {
     // CSR
     int32_t *rowptr = nullptr, *colidx = nullptr;
     float *val = nullptr;
+    float *val0 = nullptr; // raw edge weights of a weighted adjacency (gnn_graph_build_weighted), NULL for 0/1 graphs
     // CSC (CSR of the transpose); aliases the CSR arrays when symmetric
     int32_t *colptr = nullptr, *rowidx = nullptr, *perm = nullptr;
     float *valT = nullptr;

@@ -131,6 +131,72 @@ __global__ void edge_val_kernel(const int32_t *__restrict__ rowptr, const int32_
     for (int32_t k = b + lane; k < e; k += 32) val[k] = dr * dinv[colidx[k]];
 }
 
+// ---- weighted adjacency (edge_attr): keys carry the edge position so that, after a STABLE sort, the last element of
+// a run of equal (row, col) keys is the last write of the reference's assignment loop (src/graph.cpp:35-40)
+__global__ void make_keys_w_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int64_t E,
+                                   int32_t n, int cb, int add_diag, uint64_t *__restrict__ keys, uint32_t *__restrict__ pos,
+                                   int *__restrict__ err) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < E) {
+        const int32_t r = src[i], c = dst[i];
+        if (r < 0 || r >= n || c < 0 || c >= n) {
+            *err = 1;
+            keys[i] = 0;
+        } else {
+            keys[i] = ((uint64_t)(uint32_t)r << cb) | (uint32_t)c;
+        }
+        pos[i] = (uint32_t)i;
+    } else if (add_diag && i < E + n) { // appended after every edge: the forced diagonal (fill_diagonal_(1)) wins
+        const uint64_t d = (uint64_t)(i - E);
+        keys[i] = (d << cb) | d;
+        pos[i] = (uint32_t)i;
+    }
+}
+__global__ void last_flags_kernel(const uint64_t *__restrict__ keys, int64_t m, uint32_t *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    flags[i] = (i == m - 1 || keys[i] != keys[i + 1]) ? 1u : 0u;
+}
+__global__ void compact_w_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pos_in,
+                                 const uint32_t *__restrict__ pos, int64_t m, int cb, int64_t E,
+                                 const float *__restrict__ w, uint64_t *__restrict__ ukeys, int32_t *__restrict__ colidx,
+                                 float *__restrict__ val0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t p = pos[i];
+    if (pos[i + 1] != p) {
+        const uint64_t k = keys[i];
+        ukeys[p] = k;
+        colidx[p] = (int32_t)(k & (((uint64_t)1 << cb) - 1));
+        const uint32_t e = pos_in[i];
+        val0[p] = e < E ? w[e] : 1.0f;
+    }
+}
+// weighted degree = row sum of the raw weights (one warp per row), dinv = deg^-1/2, val = (w * dinv[r]) * dinv[c]
+__global__ void degree_w_kernel(const int32_t *__restrict__ rowptr, const float *__restrict__ val0, int32_t n_rows,
+                                int32_t *__restrict__ deg, float *__restrict__ dinv) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    float s = 0.f;
+    for (int32_t k = rowptr[w] + lane; k < rowptr[w + 1]; k += 32) s += val0[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        deg[w] = rowptr[w + 1] - rowptr[w];
+        dinv[w] = (float)(1.0 / sqrt((double)s));
+    }
+}
+__global__ void edge_val_w_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                  const float *__restrict__ val0, const float *__restrict__ dinv, int32_t n_rows,
+                                  float *__restrict__ val) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    const float dr = dinv[w];
+    for (int32_t k = rowptr[w] + lane; k < rowptr[w + 1]; k += 32) val[k] = (val0[k] * dr) * dinv[colidx[k]];
+}
+
 // graph::GCNConv::forward as written (reference src/graph.cpp:176-185) on the loop-free adjacency A0:
 //   dinv = (rowsum(A0) + 1)^-1/2 ;  norm[r] = dinv[r] * sum_{c in row r} dinv[c]     (one warp per row, fixed order)
 __global__ void aswritten_dinv_kernel(const int32_t *__restrict__ rowptr, int32_t n, int32_t *__restrict__ deg,
@@ -321,6 +387,70 @@ int gnn_graph_build_h(gnn_ctx_t *ctx, const int32_t *src_h, const int32_t *dst_h
     return r;
 }
 
+int gnn_graph_build_weighted(gnn_ctx_t *ctx, const int32_t *src, const int32_t *dst, const float *w, int64_t E, int32_t N,
+                             int fill_mode, gnn_graph_t **out) {
+    GNN_REQUIRE(ctx && out && src && dst && w, "gnn_graph_build_weighted: NULL argument");
+    GNN_REQUIRE(N > 0, "dims cannot be empty or zero");
+    GNN_REQUIRE(E > 0 && (fill_mode == 1 || fill_mode == 2), "gnn_graph_build_weighted: bad E or fill_mode (1 or 2)");
+    const int cb = bits_for(N);
+    const int64_t m = E + (fill_mode == 1 ? N : 0);
+    GNN_REQUIRE(m < (int64_t)0x7FFFFFFF, "gnn_graph_build_weighted: E + N = %lld exceeds int32 positions", (long long)m);
+    cudaStream_t s = ctx->stream;
+    uint64_t *keys = nullptr, *ukeys = nullptr;
+    uint32_t *pos_in = nullptr, *flags = nullptr;
+    int *err_d = nullptr;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&keys, (size_t)m * 8, s));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&pos_in, (size_t)m * 4, s));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&flags, (size_t)(m + 2) * 4, s));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&err_d, 4, s));
+    GNN_CHECK_CUDA(cudaMemsetAsync(err_d, 0, 4, s));
+    make_keys_w_kernel<<<grid_for(m, 256), 256, 0, s>>>(src, dst, E, N, cb, fill_mode == 1, keys, pos_in, err_d);
+    GNN_LAUNCHED(ctx);
+    GNN_TRY(radix_sort_u64(ctx, keys, pos_in, m, 0, 2 * cb)); // stable: equal keys keep edge order
+    last_flags_kernel<<<grid_for(m, 256), 256, 0, s>>>(keys, m, flags);
+    GNN_LAUNCHED(ctx);
+    GNN_CHECK_CUDA(cudaMemsetAsync(flags + m, 0, 8, s));
+    GNN_TRY(exclusive_scan_u32(ctx, flags, flags, m + 1, nullptr));
+    uint32_t h_nnz = 0;
+    int h_err = 0;
+    GNN_CHECK_CUDA(cudaMemcpyAsync(&h_nnz, flags + m, 4, cudaMemcpyDeviceToHost, s));
+    GNN_CHECK_CUDA(cudaMemcpyAsync(&h_err, err_d, 4, cudaMemcpyDeviceToHost, s));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    if (h_err) {
+        cudaFreeAsync(keys, s); cudaFreeAsync(pos_in, s); cudaFreeAsync(flags, s); cudaFreeAsync(err_d, s);
+        set_error("invalid input, max value in edge_index should be less than the number of nodes from x");
+        return 2;
+    }
+    gnn_graph *g = new gnn_graph();
+    g->n_rows = g->n_cols = N;
+    g->t_rows = N;
+    g->fill_mode = fill_mode;
+    g->nnz = h_nnz;
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->rowptr, (size_t)(N + 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->colidx, (size_t)(g->nnz ? g->nnz : 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->val0, (size_t)(g->nnz ? g->nnz : 1) * 4));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&ukeys, (size_t)(g->nnz ? g->nnz : 1) * 8, s));
+    compact_w_kernel<<<grid_for(m, 256), 256, 0, s>>>(keys, pos_in, flags, m, cb, E, w, ukeys, g->colidx, g->val0);
+    GNN_LAUNCHED(ctx);
+    lower_bound_kernel<<<grid_for(N + 1, 256), 256, 0, s>>>(ukeys, g->nnz, cb, ((uint64_t)1 << (64 - cb)) - 1, N, g->rowptr);
+    GNN_LAUNCHED(ctx);
+    GNN_CHECK_CUDA(cudaFreeAsync(keys, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(ukeys, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(pos_in, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(flags, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(err_d, s));
+    GNN_TRY(finish_stats(ctx, g));
+    *out = g;
+    return 0;
+}
+
+int gnn_graph_export_weights_h(gnn_ctx_t *ctx, const gnn_graph_t *g, float *val0_h) {
+    GNN_REQUIRE(ctx && g && val0_h && g->val0, "gnn_graph_export_weights_h: graph has no raw weights (gnn_graph_build_weighted)");
+    GNN_CHECK_CUDA(cudaMemcpyAsync(val0_h, g->val0, (size_t)g->nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int gnn_graph_from_csr(gnn_ctx_t *ctx, int32_t n_rows, int32_t n_cols, const int32_t *rowptr, const int32_t *colidx,
                        const float *val, gnn_graph_t **out) {
     GNN_REQUIRE(ctx && out && rowptr, "gnn_graph_from_csr: NULL argument");
@@ -404,11 +534,19 @@ int gnn_graph_normalize(gnn_ctx_t *ctx, gnn_graph_t *g) {
     if (!g->deg) GNN_CHECK_CUDA(cudaMalloc((void **)&g->deg, (size_t)g->n_rows * 4));
     if (!g->dinv) GNN_CHECK_CUDA(cudaMalloc((void **)&g->dinv, (size_t)g->n_rows * 4));
     if (!g->val) GNN_CHECK_CUDA(cudaMalloc((void **)&g->val, (size_t)nnz * 4));
-    degree_kernel<<<grid_for(g->n_rows, 256), 256, 0, s>>>(g->rowptr, g->n_rows, g->deg, g->dinv);
-    GNN_LAUNCHED(ctx);
-    edge_val_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, s>>>(g->rowptr, g->colidx, g->dinv, g->n_rows,
-                                                                           g->val);
-    GNN_LAUNCHED(ctx);
+    if (g->val0) { // weighted adjacency: weighted degree, val = (w * dinv[r]) * dinv[c]
+        degree_w_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, s>>>(g->rowptr, g->val0, g->n_rows, g->deg, g->dinv);
+        GNN_LAUNCHED(ctx);
+        edge_val_w_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, s>>>(g->rowptr, g->colidx, g->val0, g->dinv,
+                                                                                g->n_rows, g->val);
+        GNN_LAUNCHED(ctx);
+    } else {
+        degree_kernel<<<grid_for(g->n_rows, 256), 256, 0, s>>>(g->rowptr, g->n_rows, g->deg, g->dinv);
+        GNN_LAUNCHED(ctx);
+        edge_val_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, s>>>(g->rowptr, g->colidx, g->dinv, g->n_rows,
+                                                                               g->val);
+        GNN_LAUNCHED(ctx);
+    }
     if (g->colptr && !g->valT) {
         GNN_CHECK_CUDA(cudaMalloc((void **)&g->valT, (size_t)nnz * 4));
         gather_f32_kernel<<<grid_for(g->nnz, 256), 256, 0, s>>>(g->val, g->perm, g->nnz, g->valT);
@@ -450,7 +588,7 @@ int gnn_graph_normalize_as_written(gnn_ctx_t *ctx, gnn_graph_t *g, float *norm_o
 int gnn_graph_destroy(gnn_ctx_t *ctx, gnn_graph_t *g) {
     if (!g) return 0;
     if (ctx) cudaStreamSynchronize(ctx->stream);
-    cudaFree(g->rowptr); cudaFree(g->colidx); cudaFree(g->val);
+    cudaFree(g->rowptr); cudaFree(g->colidx); cudaFree(g->val); cudaFree(g->val0);
     cudaFree(g->colptr); cudaFree(g->rowidx); cudaFree(g->perm); cudaFree(g->valT);
     cudaFree(g->deg); cudaFree(g->dinv);
     delete g;
@@ -489,10 +627,11 @@ int gnn_graph_export_h(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t *rowptr_h, 
 
 int gnn_graph_to_dense(gnn_ctx_t *ctx, const gnn_graph_t *g, int weighted, float *out, int64_t ld) {
     GNN_REQUIRE(ctx && g && out, "gnn_graph_to_dense: NULL argument");
-    GNN_REQUIRE(!weighted || g->val, "gnn_graph_to_dense: values not built (call gnn_graph_normalize)");
+    GNN_REQUIRE(weighted != 1 || g->val, "gnn_graph_to_dense: values not built (call gnn_graph_normalize)");
+    GNN_REQUIRE(weighted != 2 || g->val0, "gnn_graph_to_dense: graph has no raw weights (gnn_graph_build_weighted)");
     GNN_CHECK_CUDA(cudaMemset2DAsync(out, (size_t)ld * 4, 0, (size_t)g->n_cols * 4, g->n_rows, ctx->stream));
     to_dense_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, ctx->stream>>>(g->rowptr, g->colidx,
-                                                                                    weighted ? g->val : nullptr,
+                                                                                    weighted == 2 ? g->val0 : (weighted ? g->val : nullptr),
                                                                                     g->n_rows, out, ld);
     GNN_LAUNCHED(ctx);
     return 0;

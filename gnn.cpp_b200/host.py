@@ -79,11 +79,16 @@ class Graph:
         self.ctx, self.h = ctx, handle
 
     @classmethod
-    def build(cls, ctx, src, dst, N, fill_mode=1, csc=True, normalize=True):
-        """src/dst: int32 numpy (host) or torch cuda int32 tensors."""
+    def build(cls, ctx, src, dst, N, fill_mode=1, csc=True, normalize=True, weights=None):
+        """src/dst: int32 numpy (host) or torch cuda int32 tensors; weights: optional float32 edge weights (edge_attr)."""
         h = C.c_void_p()
         E = len(src)
-        if isinstance(src, torch.Tensor):
+        if weights is not None:
+            to_dev = lambda a, dt: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(ctx.device)  # noqa: E731
+            sd, dd, wd = to_dev(src, np.int32), to_dev(dst, np.int32), to_dev(weights, np.float32)
+            capi.call("gnn_graph_build_weighted", ctx.h, _ptr(sd), _ptr(dd), _ptr(wd), E, N, fill_mode, C.byref(h))
+            torch.cuda.current_stream().synchronize()   # the temporaries above may be released now
+        elif isinstance(src, torch.Tensor):
             assert src.is_cuda and src.dtype == torch.int32 and dst.dtype == torch.int32
             capi.call("gnn_graph_build", ctx.h, _ptr(src), _ptr(dst), E, N, fill_mode, C.byref(h))
         else:
@@ -130,6 +135,11 @@ class Graph:
         g = out.get
         capi.call("gnn_graph_export_h", self.ctx.h, self.h, _ptr(out["rowptr"]), _ptr(out["colidx"]), _ptr(g("val")),
                   _ptr(g("colptr")), _ptr(g("rowidx")), _ptr(g("perm")), _ptr(g("valT")), _ptr(g("deg")), _ptr(g("dinv")))
+        return out
+
+    def export_weights(self):
+        out = np.empty(self.nnz, dtype=np.float32)
+        capi.call("gnn_graph_export_weights_h", self.ctx.h, self.h, _ptr(out))
         return out
 
     def to_dense(self, weighted=True):

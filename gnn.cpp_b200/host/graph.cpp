@@ -36,8 +36,19 @@ static size_t infer_nodes(const tensor<int> &edge_index, size_t n_nodes) {
 }
 
 tptr<float> edge_to_adj_mat(const tensor<int> &edge_index, tensor<float> *edge_attr, size_t n_nodes) {
-    if (edge_attr != nullptr) throw std::runtime_error("edge weights are outside the GCN hot path (SURVEY.md §8f rank 3): pass edge_attr = nullptr");
     const size_t N = infer_nodes(edge_index, n_nodes);
+    if (edge_attr != nullptr) { // A[src][dst] = w, last write wins (graph.cpp:38-40): weighted device build, diagonal as given
+        if (edge_index.shape()[1] != edge_attr->shape()[0])
+            throw std::runtime_error("invalid inputs, number of edges in edge_index must be equal to size of edge_attr");
+        const int64_t E = (int64_t)edge_index.shape()[1];
+        gnn_graph_t *g = nullptr;
+        device::check(gnn_graph_build_weighted(device::ctx(), edge_index.dptr(), edge_index.dptr() + E, edge_attr->dptr(), E, (int32_t)N,
+                                               /*fill_mode=*/2, &g));
+        auto h = std::make_shared<device::GraphHandle>(g);
+        auto out = std::make_shared<tensor<float>>(std::vector<size_t>{N, N}, 0.0f, false);
+        device::check(gnn_graph_to_dense(device::ctx(), g, /*raw weights*/ 2, out->dptr(), (int64_t)N));
+        return out;
+    }
     auto s = build_structure(edge_index, N, /*fill_mode=*/2, /*normalize=*/false);
     auto out = std::make_shared<tensor<float>>(std::vector<size_t>{N, N}, 0.0f, false);
     device::check(gnn_graph_to_dense(device::ctx(), s->g, 0, out->dptr(), (int64_t)N));
@@ -119,7 +130,7 @@ void Data::set_edge_index(tensor<int> *edge_index, tptr<float> edge_attr) {
 }
 tptr<float> Data::to_adj() {
     if (_edge_index == nullptr) throw std::runtime_error("pls provide adj matr or edge");
-    return edge_to_adj_mat(*_edge_index, nullptr, _num_nodes);
+    return edge_to_adj_mat(*_edge_index, _edge_attr.get(), _num_nodes); // reference graph.cpp:118-129 passes _edge_attr too
 }
 void Data::set_mask(tensor<bool> &mask, DataType type) {
     if (mask.numel() != _num_nodes) throw std::runtime_error("invalid input, mask must be 1D and of same size with num of nodes in graph");

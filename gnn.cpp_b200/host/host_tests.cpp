@@ -205,6 +205,11 @@ static void test_graph_structure() { // reference tests/graph.test.cpp:16-43 (it
     auto [el, ew] = adj_to_edge_list(*mat);
     std::valarray<int> want = {0, 1, 1, 2, 2, 3, 3, 4, 1, 1, 2, 1, 2, 0, 1, 2};
     CHECK((*el->data() == want).min() == true && ew->data()->sum() == 8.0f);
+    // edge weights land at A[src][dst] (graph.cpp:38-40); duplicates (last write wins) are covered by the directed golden
+    auto attr = T({8}, {0.5f, 1.5f, 2.0f, 3.0f, 4.0f, 5.0f, 6.0f, 7.0f});
+    auto wmat = edge_to_adj_mat(*edge_list, attr.get(), 5);
+    CHECK((*wmat)(1, 1)->item() == 0.5f && (*wmat)(3, 0)->item() == 2.0f && (*wmat)(3, 1)->item() == 7.0f && (*wmat)(2, 1)->item() == 6.0f);
+    CHECK(close(wmat->data()->sum(), 0.5f + 1.5f + 2.0f + 3.0f + 4.0f + 5.0f + 6.0f + 7.0f));
     auto [e0, w0] = add_self_loops(*edge_list, nullptr, 0, 5); // fillValue 0 REMOVES loops (graph.cpp:68-75)
     std::valarray<int> want0 = {0, 1, 2, 3, 3, 4, 1, 2, 1, 0, 1, 2};
     CHECK((*e0->data() == want0).min() == true);

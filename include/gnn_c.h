@@ -73,6 +73,15 @@ GNN_API int gnn_graph_build(gnn_ctx_t *ctx, const int32_t *src, const int32_t *d
                             int fill_mode, gnn_graph_t **out);
 GNN_API int gnn_graph_build_h(gnn_ctx_t *ctx, const int32_t *src_h, const int32_t *dst_h, int64_t E, int32_t N,
                               int fill_mode, gnn_graph_t **out);
+/* Weighted adjacency — graph::edge_to_adj_mat with edge_attr (reference src/graph.cpp:21-44): A[src][dst] = w by
+ * assignment in edge order, so the LAST weight of a duplicated (src, dst) wins; fill_mode 1 then forces the diagonal to 1
+ * (tensor::fill_diagonal_(1): the A + I of the north-star layer), 2 leaves it as given.  w: device float[E].
+ * The structure equals the unweighted build; gnn_graph_normalize then uses the weighted degree
+ * deg = rowsum(A), dinv = deg^-1/2, val = (A * dinv) * dinv^T. */
+GNN_API int gnn_graph_build_weighted(gnn_ctx_t *ctx, const int32_t *src, const int32_t *dst, const float *w, int64_t E,
+                                     int32_t N, int fill_mode, gnn_graph_t **out);
+/* raw weights of the stored entries (host float[nnz], CSR order); synchronises */
+GNN_API int gnn_graph_export_weights_h(gnn_ctx_t *ctx, const gnn_graph_t *g, float *val0_h);
 /* Adopt an existing device CSR (used by the row-partitioned multi-GPU path: local rows, global columns).
  * n_rows x n_cols, rowptr[n_rows+1] int32, colidx[nnz] int32, val[nnz] fp32 or NULL; arrays are copied. */
 GNN_API int gnn_graph_from_csr(gnn_ctx_t *ctx, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
@@ -102,7 +111,8 @@ GNN_API int gnn_graph_export_h(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t *ro
                                float *val_h, int32_t *colptr_h, int32_t *rowidx_h, int32_t *perm_h, float *valT_h,
                                int32_t *deg_h, float *dinv_h);
 /* Dense adjacency (graph::Data::to_adj / edge_to_adj_mat, src/graph.cpp:118-129) for API fidelity at small N:
- * out[n_rows, n_cols] = weighted ? val : 1 at the stored positions, 0 elsewhere. */
+ * out[n_rows, n_cols] = 1 (weighted 0), the normalised value (1) or the raw edge weight (2: Data::to_adj with edge_attr)
+ * at the stored positions, 0 elsewhere. */
 GNN_API int gnn_graph_to_dense(gnn_ctx_t *ctx, const gnn_graph_t *g, int weighted, float *out, int64_t ld);
 /* Dense matrix -> row-major sorted COO of the entries with int(a) != 0 (graph::adj_to_edge_list,
  * src/graph.cpp:46-67).  Two passes (flag + scan + compact); *count_h receives the number of entries; when
