@@ -519,6 +519,89 @@ ORC_API void orc_batchnorm_bwd(int64_t N, int32_t F, const float *X, int64_t ldx
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * nn::LayerNorm (src/nn.cpp:332-353): per row  y = (x - mean) / pow(var + eps, 0.5) * gamma + beta,
+ *   mean = x->mean(-1,true) (ascending fp32 sum / F), var = x->var(-1, 0, true) (two passes, correction 0);
+ * optional ReLU (nn::MLP puts nn::ReLU right after, include/nn.h:193-214).  order=1: fp64 statistics.
+ * mean / rstd (= 1/sqrt(var+eps)) per row are returned for the backward.
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API void orc_layernorm_fwd(int64_t N, int32_t F, const float *X, int64_t ldx, const float *gamma, const float *beta,
+                               float eps, int relu, float *Y, int64_t ldy, float *mean, float *rstd, int order) {
+    for (int64_t r = 0; r < N; r++) {
+        const float *x = X + r * ldx;
+        float m, v;
+        if (order == 0) {
+            float s = 0.0f;
+            for (int32_t c = 0; c < F; c++) s = s + x[c];
+            m = s / (float)F;
+            float q = 0.0f;
+            for (int32_t c = 0; c < F; c++) { float d = x[c] - m; q = q + powf(d, 2.0f); }
+            v = q / (float)F;
+        } else {
+            double s = 0.0;
+            for (int32_t c = 0; c < F; c++) s += x[c];
+            double md = s / F, q = 0.0;
+            for (int32_t c = 0; c < F; c++) { double d = x[c] - md; q += d * d; }
+            m = (float)md;
+            v = (float)(q / F);
+        }
+        mean[r] = m;
+        rstd[r] = 1.0f / powf(v + eps, 0.5f);
+        for (int32_t c = 0; c < F; c++) {
+            float o = (x[c] - m) / powf(v + eps, 0.5f);
+            if (gamma) o = o * gamma[c];
+            if (beta) o = o + beta[c];
+            if (relu) o = o > 0.0f ? o : 0.0f;
+            Y[r * ldy + c] = o;
+        }
+    }
+}
+/* standard layer-norm gradient (the reference autograd loses the fan-out terms, bug B2; pinned against torch) */
+ORC_API void orc_layernorm_bwd(int64_t N, int32_t F, const float *X, int64_t ldx, const float *mean, const float *rstd,
+                               const float *gamma, int relu, const float *Yout, int64_t ldy, const float *dY, int64_t ldd,
+                               float *dX, int64_t ldo, float *dgamma, float *dbeta) {
+    double *sg = (double *)calloc((size_t)F, 8), *sgx = (double *)calloc((size_t)F, 8);
+    for (int64_t r = 0; r < N; r++) {
+        double a = 0.0, b = 0.0;
+        for (int32_t c = 0; c < F; c++) {
+            double g = dY[r * ldd + c];
+            if (relu && !(Yout[r * ldy + c] > 0.0f)) g = 0.0;
+            const double xh = ((double)X[r * ldx + c] - mean[r]) * rstd[r];
+            sg[c] += g;
+            sgx[c] += g * xh;
+            const double gg = g * (gamma ? gamma[c] : 1.0);
+            a += gg;
+            b += gg * xh;
+        }
+        for (int32_t c = 0; c < F; c++) {
+            double g = dY[r * ldd + c];
+            if (relu && !(Yout[r * ldy + c] > 0.0f)) g = 0.0;
+            const double xh = ((double)X[r * ldx + c] - mean[r]) * rstd[r];
+            const double gg = g * (gamma ? gamma[c] : 1.0);
+            dX[r * ldo + c] = (float)(rstd[r] * (gg - a / F - xh * b / F));
+        }
+    }
+    for (int32_t c = 0; c < F; c++) { if (dgamma) dgamma[c] = (float)sgx[c]; if (dbeta) dbeta[c] = (float)sg[c]; }
+    free(sg); free(sgx);
+}
+/* nn::tanh as written (src/nn.cpp:355-364): s = x + 1e-12; (exp(s) - exp(-s)) / (exp(s) + exp(-s)) in fp32 */
+ORC_API void orc_tanh_fwd(int64_t n, const float *x, float *y) {
+    for (int64_t i = 0; i < n; i++) {
+        const float s = x[i] + 1e-12f;
+        const float ep = expf(s), em = expf(-s);
+        y[i] = (ep - em) / (ep + em);
+    }
+}
+/* Dropout keep-mask of the build (the reference seeds a fresh engine from time(), bug B6: unpinned): element i is kept
+ * when u_i = (splitmix-hash(seed, 77, i) >> 40) * 2^-24 >= p; kept values are scaled by 1/(1-p) (src/nn.cpp:246-266). */
+ORC_API void orc_dropout_fwd(int64_t n, const float *x, float p, uint64_t seed, float *y) {
+    const float scale = 1.0f / (1.0f - p);
+    for (int64_t i = 0; i < n; i++) {
+        const float u = (float)(orc_hash3(seed, 77, (uint64_t)i) >> 40) * (1.0f / 16777216.0f);
+        y[i] = u >= p ? x[i] * scale : 0.0f;
+    }
+}
+
 /* The factorised normalisation of graph::GCNConv::forward as written (src/graph.cpp:176-185) on the loop-free
  * adjacency A0 (CSR without diagonal):  deg = rowsum(A0)+1, dinv = pow(deg,-0.5), norm = (A0 dinv) * dinv, where the
  * matrix-vector product is the reference's descending-k fp32 dot product. */

@@ -63,6 +63,12 @@ def lib():
         L.orc_csr_build_weighted.restype = C.c_int64
         L.orc_csr_build_weighted.argtypes = [_i32p, _i32p, _f32p, C.c_int64, C.c_int32, C.c_int, _i64p, _i32p, _f32p]
         L.orc_degree_norm_weighted.argtypes = [C.c_int32, _i64p, _i32p, _f32p, _f32p, _f32p, _f32p]
+        L.orc_layernorm_fwd.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_int, _f32p,
+                                        C.c_int64, _f32p, _f32p, C.c_int]
+        L.orc_layernorm_bwd.argtypes = [C.c_int64, C.c_int32, _f32p, C.c_int64, _f32p, _f32p, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_int64, _f32p, C.c_int64, _f32p, C.c_int64, _f32p, _f32p]
+        L.orc_tanh_fwd.argtypes = [C.c_int64, _f32p, _f32p]
+        L.orc_dropout_fwd.argtypes = [C.c_int64, _f32p, C.c_float, C.c_uint64, _f32p]
         L.orc_partition_ptr.argtypes = [C.c_int64, C.c_int32, _i64p]
         L.orc_partition_rows.restype = C.c_int64
         L.orc_partition_rows.argtypes = [_i64p, _i32p, C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, C.c_void_p]
@@ -282,6 +288,49 @@ def batchnorm_bwd(X, mean, var, gamma, dY, eps=1e-5, relu_out=None):
     lib().orc_batchnorm_bwd(N, F, X, F, mean, var, np.ascontiguousarray(gamma, dtype=np.float32), eps,
                             int(relu_out is not None), _ptr(relu_out), F, dY, F, dX, F, dg, db)
     return dX, dg, db
+
+
+def layernorm_fwd(X, gamma=None, beta=None, eps=1e-5, relu=False, order=0):
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    N, F = X.shape
+    Y = np.empty_like(X); mean = np.empty(N, np.float32); rstd = np.empty(N, np.float32)
+    lib().orc_layernorm_fwd(N, F, X, F, _ptr(gamma), _ptr(beta), eps, int(relu), Y, F, mean, rstd, order)
+    return Y, mean, rstd
+
+
+def layernorm_bwd(X, mean, rstd, gamma, dY, relu_out=None):
+    X = np.ascontiguousarray(X, dtype=np.float32); dY = np.ascontiguousarray(dY, dtype=np.float32)
+    N, F = X.shape
+    dX = np.empty_like(X); dg = np.empty(F, np.float32); db = np.empty(F, np.float32)
+    lib().orc_layernorm_bwd(N, F, X, F, mean, rstd, _ptr(gamma), int(relu_out is not None), _ptr(relu_out), F, dY, F, dX, F, dg, db)
+    return dX, dg, db
+
+
+def tanh_fwd(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    lib().orc_tanh_fwd(x.size, x.reshape(-1), y.reshape(-1))
+    return y
+
+
+def dropout_fwd(x, p, seed):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    lib().orc_dropout_fwd(x.size, x.reshape(-1), p, int(seed), y.reshape(-1))
+    return y
+
+
+def mlp_fwd(X, Ws, bs, gammas, betas, order=0):
+    """nn::MLP::forward (reference include/nn.h:193-214) with dropout p = 0: per layer Linear, then LayerNorm + ReLU
+    unless the layer's width equals the last width.  gammas/betas: per layer, None where the layer has no LayerNorm."""
+    H = np.ascontiguousarray(X, dtype=np.float32)
+    outs = []
+    for W, b, g, be in zip(Ws, bs, gammas, betas):
+        H = (gemm_nt(H, W, order) + np.asarray(b, np.float32)[None, :]).astype(np.float32)
+        if g is not None:
+            H, _, _ = layernorm_fwd(H, g, be, relu=True, order=order)
+        outs.append(H)
+    return outs
 
 
 def gcnconv_as_written(src, dst, N, X, W, bias, gamma, beta, eps=1e-5, order=0):

@@ -20,6 +20,7 @@
 //   ref_gcn structure <problem.gcnp> <out.gcno>
 //   ref_gcn step      <problem.gcnp> <out.gcno>
 //   ref_gcn structure_w <problem.gcnp> <out.gcno>    (weighted adjacency + normalisation, mode B with edge_attr)
+//   ref_gcn mlp       <problem.gcnp> <out.gcno>      (nn::MLP forward + nn::tanh on the problem's X / W / b)
 //   ref_gcn aswritten <problem.gcnp> <out.gcno>      (one graph::GCNConv::forward exactly as written)
 //   ref_gcn time      <problem.gcnp> <steps>         (prints one JSON line with per-stage ms)
 #include "graph.h"
@@ -220,6 +221,42 @@ int cmd_structure_w(const Problem &p, const char *out) {
     return 0;
 }
 
+// nn::MLP (include/nn.h:193-214: Linear [+ LayerNorm + ReLU] + Dropout(p = 0) per layer) and nn::tanh (src/nn.cpp:355-364)
+// through the reference's own modules.  The MLP has widths dims[0] -> dims[1] -> ... -> dims[L]; Linear weights/biases
+// are the problem's W/b, LayerNorm gammas = 1 + b/2, betas = b/4 on the layers that have one.
+int cmd_mlp(const Problem &p, const char *out) {
+    Writer w(out);
+    std::vector<size_t> hid;
+    for (int64_t l = 1; l <= p.L; l++) hid.push_back((size_t)p.dims[l]);
+    nn::MLP mlp((size_t)p.dims[0], hid, true, 0.0f);
+    // nn::MLP::forward looks its Sequential up by name, which the reference's named_modules() cannot resolve (leaves are
+    // keyed by their class name, src/nn.cpp:87-102), so the children are reached through the public _modules lists and
+    // the Sequential's own forward (src/nn.cpp:219-227) is run — the same module chain MLP::forward was meant to run.
+    auto seq = mlp._modules[0].second;
+    auto child = [&](const std::string &n) -> std::shared_ptr<nn::Module> {
+        for (auto &kv : seq->_modules) if (kv.first == n) return kv.second;
+        fprintf(stderr, "ref_driver: no child %s\n", n.c_str()); exit(2);
+    };
+    for (int64_t l = 0; l < p.L; l++) {
+        std::valarray<float> wv(p.W[l].data(), p.W[l].size()), bv(p.b[l].data(), p.b[l].size());
+        auto lin = child("lin_" + std::to_string(l));
+        lin->_parameters["weight"]->set_data(&wv);
+        lin->_parameters["bias"]->set_data(&bv);
+        if (p.dims[l + 1] != p.dims[p.L]) {
+            std::valarray<float> gam = 1.0f + 0.5f * bv, bet = 0.25f * bv;
+            auto ln = child("lnorm_" + std::to_string(l));
+            ln->_parameters["gammas"]->set_data(&gam);
+            ln->_parameters["betas"]->set_data(&bet);
+        }
+    }
+    auto x = make_f(p.X, {(size_t)p.N, (size_t)p.dims[0]}, false);
+    auto y = seq->forward(x);
+    w.f32("mlp_out", *y->data(), y->shape());
+    auto t = nn::tanh(y);
+    w.f32("tanh_out", *t->data(), t->shape());
+    return 0;
+}
+
 // The reference's graph::GCNConv layer EXACTLY AS WRITTEN (src/graph.cpp:160-212), run through its own forward():
 //   add_self_loops(..., 0)  -> loops removed;  lin (no bias) -> BatchNorm (training statistics) -> ReLU;
 //   deg = rowsum(A0) + 1; dinv = deg^-0.5; norm = (A0 dinv) * dinv;  out = (A0 h) * norm + bias
@@ -261,6 +298,7 @@ int main(int argc, char **argv) {
     if (cmd == "step") { Writer w(argv[3]); return run_step(p, &w, nullptr); }
     if (cmd == "aswritten") return cmd_aswritten(p, argv[3]);
     if (cmd == "structure_w") return cmd_structure_w(p, argv[3]);
+    if (cmd == "mlp") return cmd_mlp(p, argv[3]);
     if (cmd == "time") {
         int steps = atoi(argv[3]);
         StepTimes tm;

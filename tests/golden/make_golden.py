@@ -76,6 +76,22 @@ def run_aswritten(prob, name, subsample=256):
     print("aswritten", name, {k: v.shape for k, v in res.items()})
 
 
+def run_mlp(prob, name, subsample=256):
+    """nn::MLP forward + nn::tanh through the reference (ref_gcn mlp)"""
+    with tempfile.TemporaryDirectory() as td:
+        pin = os.path.join(td, "p.gcnp")
+        problem_io.write_problem(pin, prob)
+        subprocess.check_call([REF, "mlp", pin, os.path.join(td, "o.gcno")])
+        res = problem_io.read_results(os.path.join(td, "o.gcno"))
+    n = res["mlp_out"].shape[0]
+    if n > subsample:
+        rows = np.arange(0, n, n // subsample, dtype=np.int64)
+        res = {k: v[rows].copy() for k, v in res.items()}
+        res["rows"] = rows
+    np.savez_compressed(os.path.join(OUT, "mlp_" + name + ".npz"), **res)
+    print("mlp", name, {k: v.shape for k, v in res.items()})
+
+
 def run_weighted(prob, name):
     """weighted adjacency + normalisation through the reference (ref_gcn structure_w)"""
     with tempfile.TemporaryDirectory() as td:
@@ -109,8 +125,9 @@ def main():
     for k in ("toy", "tiny", "directed", "tiny_pl"):
         prob = directed_problem() if k == "directed" else synth.make_problem(synth.CONFIGS[k])
         jobs["weighted_" + k] = (lambda prob=prob, k=k: run_weighted(prob, k))
+        jobs["mlp_" + k] = (lambda prob=prob, k=k: run_mlp(prob, k))
     for k, fn in jobs.items():
-        if a.only is None or a.only == k or (a.only in ("aswritten", "weighted") and k.startswith(a.only + "_")):
+        if a.only is None or a.only == k or (a.only in ("aswritten", "weighted", "mlp") and k.startswith(a.only + "_")):
             fn()
 
 

@@ -231,3 +231,57 @@ def test_weighted_adjacency_bit_exact(oracle, name):
     # structure equals the unweighted build (weights never change which entries exist)
     G1 = oracle.Graph(p.src, p.dst, p.cfg.N)
     assert np.array_equal(G.rowptr, G1.rowptr) and np.array_equal(G.colidx, G1.colidx)
+
+
+def _mlp_params(p):
+    """LayerNorm on every MLP layer whose width differs from the last width (include/nn.h:201); gammas/betas as in
+    oracle/ref_driver.cpp:cmd_mlp"""
+    last = p.cfg.dims[-1]
+    gam = [(1 + 0.5 * b).astype(np.float32) if d != last else None for b, d in zip(p.b, p.cfg.dims[1:])]
+    bet = [(0.25 * b).astype(np.float32) if d != last else None for b, d in zip(p.b, p.cfg.dims[1:])]
+    return gam, bet
+
+
+@pytest.mark.parametrize("name", ["toy", "tiny", "directed", "tiny_pl"])
+def test_mlp_layernorm_tanh_match_reference(oracle, name):
+    """SURVEY §8f row 2: nn::MLP (Linear -> LayerNorm -> ReLU -> Dropout(0) chain, include/nn.h:193-214) and nn::tanh
+    (src/nn.cpp:355-364) restated vs outputs of the REAL reference modules (`ref_gcn mlp`)."""
+    p = load_problem(name)
+    g = np.load(os.path.join(GOLDEN, "mlp_%s.npz" % name))
+    rows = g["rows"] if "rows" in g.files else slice(None)
+    gam, bet = _mlp_params(p)
+    out = oracle.mlp_fwd(p.X, p.W, p.b, gam, bet, order=0)[-1]
+    assert np.abs(out[rows] - g["mlp_out"]).max() <= AW_TOL * np.abs(g["mlp_out"]).max()
+    t = oracle.tanh_fwd(out)
+    assert np.abs(t[rows] - g["tanh_out"]).max() <= AW_TOL
+    assert np.abs(np.tanh(out.astype(np.float64)) - t).max() <= 1e-6          # the as-written formula is tanh
+
+
+def test_layernorm_backward_and_dropout(oracle):
+    """LayerNorm backward pinned to torch (the reference loses the fan-out terms, bug B2); dropout: kept fraction,
+    1/(1-p) scaling, determinism in the seed (the reference's mask is time-seeded, bug B6: unpinned)"""
+    import torch
+    rng = np.random.default_rng(6)
+    N, F = 64, 19
+    X = (rng.standard_normal((N, F)) * 3 + 0.5).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, F).astype(np.float32); beta = rng.uniform(-0.5, 0.5, F).astype(np.float32)
+    dY = rng.standard_normal((N, F)).astype(np.float32)
+    for relu in (False, True):
+        Y, mean, rstd = oracle.layernorm_fwd(X, gamma, beta, relu=relu, order=1)
+        xt = torch.tensor(X, dtype=torch.float64, requires_grad=True)
+        gt = torch.tensor(gamma, dtype=torch.float64, requires_grad=True); bt = torch.tensor(beta, dtype=torch.float64, requires_grad=True)
+        yt = torch.nn.functional.layer_norm(xt, (F,), gt, bt, eps=1e-5)
+        if relu:
+            yt = torch.relu(yt)
+        np.testing.assert_allclose(Y, yt.detach().numpy(), rtol=2e-5, atol=2e-6)
+        yt.backward(torch.tensor(dY, dtype=torch.float64))
+        dX, dg, db = oracle.layernorm_bwd(X, mean, rstd, gamma, dY, relu_out=Y if relu else None)
+        np.testing.assert_allclose(dX, xt.grad.numpy(), rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(dg, gt.grad.numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(db, bt.grad.numpy(), rtol=1e-5, atol=1e-5)
+    x = np.ones(200000, np.float32)
+    y = oracle.dropout_fwd(x, 0.3, 5)
+    kept = y != 0
+    assert abs(kept.mean() - 0.7) < 0.005 and np.allclose(y[kept], 1 / 0.7)
+    assert np.array_equal(y, oracle.dropout_fwd(x, 0.3, 5)) and not np.array_equal(y, oracle.dropout_fwd(x, 0.3, 6))
+    assert np.array_equal(oracle.dropout_fwd(x, 0.0, 5), x)
