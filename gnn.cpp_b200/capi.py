@@ -59,6 +59,11 @@ SIGNATURES = {
     "gnn_sgd_step": (C.c_int, [vp, i64, vp, vp, vp, f32, f32, f32, f32, C.c_int, C.c_int]),
     "gnn_batchnorm_fwd": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, f32, C.c_int, vp, i64, vp, vp]),
     "gnn_batchnorm_bwd": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, vp, f32, vp, i64, vp, i64, vp, i64, vp, vp]),
+    "gnn_layernorm_fwd": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, f32, C.c_int, vp, i64, vp, vp]),
+    "gnn_layernorm_bwd": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp]),
+    "gnn_tanh_fwd": (C.c_int, [vp, i64, vp, vp]),
+    "gnn_tanh_bwd": (C.c_int, [vp, i64, vp, vp, vp]),
+    "gnn_dropout": (C.c_int, [vp, i64, vp, f32, C.c_uint64, vp]),
     "gnn_adam_step": (C.c_int, [vp, i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, i64]),
     "gnn_softmax_xent_masked": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, i64, vp, vp, i64]),
     "gnn_argmax_correct": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, vp]),

@@ -531,6 +531,118 @@ __global__ void bn_bwd_apply_kernel(int64_t N, int32_t F, const float *__restric
     }
 }
 
+// ---- LayerNorm over the feature dimension (nn::LayerNorm, reference src/nn.cpp:332-353): one warp per row --------
+__global__ void __launch_bounds__(256)
+    layernorm_fwd_kernel(int64_t N, int32_t F, const float *__restrict__ X, int64_t ldx, const float *__restrict__ gamma,
+                         const float *__restrict__ beta, float eps, int relu, float *__restrict__ Y, int64_t ldy,
+                         float *__restrict__ mean, float *__restrict__ rstd) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= N) return;
+    const float *x = X + r * ldx;
+    float s = 0.f;
+    for (int32_t c = lane; c < F; c += 32) s += x[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float m = s / (float)F;
+    float q = 0.f;
+    for (int32_t c = lane; c < F; c += 32) { const float d = x[c] - m; q += d * d; } // two passes like functional::var
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rs = 1.0f / sqrtf(q / (float)F + eps);
+    if (lane == 0) { mean[r] = m; rstd[r] = rs; }
+    for (int32_t c = lane; c < F; c += 32) {
+        float v = (x[c] - m) * rs;
+        if (gamma) v *= gamma[c];
+        if (beta) v += beta[c];
+        if (relu) v = v > 0.f ? v : 0.f;
+        Y[r * ldy + c] = v;
+    }
+}
+// dX = rstd * (gg - mean(gg) - xhat * mean(gg xhat)),  gg = g * gamma, g = dY masked by the forward output
+__global__ void __launch_bounds__(256)
+    layernorm_bwd_kernel(int64_t N, int32_t F, const float *__restrict__ X, int64_t ldx, const float *__restrict__ mean,
+                         const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ Yout,
+                         int64_t ldy, const float *__restrict__ dY, int64_t ldd, float *__restrict__ dX, int64_t ldo) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= N) return;
+    const float m = mean[r], rs = rstd[r];
+    float a = 0.f, b = 0.f;
+    for (int32_t c = lane; c < F; c += 32) {
+        float g = dY[r * ldd + c];
+        if (Yout && !(Yout[r * ldy + c] > 0.f)) g = 0.f;
+        const float gg = g * (gamma ? gamma[c] : 1.f);
+        const float xh = (X[r * ldx + c] - m) * rs;
+        a += gg;
+        b += gg * xh;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    const float inv_f = 1.f / (float)F;
+    for (int32_t c = lane; c < F; c += 32) {
+        float g = dY[r * ldd + c];
+        if (Yout && !(Yout[r * ldy + c] > 0.f)) g = 0.f;
+        const float gg = g * (gamma ? gamma[c] : 1.f);
+        const float xh = (X[r * ldx + c] - m) * rs;
+        dX[r * ldo + c] = rs * (gg - a * inv_f - xh * b * inv_f);
+    }
+}
+// per-column sums of g and g * xhat with PER-ROW statistics (dbeta, dgamma of LayerNorm): same layout as bn_partial
+__global__ void __launch_bounds__(CS_THREADS)
+    ln_colred_partial_kernel(int64_t N, int32_t F, const float *__restrict__ X, int64_t ldx, const float *__restrict__ mean,
+                             const float *__restrict__ rstd, const float *__restrict__ dY, int64_t ldd,
+                             const float *__restrict__ Yout, int64_t ldy, int64_t rows_per_block, float *__restrict__ partial) {
+    __shared__ float red[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(N, r0 + rows_per_block);
+    for (int32_t c0 = 0; c0 < F; c0 += 32) {
+        const int32_t c = c0 + tx;
+        float s0 = 0.f, s1 = 0.f;
+        if (c < F)
+            for (int64_t r = r0 + ty; r < r1; r += 8) {
+                float g = dY[r * ldd + c];
+                if (Yout && !(Yout[r * ldy + c] > 0.f)) g = 0.f;
+                s0 += g;
+                s1 += g * ((X[r * ldx + c] - mean[r]) * rstd[r]);
+            }
+        red[0][ty][tx] = s0;
+        red[1][ty][tx] = s1;
+        __syncthreads();
+        if (ty == 0 && c < F) {
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { t0 += red[0][j][tx]; t1 += red[1][j][tx]; }
+            partial[(int64_t)blockIdx.x * 2 * F + c] = t0;
+            partial[(int64_t)blockIdx.x * 2 * F + F + c] = t1;
+        }
+        __syncthreads();
+    }
+}
+__global__ void tanh_fwd_kernel(int64_t n, const float *__restrict__ x, float *__restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = tanhf(x[i] + 1e-12f); // = (e^s - e^-s)/(e^s + e^-s) of nn::tanh (src/nn.cpp:355-364) without its overflow
+}
+__global__ void tanh_bwd_kernel(int64_t n, const float *__restrict__ y, const float *__restrict__ dy, float *__restrict__ dx) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dx[i] = dy[i] * (1.f - y[i] * y[i]);
+}
+// counter-based keep mask, identical to oracle/gcn_oracle.c:orc_dropout_fwd (splitmix64 of (seed, stream 77, index))
+__device__ __forceinline__ uint64_t mix64_dev(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void dropout_kernel(int64_t n, const float *__restrict__ x, float p, uint64_t base, float *__restrict__ y) {
+    const float scale = 1.f / (1.f - p);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float u = (float)(mix64_dev(base + (uint64_t)i) >> 40) * (1.0f / 16777216.0f);
+        y[i] = u >= p ? x[i] * scale : 0.f;
+    }
+}
+
 static int bn_blocks(gnn_ctx *ctx, int64_t N, int64_t *rows_per_block) {
     int64_t nblocks = (int64_t)ctx->sm_count * 4;
     int64_t rpb = ceil_div(N, nblocks);
@@ -702,6 +814,68 @@ int gnn_batchnorm_bwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *X, int6
     GNN_LAUNCHED(ctx);
     bn_bwd_apply_kernel<<<stream_grid(ctx, N * F, 256), 256, 0, ctx->stream>>>(N, F, X, ldx, mean, var, eps, gamma, dY, ldd,
                                                                               relu_out, ldy, dbeta, dgamma, dX, ldo);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_layernorm_fwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *X, int64_t ldx, const float *gamma,
+                      const float *beta, float eps, int relu, float *Y, int64_t ldy, float *mean, float *rstd) {
+    GNN_REQUIRE(ctx && X && Y && mean && rstd && N > 0 && F > 0 && ldx >= F && ldy >= F, "gnn_layernorm_fwd: bad argument");
+    layernorm_fwd_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, ctx->stream>>>(N, F, X, ldx, gamma, beta, eps, relu, Y, ldy,
+                                                                                  mean, rstd);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+int gnn_layernorm_bwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *X, int64_t ldx, const float *mean, const float *rstd,
+                      const float *gamma, const float *relu_out, int64_t ldy, const float *dY, int64_t ldd, float *dX,
+                      int64_t ldo, float *dgamma, float *dbeta) {
+    GNN_REQUIRE(ctx && X && mean && rstd && dY && dX && N > 0 && F > 0, "gnn_layernorm_bwd: bad argument");
+    layernorm_bwd_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, ctx->stream>>>(N, F, X, ldx, mean, rstd, gamma, relu_out, ldy,
+                                                                                  dY, ldd, dX, ldo);
+    GNN_LAUNCHED(ctx);
+    if (dgamma || dbeta) {
+        int64_t rpb = 0;
+        const int nb = bn_blocks(ctx, N, &rpb);
+        void *ws = nullptr;
+        GNN_TRY(ctx->workspace((size_t)nb * 2 * F * 4, &ws));
+        float *part = (float *)ws;
+        ln_colred_partial_kernel<<<nb, CS_THREADS, 0, ctx->stream>>>(N, F, X, ldx, mean, rstd, dY, ldd, relu_out, ldy, rpb, part);
+        GNN_LAUNCHED(ctx);
+        if (dbeta) {
+            bn_final_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, ctx->stream>>>(F, nb, part, 0, 1.0f, dbeta);
+            GNN_LAUNCHED(ctx);
+        }
+        if (dgamma) {
+            bn_final_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, ctx->stream>>>(F, nb, part, 1, 1.0f, dgamma);
+            GNN_LAUNCHED(ctx);
+        }
+    }
+    return 0;
+}
+
+int gnn_tanh_fwd(gnn_ctx_t *ctx, int64_t n, const float *x, float *y) {
+    GNN_REQUIRE(ctx && x && y && n > 0, "gnn_tanh_fwd: bad argument");
+    tanh_fwd_kernel<<<stream_grid(ctx, n, 256), 256, 0, ctx->stream>>>(n, x, y);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+int gnn_tanh_bwd(gnn_ctx_t *ctx, int64_t n, const float *y, const float *dy, float *dx) {
+    GNN_REQUIRE(ctx && y && dy && dx && n > 0, "gnn_tanh_bwd: bad argument");
+    tanh_bwd_kernel<<<stream_grid(ctx, n, 256), 256, 0, ctx->stream>>>(n, y, dy, dx);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+int gnn_dropout(gnn_ctx_t *ctx, int64_t n, const float *x, float p, uint64_t seed, float *y) {
+    GNN_REQUIRE(ctx && x && y && n > 0, "gnn_dropout: bad argument");
+    GNN_REQUIRE(p >= 0.f && p < 1.f, "invalid input, prob should be between 0 and 1 (inclusive)");
+    // hash3(seed, stream 77, i) of the synthetic-input generator: base = mix64(seed*K1 + 77*K2), value = mix64(base + i)
+    uint64_t z = seed * 0x9E3779B97F4A7C15ull + 77ull * 0xD1B54A32D192ED03ull;
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    dropout_kernel<<<stream_grid(ctx, n, 256), 256, 0, ctx->stream>>>(n, x, p, z, y);
     GNN_LAUNCHED(ctx);
     return 0;
 }

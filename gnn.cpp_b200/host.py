@@ -252,6 +252,42 @@ def batchnorm_bwd(ctx, X, mean, var, gamma, dY, eps=1e-5, relu_out=None):
     return dX, dg, db
 
 
+def layernorm_fwd(ctx, X, gamma=None, beta=None, eps=1e-5, relu=False):
+    N, F = X.shape
+    Y = torch.empty((N, F), dtype=torch.float32, device=X.device)
+    mean = torch.empty(N, dtype=torch.float32, device=X.device); rstd = torch.empty(N, dtype=torch.float32, device=X.device)
+    capi.call("gnn_layernorm_fwd", ctx.h, N, F, _ptr(X), X.stride(0), _ptr(gamma), _ptr(beta), eps, int(relu), _ptr(Y), F,
+              _ptr(mean), _ptr(rstd))
+    return Y, mean, rstd
+
+
+def layernorm_bwd(ctx, X, mean, rstd, gamma, dY, relu_out=None):
+    N, F = X.shape
+    dX = torch.empty((N, F), dtype=torch.float32, device=X.device)
+    dg = torch.empty(F, dtype=torch.float32, device=X.device); db = torch.empty(F, dtype=torch.float32, device=X.device)
+    capi.call("gnn_layernorm_bwd", ctx.h, N, F, _ptr(X), X.stride(0), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(relu_out),
+              relu_out.stride(0) if relu_out is not None else 0, _ptr(dY), dY.stride(0), _ptr(dX), F, _ptr(dg), _ptr(db))
+    return dX, dg, db
+
+
+def tanh_fwd(ctx, x):
+    y = torch.empty_like(x)
+    capi.call("gnn_tanh_fwd", ctx.h, x.numel(), _ptr(x), _ptr(y))
+    return y
+
+
+def tanh_bwd(ctx, y, dy):
+    dx = torch.empty_like(y)
+    capi.call("gnn_tanh_bwd", ctx.h, y.numel(), _ptr(y), _ptr(dy), _ptr(dx))
+    return dx
+
+
+def dropout(ctx, x, p, seed):
+    y = torch.empty_like(x)
+    capi.call("gnn_dropout", ctx.h, x.numel(), _ptr(x), float(p), int(seed), _ptr(y))
+    return y
+
+
 def adam_step(ctx, p, g, m, v, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1):
     capi.call("gnn_adam_step", ctx.h, p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), lr, beta1, beta2, eps, weight_decay, int(step))
 

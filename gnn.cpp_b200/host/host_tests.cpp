@@ -312,6 +312,65 @@ static void check_gcn_as_written_against_dense() {
     CHECK(Ze->shape() == Z->shape());
 }
 
+// nn::MLP / LayerNorm / tanh / Dropout (the reference Model's pre/post processing, main.cpp:10-30) vs the same chain
+// composed from tensor ops, gradients included
+static void test_mlp_layernorm_tanh_dropout() {
+    seed_rng(31);
+    const size_t N = 33, in = 7;
+    MLP mlp(in, {14, 7, 3}, true, 0.0f);
+    auto x = randn<float>({N, in}, -1.0f, 1.0f, false);
+    auto &ch = mlp._modules[0].second->_modules;
+    CHECK(ch.size() == 3 * 2 + 2 * 2); // lin + drop for 3 layers, lnorm + relu for the two widths != 3
+    auto ln0 = ch[1].second;
+    ln0->_parameters["gammas"]->uniform(0.5f, 1.5f);
+    ln0->_parameters["betas"]->uniform(-0.3f, 0.3f);
+    auto y = nn::tanh(mlp.forward(x));
+    auto G = randn<float>({N, 3}, -1.0f, 1.0f, false);
+    y->backward(G);
+    // composition from tensor ops
+    auto h = x;
+    std::vector<tptr<float>> Ws, bs, gs, bes;
+    for (size_t k = 0; k < ch.size(); k++) {
+        if (auto lin = std::dynamic_pointer_cast<Linear>(ch[k].second)) {
+            auto W = lin->_parameters["weight"]->clone(true), b = lin->_parameters["bias"]->clone(true);
+            Ws.push_back(W); bs.push_back(b);
+            h = h->mm(W->t()) + b;
+        } else if (auto ln = std::dynamic_pointer_cast<LayerNorm>(ch[k].second)) {
+            auto g2 = ln->_parameters["gammas"]->clone(true), be2 = ln->_parameters["betas"]->clone(true);
+            gs.push_back(g2); bes.push_back(be2);
+            auto mean = h->mean(-1, true);
+            auto cen = h - mean;
+            auto var = (cen * cen)->mean(-1, true);
+            auto stdv = ((var + 1e-5f)->log() * 0.5f)->exp();
+            h = (cen / stdv) * g2 + be2;
+            h = h->where(h > 0.0f, 0.0f);
+        }
+    }
+    auto e2 = (h * 2.0f)->exp();
+    auto yd = (e2 - 1.0f) / (e2 + 1.0f); // tanh
+    yd->backward(G);
+    CHECK(all_close(*y->data(), *yd->data(), 5e-5f));
+    auto lin0 = std::dynamic_pointer_cast<Linear>(ch[0].second);
+    CHECK(all_close(*lin0->_parameters["weight"]->grad(), *Ws[0]->grad(), 1e-4f));
+    CHECK(all_close(*lin0->_parameters["bias"]->grad(), *bs[0]->grad(), 1e-4f));
+    CHECK(all_close(*ln0->_parameters["gammas"]->grad(), *gs[0]->grad(), 1e-4f));
+    CHECK(all_close(*ln0->_parameters["betas"]->grad(), *bes[0]->grad(), 1e-4f));
+    // dropout: training mode zeroes ~p and scales by 1/(1-p); the gradient passes through the same mask; eval = identity
+    Dropout drop(0.25f);
+    auto big = std::make_shared<tensor<float>>(std::vector<size_t>{200, 100}, 1.0f, true);
+    auto d = drop.forward(big);
+    std::valarray<float> dv = *d->data();
+    size_t nz = 0;
+    for (float v : dv) nz += v != 0.0f;
+    const float kept = (float)nz / 20000.0f;
+    CHECK(std::fabs(kept - 0.75f) < 0.02f && close(dv.max(), 1.0f / 0.75f));
+    d->sum()->backward();
+    CHECK(all_close(*big->grad(), dv));
+    drop.eval();
+    CHECK(drop.forward(big).get() == big.get());
+    CHECK_THROWS_WITH(Dropout(1.5f), "prob should be between 0 and 1");
+}
+
 int main() {
     const std::pair<const char *, std::function<void()>> tests[] = {
         {"tensor_basics", test_tensor_basics},       {"elementwise_ops", test_elementwise_ops},
@@ -322,6 +381,7 @@ int main() {
         {"gcn_vs_dense_transform_first", [] { check_gcn_against_dense(12, 5); }},
         {"gcn_vs_dense_aggregate_first", [] { check_gcn_against_dense(6, 17); }},
         {"gcn_as_written_vs_dense", check_gcn_as_written_against_dense},
+        {"mlp_layernorm_tanh_dropout", test_mlp_layernorm_tanh_dropout},
     };
     for (auto &t : tests) {
         const int before = g_failed;

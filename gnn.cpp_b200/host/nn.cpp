@@ -192,6 +192,80 @@ tptr<float> BatchNorm::forward_relu(const tptr<float> &x, bool relu) {
     return out;
 }
 
+LayerNorm::LayerNorm(const size_t &normalized_shape, const float &eps, const bool &elementwise_affine, const bool &bias, const std::string &n)
+    : Module(n), _normalized_shape(normalized_shape), _eps(eps), _elementwise_affine(elementwise_affine), _bias(bias) {
+    std::vector<size_t> dims = {1, normalized_shape};
+    if (elementwise_affine) {
+        register_parameter("gammas", std::make_shared<tensor<float>>(dims, 1.0f, true));
+        if (_bias) register_parameter("betas", std::make_shared<tensor<float>>(dims, 0.0f, true));
+    }
+    training = true;
+}
+
+tptr<float> LayerNorm::forward_relu(const tptr<float> &x, bool relu) {
+    if (x->rank() != 2 || x->shape()[1] != _normalized_shape) throw std::runtime_error(err::size_mismatch());
+    auto gamma = _elementwise_affine ? _parameters["gammas"] : nullptr;
+    auto beta = (_elementwise_affine && _bias) ? _parameters["betas"] : nullptr;
+    auto op = std::make_unique<LayerNormOp<tensor<float>>>();
+    auto out = op->forward(x, gamma, beta, _eps, relu);
+    if (out->requires_grad()) out->grad_fn = std::move(op);
+    return out;
+}
+
+Dropout::Dropout(const float &p, const std::string &n) : Module(n), p(p) {
+    if (p > 1.0 || p < 0.0) throw std::runtime_error("invalid input, prob should be between 0 and 1 (inclusive)");
+    training = true;
+}
+
+tptr<float> Dropout::forward(const tptr<float> &input_tensor) {
+    if (!training || p == 0.0f) return input_tensor; // p = 0 keeps everything at scale 1
+    if (p >= 1.0f) return input_tensor * 0.0f;
+    auto op = std::make_unique<DropoutOp<tensor<float>>>();
+    auto out = op->forward(input_tensor, p, seed + 0x9E3779B97F4A7C15ull * (++calls));
+    if (out->requires_grad()) out->grad_fn = std::move(op);
+    return out;
+}
+
+tptr<float> tanh(const tptr<float> &x) {
+    auto op = std::make_unique<TanhOp<tensor<float>>>();
+    auto out = op->forward(x);
+    if (out->requires_grad()) out->grad_fn = std::move(op);
+    return out;
+}
+
+MLP::MLP(size_t in_channel, std::vector<size_t> hid_dims, const bool &bias, const float &dropout) : Module("MLP") {
+    auto seq = new Sequential();
+    int i = 0;
+    for (auto hid_dim : hid_dims) {
+        auto i_s = std::to_string(i);
+        seq->add_module("lin_" + i_s, new Linear(in_channel, hid_dim, bias));
+        if (hid_dim != hid_dims[hid_dims.size() - 1]) {
+            seq->add_module("lnorm_" + i_s, new LayerNorm(hid_dim));
+            seq->add_module("relu_" + i_s, new ReLU());
+        }
+        seq->add_module("drop_" + i_s, new Dropout(dropout));
+        in_channel = hid_dim;
+        i++;
+    }
+    register_module("seq", seq);
+}
+
+tptr<float> MLP::forward(const tptr<float> &input) {
+    // the chain of the registered children, with LayerNorm + ReLU fused into one kernel
+    auto &children = _modules[0].second->_modules;
+    auto out = input;
+    for (size_t k = 0; k < children.size(); k++) {
+        auto ln = std::dynamic_pointer_cast<LayerNorm>(children[k].second);
+        if (ln && k + 1 < children.size() && std::dynamic_pointer_cast<ReLU>(children[k + 1].second)) {
+            out = ln->forward_relu(out, true);
+            k++;
+            continue;
+        }
+        out = (*children[k].second)(out);
+    }
+    return out;
+}
+
 tptr<float> cross_entropy_loss(const tptr<float> logits, const tptr<int> target) {
     auto op = std::make_unique<SoftmaxCrossEntropy<tensor<float>>>();
     auto out = op->forward(logits, target);

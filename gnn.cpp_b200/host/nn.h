@@ -1,6 +1,6 @@
 // nn.h — Module tree, Linear, ReLU, Sequential, BatchNorm, softmax, cross-entropy loss and the optimisers of the GCN
-// training loop (counterpart of reference include/nn.h:28-123,155-191).  Out of scope here:
-// LayerNorm, Dropout, Sigmoid, tanh, MLP, Embedding.
+// training loop, plus LayerNorm, Dropout, tanh and MLP of the reference's Model (counterpart of reference
+// include/nn.h:28-214).  Out of scope here: Sigmoid, Softmax/LogSoftmax modules, Embedding.
 #ifndef GNNB200_NN_H
 #define GNNB200_NN_H
 
@@ -82,6 +82,42 @@ class BatchNorm : public Module {
     int _num_features;
     float _eps, _momentum;
     bool _affine, _tracking_running_stats;
+};
+
+/** reference nn.h:125-135, nn.cpp:332-353: parameters "gammas" (1) / "betas" (0) of shape {1, F}; forward_relu fuses the
+ *  nn::ReLU that nn::MLP applies next */
+class LayerNorm : public Module {
+  public:
+    LayerNorm(const size_t &normalized_shape, const float &eps = 1e-05, const bool &elementwise_affine = true, const bool &bias = true,
+              const std::string &n = "LayerNorm");
+    cyg::tptr<float> forward(const cyg::tptr<float> &x) override { return forward_relu(x, false); }
+    cyg::tptr<float> forward_relu(const cyg::tptr<float> &x, bool relu);
+    size_t _normalized_shape;
+    float _eps;
+    bool _elementwise_affine, _bias;
+};
+
+/** reference nn.h:93-103, nn.cpp:239-266: identity in evaluation mode; in training mode zeroes with probability p and
+ *  scales the rest by 1/(1-p).  The mask is a function of (seed, call counter, element index) instead of the
+ *  reference's time-seeded engine (bug B6): reproducible runs, fresh mask on every call. */
+class Dropout : public Module {
+  public:
+    explicit Dropout(const float &p = 0.5, const std::string &n = "Dropout");
+    cyg::tptr<float> forward(const cyg::tptr<float> &input_tensor) override;
+    float p;
+    uint64_t seed = 0x5eed, calls = 0;
+};
+
+/** (e^x - e^-x)/(e^x + e^-x) of x + 1e-12 — reference nn.cpp:355-364 — one fused node */
+cyg::tptr<float> tanh(const cyg::tptr<float> &x);
+
+/** reference nn.h:193-214: per hidden width Linear, then LayerNorm + ReLU unless the width equals the last width, then
+ *  Dropout; children "lin_i", "lnorm_i", "relu_i", "drop_i" inside a Sequential registered as "seq".
+ *  forward() runs that chain (the reference's forward cannot resolve "seq" through its own named_modules()). */
+class MLP : public Module {
+  public:
+    MLP(size_t in_channel, std::vector<size_t> hid_dims, const bool &bias = true, const float &dropout = 0.0);
+    cyg::tptr<float> forward(const cyg::tptr<float> &input) override;
 };
 
 /** softmax(x) = exp(x - log(sum(exp(x)))) composed from tensor ops like the reference (nn.cpp:270-278) */

@@ -497,6 +497,110 @@ template <class T> class BatchNormOp : public Operation<T> {
     }
 };
 
+/** nn::LayerNorm (+ the nn::ReLU nn::MLP applies next) as one node; standard layer-norm gradient (gnn_layernorm_bwd) */
+template <class T> class LayerNormOp : public Operation<T> {
+    device::buffer_ptr mean_, rstd_, out_;
+    bool relu_ = false;
+
+  public:
+    LayerNormOp() { this->name = "LayerNorm"; }
+    std::shared_ptr<T> forward(const std::shared_ptr<T> &x, const std::shared_ptr<T> &gamma, const std::shared_ptr<T> &beta, float eps, bool relu) {
+        if (x->rank() != 2 || (gamma && gamma->numel() != x->shape()[1])) throw std::runtime_error(err::size_mismatch());
+        const int64_t N = x->shape()[0], F = x->shape()[1];
+        const bool rg = x->requires_grad() || (gamma && gamma->requires_grad()) || (beta && beta->requires_grad());
+        auto out = functional::detail::make<float>(x->shape(), rg);
+        mean_ = device::alloc(N * 4);
+        rstd_ = device::alloc(N * 4);
+        device::check(gnn_layernorm_fwd(device::ctx(), N, (int32_t)F, x->dptr(), F, gamma ? gamma->dptr() : nullptr, beta ? beta->dptr() : nullptr,
+                                        eps, relu, out->dptr(), F, static_cast<float *>(mean_->ptr), static_cast<float *>(rstd_->ptr)));
+        if (rg) {
+            std::vector<std::shared_ptr<T>> saved{x};
+            if (gamma) saved.push_back(gamma);
+            if (beta) saved.push_back(beta);
+            this->context->save_for_backward(saved);
+            this->context->saved_data["gamma"] = gamma ? 1 : 0;
+            this->context->saved_data["beta"] = beta ? 1 : 0;
+            relu_ = relu;
+            if (relu) out_ = out->buffer();
+        }
+        return out;
+    }
+    void _backward(std::shared_ptr<T> g) override {
+        auto var = this->context->get_variables();
+        if (var.empty()) throw std::runtime_error("cant backprop without executing a forward computation first");
+        auto x = var[0];
+        const bool has_g = this->context->saved_data["gamma"], has_b = this->context->saved_data["beta"];
+        auto gamma = has_g ? var[1] : nullptr;
+        auto beta = has_b ? var[has_g ? 2 : 1] : nullptr;
+        const int64_t N = x->shape()[0], F = x->shape()[1];
+        auto dx = functional::detail::make<float>(x->shape(), false);
+        auto dg = gamma ? functional::detail::make<float>(gamma->shape(), false) : nullptr;
+        auto db = beta ? functional::detail::make<float>(beta->shape(), false) : nullptr;
+        device::check(gnn_layernorm_bwd(device::ctx(), N, (int32_t)F, x->dptr(), F, static_cast<const float *>(mean_->ptr),
+                                        static_cast<const float *>(rstd_->ptr), gamma ? gamma->dptr() : nullptr,
+                                        relu_ ? static_cast<const float *>(out_->ptr) : nullptr, F, g->dptr(), F, dx->dptr(), F,
+                                        dg ? dg->dptr() : nullptr, db ? db->dptr() : nullptr));
+        if (x->requires_grad()) x->backward(dx);
+        if (gamma && gamma->requires_grad()) gamma->backward(dg);
+        if (beta && beta->requires_grad()) beta->backward(db);
+        out_.reset();
+        this->_done = true;
+    }
+};
+
+/** nn::tanh (reference nn.cpp:355-364) as one node: y = tanh(x + 1e-12), dx = dy (1 - y^2) */
+template <class T> class TanhOp : public Operation<T> {
+    device::buffer_ptr out_;
+
+  public:
+    TanhOp() { this->name = "Tanh"; }
+    std::shared_ptr<T> forward(const std::shared_ptr<T> &x) {
+        auto out = functional::detail::make<float>(x->shape(), x->requires_grad());
+        device::check(gnn_tanh_fwd(device::ctx(), (int64_t)x->numel(), x->dptr(), out->dptr()));
+        if (x->requires_grad()) {
+            this->context->save_for_backward({x});
+            out_ = out->buffer();
+        }
+        return out;
+    }
+    void _backward(std::shared_ptr<T> g) override {
+        auto var = this->context->get_variables();
+        check_backward(var, 1);
+        auto dx = functional::detail::make<float>(var[0]->shape(), false);
+        device::check(gnn_tanh_bwd(device::ctx(), (int64_t)var[0]->numel(), static_cast<const float *>(out_->ptr), g->dptr(), dx->dptr()));
+        var[0]->backward(dx);
+        out_.reset();
+        this->_done = true;
+    }
+};
+
+/** nn::Dropout (reference nn.cpp:246-266) as one node with a seeded, counter-based keep mask */
+template <class T> class DropoutOp : public Operation<T> {
+    float p_ = 0.f;
+    uint64_t seed_ = 0;
+
+  public:
+    DropoutOp() { this->name = "Dropout"; }
+    std::shared_ptr<T> forward(const std::shared_ptr<T> &x, float p, uint64_t seed) {
+        auto out = functional::detail::make<float>(x->shape(), x->requires_grad());
+        device::check(gnn_dropout(device::ctx(), (int64_t)x->numel(), x->dptr(), p, seed, out->dptr()));
+        if (x->requires_grad()) {
+            this->context->save_for_backward({x});
+            p_ = p;
+            seed_ = seed;
+        }
+        return out;
+    }
+    void _backward(std::shared_ptr<T> g) override {
+        auto var = this->context->get_variables();
+        check_backward(var, 1);
+        auto dx = functional::detail::make<float>(var[0]->shape(), false);
+        device::check(gnn_dropout(device::ctx(), (int64_t)var[0]->numel(), g->dptr(), p_, seed_, dx->dptr()));
+        var[0]->backward(dx);
+        this->_done = true;
+    }
+};
+
 /** cross-entropy over the rows selected by a node mask (graph::Data::set_mask): gnn_softmax_xent_masked */
 template <class T> class MaskedSoftmaxCrossEntropy : public Operation<T> {
     std::shared_ptr<T> dZ_;

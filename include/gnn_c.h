@@ -182,6 +182,23 @@ GNN_API int gnn_batchnorm_fwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float 
 GNN_API int gnn_batchnorm_bwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *X, int64_t ldx, const float *mean,
                               const float *var, const float *gamma, float eps, const float *relu_out, int64_t ldy,
                               const float *dY, int64_t ldd, float *dX, int64_t ldo, float *dgamma, float *dbeta);
+/* nn::LayerNorm over the feature dimension (reference src/nn.cpp:332-353): per row mean / biased variance (two passes),
+ * Y = (X - mean) / sqrt(var + eps) * gamma + beta (gamma/beta may be NULL), optional fused ReLU (nn::MLP applies nn::ReLU
+ * next, include/nn.h:193-214); mean / rstd are device float[N] outputs for the backward.  Backward: the standard
+ * layer-norm gradient, ReLU mask from relu_out (the forward output, NULL = none); dgamma/dbeta device float[F] or NULL. */
+GNN_API int gnn_layernorm_fwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *X, int64_t ldx, const float *gamma,
+                              const float *beta, float eps, int relu, float *Y, int64_t ldy, float *mean, float *rstd);
+GNN_API int gnn_layernorm_bwd(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *X, int64_t ldx, const float *mean,
+                              const float *rstd, const float *gamma, const float *relu_out, int64_t ldy, const float *dY,
+                              int64_t ldd, float *dX, int64_t ldo, float *dgamma, float *dbeta);
+/* nn::tanh (src/nn.cpp:355-364; evaluated with tanhf, i.e. without the overflow of the as-written exp quotient) and its
+ * gradient dx = dy * (1 - y^2) */
+GNN_API int gnn_tanh_fwd(gnn_ctx_t *ctx, int64_t n, const float *x, float *y);
+GNN_API int gnn_tanh_bwd(gnn_ctx_t *ctx, int64_t n, const float *y, const float *dy, float *dx);
+/* nn::Dropout (src/nn.cpp:246-266): y = keep ? x / (1 - p) : 0 with a counter-based keep mask that depends only on
+ * (seed, element index) — the reference seeds a fresh engine from time() on every call (bug B6).  The backward is the
+ * same call on the incoming gradient with the same seed. */
+GNN_API int gnn_dropout(gnn_ctx_t *ctx, int64_t n, const float *x, float p, uint64_t seed, float *y);
 /* torch.optim.Adam semantics — the intent of nn::Adam (include/nn.h:180-188); the reference body (src/nn.cpp:419-441)
  * divides by sqrt(v)*eps and uses the parameter index as step count.  m, v: first/second moment buffers (zeroed by
  * the caller before step 1); step counts from 1. */

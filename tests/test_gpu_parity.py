@@ -544,6 +544,51 @@ def test_gcnconv_as_written_vs_reference(ctx, oracle, name):
     g.close()
 
 
+@pytest.mark.parametrize("name", ["toy", "tiny", "directed", "tiny_pl"])
+def test_mlp_layernorm_tanh_dropout_vs_reference(ctx, oracle, name):
+    """SURVEY §8f row 2 (the Model's pre/post nn::MLP and the tanh between convolutions, reference src/main.cpp:10-30):
+    Linear -> LayerNorm -> ReLU chain and nn::tanh on the device against outputs of the REAL reference modules
+    (tests/golden/mlp_*.npz), LayerNorm / tanh backward against the torch-pinned restatement, and the seeded dropout
+    mask bit-exact against the restatement."""
+    import os
+    import torch
+    from conftest import GOLDEN
+    from gnn_cpp_b200 import host
+    p = load_problem(name)
+    gold = np.load(os.path.join(GOLDEN, "mlp_%s.npz" % name))
+    rows = gold["rows"] if "rows" in gold.files else slice(None)
+    last = p.cfg.dims[-1]
+    H = _dev(p.X, ctx)
+    saved = None
+    for W, b, d in zip(p.W, p.b, p.cfg.dims[1:]):
+        lin = host.gemm_nt(ctx, H, _dev(W, ctx), bias=_dev(b, ctx), precision=0)
+        if d != last:
+            gam, bet = (1 + 0.5 * b).astype(np.float32), (0.25 * b).astype(np.float32)
+            H, mean, rstd = host.layernorm_fwd(ctx, lin, _dev(gam, ctx), _dev(bet, ctx), relu=True)
+            saved = (lin, mean, rstd, gam, H)
+        else:
+            H = lin
+    assert rel_err(H.cpu().numpy()[rows], gold["mlp_out"]) <= TOL
+    t = host.tanh_fwd(ctx, H)
+    assert np.abs(t.cpu().numpy()[rows] - gold["tanh_out"]).max() <= TOL
+    rng = np.random.default_rng(9)
+    dT = rng.standard_normal(tuple(t.shape)).astype(np.float32)
+    tn = t.cpu().numpy()
+    assert rel_err(host.tanh_bwd(ctx, t, _dev(dT, ctx)).cpu().numpy(), dT * (1 - tn * tn)) <= TOL
+    if saved is not None:
+        lin, mean, rstd, gam, Hn = saved
+        dY = rng.standard_normal(tuple(lin.shape)).astype(np.float32)
+        Yr, mr, rr = oracle.layernorm_fwd(lin.cpu().numpy(), gam, (0.25 * (gam - 1) / 0.5).astype(np.float32), relu=True, order=1)
+        dXr, dgr, dbr = oracle.layernorm_bwd(lin.cpu().numpy(), mr, rr, gam, dY, relu_out=Yr)
+        dX, dg, db = host.layernorm_bwd(ctx, lin, mean, rstd, _dev(gam, ctx), _dev(dY, ctx), relu_out=Hn)
+        assert rel_err(Hn.cpu().numpy(), Yr) <= TOL and rel_err(rstd.cpu().numpy(), rr) <= TOL
+        assert rel_err(dX.cpu().numpy(), dXr) <= 2 * TOL and rel_err(dg.cpu().numpy(), dgr) <= 2 * TOL
+        assert rel_err(db.cpu().numpy(), dbr) <= 2 * TOL
+    x = rng.standard_normal(100003).astype(np.float32)
+    for pdrop, seed in [(0.0, 1), (0.3, 5), (0.75, 123456789)]:
+        assert np.array_equal(host.dropout(ctx, _dev(x, ctx), pdrop, seed).cpu().numpy(), oracle.dropout_fwd(x, pdrop, seed))
+
+
 # ------------------------------------------------------------------------------------------------ whole train step
 def _run_trainer(ctx, p, lr=0.0, agg_mask=None, precision=1):
     from gnn_cpp_b200 import host
