@@ -2,14 +2,14 @@
 // (= CSR of A_hat^T, backward), with the bias / ReLU / ReLU-mask epilogue of K7 fused in.
 //
 // HBM/L2-gather bound.  Design (B200):
-//   - a group of LPR lanes owns one output row; lanes hold VEC vectors (128-bit when the leading
-//     dimensions allow) of the F-wide accumulator in registers, so each output row is written once and
-//     there are NO atomics: the per-row order is the stored (ascending-column) order, i.e. deterministic;
-//   - the group's lanes load LPR (column, value) pairs at a time, coalesced, and broadcast them with
-//     shuffles; feature rows are gathered with U independent 128-bit loads in flight per lane;
+//   - LPR lanes hold one F-wide row as VEC vectors (128-bit when the leading dimensions allow) of accumulators
+//     in registers, so each output row is written once and there are NO atomics: deterministic;
+//   - the lanes load a batch of (column, value) pairs at a time, coalesced, and broadcast them with shuffles;
+//     feature rows are gathered with U independent 128-bit loads in flight per lane;
 //   - index/value streams use the no-allocate path (read once), feature rows the default path (L2 reuse);
-//   - two work distributions, chosen by degree skew (use_merge): one row per lane group, or equal nonzero chunks
-//     per lane group with a fixed-order fix-up of the rows cut by chunk boundaries (hub rows).
+//   - two work distributions: equal nonzero chunks per WARP with a fixed-order fix-up of the rows cut by chunk
+//     boundaries (default: balanced whatever the degree skew, hub rows spread over warps), or one row per lane
+//     group (matrices with empty rows, ablation).
 #include "common.cuh"
 
 namespace gnn {

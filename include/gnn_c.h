@@ -135,8 +135,10 @@ GNN_API int gnn_spmm_fwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *P, i
                          int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm, int use_values);
 GNN_API int gnn_spmm_bwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *dZ, int64_t ldz, int32_t F, float *dP,
                          int64_t ldp, const float *mask, int64_t ldm, int use_values);
-/* SpMM variant selection: 0 = auto (by degree skew), 1 = row-per-lane-group, 2 = row-split (long rows cut
- * into fixed chunks, partials combined in fixed order). */
+/* SpMM variant selection: 0 = auto (the nonzero-balanced kernel unless the matrix has an empty row), 1 = one output
+ * row per lane group, 2 = nonzero-balanced ("merge"): equal chunks of nonzeros per warp, rows cut by a chunk boundary
+ * are completed by a fixed-order fix-up pass (no atomics).  Higher decimal digits are tuning knobs for experiments
+ * (csrc/spmm.cu). */
 GNN_API int gnn_set_spmm_variant(gnn_ctx_t *ctx, int variant);
 
 /* ---------------------------------------------------------------- dense transforms (K6) ------------
