@@ -6,6 +6,7 @@
 //
 //   gcn_main --config cora|pubmed|arxiv|reddit|products|tiny|tiny_pl [--epochs 5] [--lr 0.01]
 //   gcn_main --problem file.gcnp [--epochs 1] [--lr 0] [--dump out.gcno]
+//   gcn_main --config tiny_pl --model reference   (the reference's Model: pre/post MLP, GCNConv as written, tanh; Adam)
 #include <chrono>
 #include <cstring>
 #include <iostream>
@@ -42,12 +43,36 @@ class Model : public MessagePassing {
     std::vector<tptr<float>> activations;
 };
 
+// The reference's Model exactly in its own shape (src/main.cpp:10-30): "pre" MLP (F -> 2F -> F), one GCNConv as written per
+// hidden width with nn::tanh after each, "post" MLP (H -> 2H -> H -> classes).  (The reference's forward hands the
+// convolutions (tensor, edge_index) through Module::operator(), an overload GCNConv does not have; here they get the
+// Data object their forward takes.)
+class ReferenceModel : public MessagePassing {
+  public:
+    ReferenceModel(size_t n_classes, size_t input_dim, std::vector<size_t> hidden_dims, float p, bool bias) : MessagePassing() {
+        register_module("pre", new MLP(input_dim, {input_dim * 2, input_dim}, bias, p));
+        for (size_t i = 0; i < hidden_dims.size(); i++) {
+            register_module("enc" + std::to_string(i + 1), new GCNConvAsWritten(input_dim, hidden_dims[i]));
+            input_dim = hidden_dims[i];
+        }
+        register_module("post", new MLP(input_dim, {input_dim * 2, input_dim, n_classes}, bias, p));
+    }
+    tptr<float> forward(const Data &data) {
+        auto out = (*_modules[0].second)(data.x());
+        for (size_t i = 1; i + 1 < _modules.size(); i++) {
+            out = static_cast<GCNConvAsWritten *>(_modules[i].second.get())->forward(data.with_x(out));
+            out = nn::tanh(out);
+        }
+        return (*_modules.back().second)(out);
+    }
+};
+
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 int main(int argc, char **argv) {
-    std::string config, problem_path, dump_path;
+    std::string config, problem_path, dump_path, model_kind = "gcn";
     int epochs = 5;
     float lr = 0.01f;
     for (int i = 1; i < argc; i++) {
@@ -60,6 +85,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "--dump")) dump_path = next("--dump");
         else if (!strcmp(argv[i], "--epochs")) epochs = std::atoi(next("--epochs"));
         else if (!strcmp(argv[i], "--lr")) lr = (float)std::atof(next("--lr"));
+        else if (!strcmp(argv[i], "--model")) model_kind = next("--model"); // gcn (default) | reference
         else { std::cerr << "unknown argument " << argv[i] << "\n"; return 2; }
     }
     try {
@@ -96,6 +122,23 @@ int main(int argc, char **argv) {
                   << " ms\n";
 
         std::vector<size_t> layer_dims(p.dims.begin() + 1, p.dims.end());
+        if (model_kind == "reference") { // the reference's own Model shape, trained with Adam on seeded parameters
+            seed_rng(1234);
+            std::vector<size_t> hidden(layer_dims.begin(), layer_dims.end() - 1);
+            ReferenceModel rm((size_t)p.dims.back(), (size_t)p.dims[0], hidden, 0.1f, true);
+            Adam adam(rm.parameters(), lr);
+            for (int e = 0; e < epochs; e++) {
+                device::sync();
+                t0 = now_ms();
+                adam.zero_grad();
+                auto out = rm.forward(data);
+                auto l = cross_entropy_loss(out, y);
+                l->backward();
+                if (lr != 0.0f) adam.step();
+                std::cout << "epoch " << e << " loss " << l->item() << " step " << now_ms() - t0 << " ms\n";
+            }
+            return 0;
+        }
         Model model((size_t)p.dims[0], layer_dims);
         for (int64_t l = 1; l <= p.L; l++) { // inject the seeded parameters (reference init is time-seeded, bug B6)
             auto conv = model.get_module("enc" + std::to_string(l));

@@ -58,3 +58,18 @@ def test_main_driver_trains(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     losses = [float(l.split()[3]) for l in r.stdout.splitlines() if l.startswith("epoch")]
     assert len(losses) == 30 and losses[-1] < losses[0]
+
+
+@pytest.mark.gpu
+def test_reference_model_shape_trains(tmp_path):
+    """the reference's own Model (src/main.cpp:10-30: pre MLP, GCNConv as written + tanh, post MLP, dropout 0.1) built
+    from the C++ mirror and trained with Adam: finite, decreasing loss; two runs are bit-identical (seeded RNG, B6)."""
+    cmd = [os.path.join(HOST, "gcn_main"), "--config", "tiny_pl", "--model", "reference", "--epochs", "40", "--lr", "0.01"]
+    runs = []
+    for _ in range(2):
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        runs.append([float(l.split()[3]) for l in r.stdout.splitlines() if l.startswith("epoch")])
+    losses = runs[0]
+    assert len(losses) == 40 and all(l == l and abs(l) < 1e6 for l in losses) and min(losses[-5:]) < losses[0]
+    assert runs[0] == runs[1]
