@@ -91,6 +91,7 @@ SIGNATURES = {
     "gnn_gcn_last_spmm_spans": (C.c_int, [vp, vp, vp, vp, C.c_int, vp]),
     "gnn_gcn_spmm_stats": (C.c_int, [vp, vp, vp, vp]),
     "gnn_partition_ptr_h": (C.c_int, [i64, i32, vp]),
+    "gnn_partition_panels_h": (C.c_int, [i32, i32, vp, vp, vp]),
     "gnn_graph_slice_rows": (C.c_int, [vp, vp, i64, i64, pp]),
     "gnn_comm_unique_id_h": (C.c_int, [vp]),
     "gnn_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),

@@ -172,9 +172,9 @@ struct Panels {
     int n = 1;
     int32_t c0[MAX_PANELS] = {0}, w[MAX_PANELS] = {0};
 };
-static Panels panels_of(const gnn_gcn *m, int32_t ldw) {
+// the split itself (also exported as gnn_partition_panels_h so the host-side plan and its CPU tests use the same rule)
+static Panels split_panels(int32_t ldw, int32_t pc) {
     Panels P;
-    int32_t pc = m->arena ? m->panel_cols : ldw;
     if (pc <= 0 || (int64_t)pc * MAX_PANELS < ldw) pc = (int32_t)round_up(ceil_div(ldw, MAX_PANELS), 4);
     P.n = 0;
     for (int32_t c = 0; c < ldw; c += pc) {
@@ -184,6 +184,7 @@ static Panels panels_of(const gnn_gcn *m, int32_t ldw) {
     }
     return P;
 }
+static Panels panels_of(const gnn_gcn *m, int32_t ldw) { return split_panels(ldw, m->arena ? m->panel_cols : ldw); }
 // columns [c0, c0+f) of a logical [n_loc, F] matrix: pointer to (row 0, column c0) and leading dimension
 struct View {
     float *ptr;
@@ -810,6 +811,14 @@ int gnn_gcn_train_step_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const i
     GNN_TRY(gnn_gcn_train_step(ctx, m, m->Xs[m->cur_slot], m->ld[0], m->ys[m->cur_slot], lr, m->loss_d));
     GNN_CHECK_CUDA(cudaMemcpyAsync(loss_h, m->loss_d, 4, cudaMemcpyDeviceToHost, ctx->stream));
     GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int gnn_partition_panels_h(int32_t ldw, int32_t panel_cols, int32_t *c0_h, int32_t *w_h, int32_t *n_h) {
+    GNN_REQUIRE(ldw > 0 && ldw % 4 == 0 && c0_h && w_h && n_h, "gnn_partition_panels_h: ldw must be a positive multiple of 4");
+    const Panels P = split_panels(ldw, panel_cols);
+    for (int p = 0; p < P.n; p++) { c0_h[p] = P.c0[p]; w_h[p] = P.w[p]; }
+    *n_h = P.n;
     return 0;
 }
 

@@ -23,6 +23,25 @@ def padded(F):
     return (F + 3) // 4 * 4
 
 
+def panels(ldw, panel_cols=128):
+    """[(first column, width)] of the column panels of a gathered matrix of padded width ldw — the library's rule
+    (gnn_partition_panels_h, the one csrc/trainer.cu uses)."""
+    c0 = np.zeros(8, np.int32); w = np.zeros(8, np.int32); n = ctypes.c_int32(0)
+    capi.call("gnn_partition_panels_h", int(ldw), int(panel_cols), c0.ctypes.data_as(ctypes.c_void_p),
+              w.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n))
+    return [(int(c0[i]), int(w[i])) for i in range(n.value)]
+
+
+def tile_offsets(ldw, panel_cols, world, chunk, rank):
+    """float offsets of every rank-`rank` panel inside a gather region [panel][world][chunk, w]: (offset, floats)"""
+    out, base = [], 0
+    for c0, w in panels(ldw, panel_cols):
+        assert base == world * chunk * c0
+        out.append((base + rank * chunk * w, chunk * w))
+        base += world * chunk * w
+    return out
+
+
 def layer_order(dims):
     """True = aggregate first (A_hat H, then the GEMM): chosen when the input is narrower than the output."""
     return [dims[l - 1] < dims[l] for l in range(1, len(dims))]

@@ -287,6 +287,11 @@ GNN_API int gnn_gcn_spmm_stats(gnn_gcn_t *m, double *alg_bytes, int32_t *n_spmm,
  * columns) of its nodes with GLOBAL column ids; per aggregation the ranks all-gather their feature row
  * blocks (NCCL over NVLink) into a global-order buffer and aggregate locally. */
 GNN_API int gnn_partition_ptr_h(int64_t N, int32_t P, int64_t *part_ptr_h);
+/* Column panels of a gathered matrix of padded width ldw (multiple of 4): at most 4 panels of panel_cols columns
+ * (wider when ldw > 4 * panel_cols), starts c0_h[p] and widths w_h[p] (multiples of 4), *n_h panels.  Panel p of a
+ * gather region is stored panel-major, [world][rows_per_rank, w_h[p]], so a rank's panel is one contiguous range.
+ * Host-only (no device needed): the rule the fused trainer uses, exported for plans and tests. */
+GNN_API int gnn_partition_panels_h(int32_t ldw, int32_t panel_cols, int32_t *c0_h, int32_t *w_h, int32_t *n_h);
 /* Extract rank-local rows [lo,hi) of g as a new graph (n_rows = hi-lo, n_cols = N, global column ids),
  * including values and, when g has them, the matching CSC slice for the backward. */
 GNN_API int gnn_graph_slice_rows(gnn_ctx_t *ctx, const gnn_graph_t *g, int64_t lo, int64_t hi, gnn_graph_t **out);

@@ -17,7 +17,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _rank_main(rank, world, port, name, q):
+def _rank_main(rank, world, port, name, q, panel_cols=8):
     import sys
     sys.path.insert(0, ROOT)
     import gnn_cpp_b200  # noqa: F401
@@ -38,17 +38,33 @@ def _rank_main(rank, world, port, name, q):
     br, bc, bv = orc.partition_rows(G.colptr, np.ascontiguousarray(G.rowidx), G.valT, lo, hi)  # rows of A_hat^T
     n_loc = hi - lo
 
-    def gather(local):                       # all-gather equal (padded) chunks into global row order
-        buf = np.zeros((chunk, local.shape[1]), np.float32); buf[:n_loc] = local
-        outs = [torch.zeros(chunk, local.shape[1]) for _ in range(world)]
-        dist.all_gather(outs, torch.from_numpy(buf))
-        return np.concatenate([o.numpy() for o in outs])[:N]
+    def aggregate(X, ptr_, idx_, val_):
+        """the trainer's exchange (csrc/trainer.cu): the rank's rows are written panel-major into its block of a gather
+        region [panel][world][chunk, w]; every panel is exchanged on its own (each rank's panel is one contiguous tile
+        at dist_plan.tile_offsets) and aggregated as soon as it is complete — SpMM acts on columns independently."""
+        F = X.shape[1]
+        ldw = dist_plan.padded(F)
+        region = np.zeros(world * chunk * ldw, np.float32)
+        tiles = dist_plan.tile_offsets(ldw, panel_cols, world, chunk, rank)
+        Y = np.empty((n_loc, F), np.float32)
+        for pi, ((c0, w), (off, n)) in enumerate(zip(dist_plan.panels(ldw, panel_cols), tiles)):
+            f = min(w, F - c0)
+            own = region[off:off + n].reshape(chunk, w)
+            own[:n_loc, :f] = X[:, c0:c0 + f]                                  # produced in place by the rank
+            outs = [torch.zeros(chunk * w) for _ in range(world)]
+            dist.all_gather(outs, torch.from_numpy(region[off:off + n].copy()))
+            for q, o in enumerate(outs):                                       # lands at rank q's tile offset
+                qoff = dist_plan.tile_offsets(ldw, panel_cols, world, chunk, q)[pi][0]
+                region[qoff:qoff + n] = o.numpy()
+            panel = region[off - rank * n: off - rank * n + world * n].reshape(world * chunk, w)   # global row order
+            Y[:, c0:c0 + f] = orc.spmm(n_loc, ptr_, idx_, val_, panel[:N, :f], order=1)
+        return Y
 
     def spmm_f(X):
-        return orc.spmm(n_loc, fr, fc, fv, gather(X), order=1)
+        return aggregate(np.ascontiguousarray(X, dtype=np.float32), fr, fc, fv)
 
     def spmm_b(X):
-        return orc.spmm(n_loc, br, bc, bv, gather(X), order=1)
+        return aggregate(np.ascontiguousarray(X, dtype=np.float32), br, bc, bv)
 
     af = dist_plan.layer_order(dims)
     n_gathers = 0
@@ -104,6 +120,28 @@ def test_row_partitioned_schedule_world2_gloo(name):
         pr.join(timeout=300)
         assert pr.exitcode == 0
     assert q.get(timeout=5) <= 1e-5
+
+
+def test_panel_tiling_rule():
+    """column panels of a gather region (the library's rule through gnn_partition_panels_h): multiples of 4, at most 4
+    panels, exact cover; the per-rank tiles of all ranks tile the region without gaps or overlap."""
+    from gnn_cpp_b200 import dist_plan
+    assert dist_plan.panels(256, 128) == [(0, 128), (128, 128)]
+    assert dist_plan.panels(100, 128) == [(0, 100)]
+    assert dist_plan.panels(48, 64) == [(0, 48)]
+    assert dist_plan.panels(256, 64) == [(0, 64), (64, 64), (128, 64), (192, 64)]
+    assert dist_plan.panels(604, 64) == [(0, 152), (152, 152), (304, 152), (456, 148)]     # wider than 4 x 64: 4 equal panels
+    for ldw in (4, 48, 100, 128, 132, 256, 604, 1024):
+        for pc in (16, 64, 128, 1 << 20):
+            ps = dist_plan.panels(ldw, pc)
+            assert 1 <= len(ps) <= 4 and ps[0][0] == 0 and sum(w for _, w in ps) == ldw
+            assert all(w % 4 == 0 and w > 0 for _, w in ps) and all(ps[i][0] + ps[i][1] == ps[i + 1][0] for i in range(len(ps) - 1))
+            world, chunk = 3, 10
+            cover = np.zeros(world * chunk * ldw, np.int32)
+            for r in range(world):
+                for off, n in dist_plan.tile_offsets(ldw, pc, world, chunk, r):
+                    cover[off:off + n] += 1
+            assert bool((cover == 1).all())
 
 
 def test_plan_matches_trainer_counts():
