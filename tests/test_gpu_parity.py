@@ -745,3 +745,74 @@ def test_medium_graph_train_step_vs_fp64_oracle(ctx, oracle, precision):
         Z = ref["Z%d" % l]
         assert rel_err(out["A%d" % l], np.maximum(Z, 0) if l < L else Z) <= TOL
     _check_grads(out, ref, p, oracle, order=1)
+
+
+def test_no_out_of_bounds_writes(ctx, oracle):
+    """every output buffer sits between sentinel guard rows (and sentinel padding columns where the kernel must not touch
+    them); ragged sizes (rows not a multiple of the 128-row tiles, widths not a multiple of 4) must leave the guards
+    intact — the in-suite stand-in for a memory checker."""
+    import torch
+    from gnn_cpp_b200 import host
+    S, G = 12345.0, 64
+
+    def guarded(rows, cols, ld=None):
+        ld = ld or cols
+        buf = torch.full((rows + 2 * G, ld), S, device=ctx.device)
+        return buf, buf[G:G + rows, :cols]
+
+    def intact(buf, rows, cols=None, what=""):
+        assert bool((buf[:G] == S).all()) and bool((buf[G + rows:] == S).all()), what + ": guard rows overwritten"
+        if cols is not None and cols < buf.shape[1]:
+            assert bool((buf[G:G + rows, cols:] == S).all()), what + ": padding columns overwritten"
+
+    p = load_problem("tiny_pl")
+    N = p.cfg.N
+    g = host.Graph.build(ctx, p.src, p.dst, N)
+    rng = np.random.default_rng(12)
+    for F in (47, 100, 256):
+        ld = (F + 3) // 4 * 4
+        P = torch.zeros((N, ld), device=ctx.device); P[:, :F] = _dev(rng.uniform(-1, 1, (N, F)).astype(np.float32), ctx)
+        for variant in (1, 2):
+            from gnn_cpp_b200 import capi
+            capi.call("gnn_set_spmm_variant", ctx.h, variant)
+            buf, out = guarded(N, F, ld)
+            g.spmm_fwd(P[:, :F], out=out)
+            intact(buf, N, None, "spmm fwd F=%d v%d" % (F, variant))
+            buf, out = guarded(N, F, ld)
+            g.spmm_bwd(P[:, :F], out=out)
+            intact(buf, N, None, "spmm bwd F=%d v%d" % (F, variant))
+        capi.call("gnn_set_spmm_variant", ctx.h, 0)
+    g.close()
+    for M, Nn, K in [(3001, 47, 256), (4099, 256, 100), (777, 64, 48), (130, 16, 32)]:
+        A = torch.zeros((M, (K + 3) // 4 * 4), device=ctx.device)[:, :K]; A.copy_(_dev(rng.uniform(-1, 1, (M, K)).astype(np.float32), ctx))
+        W = _dev(rng.uniform(-1, 1, (Nn, K)).astype(np.float32), ctx)
+        ldn = (Nn + 3) // 4 * 4
+        for prec in (0, 1):
+            buf, out = guarded(M, Nn, ldn)
+            host.gemm_nt(ctx, A, W, bias=_dev(np.ones(Nn, np.float32), ctx), relu=True, precision=prec, out=out)
+            intact(buf, M, Nn, "gemm_nt %s p%d" % ((M, Nn, K), prec))
+            dP = torch.zeros((M, ldn), device=ctx.device)[:, :Nn]; dP.copy_(_dev(rng.uniform(-1, 1, (M, Nn)).astype(np.float32), ctx))
+            ldk = (K + 3) // 4 * 4
+            mask = torch.zeros((M, ldk), device=ctx.device)[:, :K]; mask.copy_(_dev(rng.uniform(-1, 1, (M, K)).astype(np.float32), ctx))
+            buf, out = guarded(M, K, ldk)
+            host.gemm_nn(ctx, dP, W, mask=mask, precision=prec, out=out)
+            intact(buf, M, K, "gemm_nn %s p%d" % ((M, Nn, K), prec))
+            buf, out = guarded(Nn, K, ldk)
+            host.gemm_tn(ctx, dP, A, precision=prec, out=out)
+            intact(buf, Nn, K, "gemm_tn %s p%d" % ((M, Nn, K), prec))
+    # loss tile kernel: N not a multiple of its 128-row tiles, dZ with padding columns
+    for Nr, C in [(3001, 47), (130, 7), (5, 3)]:
+        ldc = (C + 3) // 4 * 4
+        Z = torch.zeros((Nr, ldc), device=ctx.device)[:, :C]; Z.copy_(_dev(rng.uniform(-2, 2, (Nr, C)).astype(np.float32), ctx))
+        y = _dev(rng.integers(0, C, Nr).astype(np.int32), ctx)
+        buf, dZ = guarded(Nr, C, ldc)
+        loss = torch.zeros(1, device=ctx.device)
+        capi.call("gnn_softmax_xent", ctx.h, Nr, C, host._ptr(Z), Z.stride(0), host._ptr(y), Nr, host._ptr(loss), host._ptr(dZ), dZ.stride(0))
+        intact(buf, Nr, None, "softmax_xent N=%d" % Nr)
+        assert np.isfinite(float(loss.cpu()[0]))
+    # normalisation layers
+    X = _dev(rng.standard_normal((1001, 19)).astype(np.float32), ctx)
+    gam = _dev(np.ones(19, np.float32), ctx)
+    for fn in (host.batchnorm_fwd, host.layernorm_fwd):
+        Y, _, _ = fn(ctx, X, gam, gam, relu=True)
+        assert Y.shape == X.shape and bool(torch.isfinite(Y).all())
