@@ -816,3 +816,38 @@ def test_no_out_of_bounds_writes(ctx, oracle):
     for fn in (host.batchnorm_fwd, host.layernorm_fwd):
         Y, _, _ = fn(ctx, X, gam, gam, relu=True)
         assert Y.shape == X.shape and bool(torch.isfinite(Y).all())
+
+
+def test_structure_random_small_graphs_vs_dense_restatement(ctx, oracle):
+    """60 random tiny edge lists (duplicates, self loops, isolated nodes, a single edge): device CSR / CSC / raw
+    weights BIT-EXACT against a literal dense restatement of the reference loops (graph.cpp:21-75) for every fill mode."""
+    from gnn_cpp_b200 import host
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        N = int(rng.integers(1, 14)); E = int(rng.integers(1, 45))
+        src = rng.integers(0, N, E).astype(np.int32); dst = rng.integers(0, N, E).astype(np.int32)
+        w = oracle.edge_weights(E)
+        for fill in (0, 1, 2):
+            A = np.zeros((N, N), np.float32)
+            A[src, dst] = 1.0
+            if fill != 2:
+                np.fill_diagonal(A, float(fill))
+            rows, cols = np.nonzero(A)
+            g = host.Graph.build(ctx, src, dst, N, fill_mode=fill, csc=True, normalize=False)
+            e = g.export(values=False)
+            assert g.nnz == len(rows)
+            assert np.array_equal(np.repeat(np.arange(N), np.diff(e["rowptr"])), rows) and np.array_equal(e["colidx"], cols)
+            r2, c2 = np.nonzero(A.T)
+            assert np.array_equal(np.repeat(np.arange(N), np.diff(e["colptr"])), r2) and np.array_equal(e["rowidx"], c2)
+            assert np.array_equal(rows[e["perm"]], e["rowidx"])
+            g.close()
+        for fill in (1, 2):                                  # weighted: the last write of a duplicated pair wins
+            A = np.zeros((N, N), np.float32)
+            for i in range(E):
+                A[src[i], dst[i]] = w[i]
+            if fill == 1:
+                np.fill_diagonal(A, 1.0)
+            rows, cols = np.nonzero(A)
+            g = host.Graph.build(ctx, src, dst, N, fill_mode=fill, csc=False, normalize=False, weights=w)
+            assert g.nnz == len(rows) and np.array_equal(g.export_weights(), A[rows, cols])
+            g.close()
