@@ -1,4 +1,4 @@
-"""Bring-up / diagnosis script for the tcgen05 3xTF32 GEMMs (run on a B200: python tests/tc_debug.py [case...]).
+"""Bring-up / diagnosis script for the tcgen05 3xTF32 GEMMs (run on a B200: python tools/gemm_tc_debug.py [case...]).
 Not collected by pytest; the parity tests proper are in test_gpu_parity.py."""
 import sys
 import time
@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
+import gnn_cpp_b200  # noqa: E402,F401  (registers the package)
 from gnn_cpp_b200 import host  # noqa: E402
 
 
