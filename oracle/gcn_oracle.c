@@ -457,7 +457,8 @@ ORC_API void orc_sgd_step(int64_t n, float *p, const float *g, float *vel, float
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm over the node dimension, training statistics (nn::BatchNorm::forward, src/nn.cpp:301-330):
  *   mean_c = sum_r x[r,c] / N                        x->mean(-2,true): ascending fp32 sum (functional.h:266-307)
- *   var_c  = sum_r (x[r,c]-mean_c)^2 / max(0, N-0)   x->var(-2, 0, true): two passes, std::pow(.,2) (functional.h:383-387)
+ *   var_c  = sum_r (x[r,c]-mean_c)^2 / max(0, N-0)   x->var(-2, 0, true): two passes, std::pow(.,2) (functional.h:383-387),
+ *                                                    summed in DESCENDING row order (libstdc++ _Expr::sum)
  *   y      = (x - mean) / pow(var + eps, 0.5) * gamma + beta     (nn.cpp:314-318), optional ReLU (nn.cpp:229-237)
  * order=1: fp64 statistics.  mean/var are returned for the backward.
  * ---------------------------------------------------------------------------------------------- */
@@ -468,8 +469,9 @@ ORC_API void orc_batchnorm_fwd(int64_t N, int32_t F, const float *X, int64_t ldx
             float s = 0.0f;
             for (int64_t r = 0; r < N; r++) s = s + X[r * ldx + c];
             const float m = s / (float)N;
+            /* std::pow(expr, 2).sum() is libstdc++'s _Expr::sum(): it starts from the LAST element and walks down */
             float q = 0.0f;
-            for (int64_t r = 0; r < N; r++) { float d = X[r * ldx + c] - m; q = q + powf(d, 2.0f); }
+            for (int64_t r = N - 1; r >= 0; r--) { float d = X[r * ldx + c] - m; float t = powf(d, 2.0f); q = (r == N - 1) ? t : q + t; }
             mean[c] = m;
             var[c] = q / (float)(N > 0 ? N : 0);
         } else {
@@ -534,8 +536,8 @@ ORC_API void orc_layernorm_fwd(int64_t N, int32_t F, const float *X, int64_t ldx
             float s = 0.0f;
             for (int32_t c = 0; c < F; c++) s = s + x[c];
             m = s / (float)F;
-            float q = 0.0f;
-            for (int32_t c = 0; c < F; c++) { float d = x[c] - m; q = q + powf(d, 2.0f); }
+            float q = 0.0f; /* _Expr::sum(): descending */
+            for (int32_t c = F - 1; c >= 0; c--) { float d = x[c] - m; float t = powf(d, 2.0f); q = (c == F - 1) ? t : q + t; }
             v = q / (float)F;
         } else {
             double s = 0.0;
