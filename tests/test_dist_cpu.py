@@ -108,12 +108,12 @@ def _rank_main(rank, world, port, name, q, panel_cols=8):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["tiny_pl", "odd"])
-def test_row_partitioned_schedule_world2_gloo(name):
+@pytest.mark.parametrize("name,world", [("tiny_pl", 2), ("odd", 2), ("odd", 3)])
+def test_row_partitioned_schedule_world2_gloo(name, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, world, port, name, q)) for r in range(world)]
     for pr in procs:
         pr.start()
     for pr in procs:
