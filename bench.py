@@ -356,8 +356,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="products", choices=sorted(synth.CONFIGS))
     ap.add_argument("--precision", type=int, default=1, help="dense transforms: 1 = 3xTF32 on tcgen05 (default), 0 = FP32 FMA")
