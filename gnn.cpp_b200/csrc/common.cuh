@@ -61,6 +61,7 @@ struct gnn_ctx {
     // grow-only scratch (sort double buffers, scan levels, split-K partials ...)
     void *ws = nullptr;
     size_t ws_bytes = 0;
+    uint64_t ws_gen = 0; // bumped whenever `ws` is reallocated: captured CUDA graphs that bake ws pointers check it
     // NCCL (comm.cu)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -101,7 +102,8 @@ int radix_sort_u64(gnn_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int 
 // spmm.cu -----------------------------------------------------------------------------------------
 int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
                 const float *val, int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F,
-                float *Y, int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm);
+                float *Y, int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm,
+                bool may_touch_padding = true);
 int spmm_rows_range(gnn_ctx *ctx, const gnn_graph *g, int transpose, int32_t r0, int32_t r1, int64_t k0, int64_t k1,
                     const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
                     const float *mask, int64_t ldm);

@@ -21,6 +21,7 @@ int gnn_ctx::workspace(size_t bytes, void **out) {
         if (ws) GNN_CHECK_CUDA(cudaFreeAsync(ws, stream));
         ws = p;
         ws_bytes = want;
+        ws_gen++;
     }
     *out = ws;
     return 0;

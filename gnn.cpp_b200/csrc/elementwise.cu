@@ -687,14 +687,15 @@ int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, floa
 
 // loss + dZ (+ db = column sums of dZ when db != NULL, which needs the tiled kernel: returns through *db_done)
 int softmax_xent_launch(gnn_ctx *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
-                        int64_t n_total, float *loss, float *dZ, int64_t ldd, float *db) {
+                        int64_t n_total, float *loss, float *dZ, int64_t ldd, float *db, bool may_touch_padding) {
     GNN_REQUIRE(ctx && Z && y && loss, "gnn_softmax_xent: NULL argument");
     GNN_REQUIRE(N > 0 && C > 0 && ldz >= C, "invalid input, logits must be of rank 2 and targets must be 1D tensor");
     if (n_total <= 0) n_total = N;
     const float inv_n = 1.0f / (float)n_total;
     const int32_t ldw = (int32_t)round_up(C, 4);
     const bool tiled = C <= 64 && ((uintptr_t)Z % 16 == 0) && (ldz % 4 == 0) && ldz >= ldw &&
-                       (!dZ || (((uintptr_t)dZ % 16 == 0) && (ldd % 4 == 0) && ldd >= ldw));
+                       (!dZ || (((uintptr_t)dZ % 16 == 0) && (ldd % 4 == 0) && ldd >= ldw &&
+                                (may_touch_padding || C % 4 == 0))); // the tile kernel zeroes dZ columns C..ldw-1
     void *ws = nullptr;
     if (tiled) {
         int64_t nblocks = ceil_div(N, XT_ROWS);
@@ -763,7 +764,8 @@ int gnn_bias_grad(gnn_ctx_t *ctx, int64_t N, int32_t F, const float *dZ, int64_t
 
 int gnn_softmax_xent(gnn_ctx_t *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
                      int64_t n_total, float *loss, float *dZ, int64_t ldd) {
-    return softmax_xent_launch(ctx, N, C, Z, ldz, y, n_total, loss, dZ, ldd, nullptr);
+    // a dZ view wider than the padded row (a column slice of a larger matrix) keeps its neighbouring columns
+    return softmax_xent_launch(ctx, N, C, Z, ldz, y, n_total, loss, dZ, ldd, nullptr, ldd == round_up(C, 4));
 }
 
 int gnn_sgd_step(gnn_ctx_t *ctx, int64_t n, float *p, const float *g, float *vel, float lr, float momentum,

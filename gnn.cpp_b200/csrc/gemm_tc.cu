@@ -773,10 +773,10 @@ static int rows_gemm(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float 
     a.tmem_cols = 2 * a.acc_stride;
     a.C = C; a.ldc = ldc; a.bias = bias; a.relu = relu; a.mask = mask; a.ldm = ldm;
     const uint32_t smem = fixed + a.b_resident + (uint32_t)stages * a.stage_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static uint64_t attr_set = 0; // function attributes are per device: one bit per device ordinal
+    if (!(attr_set >> (ctx->device & 63) & 1)) {
         GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-        attr_set = true;
+        attr_set |= 1ull << (ctx->device & 63);
     }
     const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
     CUtensorMap tmC, tmM;
@@ -819,10 +819,10 @@ static int tn_gemm(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float 
     GNN_TRY(make_map(&tmA, A, M, K1, lda, TN_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     GNN_TRY(make_map(&tmB, B, M, K2, ldb, TN_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     const uint32_t smem = fixed + (uint32_t)stages * a.stage_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static uint64_t attr_set = 0;
+    if (!(attr_set >> (ctx->device & 63) & 1)) {
         GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-        attr_set = true;
+        attr_set |= 1ull << (ctx->device & 63);
     }
     tc_tn_kernel<<<dim3((unsigned)splits, (unsigned)halves), TN_THREADS, smem, ctx->stream>>>(tmA, tmB, a);
     GNN_LAUNCHED(ctx);

@@ -686,7 +686,9 @@ int gnn_graph_slice_rows(gnn_ctx_t *ctx, const gnn_graph_t *g, int64_t lo, int64
         gnn_graph *t = nullptr;
         const int32_t *tptr = g->symmetric ? g->rowptr : g->colptr;
         const int32_t *tidx = g->symmetric ? g->colidx : g->rowidx;
-        const float *tval = g->symmetric ? g->val : g->valT;
+        // the as-written normalisation keeps a transposed value array even on a symmetric structure (its values are
+        // constant per row, so not symmetric): same rule as spmm_rows_range / gnn_spmm_bwd
+        const float *tval = g->symmetric ? (g->valT ? g->valT : g->val) : g->valT;
         GNN_TRY(gnn_graph_from_csr(ctx, (int32_t)(hi - lo), g->n_rows, tptr + lo, tidx, tval, &t));
         l->colptr = t->rowptr; l->rowidx = t->colidx; l->valT = t->val;
         l->max_col_nnz = t->max_row_nnz;

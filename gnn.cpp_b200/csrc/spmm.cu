@@ -367,10 +367,14 @@ static bool use_merge(const gnn_ctx *ctx, int64_t nnz, int64_t k_end, int32_t mi
 // a larger matrix passes ptr + r0 with the absolute offsets ptr[r0], ptr[r1]).
 int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
                 const float *val, int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F,
-                float *Y, int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm) {
+                float *Y, int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm,
+                bool may_touch_padding) {
     if (n_out <= 0 || F <= 0) return 0;
+    // The 128-bit path reads columns F..round_up(F,4)-1 of P and WRITES the same columns of Y.  The trainer owns its
+    // padded buffers; a public-API caller may pass a column slice of a wider matrix, whose neighbouring columns must
+    // survive: such calls (F % 4 != 0 with ld wider than the padded row) take the scalar path.
     const bool vec_ok = ((uintptr_t)P % 16 == 0) && ((uintptr_t)Y % 16 == 0) && (ldp % 4 == 0) && (ldy % 4 == 0) &&
-                        ldp >= round_up(F, 4) && ldy >= round_up(F, 4);
+                        ldp >= round_up(F, 4) && ldy >= round_up(F, 4) && (may_touch_padding || F % 4 == 0);
     const int32_t block_cols = vec_ok ? 512 : 256;
     for (int32_t c0 = 0; c0 < F; c0 += block_cols) {
         const int32_t f = F - c0 < block_cols ? F - c0 : block_cols;
@@ -462,8 +466,9 @@ int gnn_spmm_fwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *P, int64_t l
     GNN_REQUIRE(F > 0 && ldp >= F && ldy >= F, "tensors are not compatible, tensors should of shape [...,A,B] and [...,B,A]");
     GNN_REQUIRE(!use_values || g->val, "gnn_spmm_fwd: edge values not built (call gnn_graph_normalize)");
     GNN_REQUIRE(P != Y, "gnn_spmm_fwd: in-place aggregation is not supported");
+    const bool pad_ok = ldy == round_up(F, 4) && ldp == round_up(F, 4); // rows are exactly the padded width: padding is the caller's own
     return spmm_launch(ctx, g->n_rows, 0, g->nnz, g->rowptr, g->colidx, use_values ? g->val : nullptr, g->min_row_nnz,
-                       g->max_row_nnz, P, ldp, F, Y, ldy, bias, relu, mask, ldm);
+                       g->max_row_nnz, P, ldp, F, Y, ldy, bias, relu, mask, ldm, pad_ok);
 }
 
 int gnn_spmm_bwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *dZ, int64_t ldz, int32_t F, float *dP, int64_t ldp,
@@ -480,7 +485,8 @@ int gnn_spmm_bwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *dZ, int64_t 
     }
     return spmm_launch(ctx, g->t_rows, 0, alias ? g->nnz : g->nnz_t, alias ? g->rowptr : g->colptr,
                        alias ? g->colidx : g->rowidx, v, alias ? g->min_row_nnz : g->min_col_nnz,
-                       alias ? g->max_row_nnz : g->max_col_nnz, dZ, ldz, F, dP, ldp, nullptr, 0, mask, ldm);
+                       alias ? g->max_row_nnz : g->max_col_nnz, dZ, ldz, F, dP, ldp, nullptr, 0, mask, ldm,
+                       ldz == round_up(F, 4) && ldp == round_up(F, 4));
 }
 
 } // extern "C"

@@ -19,7 +19,7 @@
 namespace gnn {
 int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out);
 int softmax_xent_launch(gnn_ctx *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
-                        int64_t n_total, float *loss, float *dZ, int64_t ldd, float *db);
+                        int64_t n_total, float *loss, float *dZ, int64_t ldd, float *db, bool may_touch_padding);
 int copy2d(gnn_ctx *ctx, float *dst, int64_t ldd, const float *src, int64_t lds, int64_t rows, int32_t cols);
 int spmm_rows_range(gnn_ctx *ctx, const gnn_graph *g, int transpose, int32_t r0, int32_t r1, int64_t k0, int64_t k1,
                     const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
@@ -75,13 +75,17 @@ struct gnn_gcn {
     int64_t graph_launches = 0;
     struct GraphKey {
         const float *X; int64_t ldx; const int32_t *y; float lr; float *loss_d;
-        bool operator==(const GraphKey &o) const { return X == o.X && ldx == o.ldx && y == o.y && lr == o.lr && loss_d == o.loss_d; }
-    } graph_key = {nullptr, 0, nullptr, 0.f, nullptr}, graph_key2 = {nullptr, 0, nullptr, 0.f, nullptr};
+        uint64_t ws_gen; // the captured kernels bake ctx->ws pointers in: a reallocated workspace invalidates the graph
+        bool operator==(const GraphKey &o) const {
+            return X == o.X && ldx == o.ldx && y == o.y && lr == o.lr && loss_d == o.loss_d && ws_gen == o.ws_gen;
+        }
+    } graph_key = {nullptr, 0, nullptr, 0.f, nullptr, 0}, graph_key2 = {nullptr, 0, nullptr, 0.f, nullptr, 0};
     float beta1 = 0.9f, beta2 = 0.999f, adam_eps = 1e-8f;
     float *adam_m = nullptr, *adam_v = nullptr;
     const uint8_t *train_mask = nullptr; // device uint8[n_loc]: rows that enter the loss (Data::set_mask TRAIN)
     int64_t n_train = 0;                 // selected rows over the whole graph
     int64_t steps = 0;
+    int64_t opt_steps = 0, vel_steps = 0; // optimiser steps taken (Adam bias correction) / steps the momentum buffer has seen
     // stats
     double alg_bytes = 0, gemm_flops = 0;
     int32_t n_spmm = 0;
@@ -276,8 +280,14 @@ static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
                 src = panel_region(ctx, m, op, P, p);
                 ld_src = P.w[p];
             } else if (af) {
-                // the gather needs a dense [chunk, ld] block; X may have ldx != ld[0] only in single-GPU mode
-                GNN_TRY(gather_input(ctx, m, Hin, (int32_t)ld_in, &src));
+                // the collective sends whole [chunk, ld] blocks: the caller's X holds only n_loc rows (fewer than
+                // chunk on the last rank when N % world != 0), so it is staged through an internal chunk-row buffer
+                const float *send = Hin;
+                if (m->dist && l == 1) {
+                    GNN_TRY(copy2d(ctx, m->S1, ld_in, Hin, ld_in, m->n_loc, (int32_t)ld_in));
+                    send = m->S1;
+                }
+                GNN_TRY(gather_input(ctx, m, send, (int32_t)ld_in, &src));
                 ld_src = ld_in;
             } else {
                 GNN_TRY(gather_input(ctx, m, m->S1, m->ld[l], &src));
@@ -619,6 +629,14 @@ int gnn_gcn_set_option(gnn_gcn_t *m, const char *key, double value) {
 
 static int ensure_buffers(gnn_ctx_t *ctx, gnn_gcn_t *m) {
     const int64_t rows_alloc = m->dist ? m->chunk : m->n_loc;
+    auto zeroed = [&](float **p) -> int {
+        if (*p) return 0;
+        GNN_CHECK_CUDA(cudaMalloc((void **)p, (size_t)m->n_params * 4));
+        GNN_CHECK_CUDA(cudaMemsetAsync(*p, 0, (size_t)m->n_params * 4, ctx->stream));
+        return 0;
+    };
+    if (m->optimizer == 0 && m->momentum != 0.f && !m->vel) { GNN_TRY(zeroed(&m->vel)); m->vel_steps = 0; }
+    if (m->optimizer == 1) { GNN_TRY(zeroed(&m->adam_m)); GNN_TRY(zeroed(&m->adam_v)); }
     for (int32_t l = 1; l <= m->L; l++)
         if (m->agg_first[l] && !m->M[l]) {
             GNN_CHECK_CUDA(cudaMalloc((void **)&m->M[l], (size_t)rows_alloc * m->ld[l - 1] * 4));
@@ -658,7 +676,7 @@ static int train_step_body(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t
         } else {
             // db_L (column sums of dZ_L) is produced by the same kernel from the tiles it already holds
             GNN_TRY(softmax_xent_launch(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], y, m->n_glob, loss_slot, dz.ptr, dz.ld,
-                                        m->grads + m->b_off[m->L]));
+                                        m->grads + m->b_off[m->L], true));
         }
         if (pm)
             for (int p = 0; p < PL.n; p++) {
@@ -674,24 +692,16 @@ static int train_step_body(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t
         Prof p(ctx, m, CLS_OTHER);
         GNN_TRY(gnn_allreduce_sum(ctx, m->grads, m->n_params + 1));
     }
-    if (m->momentum != 0.f && !m->vel) {
-        GNN_CHECK_CUDA(cudaMalloc((void **)&m->vel, (size_t)m->n_params * 4));
-        GNN_CHECK_CUDA(cudaMemsetAsync(m->vel, 0, (size_t)m->n_params * 4, ctx->stream));
-    }
+    // optimiser state is allocated by ensure_buffers (never inside a capture)
     if (lr != 0.f && m->optimizer == 1) {
         Prof p(ctx, m, CLS_SGD);
-        if (!m->adam_m) {
-            GNN_CHECK_CUDA(cudaMalloc((void **)&m->adam_m, (size_t)m->n_params * 4));
-            GNN_CHECK_CUDA(cudaMalloc((void **)&m->adam_v, (size_t)m->n_params * 4));
-            GNN_CHECK_CUDA(cudaMemsetAsync(m->adam_m, 0, (size_t)m->n_params * 4, ctx->stream));
-            GNN_CHECK_CUDA(cudaMemsetAsync(m->adam_v, 0, (size_t)m->n_params * 4, ctx->stream));
-        }
         GNN_TRY(gnn_adam_step(ctx, m->n_params, m->params, m->grads, m->adam_m, m->adam_v, lr, m->beta1, m->beta2,
-                              m->adam_eps, m->weight_decay, m->steps + 1));
+                              m->adam_eps, m->weight_decay, m->opt_steps + 1));
     } else if (lr != 0.f) {
         Prof p(ctx, m, CLS_SGD);
-        GNN_TRY(gnn_sgd_step(ctx, m->n_params, m->params, m->grads, m->vel, lr, m->momentum, m->dampening,
-                             m->weight_decay, m->nesterov, m->steps == 0));
+        // torch.optim.SGD: the momentum buffer is INITIALISED with the first gradient it sees (no dampening)
+        GNN_TRY(gnn_sgd_step(ctx, m->n_params, m->params, m->grads, m->momentum != 0.f ? m->vel : nullptr, lr, m->momentum,
+                             m->dampening, m->weight_decay, m->nesterov, m->vel_steps == 0));
     }
     if (loss_d) GNN_CHECK_CUDA(cudaMemcpyAsync(loss_d, loss_slot, 4, cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
@@ -706,9 +716,11 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
     m->span_used = 0;
     // Graph replay: single GPU, SGD (Adam's bias correction is a per-step kernel argument), no profiling.  Auto mode
     // turns it on for launch-bound sizes only (activations up to 32 M floats, i.e. steps of about a millisecond).
+    // (`first` of the momentum update is a kernel argument too: capture only once the buffer has seen a gradient.)
     const bool want_graph = !m->dist && !m->profile && m->optimizer == 0 && m->steps >= 1 &&
+                            (m->momentum == 0.f || lr == 0.f || m->vel_steps >= 1) &&
                             (m->use_graph == 1 || (m->use_graph < 0 && (int64_t)m->n_loc * m->maxld <= (1ll << 25)));
-    const gnn_gcn::GraphKey key = {X, ldx, y, lr, loss_d};
+    const gnn_gcn::GraphKey key = {X, ldx, y, lr, loss_d, ctx->ws_gen};
     if (want_graph) {
         if (m->graph_exec && !(m->graph_key == key)) { // keep the previous graph as the second entry (swap)
             std::swap(m->graph_exec, m->graph_exec2);
@@ -724,10 +736,17 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
             GNN_CHECK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             const int rc = train_step_body(ctx, m, X, ldx, y, lr, loss_d);
             const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-            if (rc) return rc;
-            GNN_CHECK_CUDA(ce);
-            GNN_CHECK_CUDA(cudaGraphInstantiate(&m->graph_exec, graph, 0));
+            if (rc || ce != cudaSuccess || ctx->ws_gen != key.ws_gen) {
+                // a failed capture, or a workspace that grew while capturing (the eager warm-up step sizes it, so
+                // this means the schedule changed): never keep a graph over stale pointers
+                if (graph) cudaGraphDestroy(graph);
+                if (rc) return rc;
+                GNN_CHECK_CUDA(ce);
+                GNN_REQUIRE(false, "gnn_gcn_train_step: workspace was reallocated during graph capture");
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&m->graph_exec, graph, 0);
             cudaGraphDestroy(graph);
+            GNN_CHECK_CUDA(ie);
             m->graph_launches = ctx->launches - l0;
             ctx->launches = l0;
             m->graph_key = key;
@@ -738,6 +757,10 @@ int gnn_gcn_train_step(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t ldx
         GNN_TRY(train_step_body(ctx, m, X, ldx, y, lr, loss_d));
     }
     m->steps++;
+    if (lr != 0.f) {
+        if (m->optimizer == 1) m->opt_steps++;
+        else if (m->momentum != 0.f) m->vel_steps++;
+    }
     if (m->profile) {
         GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int i = 0; i < 6; i++) m->breakdown[i] = 0;

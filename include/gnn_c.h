@@ -130,7 +130,11 @@ GNN_API int gnn_dense_to_coo(gnn_ctx_t *ctx, const float *A, int64_t rows, int64
  *     bias[F]        Z = Y + b               — Add, include/operation.h:102-129
  *     relu           H = Z > 0 ? Z : 0       — nn::ReLU / Mask, src/nn.cpp:229-237, operation.h:537-573
  *     mask[.,F]      out = mask > 0 ? out : 0 (ReLU backward, operation.h:557-562)
- * use_values = 0 treats every stored entry as 1 (plain sum aggregation, graph.cpp:204-212). */
+ * use_values = 0 treats every stored entry as 1 (plain sum aggregation, graph.cpp:204-212).
+ * Padding contract: columns >= F of a row are never written.  The 128-bit kernels are used when P and Y are 16-byte
+ * aligned with leading dimensions that are multiples of 4 and either F % 4 == 0 or both leading dimensions equal
+ * round_up(F, 4) (then the padding columns F..ld-1 of P are read and those of Y are overwritten with the aggregate of
+ * P's padding); every other view — e.g. a 47-column slice of a 256-wide matrix — takes the scalar kernels. */
 GNN_API int gnn_spmm_fwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *P, int64_t ldp, int32_t F, float *Y,
                          int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm, int use_values);
 GNN_API int gnn_spmm_bwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *dZ, int64_t ldz, int32_t F, float *dP,

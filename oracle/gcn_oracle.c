@@ -276,6 +276,57 @@ ORC_API void orc_spmm(int32_t N, const int64_t *ptr, const int32_t *idx, const f
     }
 }
 
+
+/* ---- order = 1 ("exact") fast path ---------------------------------------------------------------
+ * fp64 accumulation of fp32 x fp32 products (each product is exact in fp64, so the result does not depend on
+ * the summation order beyond 1e-16): used as the checker at sizes where the reference's own sequential fp32
+ * sums are less accurate than the 1e-5 contract.  Because the order is free here, this path is register-blocked
+ * (4 x 12 fp64 accumulators, GCC vector extensions) so that a products-shaped step takes seconds, not minutes.
+ * Nothing below is used by order 0, which stays the literal reference order. */
+typedef double orc_v4d __attribute__((vector_size(32)));
+typedef float orc_v4f __attribute__((vector_size(16)));
+static inline orc_v4d orc_ld4(const float *p) {
+    orc_v4f f;
+    memcpy(&f, p, 16);
+    return __builtin_convertvector(f, orc_v4d);
+}
+/* out[m][n] (m < 4, n < 12; leading dimension 12) = sum_{k<K} A[m*sam + k*sak] * Bp[k*ldb + n]; rows m >= mr repeat row mr-1 */
+static void orc_mk_4x12(const float *A, int64_t sam, int64_t sak, int mr, const float *Bp, int64_t ldb, int64_t K,
+                        double *out) {
+    const float *a0 = A, *a1 = A + (mr > 1 ? 1 : 0) * sam, *a2 = A + (mr > 2 ? 2 : mr - 1) * sam,
+                *a3 = A + (mr > 3 ? 3 : mr - 1) * sam;
+    orc_v4d c00 = {0, 0, 0, 0}, c01 = c00, c02 = c00, c10 = c00, c11 = c00, c12 = c00, c20 = c00, c21 = c00, c22 = c00,
+            c30 = c00, c31 = c00, c32 = c00;
+    for (int64_t k = 0; k < K; k++) {
+        const float *b = Bp + k * ldb;
+        const orc_v4d b0 = orc_ld4(b), b1 = orc_ld4(b + 4), b2 = orc_ld4(b + 8);
+        const double x0 = a0[k * sak], x1 = a1[k * sak], x2 = a2[k * sak], x3 = a3[k * sak];
+        const orc_v4d v0 = {x0, x0, x0, x0}, v1 = {x1, x1, x1, x1}, v2 = {x2, x2, x2, x2}, v3 = {x3, x3, x3, x3};
+        c00 += v0 * b0; c01 += v0 * b1; c02 += v0 * b2;
+        c10 += v1 * b0; c11 += v1 * b1; c12 += v1 * b2;
+        c20 += v2 * b0; c21 += v2 * b1; c22 += v2 * b2;
+        c30 += v3 * b0; c31 += v3 * b1; c32 += v3 * b2;
+    }
+    memcpy(out + 0, &c00, 32);  memcpy(out + 4, &c01, 32);  memcpy(out + 8, &c02, 32);
+    memcpy(out + 12, &c10, 32); memcpy(out + 16, &c11, 32); memcpy(out + 20, &c12, 32);
+    memcpy(out + 24, &c20, 32); memcpy(out + 28, &c21, 32); memcpy(out + 32, &c22, 32);
+    memcpy(out + 36, &c30, 32); memcpy(out + 40, &c31, 32); memcpy(out + 44, &c32, 32);
+}
+/* C[M,N] (fp32) = A[M,K] * Bp[K,Np] with Bp packed, zero padded to Np = multiple of 12 columns */
+static void orc_gemm_rows_f64(int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *Bp, int32_t Np,
+                              float *C, int64_t ldc) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i0 = 0; i0 < M; i0 += 4) {
+        const int mr = M - i0 < 4 ? (int)(M - i0) : 4;
+        double t[48];
+        for (int32_t j0 = 0; j0 < Np; j0 += 12) {
+            orc_mk_4x12(A + i0 * lda, lda, 1, mr, Bp + j0, Np, K, t);
+            for (int m = 0; m < mr; m++)
+                for (int32_t j = j0; j < j0 + 12 && j < N; j++) C[(i0 + m) * ldc + j] = (float)t[m * 12 + (j - j0)];
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Dense feature transforms (nn::Linear, src/nn.cpp:205-211; MatMul::_backward, operation.h:504-534;
  * Transpose::_backward, operation.h:416-433).  All row-major.
@@ -286,6 +337,15 @@ ORC_API void orc_spmm(int32_t N, const int64_t *ptr, const int32_t *idx, const f
  * ---------------------------------------------------------------------------------------------- */
 ORC_API void orc_gemm_nt(int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B, int64_t ldb,
                          float *C, int64_t ldc, int order) {
+    if (order != 0) { /* pack B^T: Bp[k][j] = B[j][k] */
+        const int32_t Np = (N + 11) / 12 * 12;
+        float *Bp = (float *)calloc((size_t)K * Np, 4);
+        for (int32_t j = 0; j < N; j++)
+            for (int32_t k = 0; k < K; k++) Bp[(size_t)k * Np + j] = B[(int64_t)j * ldb + k];
+        orc_gemm_rows_f64(M, N, K, A, lda, Bp, Np, C, ldc);
+        free(Bp);
+        return;
+    }
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < M; i++)
         for (int32_t j = 0; j < N; j++) {
@@ -303,6 +363,14 @@ ORC_API void orc_gemm_nt(int64_t M, int32_t N, int32_t K, const float *A, int64_
 }
 ORC_API void orc_gemm_nn(int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B, int64_t ldb,
                          float *C, int64_t ldc, int order) {
+    if (order != 0) {
+        const int32_t Np = (N + 11) / 12 * 12;
+        float *Bp = (float *)calloc((size_t)K * Np, 4);
+        for (int32_t k = 0; k < K; k++) memcpy(Bp + (size_t)k * Np, B + (int64_t)k * ldb, (size_t)N * 4);
+        orc_gemm_rows_f64(M, N, K, A, lda, Bp, Np, C, ldc);
+        free(Bp);
+        return;
+    }
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < M; i++) {
         const float *a = A + i * lda;
@@ -341,22 +409,33 @@ ORC_API void orc_gemm_tn(int64_t M, int32_t K1, int32_t K2, const float *A, int6
             }
         }
     } else {
+        /* node rows are cut into blocks of TNB; a thread packs the block of B (zero padded to 12-column tiles) and adds
+         * the block's 4 x 12 tile products into its private fp64 copy of the output; copies are summed at the end */
+        enum { TNB = 256 };
+        const int32_t Np = (K2 + 11) / 12 * 12;
         double *acc = (double *)calloc((size_t)K1 * K2, sizeof(double));
 #pragma omp parallel
         {
-            double *loc = (double *)calloc((size_t)K1 * K2, sizeof(double));
+            double *loc = (double *)calloc((size_t)K1 * Np, sizeof(double));
+            float *Bp = (float *)calloc((size_t)TNB * Np, 4);
+            double t[48];
 #pragma omp for schedule(static)
-            for (int64_t i = 0; i < M; i++) {
-                const float *a = A + i * lda, *b = B + i * ldb;
-                for (int32_t x = 0; x < K1; x++) {
-                    const double av = a[x];
-                    double *l = loc + (size_t)x * K2;
-                    for (int32_t j = 0; j < K2; j++) l[j] += av * (double)b[j];
+            for (int64_t i0 = 0; i0 < M; i0 += TNB) {
+                const int64_t nb = M - i0 < TNB ? M - i0 : TNB;
+                for (int64_t i = 0; i < nb; i++) memcpy(Bp + (size_t)i * Np, B + (i0 + i) * ldb, (size_t)K2 * 4);
+                for (int32_t x0 = 0; x0 < K1; x0 += 4) {
+                    const int mr = K1 - x0 < 4 ? K1 - x0 : 4;
+                    for (int32_t j0 = 0; j0 < Np; j0 += 12) {
+                        orc_mk_4x12(A + i0 * lda + x0, 1, lda, mr, Bp + j0, Np, nb, t);
+                        for (int m = 0; m < mr; m++)
+                            for (int j = 0; j < 12; j++) loc[(size_t)(x0 + m) * Np + j0 + j] += t[m * 12 + j];
+                    }
                 }
             }
 #pragma omp critical
-            for (size_t t = 0; t < (size_t)K1 * K2; t++) acc[t] += loc[t];
-            free(loc);
+            for (int32_t x = 0; x < K1; x++)
+                for (int32_t j = 0; j < K2; j++) acc[(size_t)x * K2 + j] += loc[(size_t)x * Np + j];
+            free(loc); free(Bp);
         }
         for (int32_t x = 0; x < K1; x++)
             for (int32_t j = 0; j < K2; j++) C[(int64_t)x * ldc + j] = (float)acc[(size_t)x * K2 + j];
@@ -386,6 +465,22 @@ ORC_API void orc_relu_bwd(int64_t N, int32_t F, const float *dH, int64_t ldd, co
 /* Bias gradient: db[f] = sum over rows ASCENDING (Add::_backward -> sum_to_size -> sum(0),
  * tensor.h:618-638, functional.h:285-288). */
 ORC_API void orc_bias_grad(int64_t N, int32_t F, const float *dZ, int64_t ldd, float *db, int order) {
+    if (order != 0) { /* fp64 column sums, one pass over the matrix (rows split over the threads) */
+        double *acc = (double *)calloc((size_t)F, sizeof(double));
+#pragma omp parallel
+        {
+            double *loc = (double *)calloc((size_t)F, sizeof(double));
+#pragma omp for schedule(static)
+            for (int64_t i = 0; i < N; i++)
+                for (int32_t f = 0; f < F; f++) loc[f] += (double)dZ[i * ldd + f];
+#pragma omp critical
+            for (int32_t f = 0; f < F; f++) acc[f] += loc[f];
+            free(loc);
+        }
+        for (int32_t f = 0; f < F; f++) db[f] = (float)acc[f];
+        free(acc);
+        return;
+    }
 #pragma omp parallel for schedule(static)
     for (int32_t f = 0; f < F; f++) {
         if (order == 0) {

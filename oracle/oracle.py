@@ -402,19 +402,33 @@ def train_step(g, dims, X, y, W, b, lr=0.0, order=0):
     return out
 
 
-def train_step_composed(g, dims, X, y, W, b, order=0, masks=None):
-    """The same fwd+loss+bwd as orc_gcn_train_step, composed from the primitives above in the reference's own
-    (transform-first) order.  `masks` (list of L-1 boolean [N, F_l] arrays, entries may be None) overrides which side
-    of the ReLU kink the BACKWARD takes for hidden layer l: a checker for pre-activations that sit within the forward
-    tolerance of zero, where `Z > 0` (operation.h:560) is not a continuous function of the inputs."""
+def forward_composed(g, dims, X, W, b, order=0):
+    """Forward pass from the primitives in the reference's own (transform-first) order: returns (Hs, Zs) with
+    Hs[0] = X, Hs[l] = ReLU(Z_l) for hidden layers, Zs[l-1] = Z_l (pre-activations; logits for the last layer)."""
     L = len(dims) - 1
-    H = np.ascontiguousarray(X, dtype=np.float32)
-    Hs, Zs = [H], []
+    Hs, Zs = [np.ascontiguousarray(X, dtype=np.float32)], []
     for l in range(L):
         P = gemm_nt(Hs[l], W[l], order)
-        Z, Hn = bias_relu(spmm(g.N, g.rowptr, g.colidx, g.val, P, order), b[l])
+        if l < L - 1:
+            Z, Hn = bias_relu(spmm(g.N, g.rowptr, g.colidx, g.val, P, order), b[l])
+        else:  # logits: no activation
+            Y = spmm(g.N, g.rowptr, g.colidx, g.val, P, order)
+            Z = np.empty_like(Y)
+            lib().orc_bias_relu(Y.shape[0], Y.shape[1], Y, Y.shape[1], _ptr(np.ascontiguousarray(b[l], dtype=np.float32)),
+                                _ptr(Z), Y.shape[1], None, 0)
+            Hn = None
+        del P
         Zs.append(Z)
         Hs.append(Hn)
+    return Hs, Zs
+
+
+def backward_composed(g, dims, Hs, Zs, y, W, order=0, masks=None):
+    """Loss + backward over the activations of forward_composed.  `masks` (list of L-1 boolean [N, F_l] arrays,
+    entries may be None) overrides which side of the ReLU kink the BACKWARD takes for hidden layer l: a checker for
+    pre-activations that sit within the forward tolerance of zero, where `Z > 0` (operation.h:560) is not a
+    continuous function of the inputs."""
+    L = len(dims) - 1
     loss, dZ = softmax_xent(Zs[-1], y, order)
     out = {"loss": loss, "dZ": dZ}
     for l in range(L - 1, -1, -1):
@@ -428,4 +442,13 @@ def train_step_composed(g, dims, X, y, W, b, order=0, masks=None):
                 dZ = np.where(masks[l - 1], dH, np.float32(0)).astype(np.float32)
             else:
                 dZ = relu_bwd(dH, Zs[l - 1])
+            del dH
+        del dP
     return out
+
+
+def train_step_composed(g, dims, X, y, W, b, order=0, masks=None):
+    """The same fwd+loss+bwd as orc_gcn_train_step, composed from the primitives above in the reference's own
+    (transform-first) order; see backward_composed for `masks`."""
+    Hs, Zs = forward_composed(g, dims, X, W, b, order)
+    return backward_composed(g, dims, Hs, Zs, y, W, order, masks)

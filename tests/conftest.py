@@ -49,6 +49,52 @@ def rel_err(a, ref):
     return float(np.abs(a - ref).max()) / denom
 
 
+def err_stats(a, ref, sample=4_000_000):
+    """Norm-wise AND element-wise error of `a` against `ref`:
+        norm      max|a-ref| / max|ref|                                  (the 1e-5 bar, see rel_err)
+        elem_max  max of |a-ref| / (|ref| + 1e-5 max|ref|)                 element-wise, small entries included
+        elem_p999 99.9th percentile of the same quantity (over a fixed random sample of <= `sample` entries when the
+                  array is larger: the exact maximum is always taken over every entry)
+    Processed in row chunks so that a 2.45 M x 256 activation does not need fp64 copies of the whole matrix."""
+    a = np.asarray(a); ref = np.asarray(ref)
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    a2 = a.reshape(-1); r2 = ref.reshape(-1)
+    n = a2.size
+    step = 1 << 24
+    m = 0.0
+    for s0 in range(0, n, step):
+        m = max(m, float(np.abs(r2[s0:s0 + step]).max(initial=0.0)))
+    m = max(m, 1e-30)
+    dmax, emax = 0.0, 0.0
+    for s0 in range(0, n, step):
+        r = r2[s0:s0 + step].astype(np.float64)
+        d = np.abs(a2[s0:s0 + step].astype(np.float64) - r)
+        dmax = max(dmax, float(d.max(initial=0.0)))
+        emax = max(emax, float((d / (np.abs(r) + 1e-5 * m)).max(initial=0.0)))
+    if n > sample:
+        pick = np.random.default_rng(12345).integers(0, n, sample)
+        r = r2[pick].astype(np.float64); d = np.abs(a2[pick].astype(np.float64) - r)
+    else:
+        r = r2.astype(np.float64); d = np.abs(a2.astype(np.float64) - r)
+    p999 = float(np.quantile(d / (np.abs(r) + 1e-5 * m), 0.999)) if n else 0.0
+    return {"norm": dmax / m, "elem_max": emax, "elem_p999": p999, "max_ref": m, "n": int(n)}
+
+
+def parity_report(record):
+    """Append one JSON line to gpurun_out/parity_report.jsonl (merged back from the GPU box; summaries of it are kept
+    under profiles/) and echo it, so the element-wise error distribution of every full-size comparison is recorded."""
+    import json
+    line = json.dumps(record, sort_keys=True)
+    print("[parity] " + line)
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle as orc
