@@ -88,40 +88,64 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_step_ms(cfg_name, steps=1, warmup=0):
-    """The reference's algorithm on the host cores.  cora: the real reference binary (oracle/_ref, 1 thread, dense);
-    every other config: the oracle port (sparse restatement in the reference's operation order, OpenMP over rows)
-    on a 1/div-scale sample of the same generator, time scaled by div."""
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _port_step_ms(cfg, p, steps, warmup):
+    """`steps` timed train steps (after `warmup`) of the oracle port on problem p, all host threads."""
+    from oracle import oracle as orc
+    orc.set_threads(host_threads())      # explicit: torchrun exports OMP_NUM_THREADS=1, which must not throttle this arm
+    G = orc.Graph(p.src, p.dst, cfg.N)
+    W = [w.copy() for w in p.W]; b = [x.copy() for x in p.b]
+    ts = []
+    for i in range(warmup + max(1, steps)):
+        t0 = time.perf_counter()
+        orc.train_step(G, cfg.dims, p.X, p.y, W, b, lr=LR, order=0)
+        if i >= warmup:
+            ts.append((time.perf_counter() - t0) * 1e3)
+    return float(np.mean(ts)), G.nnz, orc.max_threads()
+
+
+def cpu_step_ms(cfg_name, steps=1, warmup=0, budget_s=240.0, problem=None):
+    """The reference's algorithm on the host cores, ON THE BENCH CONFIG ITSELF.
+    cora: the real reference binary (oracle/_ref/ref_gcn: 1 thread, dense N x N, the only config it can run besides
+    Pubmed-shaped).  Every other config: the oracle port (sparse restatement in the reference's operation order, fp32,
+    OpenMP over all host threads) — the FULL workload; a 1/16-scale probe step predicts its cost first and only when
+    the full step would not fit `budget_s` does the leg fall back to the scaled sample (labelled as such)."""
     cfg = synth.CONFIGS[cfg_name]
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_gcn")
     if cfg_name == "cora" and os.path.exists(ref_bin):
         from gnn_cpp_b200 import problem_io
-        p = synth.make_problem(cfg)
+        p = problem if problem is not None else synth.make_problem(cfg)
         with tempfile.TemporaryDirectory() as td:
             pin = os.path.join(td, "p.gcnp")
             problem_io.write_problem(pin, p)
             out = subprocess.check_output([ref_bin, "time", pin, str(max(1, steps))], text=True)
         r = json.loads(out.strip().splitlines()[-1])
-        return r["ms_per_step"], {"kind": "reference", "cores": 1,
-                                  "sample": "full Cora-shaped step through the patched reference binary (mode B, dense A_hat rebuilt per step)"}
-    from oracle import oracle as orc
+        return r["ms_per_step"], {"kind": "reference", "cores": 1, "same_config": True,
+                                  "sample": "full Cora-shaped step through the patched reference binary (mode B, dense A_hat rebuilt per step), %d timed step(s)" % max(1, steps)}
     div = CPU_SAMPLE_DIV.get(cfg_name, 1)
-    scfg = synth.Config(cfg.name + "_s", max(cfg.N // div, 64), max(cfg.E // div, 2), cfg.dims, cfg.powerlaw, cfg.config_id)
-    p = synth.make_problem(scfg)
-    G = orc.Graph(p.src, p.dst, scfg.N)
-    W = [w.copy() for w in p.W]; b = [x.copy() for x in p.b]
-    cores = orc.max_threads()
-    ts = []
-    for i in range(warmup + max(1, steps)):
-        t0 = time.perf_counter()
-        orc.train_step(G, scfg.dims, p.X, p.y, W, b, lr=LR, order=0)
-        if i >= warmup:
-            ts.append((time.perf_counter() - t0) * 1e3)
-    ms = float(np.mean(ts)) * div
-    sample = ("oracle port (sparse CSR restatement, reference op order, fp32, OpenMP) on a 1/%d-scale sample "
-              "(N=%d, E=%d, nnz=%d, same dims/generator), time x%d" % (div, scfg.N, scfg.E, G.nnz, div)) if div > 1 else \
-             "oracle port (sparse CSR restatement, reference op order, fp32, OpenMP), full workload"
-    return ms, {"kind": "port", "cores": cores, "sample": sample}
+    predicted = None
+    if div > 1:
+        scfg = synth.Config(cfg.name + "_s", max(cfg.N // div, 64), max(cfg.E // div, 2), cfg.dims, cfg.powerlaw, cfg.config_id)
+        sms, snnz, cores = _port_step_ms(scfg, synth.make_problem(scfg), 1, 0)
+        predicted = sms * div / 1e3
+        if predicted * (warmup + max(1, steps)) + 30.0 > budget_s and predicted + 30.0 <= budget_s:
+            steps, warmup = 1, 0           # one full step fits, the requested number does not
+        if predicted * (warmup + max(1, steps)) + 30.0 > budget_s:
+            return sms * div, {"kind": "port", "cores": cores, "same_config": False,
+                               "sample": "FALLBACK (a full step is predicted at %.0f s, budget %.0f s): oracle port on a 1/%d-scale sample "
+                                         "(N=%d, E=%d, nnz=%d, same dims/generator), time x%d" % (predicted, budget_s, div, scfg.N, scfg.E, snnz, div)}
+    p = problem if problem is not None else synth.make_problem(cfg)
+    ms, nnz, cores = _port_step_ms(cfg, p, steps, warmup)
+    return ms, {"kind": "port", "cores": cores, "same_config": True,
+                "sample": "oracle port (sparse CSR restatement, reference op order, fp32, OpenMP over %d threads), FULL %s-shaped workload "
+                          "(N=%d, nnz=%d): %d timed step(s) after %d warm-up%s" % (cores, cfg.name, cfg.N, nnz, max(1, steps), warmup,
+                          "" if predicted is None else "; a 1/%d-scale probe predicted %.1f s/step" % (div, predicted))}
 
 
 def workload_desc(cfg, nnz=None):
@@ -138,16 +162,14 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = synth.CONFIGS[args.config]
-    # bounded: the real reference binary runs every requested step on the Cora-shaped config (~2 s each); the sparse
-    # port runs at most 3 timed + 1 warm-up steps of the scaled sample (a few seconds each) whatever K / W ask for
+    # bounded: the real reference binary runs up to 20 steps of the Cora-shaped config (~2 s each); the sparse port runs
+    # the FULL config, as many of the requested steps as fit the time budget (products-shaped: one ~1 min step)
     if args.config == "cora":
         ms, info = cpu_step_ms(args.config, steps=min(args.steps, 20), warmup=0)
     else:
-        k, w = max(1, min(args.steps, 3)), min(args.warmup, 1)
-        ms, info = cpu_step_ms(args.config, steps=k, warmup=w)
-        info["sample"] += "; mean of %d timed step(s) after %d warm-up" % (k, w)
+        ms, info = cpu_step_ms(args.config, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1), budget_s=args.cpu_budget)
     cfgd = workload_desc(cfg)
-    cfgd["parallelism"] = "host CPU"
+    cfgd["parallelism"] = "host CPU, %d thread(s)" % info["cores"]
     line = {"impl": "reference", "metric": "gcn_train_step_ms", "value": ms, "unit": "ms", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgd,
@@ -284,11 +306,16 @@ def run_ours(args):
     dom_F = max(per_width, key=lambda f: per_width[f][0])
     dom_ms, dom_bytes, dom_n = per_width[dom_F]
     dom_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes per launch of the dominant kernel come from an `ncu --set full` capture (dram__bytes_read.sum +
+    # dram__bytes_write.sum), not from this run: the value is static and labelled with the capture it was read from
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
     if os.path.exists(tpath) and world == 1:
         with open(tpath) as f:
-            traffic = json.load(f).get(args.config, {}).get(str(dom_F))
+            tj = json.load(f)
+        traffic = tj.get(args.config, {}).get(str(dom_F))
+        if traffic is not None:
+            traffic_src = "static: %s" % tj.get("_note", "ncu capture under profiles/")
     launches_detail = {str(f): {"launches_per_step": v[2] / nprof, "ms_per_launch": v[0] / v[2], "alg_bytes_per_launch": v[1] / v[2],
                                 "alg_gbs": v[1] / (v[0] * 1e-3) / 1e9, "frac": v[1] / (v[0] * 1e-3) / 1e9 / peak}
                        for f, v in sorted(per_width.items())}
@@ -316,13 +343,44 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
 
+    # ---- parity, visible to the driver at every GPU count: gradients of the FIRST train step (initial parameters,
+    # lr = 0) against the CPU oracle's exact result for this config (tests/golden/bench_parity_<config>.npz, written by
+    # tests/golden/make_bench_parity.py).  Gradients are all-reduced, so every rank holds the whole slab.
+    parity = None
+    gpath = os.path.join(ROOT, "tests", "golden", "bench_parity_%s.npz" % args.config)
+    if os.path.exists(gpath):
+        gold = np.load(gpath)
+        model.set_params(p.W, p.b)
+        loss0 = float(model.train_step(X, ybuf, 0.0, loss_d).cpu()[0])
+        per, checksum = {}, 0.0
+        for l in range(1, L + 1):
+            dW, db = model.grads(l)
+            checksum += float(dW.astype(np.float64).sum()) + float(db.astype(np.float64).sum())
+            for nm, a in (("dW%d" % l, dW), ("db%d" % l, db)):
+                r = gold[nm].astype(np.float64)
+                per[nm] = float(np.abs(a.astype(np.float64) - r).max() / max(np.abs(r).max(), 1e-30))
+        rows = gold["logit_rows"]
+        rows = rows[(rows >= lo) & (rows < hi)]
+        if len(rows):
+            Z = model.activation(L)[rows - lo].astype(np.float64)
+            r = gold["logits"][np.searchsorted(gold["logit_rows"], rows)].astype(np.float64)
+            per["logits_sample"] = float(np.abs(Z - r).max() / max(np.abs(gold["logits"]).max(), 1e-30))
+        lref = float(gold["loss"][0])
+        tol = 1e-5
+        worst = max(list(per.values()) + [abs(loss0 - lref) / abs(lref)])
+        parity = {"against": "CPU oracle, exact arithmetic (fp32 inputs, fp64 accumulation, reference op order): tests/golden/bench_parity_%s.npz" % args.config,
+                  "what": "first train step from the initial parameters (lr = 0): loss, every dW/db (whole arrays, after the gradient all-reduce), %d sampled logits rows of rank 0" % len(rows),
+                  "loss": loss0, "loss_oracle": lref, "loss_rel_err": abs(loss0 - lref) / abs(lref),
+                  "rel_err": per, "max_rel_err": worst, "grad_checksum": checksum, "tol": tol, "norm": "max|a-ref|/max|ref|",
+                  "nnz_matches": int(gold["nnz"][0]) == int(nnz), "ok": bool(worst <= tol and int(gold["nnz"][0]) == int(nnz))}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            cms, info = cpu_step_ms(args.config)
+            cms, info = cpu_step_ms(args.config, steps=1, warmup=0, budget_s=args.cpu_budget, problem=p)
             cpu = dict(info, value=cms, unit="ms")
         cfgd = workload_desc(cfg, nnz)
-        cfgd.update({"parallelism": "1-D row partition x%d, %s of aggregation inputs + NCCL grad all-reduce" % (world, "ncclAllGather" if os.environ.get("GNN_COMM") == "nccl" else "copy-engine peer pushes over NVLink (IPC arena)") if world > 1 else "single GPU",
+        cfgd.update({"parallelism": "1-D row partition x%d, %s + NCCL grad all-reduce" % (world, model.exchange_desc()) if world > 1 else "single GPU",
                      "l2_policy": "working set (feature matrices %.1f GB) larger than L2; no flush needed" % (cfg.N * max(cfg.dims) * 4 / 1e9)
                      if cfg.N * max(cfg.dims) * 4 > 2.5e8 else "small working set (L2-resident): launch-bound config",
                      "gemm_precision": "fp32 FMA" if args.precision == 0 else "3xTF32 tcgen05",
@@ -334,7 +392,7 @@ def run_ours(args):
                              "kernel": "spmm_merge_kernel, F=%d aggregation (%.0f launches per step, %.0f%% of the step's aggregation time)"
                                        % (dom_F, dom_n / nprof, 100.0 * dom_ms / nprof / bd["spmm"]),
                              "achieved": dom_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                             "frac": dom_gbs / peak, "traffic": traffic,
+                             "frac": dom_gbs / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "alg_bytes_per_launch": dom_bytes / dom_n, "ms_per_launch": dom_ms / dom_n,
                              # when frac > 1 on B_alg (L2 serves reuse) quote the touch-once bound too
                              "b_min_bytes_per_launch": 4.0 * (n_loc + 1) + 8.0 * nnz / world + 8.0 * n_loc * dom_F,
@@ -343,9 +401,10 @@ def run_ours(args):
                                                             "by_width": launches_detail}},
                 "breakdown_ms": bd,
                 "gemm_tflops": st["gemm_flops"] / (bd["gemm"] * 1e-3) / 1e12 if bd["gemm"] > 0 else None,
-                "cpu_baseline": cpu,
+                "cpu_baseline": cpu, "parity": parity,
                 "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(Xh.numel() * 4 + yh.numel() * 4),
-                        "d2h_bytes_per_step": 4, "api": "gnn_gcn_train_step_h (pinned host buffers)"},
+                        "d2h_bytes_per_step": 4, "api": "gnn_gcn_train_step_h (pinned host buffers)", "pipelined": True,
+                        "pipelining": "the upload of step i+1's inputs (copy stream, double-buffered) overlaps step i's kernels; every step's inputs cross PCIe once inside the timed region and its loss is read back"},
                 "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     model.close(); g.close(); ctx.close()
@@ -362,6 +421,7 @@ def main():
     ap.add_argument("--config", default="products", choices=sorted(synth.CONFIGS))
     ap.add_argument("--precision", type=int, default=1, help="dense transforms: 1 = 3xTF32 on tcgen05 (default), 0 = FP32 FMA")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds the CPU leg may take before it falls back to a scaled sample")
     ap.add_argument("--spmm-variant", type=int, default=0, help="0 auto (by degree skew), 1 rows kernel, 2 merge kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -90,6 +90,7 @@ SIGNATURES = {
     "gnn_gcn_last_breakdown": (C.c_int, [vp, vp, C.c_int]),
     "gnn_gcn_last_spmm_spans": (C.c_int, [vp, vp, vp, vp, C.c_int, vp]),
     "gnn_gcn_spmm_stats": (C.c_int, [vp, vp, vp, vp]),
+    "gnn_gcn_exchange_mode": (C.c_int, [vp]),
     "gnn_partition_ptr_h": (C.c_int, [i64, i32, vp]),
     "gnn_partition_panels_h": (C.c_int, [i32, i32, vp, vp, vp]),
     "gnn_graph_slice_rows": (C.c_int, [vp, vp, i64, i64, pp]),
@@ -105,7 +106,7 @@ SIGNATURES = {
     "gnn_peer_gather_wait": (C.c_int, [vp, vp, C.c_int, C.c_int]),
 }
 # int-returning functions that are NOT status codes
-_PLAIN_INT = {"gnn_version", "gnn_ctx_sm_count", "gnn_graph_is_symmetric"}
+_PLAIN_INT = {"gnn_version", "gnn_ctx_sm_count", "gnn_graph_is_symmetric", "gnn_gcn_exchange_mode"}
 
 
 class GnnError(RuntimeError):

@@ -156,6 +156,8 @@ namespace gnn {
 
 using namespace gnn;
 
+int gnn_peer_arena_transport(const gnn_peer_arena_t *a) { return a ? a->sm_mode : -1; }
+
 extern "C" {
 
 int gnn_comm_unique_id_h(void *id_h) {

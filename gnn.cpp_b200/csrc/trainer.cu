@@ -16,6 +16,7 @@
 // of the backward run while the next aggregation input is in flight (NN GEMM before TN GEMM for that reason).
 #include "common.cuh"
 
+int gnn_peer_arena_transport(const gnn_peer_arena_t *a); // comm.cu: 1 SM store kernel, 0 copy engines, 2 ncclAllGather
 namespace gnn {
 int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out);
 int softmax_xent_launch(gnn_ctx *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
@@ -878,6 +879,13 @@ int gnn_gcn_last_spmm_spans(gnn_gcn_t *m, double *ms, double *alg_bytes, int32_t
     }
     *n = k;
     return 0;
+}
+
+int gnn_gcn_exchange_mode(const gnn_gcn_t *m) {
+    if (!m || !m->dist) return 0;
+    if (!m->arena) return 1;
+    if (m->nccl_transport) return 4;
+    return gnn_peer_arena_transport(m->arena) == 0 ? 3 : 2;
 }
 
 int gnn_gcn_spmm_stats(gnn_gcn_t *m, double *alg_bytes, int32_t *n_spmm, double *gemm_flops) {

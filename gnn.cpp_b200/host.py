@@ -407,6 +407,18 @@ class GCN:
         capi.call("gnn_gcn_spmm_stats", self.h, C.byref(b), C.byref(n), C.byref(f))
         return {"spmm_alg_bytes": b.value, "n_spmm": n.value, "gemm_flops": f.value}
 
+    def exchange_mode(self):
+        return capi.load().gnn_gcn_exchange_mode(self.h)
+
+    def exchange_desc(self):
+        return {0: "no exchange (single GPU)",
+                1: "ncclAllGather of every aggregation input",
+                2: "all-gather of every aggregation input by SM store pushes into IPC-mapped peer arenas over NVLink, pipelined by column panels",
+                3: "all-gather of every aggregation input by copy-engine pushes into IPC-mapped peer arenas, pipelined by column panels",
+                4: "all-gather of every aggregation input by in-place ncclAllGather per column panel (side stream)",
+                5: "feature-column partition of the aggregation: all-to-all over IPC-mapped peer memory before and after every SpMM (replicated structure)",
+                }.get(self.exchange_mode(), "unknown")
+
     def close(self):
         if self.h:
             capi.call("gnn_gcn_destroy", self.ctx.h, self.h)

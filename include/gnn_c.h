@@ -285,6 +285,11 @@ GNN_API int gnn_gcn_last_breakdown(gnn_gcn_t *m, double *ms, int n);
 GNN_API int gnn_gcn_last_spmm_spans(gnn_gcn_t *m, double *ms, double *alg_bytes, int32_t *F, int cap, int *n);
 /* algorithmic SpMM bytes / number of SpMM launches in one train step (for the roofline line) */
 GNN_API int gnn_gcn_spmm_stats(gnn_gcn_t *m, double *alg_bytes, int32_t *n_spmm, double *gemm_flops);
+/* how the aggregation inputs of this model travel between ranks (what actually runs, for the bench line):
+ * 0 single GPU, 1 ncclAllGather per aggregation, 2 peer-arena pushes by the SM store kernel (default),
+ * 3 peer-arena pushes by copy engines, 4 pipelined panels with in-place ncclAllGather as transport,
+ * 5 feature-column partition (all-to-all over peer memory before and after every aggregation) */
+GNN_API int gnn_gcn_exchange_mode(const gnn_gcn_t *m);
 
 /* ---------------------------------------------------------------- multi-GPU (K10) ------------------
  * 1-D contiguous row partition: part_ptr[p] = min(N, p*ceil(N/P)).  Each rank owns the CSR rows (and CSC
