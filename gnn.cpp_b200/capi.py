@@ -86,11 +86,15 @@ SIGNATURES = {
     "gnn_gcn_train_step_h": (C.c_int, [vp, vp, vp, vp, f32, vp]),
     "gnn_gcn_prefetch_h": (C.c_int, [vp, vp, vp, vp]),
     "gnn_gcn_set_train_mask": (C.c_int, [vp, vp, vp, i64]),
+    "gnn_gcn_set_relu_overrides": (C.c_int, [vp, vp, i32, vp, vp, vp, i64]),
     "gnn_gcn_accuracy": (C.c_int, [vp, vp, vp, vp, vp]),
     "gnn_gcn_last_breakdown": (C.c_int, [vp, vp, C.c_int]),
     "gnn_gcn_last_spmm_spans": (C.c_int, [vp, vp, vp, vp, C.c_int, vp]),
     "gnn_gcn_spmm_stats": (C.c_int, [vp, vp, vp, vp]),
     "gnn_gcn_exchange_mode": (C.c_int, [vp]),
+    "gnn_gcn_create_grid": (C.c_int, [vp, vp, i32, vp, i32, i32, pp]),
+    "gnn_partition_col_slice_h": (C.c_int, [i32, i32, i32, vp, vp]),
+    "gnn_partition_grid_h": (C.c_int, [i64, i32, i32, i32, vp, vp, vp, vp]),
     "gnn_partition_ptr_h": (C.c_int, [i64, i32, vp]),
     "gnn_partition_panels_h": (C.c_int, [i32, i32, vp, vp, vp]),
     "gnn_graph_slice_rows": (C.c_int, [vp, vp, i64, i64, pp]),

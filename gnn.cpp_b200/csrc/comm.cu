@@ -132,6 +132,84 @@ __global__ void peer_wait_flags_kernel(const uint32_t *flags, int world, int ran
     __threadfence_system();
 }
 
+
+// ---- 2-D partition: "rows -> columns" scatter --------------------------------------------------------------------
+// The rank's block src[rows, ld] is cut into column slices; destination d receives the slice [c0[d], c0[d] + w[d]) of
+// every row as a dense [rows, w[d]] block at dst[d] (its position inside the destination's gathered column-slice
+// matrix).  One kernel serves every destination (the own rank included): consecutive threads copy consecutive
+// 16-byte vectors of one slice row, so remote stores leave as contiguous w[d]*4-byte runs.  The last CTA to finish
+// publishes the sequence number in every remote destination's flag word, exactly like peer_push_kernel.
+struct PeerScatterArgs {
+    float *dst[PEER_MAX_WORLD];
+    uint32_t *flag[PEER_MAX_WORLD]; // nullptr for the own rank
+    int32_t c0[PEER_MAX_WORLD], w[PEER_MAX_WORLD];
+    int n_dst;
+};
+__global__ void __launch_bounds__(512)
+    peer_scatter_kernel(const PeerScatterArgs a, const float *__restrict__ src, int64_t ld, int64_t rows, uint32_t seq,
+                        unsigned *done) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int d = 0; d < a.n_dst; d++) {
+        const int32_t wv = a.w[d] >> 2;
+        if (wv <= 0) continue;
+        const size_t n = (size_t)rows * wv;
+        const float *s0 = src + a.c0[d];
+        uint4 *o = reinterpret_cast<uint4 *>(a.dst[d]);
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n; i += 4 * stride) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const size_t e = i + u * stride;
+                const size_t r = e / wv;
+                v[u] = __ldg(reinterpret_cast<const uint4 *>(s0 + r * ld) + (e - r * wv));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) __stcs(o + i + u * stride, v[u]);
+        }
+        for (; i < n; i += stride) {
+            const size_t r = i / wv;
+            __stcs(o + i, __ldg(reinterpret_cast<const uint4 *>(s0 + r * ld) + (i - r * wv)));
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {
+            *done = 0;
+            __threadfence_system();
+            for (int d = 0; d < a.n_dst; d++)
+                if (a.flag[d]) *reinterpret_cast<volatile uint32_t *>(a.flag[d]) = seq;
+            __threadfence_system();
+        }
+    }
+}
+// publish `seq` in the flag words of a set of peers: everything enqueued before it on the stream (e.g. an aggregation
+// kernel whose epilogue stored into the peers' arenas) is complete and fenced first
+struct PeerSignalArgs {
+    uint32_t *flag[PEER_MAX_WORLD];
+    int n;
+};
+__global__ void peer_signal_kernel(const PeerSignalArgs a, uint32_t seq) {
+    __threadfence_system();
+    if (threadIdx.x < a.n) *reinterpret_cast<volatile uint32_t *>(a.flag[threadIdx.x]) = seq;
+    __threadfence_system();
+}
+// lane q (bit q of peer_mask set) polls the flag of peer q for one slot
+__global__ void peer_wait_mask_kernel(const uint32_t *flags, uint32_t peer_mask, uint32_t seq) {
+    const int q = threadIdx.x;
+    if (q < PEER_MAX_WORLD && ((peer_mask >> q) & 1u)) {
+        const long long t0 = clock64();
+        const volatile uint32_t *f = flags + q;
+        while ((int32_t)(*f - seq) < 0) {
+            __nanosleep(100);
+            if (clock64() - t0 > 40000000000LL) __trap();
+        }
+    }
+    __threadfence_system();
+}
+
 } // namespace gnn
 
 struct gnn_peer_arena {
@@ -145,13 +223,73 @@ struct gnn_peer_arena {
     // on the side stream (the pipelined schedule with NCCL's transport, e.g. NVLS multicast on 8 ranks)
     std::vector<cudaEvent_t> ev_slot;          // transport 2: completion event per slot
     int sm_mode = 1, sm_ctas = 64; // 64 CTAs: 649 GB/s between two B200s (32: 617, 16: 458; ncclAllGather: 467)
-    cudaEvent_t ev_ready = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_self = nullptr;
     uint32_t seq[gnn::PEER_MAX_SLOTS] = {};      // last sequence number begun per slot (identical on every rank)
     uint32_t *flags(int r) const { return reinterpret_cast<uint32_t *>(base[r] + bytes); }
 };
 
 namespace gnn {
 
+} // namespace gnn
+
+
+namespace gnn {
+// ---- 2-D partition plumbing used by trainer_grid.cu (internal; exercised through gnn_gcn_create_grid) ------------
+char *peer_base(gnn_peer_arena *a, int rank) { return a->base[rank]; }
+
+// after the work already enqueued on the context's stream: scatter column slices of src[rows, ld] (see
+// peer_scatter_kernel) on the side stream; destination i is rank dst_rank[i], byte offset dst_off[i] of its arena
+int peer_scatter_begin(gnn_ctx *ctx, gnn_peer_arena *a, int slot, const float *src, int64_t ld, int64_t rows, int n_dst,
+                       const int *dst_rank, const size_t *dst_off, const int32_t *c0, const int32_t *w) {
+    GNN_REQUIRE(ctx && a && slot >= 0 && slot < PEER_MAX_SLOTS - 1 && n_dst <= PEER_MAX_WORLD, "peer_scatter_begin: bad argument");
+    GNN_REQUIRE(((uintptr_t)src & 15) == 0 && (ld & 3) == 0, "peer_scatter_begin: source must be 16-byte aligned with ld %% 4 == 0");
+    const uint32_t seq = ++a->seq[slot];
+    PeerScatterArgs pa;
+    pa.n_dst = n_dst;
+    for (int i = 0; i < n_dst; i++) {
+        const int r = dst_rank[i];
+        GNN_REQUIRE(r >= 0 && r < a->world && (dst_off[i] & 15) == 0 && (w[i] & 3) == 0 && (c0[i] & 3) == 0 &&
+                        dst_off[i] + (size_t)rows * w[i] * 4 <= a->bytes,
+                    "peer_scatter_begin: destination %d outside the arena or misaligned", i);
+        pa.dst[i] = reinterpret_cast<float *>(a->base[r] + dst_off[i]);
+        pa.flag[i] = r == a->rank ? nullptr : a->flags(r) + slot * PEER_MAX_WORLD + a->rank;
+        pa.c0[i] = c0[i];
+        pa.w[i] = w[i];
+    }
+    GNN_CHECK_CUDA(cudaEventRecord(a->ev_ready, ctx->stream));
+    GNN_CHECK_CUDA(cudaStreamWaitEvent(a->push_sm, a->ev_ready, 0));
+    peer_scatter_kernel<<<a->sm_ctas, 512, 0, a->push_sm>>>(pa, src, ld, rows, seq, a->done);
+    GNN_LAUNCHED(ctx);
+    // the own rank's slice is a local store of the same kernel: peer_wait_mask(.., after_own_scatter) orders the
+    // compute stream after it (not here, so that work enqueued in between overlaps the transfer)
+    GNN_CHECK_CUDA(cudaEventRecord(a->ev_self, a->push_sm));
+    return 0;
+}
+
+// compute stream: publish the next sequence number of `slot` to the peers in peer_mask (bit q = rank q)
+int peer_signal(gnn_ctx *ctx, gnn_peer_arena *a, int slot, uint32_t peer_mask) {
+    GNN_REQUIRE(ctx && a && slot >= 0 && slot < PEER_MAX_SLOTS - 1, "peer_signal: bad argument");
+    const uint32_t seq = ++a->seq[slot];
+    PeerSignalArgs sa;
+    sa.n = 0;
+    for (int q = 0; q < a->world; q++)
+        if (((peer_mask >> q) & 1u) && q != a->rank) sa.flag[sa.n++] = a->flags(q) + slot * PEER_MAX_WORLD + a->rank;
+    if (sa.n == 0) return 0;
+    peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(sa, seq);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+// compute stream: wait until every peer in peer_mask has published the current sequence number of `slot`
+int peer_wait_mask(gnn_ctx *ctx, gnn_peer_arena *a, int slot, uint32_t peer_mask, bool after_own_scatter) {
+    GNN_REQUIRE(ctx && a && slot >= 0 && slot < PEER_MAX_SLOTS - 1, "peer_wait_mask: bad argument");
+    if (after_own_scatter) GNN_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, a->ev_self, 0)); // latest peer_scatter_begin
+    peer_mask &= ~(1u << a->rank);
+    if (!peer_mask) return 0;
+    peer_wait_mask_kernel<<<1, 32, 0, ctx->stream>>>(a->flags(a->rank) + slot * PEER_MAX_WORLD, peer_mask, a->seq[slot]);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
 } // namespace gnn
 
 using namespace gnn;
@@ -284,6 +422,7 @@ int gnn_peer_arena_create(gnn_ctx_t *ctx, size_t bytes, gnn_peer_arena_t **out) 
         if (const char *e = getenv("GNN_PEER_CTAS")) a->sm_ctas = atoi(e) > 0 ? atoi(e) : a->sm_ctas;
     }
     GNN_CHECK_CUDA(cudaEventCreateWithFlags(&a->ev_ready, cudaEventDisableTiming));
+    GNN_CHECK_CUDA(cudaEventCreateWithFlags(&a->ev_self, cudaEventDisableTiming));
     *out = a;
     return 0;
 }
@@ -298,6 +437,7 @@ int gnn_peer_arena_destroy(gnn_ctx_t *ctx, gnn_peer_arena_t *a) {
     if (a->push_sm) { cudaStreamSynchronize(a->push_sm); cudaStreamDestroy(a->push_sm); }
     if (a->done) cudaFree(a->done);
     if (a->ev_ready) cudaEventDestroy(a->ev_ready);
+    if (a->ev_self) cudaEventDestroy(a->ev_self);
     for (auto e : a->ev_slot)
         if (e) cudaEventDestroy(e);
     // an exporter must not free memory a peer still has mapped: order all ranks (collective) before the free

@@ -100,11 +100,20 @@ int exclusive_scan_u32(gnn_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t 
 // keys/vals are overwritten with the sorted sequence (scratch comes from ctx->workspace).
 int radix_sort_u64(gnn_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int bit_lo, int bit_hi);
 // spmm.cu -----------------------------------------------------------------------------------------
+// Where the output rows of an aggregation go.  rows_per == 0: the plain matrix Y (base[0] = Y).  Otherwise output row
+// r belongs to destination q = r / rows_per and is written to base[q] + (r - q * rows_per) * ldy: the 2-D partitioned
+// trainer points base[q] at peer q's IPC-mapped activation buffer, so the aggregation kernel itself performs the
+// "columns -> rows" exchange with its epilogue stores (compute and transfer fused in one kernel).
+constexpr int SPMM_MAX_DEST = 8;
+struct YDest {
+    float *base[SPMM_MAX_DEST];
+    int32_t rows_per;
+};
 int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
                 const float *val, int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F,
                 float *Y, int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm,
-                bool may_touch_padding = true);
+                bool may_touch_padding = true, const YDest *dest = nullptr);
 int spmm_rows_range(gnn_ctx *ctx, const gnn_graph *g, int transpose, int32_t r0, int32_t r1, int64_t k0, int64_t k1,
                     const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
-                    const float *mask, int64_t ldm);
+                    const float *mask, int64_t ldm, const YDest *dest = nullptr);
 } // namespace gnn

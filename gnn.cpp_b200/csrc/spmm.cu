@@ -54,6 +54,13 @@ __device__ __forceinline__ float epilogue1(float v, int col, int F, const float 
     return v;
 }
 
+// output row pointer (see YDest in common.cuh)
+__device__ __forceinline__ float *yd_row(const YDest &d, int32_t row, int64_t ldy) {
+    if (d.rows_per == 0) return d.base[0] + (int64_t)row * ldy;
+    const int32_t q = row / d.rows_per;
+    return d.base[q] + (int64_t)(row - q * d.rows_per) * ldy;
+}
+
 constexpr int SPMM_THREADS = 256;
 // Loads in flight per lane (U nonzeros x VEC vectors) and whether the next (column, value) batch is requested
 // before the current one is consumed.  Measured on B200 (tools/spmm_probe.py, products-shaped, merge kernel):
@@ -180,7 +187,7 @@ template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF>
 __global__ void __launch_bounds__(SPMM_THREADS)
     spmm_rows_kernel(int32_t n_out, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
                      const float *__restrict__ val, const float *__restrict__ P, int64_t ldp, int32_t F,
-                     float *__restrict__ Y, int64_t ldy, const float *__restrict__ bias, int relu,
+                     const YDest yd, int64_t ldy, const float *__restrict__ bias, int relu,
                      const float *__restrict__ mask, int64_t ldm) {
     using T = VecTraits<V>;
     constexpr int GROUPS = SPMM_THREADS / LPR;
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 #pragma unroll
     for (int v = 0; v < VEC; v++) acc[v] = T::zero();
     accumulate_range<V, LPR, 1, VEC, USE_VAL, U, PF>(acc, idx, val, ptr[row], ptr[row + 1], P, ldp, nvec, sub, gmask);
-    store_row<V, LPR, VEC>(acc, Y + row * ldy, nvec, sub, F, bias, relu, mask ? mask + row * ldm : nullptr);
+    store_row<V, LPR, VEC>(acc, yd_row(yd, (int32_t)row, ldy), nvec, sub, F, bias, relu, mask ? mask + row * ldm : nullptr);
 }
 
 // ---- variant 2: nonzero-balanced (merge-path style) ------------------------------------------------------------
@@ -212,7 +219,7 @@ template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF>
 __global__ void __launch_bounds__(SPMM_THREADS)
     spmm_merge_kernel(int32_t n_out, int32_t k_base, int32_t nnz, int32_t n_chunks, int32_t MERGE_CHUNK,
                       const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx, const float *__restrict__ val,
-                      const float *__restrict__ P, int64_t ldp, int32_t F, float *__restrict__ Y, int64_t ldy,
+                      const float *__restrict__ P, int64_t ldp, int32_t F, const YDest yd, int64_t ldy,
                       const float *__restrict__ bias, int relu, const float *__restrict__ mask, int64_t ldm,
                       float *__restrict__ head, float *__restrict__ tail, int32_t *__restrict__ head_row,
                       int32_t *__restrict__ tail_row, int32_t ldw) {
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
         reduce_slots<V, LPR, S, VEC>(acc, gmask);
         const bool starts = (k == rb), ends = (seg_end == re);
         if (starts && ends) {
-            store_row<V, LPR, VEC>(acc, Y + (int64_t)row * ldy, nvec_st, sub, F, bias, relu,
+            store_row<V, LPR, VEC>(acc, yd_row(yd, row, ldy), nvec_st, sub, F, bias, relu,
                                    mask ? mask + (int64_t)row * ldm : nullptr);
         } else {
             float *dst = (ends ? head : tail) + (int64_t)g * ldw;
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 __global__ void __launch_bounds__(256)
     spmm_merge_fixup_kernel(int32_t n_chunks, int32_t F, const float *__restrict__ head, const float *__restrict__ tail,
                             const int32_t *__restrict__ head_row, const int32_t *__restrict__ tail_row, int32_t ldw,
-                            float *__restrict__ Y, int64_t ldy, const float *__restrict__ bias, int relu,
+                            const YDest yd, int64_t ldy, const float *__restrict__ bias, int relu,
                             const float *__restrict__ mask, int64_t ldm) {
     const int32_t g = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -285,11 +292,12 @@ __global__ void __launch_bounds__(256)
     int32_t first = g;
     while (first > 0 && tail_row[first - 1] == row) first--;
     const float *mrow = mask ? mask + (int64_t)row * ldm : nullptr;
+    float *yrow = yd_row(yd, row, ldy);
     for (int32_t c = lane; c < F; c += 32) {
         float s = 0.f;
         for (int32_t t = first; t < g; t++) s += tail[(int64_t)t * ldw + c];
         s += head[(int64_t)g * ldw + c];
-        Y[(int64_t)row * ldy + c] = epilogue1(s, c, F, bias, relu, mrow);
+        yrow[c] = epilogue1(s, c, F, bias, relu, mrow);
     }
 }
 
@@ -306,7 +314,7 @@ static inline int32_t merge_chunk(const gnn_ctx *ctx, int lpr, int64_t nnz) {
 
 template <typename V, int LPR, int VEC, int U, bool PF>
 static int launch_rows(gnn_ctx *ctx, int32_t n_out, const int32_t *ptr, const int32_t *idx, const float *val,
-                       const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
+                       const float *P, int64_t ldp, int32_t F, const YDest &Y, int64_t ldy, const float *bias, int relu,
                        const float *mask, int64_t ldm) {
     constexpr int GROUPS = SPMM_THREADS / LPR;
     const unsigned grid = (unsigned)ceil_div(n_out, GROUPS);
@@ -322,7 +330,7 @@ static int launch_rows(gnn_ctx *ctx, int32_t n_out, const int32_t *ptr, const in
 
 template <typename V, int LPR, int VEC, int U, bool PF>
 static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
-                        const float *val, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy,
+                        const float *val, const float *P, int64_t ldp, int32_t F, const YDest &Y, int64_t ldy,
                         const float *bias, int relu, const float *mask, int64_t ldm) {
     constexpr int GROUPS = SPMM_THREADS / 32; // one warp per chunk
     const int32_t MERGE_CHUNK = merge_chunk(ctx, LPR, nnz - k_base);
@@ -368,8 +376,9 @@ static bool use_merge(const gnn_ctx *ctx, int64_t nnz, int64_t k_end, int32_t mi
 int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
                 const float *val, int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F,
                 float *Y, int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm,
-                bool may_touch_padding) {
+                bool may_touch_padding, const YDest *dest) {
     if (n_out <= 0 || F <= 0) return 0;
+    if (dest) Y = dest->base[0]; // alignment check below: every destination shares base[0]'s alignment (same arena offset)
     // The 128-bit path reads columns F..round_up(F,4)-1 of P and WRITES the same columns of Y.  The trainer owns its
     // padded buffers; a public-API caller may pass a column slice of a wider matrix, whose neighbouring columns must
     // survive: such calls (F % 4 != 0 with ld wider than the padded row) take the scalar path.
@@ -379,7 +388,9 @@ int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const 
     for (int32_t c0 = 0; c0 < F; c0 += block_cols) {
         const int32_t f = F - c0 < block_cols ? F - c0 : block_cols;
         const float *Pc = P + c0;
-        float *Yc = Y + c0;
+        YDest Yc;
+        Yc.rows_per = dest ? dest->rows_per : 0;
+        for (int q = 0; q < SPMM_MAX_DEST; q++) Yc.base[q] = dest ? (dest->base[q] ? dest->base[q] + c0 : nullptr) : (q == 0 ? Y + c0 : nullptr);
         const float *bc = bias ? bias + c0 : nullptr;
         const float *mc = mask ? mask + c0 : nullptr;
 #define GO2(V, LPR, VEC, U, PF)                                                                                      \
@@ -431,14 +442,14 @@ int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const 
 // Y and mask point at row r0.
 int spmm_rows_range(gnn_ctx *ctx, const gnn_graph *g, int transpose, int32_t r0, int32_t r1, int64_t k0, int64_t k1,
                     const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
-                    const float *mask, int64_t ldm) {
+                    const float *mask, int64_t ldm, const YDest *dest) {
     const bool alias = transpose && g->symmetric;
     const int32_t *ptr = (!transpose || alias) ? g->rowptr : g->colptr;
     const int32_t *idx = (!transpose || alias) ? g->colidx : g->rowidx;
     const float *val = !transpose ? g->val : (alias ? (g->valT ? g->valT : g->val) : g->valT);
     const int32_t mn = (!transpose || alias) ? g->min_row_nnz : g->min_col_nnz;
     const int32_t mx = (!transpose || alias) ? g->max_row_nnz : g->max_col_nnz;
-    return spmm_launch(ctx, r1 - r0, k0, k1, ptr + r0, idx, val, mn, mx, P, ldp, F, Y, ldy, bias, relu, mask, ldm);
+    return spmm_launch(ctx, r1 - r0, k0, k1, ptr + r0, idx, val, mn, mx, P, ldp, F, Y, ldy, bias, relu, mask, ldm, true, dest);
 }
 
 } // namespace gnn

@@ -14,122 +14,9 @@
 // copy-engine push of the rank's block into every peer's arena over NVLink (comm.cu), started as soon as the
 // block is produced and awaited right before the aggregation, so the bias-gradient column sums and the dW GEMMs
 // of the backward run while the next aggregation input is in flight (NN GEMM before TN GEMM for that reason).
-#include "common.cuh"
-
-int gnn_peer_arena_transport(const gnn_peer_arena_t *a); // comm.cu: 1 SM store kernel, 0 copy engines, 2 ncclAllGather
-namespace gnn {
-int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out);
-int softmax_xent_launch(gnn_ctx *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
-                        int64_t n_total, float *loss, float *dZ, int64_t ldd, float *db, bool may_touch_padding);
-int copy2d(gnn_ctx *ctx, float *dst, int64_t ldd, const float *src, int64_t lds, int64_t rows, int32_t cols);
-int spmm_rows_range(gnn_ctx *ctx, const gnn_graph *g, int transpose, int32_t r0, int32_t r1, int64_t k0, int64_t k1,
-                    const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy, const float *bias, int relu,
-                    const float *mask, int64_t ldm);
-}
-
-struct gnn_gcn {
-    const gnn_graph *g = nullptr;
-    int32_t L = 0;
-    std::vector<int32_t> dims, ld;   // F_l and padded leading dimension (multiple of 4)
-    std::vector<char> agg_first;     // per layer (index 1..L)
-    int64_t n_loc = 0, n_glob = 0, chunk = 0; // local rows, global nodes, rows per rank (dist)
-    bool dist = false;
-    // parameter slab: [W_1, b_1, ..., W_L, b_L] ; gradient slab same layout + 1 float (local loss sum / N)
-    float *params = nullptr, *grads = nullptr, *vel = nullptr;
-    int64_t n_params = 0;
-    std::vector<int64_t> w_off, b_off;
-    // activations
-    std::vector<float *> H;  // H[l], l = 1..L  [n_loc, ld[l]]
-    std::vector<float *> M;  // aggregated inputs of AF layers [n_loc, ld[l-1]]
-    float *S1 = nullptr, *G0 = nullptr, *G1 = nullptr; // scratch [n_loc, maxld]
-    float *AG = nullptr;                                 // all-gather buffer [world*chunk, maxld] (dist, NCCL mode)
-    // dist, peer mode: one gather region [world][chunk, ldw] per aggregation of a step inside the peer arena;
-    // slot(l, dir) = 2*(l-1) + dir (dir 0 forward, 1 backward); the rank produces its own block in place
-    gnn_peer_arena_t *arena = nullptr;
-    std::vector<size_t> slot_off;
-    int comm_mode = 1; // 1 = peer arena pushes (falls back to 0 when IPC is unavailable), 0 = ncclAllGather
-    bool nccl_transport = false; // GNN_PEER_COPY=nccl: tiles travel by in-place ncclAllGather on the side stream
-    int32_t panel_cols = 128; // peer mode: column panel width of a gathered matrix (pipelines transfer and SpMM)
-    // row blocks of the rank's rows (peer mode; one block otherwise): rows rb_row[i]..rb_row[i+1], with the matching
-    // nonzero offsets of the forward (CSR) and backward (CSC) structure
-    int n_rb = 1;
-    int64_t rb_row[9] = {0}, rb_kf[9] = {0}, rb_kb[9] = {0};
-    float *Xs[2] = {nullptr, nullptr};                   // double-buffered staged inputs for *_h entry points
-    int32_t *ys[2] = {nullptr, nullptr};
-    int cur_slot = 0;
-    bool prefetched = false;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_uploaded = nullptr, ev_consumed = nullptr;
-    const int32_t *last_y = nullptr;
-    float *loss_d = nullptr;
-    int32_t maxld = 0;
-    // options
-    int precision = 1, profile = 0; // dense transforms: 1 = 3xTF32 on tcgen05 (falls back per shape), 0 = FP32 FMA
-    float momentum = 0.f, dampening = 0.f, weight_decay = 0.f;
-    int nesterov = 0;
-    int optimizer = 0; // 0 = SGD (nn::SGD), 1 = Adam (nn::Adam)
-    // CUDA graph of the whole step for launch-bound (small) problems: -1 auto, 0 off, 1 on.  The step is a fixed
-    // launch sequence over preallocated buffers, so it is captured once (after an eager warm-up step that sizes the
-    // workspace) and replayed while the arguments stay the same.
-    int use_graph = -1;
-    cudaGraphExec_t graph_exec = nullptr, graph_exec2 = nullptr; // two entries: the host-buffer path alternates slots
-    int64_t graph_launches = 0;
-    struct GraphKey {
-        const float *X; int64_t ldx; const int32_t *y; float lr; float *loss_d;
-        uint64_t ws_gen; // the captured kernels bake ctx->ws pointers in: a reallocated workspace invalidates the graph
-        bool operator==(const GraphKey &o) const {
-            return X == o.X && ldx == o.ldx && y == o.y && lr == o.lr && loss_d == o.loss_d && ws_gen == o.ws_gen;
-        }
-    } graph_key = {nullptr, 0, nullptr, 0.f, nullptr, 0}, graph_key2 = {nullptr, 0, nullptr, 0.f, nullptr, 0};
-    float beta1 = 0.9f, beta2 = 0.999f, adam_eps = 1e-8f;
-    float *adam_m = nullptr, *adam_v = nullptr;
-    const uint8_t *train_mask = nullptr; // device uint8[n_loc]: rows that enter the loss (Data::set_mask TRAIN)
-    int64_t n_train = 0;                 // selected rows over the whole graph
-    int64_t steps = 0;
-    int64_t opt_steps = 0, vel_steps = 0; // optimiser steps taken (Adam bias correction) / steps the momentum buffer has seen
-    // stats
-    double alg_bytes = 0, gemm_flops = 0;
-    int32_t n_spmm = 0;
-    // profiling
-    struct Span { int cls; cudaEvent_t a, b; int32_t F; double bytes; float ms; };
-    std::vector<Span> spans;
-    size_t span_used = 0;
-    double breakdown[6] = {0, 0, 0, 0, 0, 0};
-};
+#include "trainer.cuh"
 
 namespace gnn {
-
-enum { CLS_SPMM = 0, CLS_GEMM = 1, CLS_LOSS = 2, CLS_BIAS = 3, CLS_SGD = 4, CLS_OTHER = 5 };
-
-struct Prof {
-    gnn_ctx *ctx;
-    gnn_gcn *m;
-    int idx = -1;
-    Prof(gnn_ctx *c, gnn_gcn *mm, int cls, int32_t F = 0, double bytes = 0) : ctx(c), m(mm) {
-        if (!m->profile) return;
-        if (m->span_used == m->spans.size()) {
-            gnn_gcn::Span s;
-            s.cls = cls;
-            s.F = 0; s.bytes = 0; s.ms = 0;
-            cudaEventCreate(&s.a);
-            cudaEventCreate(&s.b);
-            m->spans.push_back(s);
-        }
-        idx = (int)m->span_used++;
-        m->spans[idx].cls = cls;
-        m->spans[idx].F = F;
-        m->spans[idx].bytes = bytes;
-        cudaEventRecord(m->spans[idx].a, ctx->stream);
-    }
-    ~Prof() {
-        if (idx >= 0) cudaEventRecord(m->spans[idx].b, ctx->stream);
-    }
-};
-
-static double spmm_alg_bytes(int64_t n_out, int64_t nnz, int32_t F) {
-    // B_alg = 4(N+1) + nnz*(8 + 4F) + 4*N*F
-    return 4.0 * (n_out + 1) + (double)nnz * (8.0 + 4.0 * F) + 4.0 * n_out * F;
-}
 
 static void recompute_stats(gnn_gcn *m) {
     // statistics for the roofline line: every SpMM of one train step
@@ -146,6 +33,25 @@ static void recompute_stats(gnn_gcn *m) {
         }
         m->gemm_flops += 2.0 * m->n_loc * Fi * Fo * (l > 1 ? 3 : 2);
     }
+}
+
+__global__ void relu_override_kernel(float *__restrict__ H, int64_t ld, const int32_t *__restrict__ rows,
+                                     const int32_t *__restrict__ cols, const uint8_t *__restrict__ positive, int64_t n,
+                                     int64_t r0, int64_t r1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t r = rows[i];
+    if (r < r0 || r >= r1) return;
+    float *p = H + r * ld + cols[i];
+    *p = positive[i] ? fmaxf(*p, 1e-30f) : 0.f;
+}
+// rows [r0, r1) of H_l are complete: apply the layer's tie-break overrides before anything reads them
+int apply_relu_overrides(gnn_ctx *ctx, gnn_gcn *m, int32_t l, int64_t r0, int64_t r1) {
+    if (l >= m->L || (size_t)l >= m->overrides.size() || m->overrides[l].n <= 0 || r1 <= r0) return 0;
+    const gnn_gcn::Override &o = m->overrides[l];
+    relu_override_kernel<<<(unsigned)ceil_div(o.n, 256), 256, 0, ctx->stream>>>(m->H[l], m->ld[l], o.rows, o.cols, o.positive, o.n, r0, r1);
+    GNN_LAUNCHED(ctx);
+    return 0;
 }
 
 // aggregation input must be visible in global row order: all-gather under row partitioning (NCCL mode)
@@ -260,6 +166,7 @@ static int produce_fwd(gnn_ctx *ctx, gnn_gcn *m, int32_t l, int rb, const float 
 }
 
 static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
+    if (m->grid) return forward_grid(ctx, m, X, ldx);
     const gnn_graph *g = m->g;
     const float *Hin = X;
     int64_t ld_in = ldx;
@@ -309,6 +216,7 @@ static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
                     GNN_TRY(gnn_gemm_nt(ctx, r1 - r0, Fo, Fi, m->M[l] + r0 * m->ld[l - 1], m->ld[l - 1], W, Fi,
                                         m->H[l] + r0 * m->ld[l], m->ld[l], b, relu, m->precision));
                 }
+                GNN_TRY(apply_relu_overrides(ctx, m, l, r0, r1));
                 if (l < m->L) GNN_TRY(produce_fwd(ctx, m, l + 1, rb, m->H[l], m->ld[l]));
             }
         }
@@ -320,6 +228,7 @@ static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
 
 // dZ_L has been written to dz_view(L, .) (and, in peer mode with a transform-first last layer, its tiles pushed)
 static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
+    if (m->grid) return backward_grid(ctx, m, X, ldx);
     const gnn_graph *g = m->g;
     for (int32_t l = m->L; l >= 1; l--) {
         const int32_t Fi = m->dims[l - 1], Fo = m->dims[l];
@@ -535,10 +444,16 @@ int gnn_gcn_destroy(gnn_ctx_t *ctx, gnn_gcn_t *m) {
     if (!m) return 0;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     drop_graph(m);
-    cudaFree(m->params); cudaFree(m->grads); cudaFree(m->vel); cudaFree(m->adam_m); cudaFree(m->adam_v);
-    for (auto p : m->H) cudaFree(p);
-    for (auto p : m->M) cudaFree(p);
-    cudaFree(m->S1); cudaFree(m->G0); cudaFree(m->G1); cudaFree(m->AG);
+    cudaFree(m->vel); cudaFree(m->adam_m); cudaFree(m->adam_v);
+    if (m->grid) { // activations live in the arena; everything cudaMalloc'ed is listed in `owned`
+        for (auto p : m->owned) cudaFree(p);
+        m->loss_d = nullptr;
+    } else {
+        cudaFree(m->params); cudaFree(m->grads);
+        for (auto p : m->H) cudaFree(p);
+        for (auto p : m->M) cudaFree(p);
+        cudaFree(m->S1); cudaFree(m->G0); cudaFree(m->G1); cudaFree(m->AG);
+    }
     if (m->arena) gnn_peer_arena_destroy(ctx, m->arena);
     for (int i = 0; i < 2; i++) { cudaFree(m->Xs[i]); cudaFree(m->ys[i]); }
     if (m->copy_stream) { cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_uploaded); cudaEventDestroy(m->ev_consumed); }
@@ -620,7 +535,12 @@ int gnn_gcn_set_option(gnn_gcn_t *m, const char *key, double value) {
 
     else if (!strcmp(key, "agg_first_mask")) { // bit l-1 set -> layer l aggregates first (tests / ablation)
         for (int32_t l = 1; l <= m->L; l++) m->agg_first[l] = (((int64_t)value) >> (l - 1)) & 1;
-        recompute_stats(m);
+        if (m->grid) {
+            for (int32_t l = 1; l <= m->L; l++) m->H[l] = m->agg_first[l] ? m->H_local[l] : m->M[l]; // M[l] = forward output region
+            recompute_stats_grid(m);
+        } else {
+            recompute_stats(m);
+        }
     } else {
         set_error("gnn_gcn_set_option: unknown key '%s'", key);
         return 2;
@@ -668,8 +588,9 @@ static int train_step_body(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X, int64_t
         // dZ_L goes where the backward expects it; a panel-major destination with more than one panel is staged
         // through the row-major buffer
         const Panels PL = panels_of(m, m->ld[m->L]);
-        const bool pm = m->arena && !m->agg_first[m->L];
-        const View dz = (pm && PL.n > 1) ? View{m->G0, m->ld[m->L]} : dz_view(ctx, m, m->L, PL, 0);
+        const bool pm = m->arena && !m->agg_first[m->L] && !m->grid;
+        const View dz = m->grid ? View{dz_buffer_grid(m, m->L), m->ld[m->L]}
+                                : ((pm && PL.n > 1) ? View{m->G0, m->ld[m->L]} : dz_view(ctx, m, m->L, PL, 0));
         if (m->train_mask) { // loss over the training nodes only
             GNN_TRY(gnn_softmax_xent_masked(ctx, m->n_loc, C, m->H[m->L], m->ld[m->L], y, m->train_mask, m->n_train,
                                             loss_slot, dz.ptr, dz.ld));
@@ -846,6 +767,17 @@ int gnn_partition_panels_h(int32_t ldw, int32_t panel_cols, int32_t *c0_h, int32
     return 0;
 }
 
+int gnn_gcn_set_relu_overrides(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, const int32_t *rows, const int32_t *cols,
+                               const uint8_t *positive, int64_t n) {
+    GNN_REQUIRE(ctx && m && layer >= 1 && layer < m->L && n >= 0 && (n == 0 || (rows && cols && positive)),
+                "gnn_gcn_set_relu_overrides: layer must be a hidden layer (1..L-1) and the arrays non-NULL");
+    drop_graph(m);
+    if (m->overrides.size() <= (size_t)m->L) m->overrides.resize(m->L + 1);
+    m->overrides[layer].rows = rows; m->overrides[layer].cols = cols; m->overrides[layer].positive = positive;
+    m->overrides[layer].n = n;
+    return 0;
+}
+
 int gnn_gcn_set_train_mask(gnn_ctx_t *ctx, gnn_gcn_t *m, const uint8_t *mask, int64_t n_selected_total) {
     GNN_REQUIRE(ctx && m && (!mask || n_selected_total > 0), "invalid input, mask must be 1D and of same size with num of nodes in graph");
     drop_graph(m);
@@ -883,6 +815,7 @@ int gnn_gcn_last_spmm_spans(gnn_gcn_t *m, double *ms, double *alg_bytes, int32_t
 
 int gnn_gcn_exchange_mode(const gnn_gcn_t *m) {
     if (!m || !m->dist) return 0;
+    if (m->grid) return 6;
     if (!m->arena) return 1;
     if (m->nccl_transport) return 4;
     return gnn_peer_arena_transport(m->arena) == 0 ? 3 : 2;

@@ -72,3 +72,38 @@ def comm_bytes_per_step(N, dims, world):
     gathers = sum(w for _, _, _, w in exchange_schedule(dims)) * 4 * c * (world - 1)
     n_params = sum(dims[l] * dims[l - 1] + dims[l] for l in range(1, len(dims)))
     return gathers + (2 * 4 * n_params * (world - 1)) // max(world, 1)
+
+
+# ---- 2-D partition (gnn_gcn_create_grid, csrc/trainer_grid.cu) ---------------------------------------------------
+def col_slice(ldw, Pc, j):
+    """(first column, width) of the column slice group j of Pc receives of a matrix of padded width ldw — the library's
+    rule (gnn_partition_col_slice_h)."""
+    c0 = ctypes.c_int32(0); w = ctypes.c_int32(0)
+    capi.call("gnn_partition_col_slice_h", int(ldw), int(Pc), int(j), ctypes.byref(c0), ctypes.byref(w))
+    return int(c0.value), int(w.value)
+
+
+def grid_partition(N, world, Pc, rank):
+    """((rows_lo, rows_hi), (group_lo, group_hi)): activation rows the rank owns and the structure rows of its row group."""
+    v = [ctypes.c_int64(0) for _ in range(4)]
+    capi.call("gnn_partition_grid_h", int(N), int(world), int(Pc), int(rank), *[ctypes.byref(x) for x in v])
+    return (int(v[0].value), int(v[1].value)), (int(v[2].value), int(v[3].value))
+
+
+def default_grid(world):
+    """(Pr, Pc) bench.py uses per world size (GNN_GRID=PrxPc overrides): the 1-D row partition (None) up to 2 ranks,
+    where its exchange still hides behind the aggregation; 2 row groups beyond, which bounds the loss of SpMM
+    efficiency from narrow column slices while cutting the received bytes ~2x (4 ranks) / ~3x (8 ranks)."""
+    return None if world <= 2 else (2, world // 2)
+
+
+def comm_bytes_per_step_grid(N, dims, world, Pc):
+    """bytes RECEIVED per rank per step under the 2-D partition (widest column group): N F / Pc minus the own rows for the
+    column-slice scatter + c F (Pc-1)/Pc for the row exchange fused into the aggregation, + the gradient all-reduce."""
+    c = chunk_rows(N, world)
+    total = 0
+    for _, _, _, w in exchange_schedule(dims):
+        wj = max(col_slice(w, Pc, j)[1] for j in range(Pc))
+        total += 4 * (world - 1) * c * wj + 4 * c * (w - min(col_slice(w, Pc, j)[1] for j in range(Pc)))
+    n_params = sum(dims[l] * dims[l - 1] + dims[l] for l in range(1, len(dims)))
+    return total + (2 * 4 * n_params * (world - 1)) // max(world, 1)

@@ -323,20 +323,42 @@ class GCN:
         n = int(self._mask.sum().item()) if n_selected_total is None else int(n_selected_total)
         capi.call("gnn_gcn_set_train_mask", self.ctx.h, self.h, _ptr(self._mask), n)
 
+    def set_relu_overrides(self, layer, rows, cols, positive):
+        """rows/cols: int32 numpy (LOCAL row ids, column ids), positive: bool/uint8 numpy; see gnn_gcn_set_relu_overrides."""
+        if not hasattr(self, "_ov"):
+            self._ov = {}
+        n = len(rows)
+        if n == 0:
+            self._ov.pop(layer, None)
+            capi.call("gnn_gcn_set_relu_overrides", self.ctx.h, self.h, layer, None, None, None, 0)
+            return
+        dev = self.ctx.device
+        t = (torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int32)).to(dev),
+             torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int32)).to(dev),
+             torch.from_numpy(np.ascontiguousarray(positive, dtype=np.uint8)).to(dev))
+        self._ov[layer] = t        # keep alive: the library stores the pointers
+        capi.call("gnn_gcn_set_relu_overrides", self.ctx.h, self.h, layer, _ptr(t[0]), _ptr(t[1]), _ptr(t[2]), n)
+
     def accuracy(self, y, mask=None):
         cnt = torch.zeros(1, dtype=torch.int64, device=y.device)
         m8 = None if mask is None else mask.to(torch.uint8).contiguous()
         capi.call("gnn_gcn_accuracy", self.ctx.h, self.h, _ptr(y), _ptr(m8), _ptr(cnt))
         return int(cnt.item())
 
-    def __init__(self, ctx, graph, dims):
+    def __init__(self, ctx, graph, dims, grid=None, n_loc=None):
+        """grid = (Pr, Pc): 2-D partition (gnn_gcn_create_grid); `graph` is then the row group's structure slice and
+        n_loc the number of activation rows this rank owns."""
         self.ctx, self.graph, self.dims = ctx, graph, list(dims)
         self.L = len(dims) - 1
         h = C.c_void_p()
         d = np.asarray(dims, dtype=np.int32)
-        capi.call("gnn_gcn_create", ctx.h, graph.h, self.L, _ptr(d), C.byref(h))
+        if grid is not None:
+            capi.call("gnn_gcn_create_grid", ctx.h, graph.h, self.L, _ptr(d), int(grid[0]), int(grid[1]), C.byref(h))
+            self.n_loc = int(n_loc)
+        else:
+            capi.call("gnn_gcn_create", ctx.h, graph.h, self.L, _ptr(d), C.byref(h))
+            self.n_loc = graph.n_rows
         self.h = h
-        self.n_loc = graph.n_rows
 
     def set_option(self, key, value):
         capi.call("gnn_gcn_set_option", self.h, key.encode(), float(value))
@@ -416,7 +438,7 @@ class GCN:
                 2: "all-gather of every aggregation input by SM store pushes into IPC-mapped peer arenas over NVLink, pipelined by column panels",
                 3: "all-gather of every aggregation input by copy-engine pushes into IPC-mapped peer arenas, pipelined by column panels",
                 4: "all-gather of every aggregation input by in-place ncclAllGather per column panel (side stream)",
-                5: "feature-column partition of the aggregation: all-to-all over IPC-mapped peer memory before and after every SpMM (replicated structure)",
+                6: "2-D partition of the aggregation (row groups x feature-column groups): column-slice scatter into IPC-mapped peer arenas before, row exchange fused into the SpMM epilogue stores",
                 }.get(self.exchange_mode(), "unknown")
 
     def close(self):

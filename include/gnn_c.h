@@ -273,6 +273,14 @@ GNN_API int gnn_gcn_train_step_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h,
 GNN_API int gnn_gcn_prefetch_h(gnn_ctx_t *ctx, gnn_gcn_t *m, const float *X_h, const int32_t *y_h);
 /* Training-node mask (graph::Data::set_mask(mask, TRAIN), src/graph.cpp:130-151): device uint8[local rows]; the
  * loss becomes the mean over the n_selected_total selected nodes of the whole graph (all ranks).  NULL = all nodes. */
+/* ReLU tie-break overrides for cross-implementation parity checks: entries (rows[i], cols[i]) — LOCAL row ids — of
+ * hidden layer `layer`'s output H_l are forced, right after the forward produces them, to max(H, 1e-30) (positive[i] != 0)
+ * or to 0.  `Z > 0` (nn::ReLU, src/nn.cpp:229-237; Mask::_backward, operation.h:557-562) is discontinuous, so two correct
+ * fp32 implementations legitimately disagree on the mask of pre-activations within rounding distance of zero; listing
+ * exactly those entries (|Z| <= 1e-5 max|Z| in the other implementation) makes the backward masks identical while
+ * changing no forward value by more than the 1e-5 tolerance.  Device arrays, caller-owned; n = 0 clears the layer. */
+GNN_API int gnn_gcn_set_relu_overrides(gnn_ctx_t *ctx, gnn_gcn_t *m, int32_t layer, const int32_t *rows, const int32_t *cols,
+                                       const uint8_t *positive, int64_t n);
 GNN_API int gnn_gcn_set_train_mask(gnn_ctx_t *ctx, gnn_gcn_t *m, const uint8_t *mask, int64_t n_selected_total);
 /* correct predictions (arg-max of the logits of the last forward) among the rows selected by mask (val/test mask;
  * NULL = all local rows); *count is a device int64 (per rank: sum over ranks on the host side). */
@@ -288,8 +296,24 @@ GNN_API int gnn_gcn_spmm_stats(gnn_gcn_t *m, double *alg_bytes, int32_t *n_spmm,
 /* how the aggregation inputs of this model travel between ranks (what actually runs, for the bench line):
  * 0 single GPU, 1 ncclAllGather per aggregation, 2 peer-arena pushes by the SM store kernel (default),
  * 3 peer-arena pushes by copy engines, 4 pipelined panels with in-place ncclAllGather as transport,
- * 5 feature-column partition (all-to-all over peer memory before and after every aggregation) */
+ * 6 2-D partition (gnn_gcn_create_grid: column-slice scatter before, fused row exchange inside every aggregation) */
 GNN_API int gnn_gcn_exchange_mode(const gnn_gcn_t *m);
+/* Fused trainer under a 2-D partition of the aggregation: world = Pr row groups x Pc feature-column groups, this rank =
+ * gi * Pc + gj.  `g` holds the structure rows of row group gi — gnn_graph_slice_rows(global, lo, hi) with
+ * lo = min(N, gi Pc c), hi = min(N, (gi+1) Pc c), c = ceil(N / world) — all columns.  Activations, X and y stay 1-D
+ * row-partitioned (rank r owns rows [r c, (r+1) c)), so every other gnn_gcn_* entry point is used unchanged.
+ * Per aggregation each rank receives N F / Pc + c F (Pc-1)/Pc floats instead of the N F (world-1)/world of the 1-D row
+ * partition's all-gather (src/graph.cpp:204-212 is the aggregation being sharded).  Needs CUDA IPC peer mapping
+ * (returns 5 otherwise; there is no NCCL variant of this mode). */
+/* Host-only rules of that partition (what the trainer itself uses; exported for plans and CPU tests):
+ * column slice [c0, c0 + w) that column group j of Pc receives of a matrix of padded width ldw (16-byte units dealt out
+ * in order, the first ldw/4 % Pc groups get one more); and for `rank` of `world` = Pr x Pc the activation rows
+ * [rows_lo, rows_hi) it owns and the structure rows [group_lo, group_hi) of its row group (rank / Pc). */
+GNN_API int gnn_partition_col_slice_h(int32_t ldw, int32_t Pc, int32_t j, int32_t *c0_h, int32_t *w_h);
+GNN_API int gnn_partition_grid_h(int64_t N, int32_t world, int32_t Pc, int32_t rank, int64_t *rows_lo_h, int64_t *rows_hi_h,
+                                 int64_t *group_lo_h, int64_t *group_hi_h);
+GNN_API int gnn_gcn_create_grid(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_t *dims, int32_t Pr, int32_t Pc,
+                                gnn_gcn_t **out);
 
 /* ---------------------------------------------------------------- multi-GPU (K10) ------------------
  * 1-D contiguous row partition: part_ptr[p] = min(N, p*ceil(N/P)).  Each rank owns the CSR rows (and CSC

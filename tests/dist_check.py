@@ -14,7 +14,48 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import gnn_cpp_b200  # noqa: E402,F401
-from gnn_cpp_b200 import host, synth  # noqa: E402
+from gnn_cpp_b200 import dist_plan, host, synth  # noqa: E402
+
+
+def parse_grid(world):
+    """GNN_GRID=PrxPc selects the 2-D partition (csrc/trainer_grid.cu), GNN_GRID=row (or unset) the 1-D row partition."""
+    e = os.environ.get("GNN_GRID", "row")
+    if e in ("", "row"):
+        return None
+    if e == "auto":
+        return dist_plan.default_grid(world)
+    pr, pc = (int(x) for x in e.lower().split("x"))
+    assert pr * pc == world, "GNN_GRID=%s does not match world %d" % (e, world)
+    return pr, pc
+
+
+def check_big(ctx, m, p, cfg, X, yb, lo, hi, rank, world, grid):
+    """>= 200 k nodes: one train step (lr = 0) against the exact oracle at 1e-5, ReLU ties taken from the oracle
+    (gnn_gcn_set_relu_overrides) exactly as bench.py's parity probe does."""
+    from oracle import oracle as orc
+    orc.set_threads(max(1, (os.cpu_count() or world) // world))
+    L = len(cfg.dims) - 1
+    G = orc.Graph(p.src, p.dst, cfg.N)
+    ref = orc.train_step(G, cfg.dims, p.X, p.y, [w.copy() for w in p.W], [b.copy() for b in p.b], lr=0.0, order=1)
+    ties = 0
+    for l in range(1, L):
+        Z = ref["Z%d" % l]
+        r, c = np.nonzero(np.abs(Z[lo:hi]) <= 1e-5 * float(np.abs(Z).max()))
+        m.set_relu_overrides(l, r.astype(np.int32), c.astype(np.int32), (Z[lo:hi][r, c] > 0))
+        ties += len(r)
+    loss = float(m.train_step(X, yb, 0.0).cpu()[0])
+    errs = [abs(loss - ref["loss"]) / abs(ref["loss"])]
+    for l in range(1, L + 1):
+        dW, db = m.grads(l)
+        errs.append(np.abs(dW - ref["dW%d" % l]).max() / np.abs(ref["dW%d" % l]).max())
+        errs.append(np.abs(db - ref["db%d" % l]).max() / np.abs(ref["db%d" % l]).max())
+    errs.append(np.abs(m.activation(L) - ref["Z%d" % L][lo:hi]).max() / np.abs(ref["Z%d" % L]).max())
+    t = torch.tensor([max(errs)], device=ctx.device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)            # logits are checked on every rank's rows
+    if rank == 0:
+        print("[dist_check] %s (N=%d) world=%d grid=%s mode=%d loss=%.6f ref=%.6f max_rel_err=%.2e (tol 1e-5, %d relu ties on rank 0)" %
+              (cfg.name, cfg.N, world, grid, m.exchange_mode(), loss, ref["loss"], float(t.item()), ties), flush=True)
+    return float(t.item()) <= 1e-5
 
 
 def main():
@@ -24,23 +65,40 @@ def main():
     ctx = host.Context(local)
     ctx.init_comm_from_torch()
     ok = True
-    for cfg in [synth.CONFIGS["tiny_pl"], synth.Config("odd", 1237, 9000, [20, 33, 12, 6], True, 95)]:
+    grid = parse_grid(world)
+    big = synth.Config("mid_pl", 250000, 5000000, [40, 96, 64, 19], True, 96)     # >= 200 k nodes
+    cfgs = [synth.CONFIGS["tiny_pl"], synth.Config("odd", 1237, 9000, [20, 33, 12, 6], True, 95),
+            synth.Config("widen", 1500, 12000, [12, 8, 24, 5], True, 97)]      # layer 2 aggregates first with l > 1
+    if os.environ.get("GNN_DIST_BIG", "1") != "0":
+        cfgs.append(big)
+    for cfg in cfgs:
         for mask in (None, 0, 0xFF):
+            if cfg.name == "mid_pl" and mask is not None:
+                continue                      # the big graph runs the automatic layer order only
             p = synth.make_problem(cfg)
             gfull = host.Graph.build(ctx, p.src, p.dst, cfg.N)
             chunk = (cfg.N + world - 1) // world
             lo, hi = min(cfg.N, rank * chunk), min(cfg.N, (rank + 1) * chunk)
-            g = gfull.slice_rows(lo, hi)
+            if grid is None:
+                g = gfull.slice_rows(lo, hi)
+            else:
+                (rlo, rhi), (glo, ghi) = dist_plan.grid_partition(cfg.N, world, grid[1], rank)
+                assert (rlo, rhi) == (lo, hi)
+                g = gfull.slice_rows(glo, ghi)
             ld0 = (cfg.dims[0] + 3) // 4 * 4
             Xb = torch.zeros((chunk, ld0), device=ctx.device)
             X = Xb[:hi - lo, :cfg.dims[0]]
             X.copy_(torch.from_numpy(p.X[lo:hi]))
             yb = torch.zeros(chunk, dtype=torch.int32, device=ctx.device)
             yb[:hi - lo].copy_(torch.from_numpy(p.y[lo:hi]))
-            m = host.GCN(ctx, g, cfg.dims)
+            m = host.GCN(ctx, g, cfg.dims) if grid is None else host.GCN(ctx, g, cfg.dims, grid=grid, n_loc=hi - lo)
             if mask is not None:
                 m.set_option("agg_first_mask", mask)
             m.set_params(p.W, p.b)
+            if cfg.name == "mid_pl":
+                ok &= check_big(ctx, m, p, cfg, X, yb, lo, hi, rank, world, grid)
+                m.close(); g.close(); gfull.close()
+                continue
             losses = [float(m.train_step(X, yb, 0.05).cpu()[0]) for _ in range(3)]
             L = len(cfg.dims) - 1
             grads = [m.grads(l) for l in range(1, L + 1)]
@@ -61,8 +119,8 @@ def main():
                     errs.append(np.abs(params[l][0] - W[l]).max() / np.abs(W[l]).max())
                 errs.append(np.abs(logits - ref["Z%d" % L][lo:hi]).max() / np.abs(ref["Z%d" % L]).max())
                 ok &= max(errs) <= 2e-5
-                print("[dist_check] %s world=%d mask=%s loss=%.6f ref=%.6f max_rel_err=%.2e" %
-                      (cfg.name, world, mask, losses[-1], ref["loss"], max(errs)), flush=True)
+                print("[dist_check] %s world=%d grid=%s mode=%d mask=%s loss=%.6f ref=%.6f max_rel_err=%.2e" %
+                      (cfg.name, world, grid, m.exchange_mode(), mask, losses[-1], ref["loss"], max(errs)), flush=True)
             m.close(); g.close(); gfull.close()
     flag = torch.tensor([1 if ok else 0], device=ctx.device)
     dist.broadcast(flag, 0)

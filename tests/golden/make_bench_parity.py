@@ -30,6 +30,16 @@ for name in sys.argv[1:] or ["products"]:
     for l in range(1, L + 1):
         out["dW%d" % l] = ref["dW%d" % l]
         out["db%d" % l] = ref["db%d" % l]
+    # ReLU tie-break list: hidden pre-activations within 1e-5 max|Z_l| of zero, where `Z > 0` may legitimately come out
+    # on the other side in another correct fp32 implementation (gnn_gcn_set_relu_overrides takes the oracle's decision)
+    for l in range(1, L):
+        Z = ref["Z%d" % l]
+        thr = 1e-5 * float(np.abs(Z).max())
+        r, c = np.nonzero(np.abs(Z) <= thr)
+        out["kink%d_rows" % l] = r.astype(np.int32)
+        out["kink%d_cols" % l] = c.astype(np.int16)
+        out["kink%d_pos" % l] = (Z[r, c] > 0).astype(np.uint8)
+        print("  layer %d: %d of %d pre-activations within %.3g of zero" % (l, len(r), Z.size, thr), flush=True)
     # a fixed sample of logits rows (row ids + values) so the forward is pinned too
     rows = np.unique(np.random.default_rng(cfg.seed).integers(0, cfg.N, 4096)).astype(np.int64)
     out["logit_rows"] = rows

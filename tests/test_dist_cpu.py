@@ -17,7 +17,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _rank_main(rank, world, port, name, q, panel_cols=8):
+def _rank_main(rank, world, port, name, q, panel_cols=8, grid=None):
     import sys
     sys.path.insert(0, ROOT)
     import gnn_cpp_b200  # noqa: F401
@@ -60,11 +60,55 @@ def _rank_main(rank, world, port, name, q, panel_cols=8):
             Y[:, c0:c0 + f] = orc.spmm(n_loc, ptr_, idx_, val_, panel[:N, :f], order=1)
         return Y
 
+    if grid is not None:
+        # 2-D partition (csrc/trainer_grid.cu): world = Pr x Pc; the rank aggregates the structure rows of its row group
+        # over its column slice of ALL nodes' rows, and every output row goes to the rank that owns it
+        Pr, Pc = grid
+        assert Pr * Pc == world
+        (rlo, rhi), (glo, ghi) = dist_plan.grid_partition(N, world, Pc, rank)
+        assert (rlo, rhi) == (lo, hi)
+        gi, gj = rank // Pc, rank % Pc
+        gfr, gfc, gfv = orc.partition_rows(G.rowptr, G.colidx, G.val, glo, ghi)
+        gbr, gbc, gbv = orc.partition_rows(G.colptr, np.ascontiguousarray(G.rowidx), G.valT, glo, ghi)
+
+        def aggregate_grid(X, ptr_, idx_, val_):
+            F = X.shape[1]
+            ldw = dist_plan.padded(F)
+            slices = [dist_plan.col_slice(ldw, Pc, j) for j in range(Pc)]
+            assert slices[0][0] == 0 and sum(w for _, w in slices) == ldw and all(w % 4 == 0 for _, w in slices)
+            assert all(slices[j][0] + slices[j][1] == slices[j + 1][0] for j in range(Pc - 1))
+            # 1. rows -> columns: rank q's rows land at rows [q chunk, ...) of every rank's gathered slice matrix
+            mine = np.zeros((chunk, ldw), np.float32); mine[:n_loc, :F] = X
+            blocks = [torch.zeros(chunk * ldw) for _ in range(world)]
+            dist.all_gather(blocks, torch.from_numpy(mine.reshape(-1)))
+            c0, w = slices[gj]
+            f = max(0, min(w, F - c0))
+            PC = np.zeros((world * chunk, max(w, 1)), np.float32)
+            for q_, blk in enumerate(blocks):
+                PC[q_ * chunk:(q_ + 1) * chunk, :w] = blk.numpy().reshape(chunk, ldw)[:, c0:c0 + w]
+            # 2. aggregation over the row group's structure rows at the slice width
+            part = np.zeros((Pc * chunk, ldw), np.float32)
+            if f > 0 and ghi > glo:
+                part[:ghi - glo, c0:c0 + f] = orc.spmm(ghi - glo, ptr_, idx_, val_, np.ascontiguousarray(PC[:N, :f]), order=1)
+            # 3. columns -> rows: output row r of the group belongs to rank gi Pc + r // chunk, local row r % chunk
+            parts = [torch.zeros(Pc * chunk * ldw) for _ in range(world)]
+            dist.all_gather(parts, torch.from_numpy(part.reshape(-1)))
+            Y = np.zeros((n_loc, F), np.float32)
+            for j in range(Pc):
+                src_rank = gi * Pc + j
+                cj, wj = slices[j]
+                fj = max(0, min(wj, F - cj))
+                blk = parts[src_rank].numpy().reshape(Pc * chunk, ldw)
+                Y[:, cj:cj + fj] = blk[gj * chunk: gj * chunk + n_loc, cj:cj + fj]
+            return Y
+
     def spmm_f(X):
-        return aggregate(np.ascontiguousarray(X, dtype=np.float32), fr, fc, fv)
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        return aggregate_grid(X, gfr, gfc, gfv) if grid is not None else aggregate(X, fr, fc, fv)
 
     def spmm_b(X):
-        return aggregate(np.ascontiguousarray(X, dtype=np.float32), br, bc, bv)
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        return aggregate_grid(X, gbr, gbc, gbv) if grid is not None else aggregate(X, br, bc, bv)
 
     af = dist_plan.layer_order(dims)
     n_gathers = 0
@@ -120,6 +164,39 @@ def test_row_partitioned_schedule_world2_gloo(name, world):
         pr.join(timeout=300)
         assert pr.exitcode == 0
     assert q.get(timeout=5) <= 1e-5
+
+
+@pytest.mark.parametrize("name,world,grid", [("odd", 2, (1, 2)), ("odd", 4, (2, 2)), ("tiny_pl", 3, (1, 3)), ("odd", 3, (3, 1))])
+def test_grid_partitioned_schedule_gloo(name, world, grid):
+    """the 2-D (row groups x column groups) schedule of csrc/trainer_grid.cu — column-slice scatter, aggregation over the
+    row group's structure at the slice width, row exchange — with the library's own partition rules."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rank_main, args=(r, world, port, name, q, 8, grid)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=300)
+        assert pr.exitcode == 0
+    assert q.get(timeout=5) <= 1e-5
+
+
+def test_grid_partition_rules():
+    from gnn_cpp_b200 import dist_plan
+    assert [dist_plan.col_slice(256, 4, j) for j in range(4)] == [(0, 64), (64, 64), (128, 64), (192, 64)]
+    assert [dist_plan.col_slice(100, 4, j) for j in range(4)] == [(0, 28), (28, 24), (52, 24), (76, 24)]
+    assert [dist_plan.col_slice(48, 8, j) for j in range(8)] == [(0, 8), (8, 8), (16, 8), (24, 8), (32, 4), (36, 4), (40, 4), (44, 4)]
+    assert [dist_plan.col_slice(4, 2, j) for j in range(2)] == [(0, 4), (4, 0)]          # narrower than the group count
+    (rows, grp) = dist_plan.grid_partition(2450000, 8, 4, 5)
+    assert rows == (5 * 306250, 6 * 306250) and grp == (4 * 306250, 2450000)
+    (rows, grp) = dist_plan.grid_partition(10, 4, 2, 3)
+    assert rows == (9, 10) and grp == (6, 10)
+    # received bytes per rank and step, products-shaped: the 2 x 4 grid moves ~2.7x less than the all-gather
+    dims = [100, 256, 256, 47]
+    ag = dist_plan.comm_bytes_per_step(2450000, dims, 8)
+    gr = dist_plan.comm_bytes_per_step_grid(2450000, dims, 8, 4)
+    assert 2.3 < ag / gr < 3.2, (ag, gr)
 
 
 def test_panel_tiling_rule():
