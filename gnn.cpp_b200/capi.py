@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgnn_b200.so")
+LIB_PATH = os.environ.get("GNN_LIB") or os.path.join(_HERE, "libgnn_b200.so")   # GNN_LIB: experiment builds (tools/)
 _lib = None
 
 vp, i32, i64, f32, f64, cp, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_char_p, C.c_size_t
@@ -98,6 +98,12 @@ SIGNATURES = {
     "gnn_partition_ptr_h": (C.c_int, [i64, i32, vp]),
     "gnn_partition_panels_h": (C.c_int, [i32, i32, vp, vp, vp]),
     "gnn_graph_slice_rows": (C.c_int, [vp, vp, i64, i64, pp]),
+    "gnn_partition_build": (C.c_int, [vp, vp, i64, i64, C.c_int, pp]),
+    "gnn_partition_halo_count": (i64, [vp]),
+    "gnn_partition_interior_count": (i64, [vp]),
+    "gnn_partition_nnz": (i64, [vp]),
+    "gnn_partition_export_h": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "gnn_partition_destroy": (C.c_int, [vp, vp]),
     "gnn_comm_unique_id_h": (C.c_int, [vp]),
     "gnn_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "gnn_comm_destroy": (C.c_int, [vp]),
@@ -127,6 +133,8 @@ def load():
                        "there is no CPU fallback" % LIB_PATH)
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("GNN_LIB") and not hasattr(lib, name):
+            continue             # an older experiment build (A/B runs under tools/) may lack newer entry points
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args

@@ -58,6 +58,7 @@ struct gnn_ctx {
     bool own_stream = false;
     int64_t launches = 0;
     int spmm_variant = 0, spmm_tune_u = 0, spmm_tune_pf = 1, spmm_chunk = 0;
+    int spmm_alt = 0; // lane mapping for non-power-of-two vector counts (GNN_SPMM_ALT, see spmm_launch)
     // grow-only scratch (sort double buffers, scan levels, split-K partials ...)
     void *ws = nullptr;
     size_t ws_bytes = 0;

@@ -1,5 +1,6 @@
 // ctx.cu — context, error state and device storage entry points of the C ABI (include/gnn_c.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -60,6 +61,7 @@ int gnn_ctx_create(int device, void *stream, gnn_ctx_t **out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->l2_bytes = (size_t)prop.l2CacheSize;
+    if (const char *e = getenv("GNN_SPMM_ALT")) c->spmm_alt = atoi(e);
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {

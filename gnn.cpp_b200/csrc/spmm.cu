@@ -183,11 +183,13 @@ __device__ __forceinline__ void store_row(const V (&acc)[VEC], float *__restrict
 // ---- variant 1: one output row per lane group ------------------------------------------------------------------
 // V = float4: requires P/Y 16-byte aligned and ldp/ldy multiples of 4 (padding columns may be touched).
 // V = float : no alignment requirement.
-template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF>
+// MULTI = false: the plain output matrix Y (the single-GPU / row-partition kernels, exactly the r1 code: routing the
+// plain case through the destination table as well cost 9 % on the F = 256 launch); MULTI = true: rows go to YDest.
+template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF, bool MULTI>
 __global__ void __launch_bounds__(SPMM_THREADS)
     spmm_rows_kernel(int32_t n_out, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
                      const float *__restrict__ val, const float *__restrict__ P, int64_t ldp, int32_t F,
-                     const YDest yd, int64_t ldy, const float *__restrict__ bias, int relu,
+                     float *__restrict__ Y, const __grid_constant__ YDest yd, int64_t ldy, const float *__restrict__ bias, int relu,
                      const float *__restrict__ mask, int64_t ldm) {
     using T = VecTraits<V>;
     constexpr int GROUPS = SPMM_THREADS / LPR;
@@ -202,7 +204,10 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 #pragma unroll
     for (int v = 0; v < VEC; v++) acc[v] = T::zero();
     accumulate_range<V, LPR, 1, VEC, USE_VAL, U, PF>(acc, idx, val, ptr[row], ptr[row + 1], P, ldp, nvec, sub, gmask);
-    store_row<V, LPR, VEC>(acc, yd_row(yd, (int32_t)row, ldy), nvec, sub, F, bias, relu, mask ? mask + row * ldm : nullptr);
+    float *yrow;
+    if constexpr (MULTI) yrow = yd_row(yd, (int32_t)row, ldy);
+    else yrow = Y + row * ldy;
+    store_row<V, LPR, VEC>(acc, yrow, nvec, sub, F, bias, relu, mask ? mask + row * ldm : nullptr);
 }
 
 // ---- variant 2: nonzero-balanced (merge-path style) ------------------------------------------------------------
@@ -215,11 +220,28 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 // Requires every row to hold at least one nonzero (the dispatcher checks min_nnz_row >= 1).
 constexpr int MERGE_CHUNK_MIN = 256;
 
-template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF>
-__global__ void __launch_bounds__(SPMM_THREADS)
+// Resident CTAs per SM the register allocation must allow.  The narrow configurations (one 128-bit vector per lane)
+// are latency-bound gathers: ncu on the F=16 launch showed 64 registers -> 4 CTAs -> 46 % of the warp slots active
+// with DRAM at 50 % and every pipe under 50 %, so they trade registers for resident warps.
+// Measured on one B200 (tools/spmm_width_probe.py, products-shaped, ms per launch; profiles/r2_spmm_occupancy_ab.md):
+//   width            12     16     24     32     48     64    100    128
+//   4 CTAs (r1)    1.42   1.46   2.23   2.15   3.41   3.35   5.27   5.29
+//   5 CTAs         1.32   1.34   1.97   1.88   2.99   2.96   5.28   5.28
+//   6 CTAs         1.54   1.53   2.10   1.91   3.05   3.04   5.41   5.45   (40 registers: ~100 bytes of spills)
+// The wider configurations (two or four vectors per lane) are HBM-bound already and keep the default allocation.
+#ifndef SPMM_MIN_CTAS_NARROW
+#define SPMM_MIN_CTAS_NARROW 5
+#endif
+template <typename V, int VEC> struct Occupancy {
+    static constexpr int MIN_CTAS = (sizeof(V) * VEC <= 16) ? SPMM_MIN_CTAS_NARROW : 0; // 0 = unspecified
+};
+
+template <typename V, int LPR, int VEC, bool USE_VAL, int U, bool PF, bool MULTI>
+__global__ void __launch_bounds__(SPMM_THREADS, (Occupancy<V, VEC>::MIN_CTAS))
     spmm_merge_kernel(int32_t n_out, int32_t k_base, int32_t nnz, int32_t n_chunks, int32_t MERGE_CHUNK,
                       const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx, const float *__restrict__ val,
-                      const float *__restrict__ P, int64_t ldp, int32_t F, const YDest yd, int64_t ldy,
+                      const float *__restrict__ P, int64_t ldp, int32_t F, float *__restrict__ Y,
+                      const __grid_constant__ YDest yd, int64_t ldy,
                       const float *__restrict__ bias, int relu, const float *__restrict__ mask, int64_t ldm,
                       float *__restrict__ head, float *__restrict__ tail, int32_t *__restrict__ head_row,
                       int32_t *__restrict__ tail_row, int32_t ldw) {
@@ -255,7 +277,10 @@ __global__ void __launch_bounds__(SPMM_THREADS)
         reduce_slots<V, LPR, S, VEC>(acc, gmask);
         const bool starts = (k == rb), ends = (seg_end == re);
         if (starts && ends) {
-            store_row<V, LPR, VEC>(acc, yd_row(yd, row, ldy), nvec_st, sub, F, bias, relu,
+            float *yrow;
+            if constexpr (MULTI) yrow = yd_row(yd, row, ldy);
+            else yrow = Y + (int64_t)row * ldy;
+            store_row<V, LPR, VEC>(acc, yrow, nvec_st, sub, F, bias, relu,
                                    mask ? mask + (int64_t)row * ldm : nullptr);
         } else {
             float *dst = (ends ? head : tail) + (int64_t)g * ldw;
@@ -282,7 +307,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 __global__ void __launch_bounds__(256)
     spmm_merge_fixup_kernel(int32_t n_chunks, int32_t F, const float *__restrict__ head, const float *__restrict__ tail,
                             const int32_t *__restrict__ head_row, const int32_t *__restrict__ tail_row, int32_t ldw,
-                            const YDest yd, int64_t ldy, const float *__restrict__ bias, int relu,
+                            const __grid_constant__ YDest yd, int64_t ldy, const float *__restrict__ bias, int relu,
                             const float *__restrict__ mask, int64_t ldm) {
     const int32_t g = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -318,12 +343,11 @@ static int launch_rows(gnn_ctx *ctx, int32_t n_out, const int32_t *ptr, const in
                        const float *mask, int64_t ldm) {
     constexpr int GROUPS = SPMM_THREADS / LPR;
     const unsigned grid = (unsigned)ceil_div(n_out, GROUPS);
-    if (val)
-        spmm_rows_kernel<V, LPR, VEC, true, U, PF><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n_out, ptr, idx, val, P, ldp, F, Y,
-                                                                                   ldy, bias, relu, mask, ldm);
-    else
-        spmm_rows_kernel<V, LPR, VEC, false, U, PF><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n_out, ptr, idx, val, P, ldp, F,
-                                                                                    Y, ldy, bias, relu, mask, ldm);
+    float *Y0 = Y.base[0];
+#define ROWS_GO(UV, MU) spmm_rows_kernel<V, LPR, VEC, UV, U, PF, MU><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n_out, ptr, idx, val, P, ldp, F, Y0, Y, ldy, bias, relu, mask, ldm)
+    if (Y.rows_per) { if (val) ROWS_GO(true, true); else ROWS_GO(false, true); }
+    else { if (val) ROWS_GO(true, false); else ROWS_GO(false, false); }
+#undef ROWS_GO
     GNN_LAUNCHED(ctx);
     return 0;
 }
@@ -342,14 +366,14 @@ static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz
     float *head = (float *)ws, *tail = head + (size_t)n_chunks * ldw;
     int32_t *head_row = (int32_t *)(tail + (size_t)n_chunks * ldw), *tail_row = head_row + n_chunks;
     const unsigned grid = (unsigned)ceil_div(n_chunks, GROUPS);
-    if (val)
-        spmm_merge_kernel<V, LPR, VEC, true, U, PF><<<grid, SPMM_THREADS, 0, ctx->stream>>>(
-            n_out, (int32_t)k_base, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, val, P, ldp, F, Y, ldy, bias, relu, mask, ldm, head, tail, head_row,
-            tail_row, ldw);
-    else
-        spmm_merge_kernel<V, LPR, VEC, false, U, PF><<<grid, SPMM_THREADS, 0, ctx->stream>>>(
-            n_out, (int32_t)k_base, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, val, P, ldp, F, Y, ldy, bias, relu, mask, ldm, head, tail, head_row,
-            tail_row, ldw);
+    float *Y0 = Y.base[0];
+#define MERGE_GO(UV, MU)                                                                                            \
+    spmm_merge_kernel<V, LPR, VEC, UV, U, PF, MU><<<grid, SPMM_THREADS, 0, ctx->stream>>>(                          \
+        n_out, (int32_t)k_base, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, val, P, ldp, F, Y0, Y, ldy, bias, relu, mask, ldm, head, \
+        tail, head_row, tail_row, ldw)
+    if (Y.rows_per) { if (val) MERGE_GO(true, true); else MERGE_GO(false, true); }
+    else { if (val) MERGE_GO(true, false); else MERGE_GO(false, false); }
+#undef MERGE_GO
     GNN_LAUNCHED(ctx);
     spmm_merge_fixup_kernel<<<(unsigned)ceil_div((int64_t)n_chunks * 32, 256), 256, 0, ctx->stream>>>(
         n_chunks, F, head, tail, head_row, tail_row, ldw, Y, ldy, bias, relu, mask, ldm);

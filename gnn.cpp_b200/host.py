@@ -168,6 +168,20 @@ class Graph:
                   mask.stride(0) if mask is not None else 0, int(use_values))
         return dP
 
+    def partition_arrays(self, lo, hi, transpose=False):
+        """halo_ids / local_colidx / interior flags and row lists of this row block [lo, hi) (gnn_partition_build)"""
+        ph = C.c_void_p()
+        capi.call("gnn_partition_build", self.ctx.h, self.h, int(lo), int(hi), int(transpose), C.byref(ph))
+        L = capi.load()
+        n_halo, n_int, nnz = L.gnn_partition_halo_count(ph), L.gnn_partition_interior_count(ph), L.gnn_partition_nnz(ph)
+        n = hi - lo
+        out = {"halo_ids": np.empty(n_halo, np.int32), "local_colidx": np.empty(nnz, np.int32), "interior": np.empty(n, np.uint8),
+               "interior_rows": np.empty(n_int, np.int32), "boundary_rows": np.empty(n - n_int, np.int32)}
+        capi.call("gnn_partition_export_h", self.ctx.h, ph, _ptr(out["halo_ids"]), _ptr(out["local_colidx"]), _ptr(out["interior"]),
+                  _ptr(out["interior_rows"]), _ptr(out["boundary_rows"]))
+        capi.call("gnn_partition_destroy", self.ctx.h, ph)
+        return out
+
     def close(self):
         if self.h:
             capi.call("gnn_graph_destroy", self.ctx.h, self.h)

@@ -328,6 +328,23 @@ GNN_API int gnn_partition_panels_h(int32_t ldw, int32_t panel_cols, int32_t *c0_
 /* Extract rank-local rows [lo,hi) of g as a new graph (n_rows = hi-lo, n_cols = N, global column ids),
  * including values and, when g has them, the matching CSC slice for the backward. */
 GNN_API int gnn_graph_slice_rows(gnn_ctx_t *ctx, const gnn_graph_t *g, int64_t lo, int64_t hi, gnn_graph_t **out);
+/* Per-rank partition arrays of a row block, built on the device, BIT-EXACT against the CPU
+ * restatement (oracle: orc_partition_halo / orc_partition_interior).  `g` is a gnn_graph_slice_rows block holding rows
+ * [lo, hi) with global column ids; transpose = 1 uses its backward (CSC) block instead.
+ *   halo_ids[n_halo]      sorted unique columns outside [lo, hi): the remote feature rows the block needs
+ *   local_colidx[nnz]     columns renumbered for a [own rows ; halo rows] input matrix (c - lo, or n_loc + halo position)
+ *   interior[n_rows]      1 = every column is owned: the row can be aggregated before any halo row has arrived;
+ *   interior_rows / boundary_rows: the two ascending row lists (overlap of the exchange with interior-row aggregation).
+ * Export pointers may be NULL. */
+typedef struct gnn_partition gnn_partition_t;
+GNN_API int gnn_partition_build(gnn_ctx_t *ctx, const gnn_graph_t *g, int64_t lo, int64_t hi, int transpose,
+                                gnn_partition_t **out);
+GNN_API int64_t gnn_partition_halo_count(const gnn_partition_t *p);
+GNN_API int64_t gnn_partition_interior_count(const gnn_partition_t *p);
+GNN_API int64_t gnn_partition_nnz(const gnn_partition_t *p);
+GNN_API int gnn_partition_export_h(gnn_ctx_t *ctx, const gnn_partition_t *p, int32_t *halo_ids_h, int32_t *local_colidx_h,
+                                   uint8_t *interior_h, int32_t *interior_rows_h, int32_t *boundary_rows_h);
+GNN_API int gnn_partition_destroy(gnn_ctx_t *ctx, gnn_partition_t *p);
 /* NCCL communicator owned by the context.  id_h: 128-byte ncclUniqueId produced by gnn_comm_unique_id_h on
  * rank 0 and distributed by the caller (torch.distributed / MPI / files). */
 GNN_API int gnn_comm_unique_id_h(void *id_h /* 128 bytes */);

@@ -808,6 +808,30 @@ ORC_API int64_t orc_partition_interior(const int64_t *l_rowptr, const int32_t *l
     return cnt;
 }
 
+/* Halo of the local block rows [lo,hi): halo_ids = sorted unique column ids outside [lo,hi) (capacity: n_cols), and the
+ * locally renumbered column array: an owned column c becomes c - lo, a halo column n_loc + its position in halo_ids
+ * (so the aggregation input is one matrix [own rows ; halo rows]).  Returns the halo size. */
+ORC_API int64_t orc_partition_halo(const int64_t *l_rowptr, const int32_t *l_colidx, int64_t nrows, int64_t n_cols,
+                                   int64_t lo, int64_t hi, int32_t *halo_ids, int32_t *local_colidx) {
+    int32_t *pos = (int32_t *)malloc((size_t)(n_cols > 0 ? n_cols : 1) * 4);
+    for (int64_t c = 0; c < n_cols; c++) pos[c] = -1;
+    const int64_t nnz = l_rowptr[nrows];
+    for (int64_t k = 0; k < nnz; k++) {
+        int32_t c = l_colidx[k];
+        if (c < lo || c >= hi) pos[c] = 0;
+    }
+    int64_t n_halo = 0;
+    for (int64_t c = 0; c < n_cols; c++)
+        if (pos[c] == 0) { halo_ids[n_halo] = (int32_t)c; pos[c] = (int32_t)n_halo++; }
+    if (local_colidx)
+        for (int64_t k = 0; k < nnz; k++) {
+            int32_t c = l_colidx[k];
+            local_colidx[k] = (c >= lo && c < hi) ? (int32_t)(c - lo) : (int32_t)(hi - lo) + pos[c];
+        }
+    free(pos);
+    return n_halo;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Whole train step (forward + loss + backward + SGD) for an L-layer GCN in the reference's operation
  * order:  Z_l = Ahat (H_{l-1} W_l^T) + b_l,  H_l = ReLU(Z_l) for l < L;  logits = Z_L.

@@ -74,6 +74,8 @@ def lib():
         L.orc_partition_rows.argtypes = [_i64p, _i32p, C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, C.c_void_p]
         L.orc_partition_interior.restype = C.c_int64
         L.orc_partition_interior.argtypes = [_i64p, _i32p, C.c_int64, C.c_int64, C.c_int64, _u8p]
+        L.orc_partition_halo.restype = C.c_int64
+        L.orc_partition_halo.argtypes = [_i64p, _i32p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p]
         L.orc_gcn_train_step.restype = C.c_float
         _LIB = L
     return _LIB
@@ -370,6 +372,15 @@ def partition_interior(l_rowptr, l_colidx, lo, hi):
     flags = np.empty(max(nrows, 1), dtype=np.uint8)
     cnt = lib().orc_partition_interior(l_rowptr, np.ascontiguousarray(l_colidx), nrows, lo, hi, flags)
     return flags[:nrows], int(cnt)
+
+
+def partition_halo(l_rowptr, l_colidx, n_cols, lo, hi):
+    """(halo_ids sorted unique remote columns, locally renumbered colidx) of a row block; see orc_partition_halo"""
+    nrows = len(l_rowptr) - 1
+    halo = np.empty(max(n_cols, 1), dtype=np.int32)
+    local = np.empty(max(len(l_colidx), 1), dtype=np.int32)
+    n = lib().orc_partition_halo(l_rowptr, np.ascontiguousarray(l_colidx), nrows, n_cols, lo, hi, halo, local)
+    return halo[:n].copy(), local[:len(l_colidx)].copy()
 
 
 def train_step(g, dims, X, y, W, b, lr=0.0, order=0):

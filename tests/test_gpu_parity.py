@@ -851,3 +851,49 @@ def test_structure_random_small_graphs_vs_dense_restatement(ctx, oracle):
             g = host.Graph.build(ctx, src, dst, N, fill_mode=fill, csc=False, normalize=False, weights=w)
             assert g.nnz == len(rows) and np.array_equal(g.export_weights(), A[rows, cols])
             g.close()
+
+
+# ------------------------------------------------------------------------------------------------ partition arrays
+@pytest.mark.parametrize("name,world", [("tiny_pl", 2), ("tiny_pl", 3), ("directed", 4), ("odd", 8), ("local", 4)])
+def test_partition_arrays_bit_exact(ctx, oracle, name, world):
+    """part_ptr, halo_ids, locally renumbered colidx, interior / boundary row lists of every rank's row
+    block — forward (CSR) and backward (CSC) blocks — BIT-EXACT against the CPU restatement (orc_partition_*)."""
+    from gnn_cpp_b200 import dist_plan, host, synth
+    if name == "odd":
+        p = synth.make_problem(synth.Config("odd", 1237, 9000, [20, 33, 12, 6], True, 95))
+    elif name == "local":   # a banded graph: node i is linked to i +- 1..40, so most rows of a block are interior
+        N = 5000
+        i = np.repeat(np.arange(N, dtype=np.int64), 12)
+        off = np.tile(np.array([1, 2, 3, 5, 8, 13, 21, 34, 40, 7, 11, 17], np.int64), N)
+        j = (i + off) % N
+        p = synth.make_problem(synth.Config("local", N, 2, [8, 4], False, 98))
+        p.src = np.concatenate([i, j]).astype(np.int32); p.dst = np.concatenate([j, i]).astype(np.int32)
+    else:
+        p = load_problem(name)
+    N = p.cfg.N
+    G = oracle.Graph(p.src, p.dst, N)
+    gfull = host.Graph.build(ctx, p.src, p.dst, N)
+    ptr = dist_plan.partition(N, world)
+    assert np.array_equal(ptr, oracle.partition_ptr(N, world))
+    seen_interior = 0
+    for r in range(world):
+        lo, hi = int(ptr[r]), int(ptr[r + 1])
+        if hi <= lo:
+            continue
+        g = gfull.slice_rows(lo, hi)
+        for transpose, (gp, gi) in enumerate([(G.rowptr, G.colidx), (G.colptr, np.ascontiguousarray(G.rowidx))]):
+            lr, lc, _ = oracle.partition_rows(gp, gi, None, lo, hi)
+            halo, local = oracle.partition_halo(lr, lc, N, lo, hi)
+            flags, cnt = oracle.partition_interior(lr, lc, lo, hi)
+            a = g.partition_arrays(lo, hi, transpose=bool(transpose))
+            assert np.array_equal(a["halo_ids"], halo), (r, transpose)
+            assert np.array_equal(a["local_colidx"], local), (r, transpose)
+            assert np.array_equal(a["interior"], flags) and len(a["interior_rows"]) == cnt
+            assert np.array_equal(a["interior_rows"], np.nonzero(flags)[0].astype(np.int32))
+            assert np.array_equal(a["boundary_rows"], np.nonzero(flags == 0)[0].astype(np.int32))
+            assert local.max(initial=0) < (hi - lo) + len(halo)
+            seen_interior += cnt
+        g.close()
+    if name == "local":
+        assert seen_interior > 0.8 * 2 * N          # the banded graph is mostly interior: the overlap has work to hide behind
+    gfull.close()

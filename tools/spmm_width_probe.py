@@ -49,7 +49,10 @@ def run(tag, s, d):
     return e["deg"]
 
 
-deg = run("natural", src, dst)
+deg = run("natural" + os.environ.get("PROBE_TAG", ""), src, dst)
+if os.environ.get("PROBE_SORTED", "1") == "0":
+    ctx.close()
+    sys.exit(0)
 order = np.argsort(-deg.astype(np.int64), kind="stable")          # new id -> old id
 inv = np.empty(N, np.int32); inv[order] = np.arange(N, dtype=np.int32)
 run("degree-sorted", inv[src], inv[dst])
