@@ -222,6 +222,7 @@ struct gnn_peer_arena {
     // transport of a tile: 1 = SM store kernel (default), 0 = copy engines, 2 = in-place ncclAllGather of the panel
     // on the side stream (the pipelined schedule with NCCL's transport, e.g. NVLS multicast on 8 ranks)
     std::vector<cudaEvent_t> ev_slot;          // transport 2: completion event per slot
+    bool sm_ctas_set = false;       // GNN_PEER_CTAS given
     int sm_mode = 1, sm_ctas = 64; // 64 CTAs: 649 GB/s between two B200s (32: 617, 16: 458; ncclAllGather: 467)
     cudaEvent_t ev_ready = nullptr, ev_self = nullptr;
     uint32_t seq[gnn::PEER_MAX_SLOTS] = {};      // last sequence number begun per slot (identical on every rank)
@@ -258,7 +259,11 @@ int peer_scatter_begin(gnn_ctx *ctx, gnn_peer_arena *a, int slot, const float *s
     }
     GNN_CHECK_CUDA(cudaEventRecord(a->ev_ready, ctx->stream));
     GNN_CHECK_CUDA(cudaStreamWaitEvent(a->push_sm, a->ev_ready, 0));
-    peer_scatter_kernel<<<a->sm_ctas, 512, 0, a->push_sm>>>(pa, src, ld, rows, seq, a->done);
+    // Unlike the all-gather pushes of the row partition (64 CTAs: more of them only took SMs from the aggregation running
+    // beside them), the scatter mostly runs alone, and the link rate keeps rising with the CTA count (2 B200s, 1 x 2
+    // grid, exposed exchange per step: 64 CTAs 2.68 ms, 296: 2.74, 592: 1.93) — 4 CTAs per SM unless GNN_PEER_CTAS says otherwise
+    const int ctas = a->sm_ctas_set ? a->sm_ctas : 4 * ctx->sm_count;
+    peer_scatter_kernel<<<ctas, 512, 0, a->push_sm>>>(pa, src, ld, rows, seq, a->done);
     GNN_LAUNCHED(ctx);
     // the own rank's slice is a local store of the same kernel: peer_wait_mask(.., after_own_scatter) orders the
     // compute stream after it (not here, so that work enqueued in between overlaps the transfer)
@@ -419,7 +424,7 @@ int gnn_peer_arena_create(gnn_ctx_t *ctx, size_t bytes, gnn_peer_arena_t **out) 
         GNN_CHECK_CUDA(cudaMalloc((void **)&a->done, 4));
         GNN_CHECK_CUDA(cudaMemsetAsync(a->done, 0, 4, ctx->stream));
         if (const char *e = getenv("GNN_PEER_COPY")) a->sm_mode = !strcmp(e, "ce") ? 0 : (!strcmp(e, "nccl") ? 2 : 1);
-        if (const char *e = getenv("GNN_PEER_CTAS")) a->sm_ctas = atoi(e) > 0 ? atoi(e) : a->sm_ctas;
+        if (const char *e = getenv("GNN_PEER_CTAS")) { a->sm_ctas = atoi(e) > 0 ? atoi(e) : a->sm_ctas; a->sm_ctas_set = atoi(e) > 0; }
     }
     GNN_CHECK_CUDA(cudaEventCreateWithFlags(&a->ev_ready, cudaEventDisableTiming));
     GNN_CHECK_CUDA(cudaEventCreateWithFlags(&a->ev_self, cudaEventDisableTiming));

@@ -19,17 +19,36 @@ inline void check(int rc) {
     if (rc != 0) throw std::runtime_error(gnn_last_error());
 }
 
-// process-wide context (device from GNN_DEVICE, default 0); created on first use
+// process-wide context (device from GNN_DEVICE, else LOCAL_RANK of a multi-process launch, default 0); created on first use
 inline gnn_ctx_t *ctx() {
     static gnn_ctx_t *c = [] {
         gnn_ctx_t *p = nullptr;
         const char *d = std::getenv("GNN_DEVICE");
+        if (!d) d = std::getenv("LOCAL_RANK");
         check(gnn_ctx_create(d ? std::atoi(d) : 0, nullptr, &p));
         return p;
     }();
     return c;
 }
 inline void sync() { check(gnn_ctx_sync(ctx())); }
+
+// ---- one process per GPU: nodes are 1-D row-partitioned, rank r owns rows [lo, hi) ----------------
+struct Dist {
+    int rank = 0, world = 1;
+    int64_t n_global = 0, chunk = 0, lo = 0, hi = 0; // set by graph::Data::partitioned
+    bool active() const { return world > 1; }
+};
+inline Dist &dist() {
+    static Dist d;
+    return d;
+}
+/** Join the job described by RANK / WORLD_SIZE (what `gcn_main --gpus N` and torchrun export): rank 0 creates the NCCL
+ *  id and publishes it through the file GNN_RDV (written atomically), the other ranks wait for it. */
+void init_distributed();
+/** sum over ranks, in place (gradients after backward, the scalar loss for reporting) */
+inline void allreduce_sum(float *dptr, int64_t n) {
+    if (dist().active()) check(gnn_allreduce_sum(ctx(), dptr, n));
+}
 
 struct Buffer {
     void *ptr = nullptr;

@@ -79,8 +79,43 @@ std::tuple<tptr<int>, tptr<float>> adj_to_edge_list(tensor<float> &adj) {
 }
 
 std::tuple<tptr<int>, tptr<float>> add_self_loops(const tensor<int> &edge_index, tensor<float> *edge_attr, const float &fillValue, const int &num_nodes) {
-    if (edge_attr != nullptr) throw std::runtime_error("edge weights are outside the GCN hot path (SURVEY.md §8f rank 3): pass edge_attr = nullptr");
     const size_t N = infer_nodes(edge_index, (size_t)num_nodes);
+    if (edge_attr != nullptr) {
+        // the reference's dense round trip with weights (graph.cpp:68-75 over :21-67): A[src][dst] = w (last write wins),
+        // the whole diagonal := fillValue, then every entry with int(a) != 0 in row-major order — so weights with
+        // |w| < 1 disappear, exactly as they do in the reference
+        if (edge_index.shape()[1] != edge_attr->numel())
+            throw std::runtime_error("invalid inputs, number of edges in edge_index must be equal to size of edge_attr");
+        const int64_t E = (int64_t)edge_index.shape()[1];
+        gnn_graph_t *g = nullptr;
+        device::check(gnn_graph_build_weighted(device::ctx(), edge_index.dptr(), edge_index.dptr() + E, edge_attr->dptr(), E, (int32_t)N,
+                                               /*fill_mode=*/2, &g));
+        device::GraphHandle h(g);
+        const size_t nnz = (size_t)gnn_graph_nnz(g);
+        std::vector<int32_t> rowptr(N + 1), col(nnz ? nnz : 1);
+        std::vector<float> w(nnz ? nnz : 1);
+        device::check(gnn_graph_export_h(device::ctx(), g, rowptr.data(), col.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        device::check(gnn_graph_export_weights_h(device::ctx(), g, w.data()));
+        std::vector<int> rs, cs;
+        std::vector<float> vs;
+        const bool keep_diag = (int)fillValue != 0;
+        for (size_t r = 0; r < N; r++) {
+            bool diag_done = !keep_diag;
+            for (int32_t k = rowptr[r]; k < rowptr[r + 1]; k++) {
+                const size_t c = (size_t)col[k];
+                if (!diag_done && c >= r) { rs.push_back((int)r); cs.push_back((int)r); vs.push_back(fillValue); diag_done = true; }
+                if (c == r) continue;                       // the stored diagonal was overwritten by fill_diagonal_
+                if ((int)w[k] != 0) { rs.push_back((int)r); cs.push_back((int)c); vs.push_back(w[k]); }
+            }
+            if (!diag_done) { rs.push_back((int)r); cs.push_back((int)r); vs.push_back(fillValue); }
+        }
+        const size_t n = rs.size();
+        if (n == 0) return coo_from_device(nullptr, nullptr, nullptr, 0);
+        auto *eh = new std::valarray<int>(2 * n);
+        auto *wh = new std::valarray<float>(n);
+        for (size_t i = 0; i < n; i++) { (*eh)[i] = rs[i]; (*eh)[n + i] = cs[i]; (*wh)[i] = vs[i]; }
+        return {std::make_shared<tensor<int>>(std::vector<size_t>{2, n}, eh, false), std::make_shared<tensor<float>>(std::vector<size_t>{n}, wh, false)};
+    }
     const int fill_mode = ((int)fillValue != 0) ? 1 : 0; // adj_to_edge_list keeps int(a) != 0 (graph.cpp:54)
     gnn_graph_t *g = nullptr;
     const int64_t E = (int64_t)edge_index.shape()[1];
@@ -117,6 +152,23 @@ Data::Data(const tptr<float> &x, tensor<int> *edge_index, tptr<float> edge_attr,
         structure();
     }
 }
+Data Data::partitioned(const tptr<float> &x_local, tensor<int> *edge_index, size_t n_global, size_t lo, size_t hi) {
+    if (x_local->rank() != 2 || x_local->shape()[0] != hi - lo || hi > n_global || lo >= hi)
+        throw std::runtime_error("invalid input for x, must be 2D");
+    if (edge_index == nullptr || edge_index->rank() != 2 || edge_index->shape()[0] != 2) throw std::runtime_error("invalid input for x, must be of 2D");
+    Data d;
+    d._x = x_local;
+    d._num_nodes = hi - lo;
+    d._num_node_features = x_local->shape()[1];
+    d._edge_index = edge_index;
+    d._num_edges = edge_index->shape()[1];
+    d._n_global = n_global; d._part_lo = lo; d._part_hi = hi;
+    auto &ds = device::dist();
+    ds.n_global = (int64_t)n_global; ds.lo = (int64_t)lo; ds.hi = (int64_t)hi;
+    ds.chunk = ((int64_t)n_global + ds.world - 1) / ds.world;
+    d.structure();
+    return d;
+}
 tensor<int> *Data::edge_index() {
     if (_edge_index == nullptr) throw std::runtime_error("pls provide adj matr or edge");
     return _edge_index;
@@ -142,7 +194,27 @@ void Data::set_mask(tensor<bool> &mask, DataType type) {
 }
 device::graph_ptr Data::structure() const {
     if (_edge_index == nullptr) throw std::runtime_error("pls provide adj matr or edge");
-    if (!_structure) _structure = build_structure(*_edge_index, _num_nodes, /*fill_mode=*/1, /*normalize=*/true);
+    if (!_structure) {
+        if (_n_global) { // row block [lo, hi) of the global structure (forward CSR rows + backward CSC rows), global column ids
+            auto full = build_structure(*_edge_index, _n_global, /*fill_mode=*/1, /*normalize=*/true);
+            gnn_graph_t *l = nullptr;
+            device::check(gnn_graph_slice_rows(device::ctx(), full->g, (int64_t)_part_lo, (int64_t)_part_hi, &l));
+            _structure = std::make_shared<device::GraphHandle>(l);
+        } else if (_edge_attr != nullptr) {
+            // edge weights (edge_to_adj_mat with edge_attr, reference src/graph.cpp:21-44): weighted A0, last write wins,
+            // unit diagonal, then the weighted-degree normalisation
+            if (_edge_attr->numel() != _num_edges) throw std::runtime_error("invalid inputs, number of edges in edge_index must be equal to size of edge_attr");
+            const int64_t E = (int64_t)_num_edges;
+            gnn_graph_t *g = nullptr;
+            device::check(gnn_graph_build_weighted(device::ctx(), _edge_index->dptr(), _edge_index->dptr() + E, _edge_attr->dptr(), E,
+                                                   (int32_t)_num_nodes, /*fill_mode=*/1, &g));
+            _structure = std::make_shared<device::GraphHandle>(g);
+            device::check(gnn_graph_build_csc(device::ctx(), g));
+            device::check(gnn_graph_normalize(device::ctx(), g));
+        } else {
+            _structure = build_structure(*_edge_index, _num_nodes, /*fill_mode=*/1, /*normalize=*/true);
+        }
+    }
     return _structure;
 }
 

@@ -36,6 +36,11 @@ class Data {
   public:
     Data() {}
     Data(const cyg::tptr<float> &x, cyg::tensor<int> *edge_index = nullptr, cyg::tptr<float> edge_attr = nullptr, cyg::tensor<float> *y = nullptr);
+    /** one process per GPU: this rank's rows [lo, hi) of the node features of an N-node graph, the WHOLE edge list (every
+     *  rank builds the structure on its GPU and keeps its row block of A_hat and of A_hat^T with global column ids).
+     *  Layers then exchange aggregation inputs between the ranks (SpMM node, operation.h); reference layer being
+     *  sharded: src/graph.cpp:170-212. */
+    static Data partitioned(const cyg::tptr<float> &x_local, cyg::tensor<int> *edge_index, size_t n_global, size_t lo, size_t hi);
     cyg::tensor<int> *edge_index();
     void set_edge_index(cyg::tensor<int> *edge_index, cyg::tptr<float> edge_attr = nullptr);
     cyg::tptr<float> to_adj();
@@ -65,6 +70,7 @@ class Data {
     cyg::tensor<float> *_y = nullptr;
     cyg::tptr<float> _x, _edge_attr;
     mutable cyg::device::graph_ptr _structure, _structure_as_written;
+    size_t _n_global = 0, _part_lo = 0, _part_hi = 0; // row partition (Data::partitioned); 0 = whole graph
   public:
     /** loop-free structure with the factorised normalisation of the reference's GCNConv::forward as written
      *  (values norm[row], graph.cpp:172-185), cached like structure() */

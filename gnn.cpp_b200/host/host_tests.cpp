@@ -215,7 +215,37 @@ static void test_graph_structure() { // reference tests/graph.test.cpp:16-43 (it
     CHECK((*e0->data() == want0).min() == true);
     auto [e1, w1] = add_self_loops(*edge_list, nullptr, 1, 5);
     CHECK(e1->shape()[1] == 11);
+    // with weights the reference's dense round trip keeps entries with int(w) != 0 only (graph.cpp:54): 0.5 (edge 1->1)
+    // is the overwritten diagonal anyway; every row gets the diagonal fillValue
+    auto [e2, w2] = add_self_loops(*edge_list, attr.get(), 1, 5);
+    CHECK(e2->shape()[1] == 11 && w2->shape()[0] == 11);
+    {   // rows 0..4 in order: (0,0)=1 (0,1)=3 | (1,1)=1 (1,2)=5 | (2,1)=6 (2,2)=1 | (3,0)=2 (3,1)=7 (3,3)=1 | (4,2)=4 (4,4)=1
+        std::valarray<int> want2 = {0, 0, 1, 1, 2, 2, 3, 3, 3, 4, 4, 0, 1, 1, 2, 1, 2, 0, 1, 3, 2, 4};
+        std::valarray<float> wv = {1, 3, 1, 5, 6, 1, 2, 7, 1, 4, 1};
+        CHECK((*e2->data() == want2).min() == true && all_close(*w2->data(), wv));
+    }
+    auto small_w = T({8}, {0.5f, 0.25f, 2.0f, 3.0f, 0.75f, 5.0f, 6.0f, 7.0f});     // |w| < 1 entries vanish like in the reference
+    auto [e3, w3] = add_self_loops(*edge_list, small_w.get(), 0, 5);
+    CHECK(e3->shape()[1] == 5 && close(w3->data()->sum(), 2.0f + 3.0f + 5.0f + 6.0f + 7.0f));
     auto x = randn<float>({15, 10}, 0.0f, 2.0f, true);
+    {   // a weighted Data feeds the WEIGHTED normalised adjacency to the layer: same as the dense composition
+        auto xs = randn<float>({5, 3}, 0.0f, 1.0f, false);
+        auto attr2 = T({8, 1}, {0.5f, 1.5f, 2.0f, 3.0f, 4.0f, 5.0f, 6.0f, 7.0f});
+        Data wd(xs, edge_list.get(), attr2);
+        auto A = edge_to_adj_mat(*edge_list, attr.get(), 5);
+        A->fill_diagonal_(1);
+        auto deg = A->sum(-1, true);
+        cyg::tensor<float> mhalf(std::vector<size_t>{1}, -0.5f, false);
+        auto dinv = functional::pow(*deg, mhalf);
+        auto Ahat = (A * dinv) * dinv->t();
+        auto agg = std::make_unique<SpMM<tensor<float>>>();
+        auto got = agg->forward(wd.structure(), xs);
+        auto want_y = Ahat->mm(xs);
+        CHECK(all_close(*got->data(), *want_y->data()));
+        Data ud(xs, edge_list.get());
+        auto agg2 = std::make_unique<SpMM<tensor<float>>>();
+        CHECK(!all_close(*agg2->forward(ud.structure(), xs)->data(), *want_y->data()));   // the unweighted structure differs
+    }
     Data data(x, edge_list.get());
     CHECK(data.num_nodes() == 15 && data.num_node_features() == 10 && data.num_edges() == 8);
     CHECK(data.to_adj()->shape() == (std::vector<size_t>{15, 15}));

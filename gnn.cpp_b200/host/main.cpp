@@ -7,6 +7,13 @@
 //   gcn_main --config cora|pubmed|arxiv|reddit|products|tiny|tiny_pl [--epochs 5] [--lr 0.01]
 //   gcn_main --problem file.gcnp [--epochs 1] [--lr 0] [--dump out.gcno]
 //   gcn_main --config tiny_pl --model reference   (the reference's Model: pre/post MLP, GCNConv as written, tanh; Adam)
+//   gcn_main --gpus N --config products            (one process per GPU: the launcher re-executes itself N times with
+//                                                   RANK / WORLD_SIZE / LOCAL_RANK set; nodes are 1-D row-partitioned,
+//                                                   graph::Data::partitioned holds the rank's rows, the SpMM node
+//                                                   exchanges aggregation inputs, gradients are all-reduced)
+#include <sys/wait.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <cstring>
 #include <iostream>
@@ -71,9 +78,39 @@ static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// `--gpus N` without RANK in the environment: start N copies of this binary, one per GPU, and wait for them
+static int launch_ranks(int n, char **argv) {
+    char rdv[] = "/tmp/gcn_main_rdv_XXXXXX";
+    const int fd = mkstemp(rdv);
+    if (fd >= 0) close(fd);
+    unlink(rdv); // rank 0 creates it (atomically) once the NCCL id exists
+    std::vector<pid_t> pids;
+    for (int r = 0; r < n; r++) {
+        const pid_t pid = fork();
+        if (pid == 0) {
+            setenv("RANK", std::to_string(r).c_str(), 1);
+            setenv("LOCAL_RANK", std::to_string(r).c_str(), 1);
+            setenv("WORLD_SIZE", std::to_string(n).c_str(), 1);
+            setenv("GNN_RDV", rdv, 1);
+            execv("/proc/self/exe", argv);
+            std::perror("execv");
+            _exit(127);
+        }
+        pids.push_back(pid);
+    }
+    int rc = 0;
+    for (pid_t pid : pids) {
+        int st = 0;
+        waitpid(pid, &st, 0);
+        if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) rc = 1;
+    }
+    unlink(rdv);
+    return rc;
+}
+
 int main(int argc, char **argv) {
     std::string config, problem_path, dump_path, model_kind = "gcn";
-    int epochs = 5;
+    int epochs = 5, gpus = 1;
     float lr = 0.01f;
     for (int i = 1; i < argc; i++) {
         auto next = [&](const char *flag) -> const char * {
@@ -86,9 +123,14 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "--epochs")) epochs = std::atoi(next("--epochs"));
         else if (!strcmp(argv[i], "--lr")) lr = (float)std::atof(next("--lr"));
         else if (!strcmp(argv[i], "--model")) model_kind = next("--model"); // gcn (default) | reference
+        else if (!strcmp(argv[i], "--gpus")) gpus = std::atoi(next("--gpus"));
         else { std::cerr << "unknown argument " << argv[i] << "\n"; return 2; }
     }
+    if (gpus > 1 && !std::getenv("RANK")) return launch_ranks(gpus, argv);
     try {
+        device::init_distributed(); // no-op for a single process
+        const auto &ds = device::dist();
+        const bool root = ds.rank == 0;
         problem_io::Problem p;
         if (!problem_path.empty()) {
             p = problem_io::load(problem_path);
@@ -112,14 +154,19 @@ int main(int argc, char **argv) {
             }
         }
         const size_t N = (size_t)p.N;
-        auto x = std::make_shared<tensor<float>>(std::vector<size_t>{N, (size_t)p.dims[0]}, new std::valarray<float>(p.X.data(), p.X.size()), false);
-        auto y = std::make_shared<tensor<int>>(std::vector<size_t>{N}, new std::valarray<int>(p.y.data(), p.y.size()), false);
+        // this rank's rows [lo, hi) of the node features and labels (all of them for a single process)
+        const size_t chunk = (N + ds.world - 1) / ds.world;
+        const size_t lo = std::min(N, (size_t)ds.rank * chunk), hi = std::min(N, (size_t)(ds.rank + 1) * chunk), n_loc = hi - lo;
+        const size_t F0 = (size_t)p.dims[0];
+        auto x = std::make_shared<tensor<float>>(std::vector<size_t>{n_loc, F0}, new std::valarray<float>(p.X.data() + lo * F0, n_loc * F0), false);
+        auto y = std::make_shared<tensor<int>>(std::vector<size_t>{n_loc}, new std::valarray<int>(p.y.data() + lo, n_loc), false);
         auto edge_index = vec_to_edge_list(p.src, p.dst);
         double t0 = now_ms();
-        Data data(x, edge_index.get());
+        Data data = ds.active() ? Data::partitioned(x, edge_index.get(), N, lo, hi) : Data(x, edge_index.get());
         device::sync();
-        std::cout << "graph: N=" << N << " E=" << p.E << " nnz(A+I)=" << gnn_graph_nnz(data.structure()->g) << " structure build " << now_ms() - t0
-                  << " ms\n";
+        if (root)
+            std::cout << "graph: N=" << N << " E=" << p.E << " ranks=" << ds.world << " nnz(A+I) of rank 0's rows=" << gnn_graph_nnz(data.structure()->g)
+                      << " structure build " << now_ms() - t0 << " ms\n";
 
         std::vector<size_t> layer_dims(p.dims.begin() + 1, p.dims.end());
         if (model_kind == "reference") { // the reference's own Model shape, trained with Adam on seeded parameters
@@ -155,17 +202,21 @@ int main(int argc, char **argv) {
             logits = model.forward(data);
             loss = cross_entropy_loss(logits, y);
             loss->backward();
+            if (ds.active()) { // every rank holds its rows' share: sum the parameter gradients and the loss over the ranks
+                for (auto &prm : model.parameters()) device::allreduce_sum(prm->grad_dptr(), (int64_t)prm->numel());
+                device::allreduce_sum(loss->dptr(), 1);
+            }
             if (lr != 0.0f) opt.step();
             const float l = loss->item(); // device -> host read of the scalar (synchronises)
-            std::cout << "epoch " << e << " loss " << l << " step " << now_ms() - t0 << " ms\n";
+            if (root) std::cout << "epoch " << e << " loss " << l << " step " << now_ms() - t0 << " ms\n";
         }
-        if (!dump_path.empty()) {
+        if (!dump_path.empty() && root) { // (a partitioned run dumps rank 0's rows of every activation)
             problem_io::Writer w(dump_path);
             float l = loss->item();
             w.f32("loss", &l, {1});
             for (size_t i = 0; i < model.activations.size(); i++) {
                 auto *h = model.activations[i]->data();
-                w.f32("A" + std::to_string(i + 1), &(*h)[0], {(int64_t)N, (int64_t)model.activations[i]->shape()[1]});
+                w.f32("A" + std::to_string(i + 1), &(*h)[0], {(int64_t)n_loc, (int64_t)model.activations[i]->shape()[1]});
             }
             for (int64_t l2 = 1; l2 <= p.L; l2++) {
                 auto conv = model.get_module("enc" + std::to_string(l2));

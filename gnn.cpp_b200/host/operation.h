@@ -382,11 +382,16 @@ template <class T> class SpMM : public Operation<T> {
     SpMM() { this->name = "SpMM"; }
     std::shared_ptr<T> forward(const device::graph_ptr &graph, const std::shared_ptr<T> &P, const std::shared_ptr<T> &b = nullptr, bool relu = false,
                                bool use_values = true) {
-        if (P->rank() != 2 || (int64_t)P->shape()[0] != gnn_graph_cols(graph->g)) throw std::runtime_error(err::mm_compatible());
         const int64_t n = gnn_graph_rows(graph->g), F = P->shape()[1];
+        // a row block of a partitioned graph (Data::partitioned): P holds this rank's rows, the aggregation needs every rank's
+        const bool part = device::dist().active() && n != gnn_graph_cols(graph->g);
+        if (P->rank() != 2 || (int64_t)P->shape()[0] != (part ? n : (int64_t)gnn_graph_cols(graph->g))) throw std::runtime_error(err::mm_compatible());
         const bool rg = P->requires_grad() || (b && b->requires_grad());
         auto out = functional::detail::make<float>({(size_t)n, (size_t)F}, rg);
-        device::check(gnn_spmm_fwd(device::ctx(), graph->g, P->dptr(), F, (int32_t)F, out->dptr(), F, b ? b->dptr() : nullptr, relu, nullptr, 0, use_values));
+        device::buffer_ptr gathered;
+        const float *src = P->dptr();
+        if (part) src = gather_rows(P->dptr(), n, F, gathered);
+        device::check(gnn_spmm_fwd(device::ctx(), graph->g, src, F, (int32_t)F, out->dptr(), F, b ? b->dptr() : nullptr, relu, nullptr, 0, use_values));
         if (rg) {
             this->context->save_for_backward(b ? std::vector<std::shared_ptr<T>>{P, b} : std::vector<std::shared_ptr<T>>{P});
             graph_ = graph;
@@ -413,11 +418,27 @@ template <class T> class SpMM : public Operation<T> {
         }
         if (P->requires_grad()) {
             auto dP = functional::detail::make<float>(P->shape(), false);
-            device::check(gnn_spmm_bwd(device::ctx(), graph_->g, g->dptr(), F, (int32_t)F, dP->dptr(), F, nullptr, 0, use_values_));
+            device::buffer_ptr gathered;
+            const float *src = g->dptr();
+            if (device::dist().active() && gnn_graph_rows(graph_->g) != gnn_graph_cols(graph_->g)) src = gather_rows(g->dptr(), n, F, gathered);
+            device::check(gnn_spmm_bwd(device::ctx(), graph_->g, src, F, (int32_t)F, dP->dptr(), F, nullptr, 0, use_values_));
             P->backward(dP);
         }
         out_.reset();
         this->_done = true;
+    }
+
+  private:
+    /** all ranks' row blocks in global row order (the exchange of the row-partitioned aggregation, K10): the rank's n rows
+     *  are staged into a chunk-row block (the last rank may own fewer) and all-gathered over NCCL */
+    static const float *gather_rows(const float *local, int64_t n, int64_t F, device::buffer_ptr &keep) {
+        const auto &d = device::dist();
+        keep = device::alloc((size_t)(d.world + 1) * d.chunk * F * 4);
+        float *all = static_cast<float *>(keep->ptr), *stage = all + (size_t)d.world * d.chunk * F;
+        device::check(gnn_memset(device::ctx(), stage, 0, (size_t)d.chunk * F * 4));
+        device::check(gnn_memcpy_d2d(device::ctx(), stage, local, (size_t)n * F * 4));
+        device::check(gnn_allgather_rows(device::ctx(), stage, all, d.chunk, (int32_t)F));
+        return all;
     }
 };
 
@@ -437,7 +458,9 @@ template <class T> class SoftmaxCrossEntropy : public Operation<T> {
             dZ_ = functional::detail::make<float>(logits->shape(), false);
             this->context->save_for_backward({logits});
         }
-        device::check(gnn_softmax_xent(device::ctx(), N, (int32_t)C, logits->dptr(), C, target->dptr(), N, out->dptr(), dZ_ ? dZ_->dptr() : nullptr, C));
+        // under a row partition the mean runs over ALL nodes: the local value is this rank's share of the global loss
+        const int64_t n_total = device::dist().active() && device::dist().n_global ? device::dist().n_global : N;
+        device::check(gnn_softmax_xent(device::ctx(), N, (int32_t)C, logits->dptr(), C, target->dptr(), n_total, out->dptr(), dZ_ ? dZ_->dptr() : nullptr, C));
         return out;
     }
     void _backward(std::shared_ptr<T> g) override {

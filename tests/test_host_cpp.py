@@ -73,3 +73,33 @@ def test_reference_model_shape_trains(tmp_path):
     losses = runs[0]
     assert len(losses) == 40 and all(l == l and abs(l) < 1e6 for l in losses) and min(losses[-5:]) < losses[0]
     assert runs[0] == runs[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,world", [("tiny_pl", 2), ("directed", 2), ("tiny_pl", 3), ("cora", 4)])
+def test_main_driver_multi_gpu_matches_single(name, world, tmp_path):
+    """`gcn_main --gpus N` (one process per GPU; graph::Data::partitioned, the SpMM node exchanges aggregation inputs,
+    gradients all-reduced) against the same binary on one GPU: loss, rank 0's rows of every activation, every gradient."""
+    import torch
+    from gnn_cpp_b200 import problem_io
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    p = load_problem(name)
+    pin = str(tmp_path / "p.gcnp")
+    problem_io.write_problem(pin, p)
+    outs = []
+    for n in (1, world):
+        pout = str(tmp_path / ("o%d.gcno" % n))
+        r = subprocess.run([os.path.join(HOST, "gcn_main"), "--gpus", str(n), "--problem", pin, "--epochs", "1", "--lr", "0", "--dump", pout],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(problem_io.read_results(pout))
+    one, many = outs
+    L = len(p.cfg.dims) - 1
+    assert abs(float(one["loss"][0]) - float(many["loss"][0])) <= 1e-5 * abs(float(one["loss"][0]))
+    for l in range(1, L + 1):
+        n_loc = many["A%d" % l].shape[0]
+        assert n_loc == (p.cfg.N + world - 1) // world
+        assert rel_err(many["A%d" % l], one["A%d" % l][:n_loc]) <= 1e-5
+        assert rel_err(many["dW%d" % l], one["dW%d" % l]) <= 1e-5
+        assert rel_err(many["db%d" % l], one["db%d" % l]) <= 1e-5
