@@ -399,6 +399,32 @@ def run_ours(args):
         for l in range(1, L):
             model.set_relu_overrides(l, [], [], [])
 
+    # dense transforms: roofline = max(HBM time of operands read once + outputs written once, 3 x TF32 MMA time at the
+    # MEASURED dense TF32 peak of this GPU) summed over the step's GEMM launches
+    import ctypes
+    from gnn_cpp_b200 import capi as _capi
+    tf32 = ctypes.c_double(0.0)
+    _capi.call("gnn_tf32_peak_probe", ctx.h, ctypes.byref(tf32))
+    gemm_roof = None
+    if bd["gemm"] > 0:
+        af = [cfg.dims[l - 1] < cfg.dims[l] for l in range(1, L + 1)]
+        hbm_ms = mma_ms = floor_ms = 0.0
+        for l in range(1, L + 1):
+            fi, fo = cfg.dims[l - 1], cfg.dims[l]
+            shapes = [(fi, fo, 0)]                                  # forward: read [n, fi], write [n, fo]
+            shapes.append((fi + fo, 0, 0))                          # dW: read both operands
+            if l > 1:
+                shapes.append((fo, fi, fi))                         # dH: read dP, write dH, read the ReLU mask
+            for rd, wr, mask in shapes:
+                by = 4.0 * n_loc * (rd + wr + mask)
+                fl = 2.0 * n_loc * fi * fo * 3                      # three TF32 MMAs per product
+                h, c = by / (peak * 1e9) * 1e3, fl / (tf32.value * 1e12) * 1e3
+                hbm_ms += h; mma_ms += c; floor_ms += max(h, c)
+        gemm_roof = {"kernels": "tc_rows_kernel / tc_tn_kernel (tcgen05 3xTF32), %d launches per step" % (3 * L - 1),
+                     "ms": bd["gemm"], "floor_ms": floor_ms, "frac": floor_ms / bd["gemm"], "hbm_floor_ms": hbm_ms,
+                     "mma_floor_ms": mma_ms, "tf32_peak_tflops_measured": tf32.value,
+                     "how": "floor = sum over launches of max(operand+output bytes / HBM peak, 3 * 2MNK / measured TF32 peak)"}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -426,6 +452,7 @@ def run_ours(args):
                                                             "by_width": launches_detail}},
                 "breakdown_ms": bd,
                 "gemm_tflops": st["gemm_flops"] / (bd["gemm"] * 1e-3) / 1e12 if bd["gemm"] > 0 else None,
+                "gemm_roofline": gemm_roof,
                 "cpu_baseline": cpu, "parity": parity,
                 "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(Xh.numel() * 4 + yh.numel() * 4),
                         "d2h_bytes_per_step": 4, "api": "gnn_gcn_train_step_h (pinned host buffers)", "pipelined": True,

@@ -95,6 +95,7 @@ SIGNATURES = {
     "gnn_gcn_create_grid": (C.c_int, [vp, vp, i32, vp, i32, i32, pp]),
     "gnn_partition_col_slice_h": (C.c_int, [i32, i32, i32, vp, vp]),
     "gnn_partition_grid_h": (C.c_int, [i64, i32, i32, i32, vp, vp, vp, vp]),
+    "gnn_tf32_peak_probe": (C.c_int, [vp, vp]),
     "gnn_partition_ptr_h": (C.c_int, [i64, i32, vp]),
     "gnn_partition_panels_h": (C.c_int, [i32, i32, vp, vp, vp]),
     "gnn_graph_slice_rows": (C.c_int, [vp, vp, i64, i64, pp]),

@@ -678,6 +678,46 @@ __global__ void prep_weights_kernel(const float *__restrict__ B, int64_t ldb, in
     out[(int64_t)Npad * Kpad + i] = lo;
 }
 
+
+// ------------------------------------------------------------------------------------------------ TF32 peak probe
+// Dense TF32 tensor-core peak of this GPU, measured (BASELINE.md §3 asks for it as the compute-side roofline
+// denominator of the dense transforms): every CTA issues a long dependent-free stream of 128 x 256 x 8
+// tcgen05.mma kind::tf32 on one zero-filled shared-memory operand pair (the operands are re-read from shared memory by
+// every instruction, as in the real kernels), no global traffic.
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw_u32);
+    const uint32_t bar = base, tmem_slot = base + 16, a_tile = base + 1024, b_tile = a_tile + 128 * 128;
+    for (uint32_t i = threadIdx.x; i < (128 * 128 + 256 * 128) / 16; i += blockDim.x)
+        reinterpret_cast<float4 *>(gbase + 1024)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gbase + 16);
+    if (warp == 0 && lane == 0) {
+        const uint32_t idesc = instr_desc(128, 256, 0, 0);
+        const uint64_t da = smem_desc(a_tile, 16, 1024), db = smem_desc(b_tile, 16, 1024);
+        uint32_t ph = 0;
+        for (int it = 0; it < iters; it++) {
+            for (uint32_t k = 0; k < 4; k++) mma_tf32(tmem_base, da + (uint64_t)(k * 32 >> 4), db + (uint64_t)(k * 32 >> 4), idesc, 1);
+            if ((it & 63) == 63 || it + 1 == iters) { // bound the number of MMAs in flight
+                mma_commit(bar);
+                mbar_wait(bar, ph);
+                ph ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -834,6 +874,30 @@ static int tn_gemm(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float 
 }
 
 } // namespace tc
+
+} // namespace gnn
+extern "C" int gnn_tf32_peak_probe(gnn_ctx_t *ctx, double *tflops_h) {
+    using namespace gnn;
+    GNN_REQUIRE(ctx && tflops_h, "gnn_tf32_peak_probe: NULL argument");
+    const int iters = 20000, grid = ctx->sm_count;
+    const size_t smem = 1024 + 1024 + 128 * 128 + 256 * 128;
+    GNN_CHECK_CUDA(cudaFuncSetAttribute(tc::tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t a, b;
+    GNN_CHECK_CUDA(cudaEventCreate(&a));
+    GNN_CHECK_CUDA(cudaEventCreate(&b));
+    tc::tf32_peak_kernel<<<grid, 128, smem, ctx->stream>>>(iters / 10); // warm-up
+    GNN_CHECK_CUDA(cudaEventRecord(a, ctx->stream));
+    tc::tf32_peak_kernel<<<grid, 128, smem, ctx->stream>>>(iters);
+    GNN_LAUNCHED(ctx);
+    GNN_CHECK_CUDA(cudaEventRecord(b, ctx->stream));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    GNN_CHECK_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *tflops_h = (double)grid * iters * 4.0 * 2.0 * 128 * 256 * 8 / (ms * 1e-3) / 1e12;
+    return 0;
+}
+namespace gnn {
 
 // The TMA path needs 16-byte aligned rows; anything else goes back to the FP32 FMA kernel (return -1).
 // The rows kernel keeps a whole reduction in one TMEM accumulator, whose truncating adds cost ~2e-6 of relative

@@ -119,8 +119,12 @@ __global__ void __launch_bounds__(RS_THREADS)
                       uint32_t mask, const uint32_t *__restrict__ offsets, int64_t nb, uint64_t *__restrict__ keys_out,
                       uint32_t *__restrict__ vals_out) {
     // per-warp running digit counts, later turned into per-warp exclusive offsets
-    __shared__ uint32_t whist[RS_WARPS][RS_RADIX];
-    __shared__ uint32_t gbase[RS_RADIX];
+    // dynamic shared memory (the payload variant needs 59 KB): staged keys | staged payloads | per-warp histograms | ...
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(rs_smem);
+    uint32_t *svals = reinterpret_cast<uint32_t *>(rs_smem + RS_TILE * 8);
+    uint32_t(*whist)[RS_RADIX] = reinterpret_cast<uint32_t(*)[RS_RADIX]>(rs_smem + RS_TILE * 8 + (HAS_VALS ? RS_TILE * 4 : 0));
+    uint32_t *gbase = &whist[RS_WARPS][0], *dstart = gbase + RS_RADIX, *wsum = dstart + RS_RADIX;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; w++) whist[w][tid] = 0;
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         __syncwarp();
     }
     __syncthreads();
-    // exclusive prefix over warps for digit = tid
+    // exclusive prefix over warps for digit = tid; dstart[d] = first position of digit d inside the tile's sorted order
     {
         uint32_t run = 0;
 #pragma unroll
@@ -159,22 +163,52 @@ __global__ void __launch_bounds__(RS_THREADS)
             whist[w][tid] = run;
             run += c;
         }
+        // exclusive scan of the 256 digit totals (one per thread)
+        const uint32_t incl = warp_incl_scan(run, lane);
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) before += w < warp ? wsum[w] : 0u;
+        dstart[tid] = before + incl - run;
     }
     __syncthreads();
+    // stage the tile in digit order in shared memory, then write it out in that order: keys of one digit leave as one
+    // contiguous run (a direct scatter writes 8-byte pieces to 256 places and used ~4x the DRAM sectors)
+    int64_t tile_n = n - (int64_t)blockIdx.x * RS_TILE;
+    if (tile_n > RS_TILE) tile_n = RS_TILE;
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         const int64_t k = wbase + i * 32 + lane;
         if (k < n) {
             const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-            const int64_t pos = (int64_t)gbase[d] + whist[warp][d] + rank[i];
-            keys_out[pos] = key[i];
-            if (HAS_VALS) vals_out[pos] = vals[k];
+            const uint32_t j = dstart[d] + whist[warp][d] + rank[i];
+            skeys[j] = key[i];
+            if (HAS_VALS) svals[j] = vals[k];
         }
     }
+    __syncthreads();
+    for (int j = tid; j < (int)tile_n; j += RS_THREADS) {
+        const uint64_t kk = skeys[j];
+        const uint32_t d = (uint32_t)(kk >> shift) & mask;
+        const int64_t pos = (int64_t)gbase[d] + ((uint32_t)j - dstart[d]);
+        keys_out[pos] = kk;
+        if (HAS_VALS) vals_out[pos] = svals[j];
+    }
+}
+
+static constexpr size_t rs_smem_bytes(bool has_vals) {
+    return (size_t)RS_TILE * 8 + (has_vals ? (size_t)RS_TILE * 4 : 0) + (size_t)RS_WARPS * RS_RADIX * 4 + 2 * RS_RADIX * 4 + RS_WARPS * 4;
 }
 
 int radix_sort_u64(gnn_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int bit_lo, int bit_hi) {
     if (n <= 1 || bit_hi <= bit_lo) return 0;
+    static uint64_t attr_set = 0; // per device: the payload variant needs more than the default 48 KB of shared memory
+    if (!(attr_set >> (ctx->device & 63) & 1)) {
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true)));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false)));
+        attr_set |= 1ull << (ctx->device & 63);
+    }
     GNN_REQUIRE(n < (int64_t)0xFFFFFFFFll, "radix_sort_u64: n=%lld exceeds 32-bit offsets", (long long)n);
     const int64_t nb = ceil_div(n, RS_TILE);
     const size_t counts_bytes = (size_t)round_up(nb * RS_RADIX * 4, 256);
@@ -194,11 +228,11 @@ int radix_sort_u64(gnn_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int 
         GNN_LAUNCHED(ctx);
         GNN_TRY(exclusive_scan_u32(ctx, counts, counts, nb * RS_RADIX, nullptr));
         if (vals)
-            rs_scatter_kernel<true><<<(unsigned)nb, RS_THREADS, 0, ctx->stream>>>(kin, vin, n, shift, mask, counts, nb,
-                                                                                kout, vout);
+            rs_scatter_kernel<true><<<(unsigned)nb, RS_THREADS, rs_smem_bytes(true), ctx->stream>>>(kin, vin, n, shift, mask, counts,
+                                                                                                 nb, kout, vout);
         else
-            rs_scatter_kernel<false><<<(unsigned)nb, RS_THREADS, 0, ctx->stream>>>(kin, nullptr, n, shift, mask,
-                                                                                 counts, nb, kout, nullptr);
+            rs_scatter_kernel<false><<<(unsigned)nb, RS_THREADS, rs_smem_bytes(false), ctx->stream>>>(kin, nullptr, n, shift, mask,
+                                                                                                   counts, nb, kout, nullptr);
         GNN_LAUNCHED(ctx);
         uint64_t *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;

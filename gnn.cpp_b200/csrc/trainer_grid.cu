@@ -70,7 +70,7 @@ static int issue_scatter(gnn_ctx *ctx, gnn_gcn *m, int op, const float *src, int
         const int q = (ctx->rank + i) % ctx->world;
         int32_t c0, w;
         col_slice(ldF, m->Pc, q % m->Pc, &c0, &w);
-        if (w == 0) continue;
+        // a column group that gets no columns of a narrow matrix (w == 0) still receives the flag: it waits for every rank
         ranks[n] = q;
         offs[n] = m->pc_off[op] + (size_t)ctx->rank * m->chunk * w * 4;
         c0s[n] = c0;

@@ -315,6 +315,11 @@ GNN_API int gnn_partition_grid_h(int64_t N, int32_t world, int32_t Pc, int32_t r
 GNN_API int gnn_gcn_create_grid(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_t *dims, int32_t Pr, int32_t Pc,
                                 gnn_gcn_t **out);
 
+/* Measured dense TF32 tensor-core peak of the device (TFLOP/s, 2MNK per 128 x 256 x 8 tcgen05.mma kind::tf32 streamed
+ * from shared-memory operands on every SM): the compute-side roofline denominator of the dense transforms, which issue
+ * three such MMAs per product (3xTF32). */
+GNN_API int gnn_tf32_peak_probe(gnn_ctx_t *ctx, double *tflops_h);
+
 /* ---------------------------------------------------------------- multi-GPU (K10) ------------------
  * 1-D contiguous row partition: part_ptr[p] = min(N, p*ceil(N/P)).  Each rank owns the CSR rows (and CSC
  * columns) of its nodes with GLOBAL column ids; per aggregation the ranks all-gather their feature row
