@@ -435,13 +435,15 @@ def run_ours(args):
                      "l2_policy": "working set (feature matrices %.1f GB) larger than L2; no flush needed" % (cfg.N * max(cfg.dims) * 4 / 1e9)
                      if cfg.N * max(cfg.dims) * 4 > 2.5e8 else "small working set (L2-resident): launch-bound config",
                      "gemm_precision": "fp32 FMA" if args.precision == 0 else "3xTF32 tcgen05",
-                     "spmm_launches_per_step": st["n_spmm"], "structure_build_ms": build_ms, "structure_build_warm_ms": build_warm_ms, "final_loss": final_loss})
+                     "exchange": model.exchange_stats() if grid is not None else None, "spmm_launches_per_step": st["n_spmm"], "structure_build_ms": build_ms, "structure_build_warm_ms": build_warm_ms, "final_loss": final_loss})
         line = {"metric": "gcn_train_step_ms", "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgd,
                 "roofline": {"bound": "hbm",
-                             "kernel": "spmm_merge_kernel, F=%d aggregation (%.0f launches per step, %.0f%% of the step's aggregation time)"
-                                       % (dom_F, dom_n / nprof, 100.0 * dom_ms / nprof / bd["spmm"]),
+                             "kernel": "%s, F=%d aggregation (%.0f launches per step, %.0f%% of the step's aggregation time)"
+                                       % ("spmm_merge_kernel (nonzero-balanced; chosen by degree skew)" if _capi.load().gnn_graph_spmm_variant(ctx.h, g.h, 0) == 2
+                                          else "spmm_rows_kernel (one row per lane group; chosen by degree skew)", dom_F, dom_n / nprof,
+                                          100.0 * dom_ms / nprof / bd["spmm"]),
                              "achieved": dom_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                              "frac": dom_gbs / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "alg_bytes_per_launch": dom_bytes / dom_n, "ms_per_launch": dom_ms / dom_n,

@@ -49,6 +49,7 @@ SIGNATURES = {
     "gnn_spmm_fwd": (C.c_int, [vp, vp, vp, i64, i32, vp, i64, vp, C.c_int, vp, i64, C.c_int]),
     "gnn_spmm_bwd": (C.c_int, [vp, vp, vp, i64, i32, vp, i64, vp, i64, C.c_int]),
     "gnn_set_spmm_variant": (C.c_int, [vp, C.c_int]),
+    "gnn_graph_spmm_variant": (C.c_int, [vp, vp, C.c_int]),
     "gnn_gemm_nt": (C.c_int, [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, C.c_int, C.c_int]),
     "gnn_gemm_nn": (C.c_int, [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, C.c_int]),
     "gnn_gemm_tn": (C.c_int, [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, C.c_int]),
@@ -93,6 +94,7 @@ SIGNATURES = {
     "gnn_gcn_spmm_stats": (C.c_int, [vp, vp, vp, vp]),
     "gnn_gcn_exchange_mode": (C.c_int, [vp]),
     "gnn_gcn_create_grid": (C.c_int, [vp, vp, i32, vp, i32, i32, pp]),
+    "gnn_gcn_exchange_stats": (C.c_int, [vp, vp, vp, vp, vp]),
     "gnn_partition_col_slice_h": (C.c_int, [i32, i32, i32, vp, vp]),
     "gnn_partition_grid_h": (C.c_int, [i64, i32, i32, i32, vp, vp, vp, vp]),
     "gnn_tf32_peak_probe": (C.c_int, [vp, vp]),
@@ -117,7 +119,7 @@ SIGNATURES = {
     "gnn_peer_gather_wait": (C.c_int, [vp, vp, C.c_int, C.c_int]),
 }
 # int-returning functions that are NOT status codes
-_PLAIN_INT = {"gnn_version", "gnn_ctx_sm_count", "gnn_graph_is_symmetric", "gnn_gcn_exchange_mode"}
+_PLAIN_INT = {"gnn_version", "gnn_ctx_sm_count", "gnn_graph_is_symmetric", "gnn_gcn_exchange_mode", "gnn_graph_spmm_variant"}
 
 
 class GnnError(RuntimeError):

@@ -143,6 +143,10 @@ struct PeerScatterArgs {
     float *dst[PEER_MAX_WORLD];
     uint32_t *flag[PEER_MAX_WORLD]; // nullptr for the own rank
     int32_t c0[PEER_MAX_WORLD], w[PEER_MAX_WORLD];
+    // halo-only exchange: destination d needs only the rows list[d][0 .. cnt[d]) of the block (ascending local row ids;
+    // they keep their position in the destination's gathered matrix); list[d] == nullptr sends all `rows` rows
+    const int32_t *list[PEER_MAX_WORLD];
+    int64_t cnt[PEER_MAX_WORLD];
     int n_dst;
 };
 __global__ void __launch_bounds__(512)
@@ -152,10 +156,20 @@ __global__ void __launch_bounds__(512)
     for (int d = 0; d < a.n_dst; d++) {
         const int32_t wv = a.w[d] >> 2;
         if (wv <= 0) continue;
-        const size_t n = (size_t)rows * wv;
         const float *s0 = src + a.c0[d];
         uint4 *o = reinterpret_cast<uint4 *>(a.dst[d]);
         size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (a.list[d]) { // listed rows only
+            const int32_t *__restrict__ lst = a.list[d];
+            const size_t n = (size_t)a.cnt[d] * wv;
+            for (; i < n; i += stride) {
+                const size_t li = i / wv, v = i - li * wv;
+                const size_t r = (size_t)__ldg(lst + li);
+                __stcs(o + r * wv + v, __ldg(reinterpret_cast<const uint4 *>(s0 + r * ld) + v));
+            }
+            continue;
+        }
+        const size_t n = (size_t)rows * wv;
         for (; i + 3 * stride < n; i += 4 * stride) {
             uint4 v[4];
 #pragma unroll
@@ -241,7 +255,8 @@ char *peer_base(gnn_peer_arena *a, int rank) { return a->base[rank]; }
 // after the work already enqueued on the context's stream: scatter column slices of src[rows, ld] (see
 // peer_scatter_kernel) on the side stream; destination i is rank dst_rank[i], byte offset dst_off[i] of its arena
 int peer_scatter_begin(gnn_ctx *ctx, gnn_peer_arena *a, int slot, const float *src, int64_t ld, int64_t rows, int n_dst,
-                       const int *dst_rank, const size_t *dst_off, const int32_t *c0, const int32_t *w) {
+                       const int *dst_rank, const size_t *dst_off, const int32_t *c0, const int32_t *w,
+                       const int32_t *const *lists, const int64_t *counts) {
     GNN_REQUIRE(ctx && a && slot >= 0 && slot < PEER_MAX_SLOTS - 1 && n_dst <= PEER_MAX_WORLD, "peer_scatter_begin: bad argument");
     GNN_REQUIRE(((uintptr_t)src & 15) == 0 && (ld & 3) == 0, "peer_scatter_begin: source must be 16-byte aligned with ld %% 4 == 0");
     const uint32_t seq = ++a->seq[slot];
@@ -256,6 +271,8 @@ int peer_scatter_begin(gnn_ctx *ctx, gnn_peer_arena *a, int slot, const float *s
         pa.flag[i] = r == a->rank ? nullptr : a->flags(r) + slot * PEER_MAX_WORLD + a->rank;
         pa.c0[i] = c0[i];
         pa.w[i] = w[i];
+        pa.list[i] = lists ? lists[i] : nullptr;
+        pa.cnt[i] = lists && lists[i] ? counts[i] : rows;
     }
     GNN_CHECK_CUDA(cudaEventRecord(a->ev_ready, ctx->stream));
     GNN_CHECK_CUDA(cudaStreamWaitEvent(a->push_sm, a->ev_ready, 0));

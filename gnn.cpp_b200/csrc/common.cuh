@@ -109,6 +109,8 @@ constexpr int SPMM_MAX_DEST = 8;
 struct YDest {
     float *base[SPMM_MAX_DEST];
     int32_t rows_per;
+    const int32_t *row_map; // optional: kernel row i is output row row_map[i] (aggregation over a row SUBSET: the interior /
+                            // boundary split of the partitioned trainer); nullptr = identity
 };
 int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
                 const float *val, int32_t min_nnz_row, int32_t max_nnz_row, const float *P, int64_t ldp, int32_t F,

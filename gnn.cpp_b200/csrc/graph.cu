@@ -321,10 +321,10 @@ int gnn_graph_build(gnn_ctx_t *ctx, const int32_t *src, const int32_t *dst, int6
     g->n_rows = g->n_cols = N;
     g->t_rows = N;
     g->fill_mode = fill_mode;
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->rowptr, (size_t)(N + 1) * 4, ctx->stream));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->rowptr, (size_t)(N + 1) * 4));
     if (m == 0) {
         GNN_CHECK_CUDA(cudaMemsetAsync(g->rowptr, 0, (size_t)(N + 1) * 4, s));
-        GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->colidx, 4, ctx->stream));
+        GNN_CHECK_CUDA(cudaMalloc((void **)&g->colidx, 4));
         g->nnz = 0;
         *out = g;
         return 0;
@@ -358,7 +358,7 @@ int gnn_graph_build(gnn_ctx_t *ctx, const int32_t *src, const int32_t *dst, int6
         return 2;
     }
     g->nnz = h_nnz;
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->colidx, (size_t)(g->nnz ? g->nnz : 1) * 4, ctx->stream));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->colidx, (size_t)(g->nnz ? g->nnz : 1) * 4));
     GNN_CHECK_CUDA(cudaMallocAsync((void **)&ukeys, (size_t)(g->nnz ? g->nnz : 1) * 8, s));
     compact_kernel<<<grid_for(m, 256), 256, 0, s>>>(keys, flags, m, cb, ukeys, g->colidx);
     GNN_LAUNCHED(ctx);
@@ -426,9 +426,9 @@ int gnn_graph_build_weighted(gnn_ctx_t *ctx, const int32_t *src, const int32_t *
     g->t_rows = N;
     g->fill_mode = fill_mode;
     g->nnz = h_nnz;
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->rowptr, (size_t)(N + 1) * 4, ctx->stream));
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->colidx, (size_t)(g->nnz ? g->nnz : 1) * 4, ctx->stream));
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->val0, (size_t)(g->nnz ? g->nnz : 1) * 4, ctx->stream));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->rowptr, (size_t)(N + 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->colidx, (size_t)(g->nnz ? g->nnz : 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->val0, (size_t)(g->nnz ? g->nnz : 1) * 4));
     GNN_CHECK_CUDA(cudaMallocAsync((void **)&ukeys, (size_t)(g->nnz ? g->nnz : 1) * 8, s));
     compact_w_kernel<<<grid_for(m, 256), 256, 0, s>>>(keys, pos_in, flags, m, cb, E, w, ukeys, g->colidx, g->val0);
     GNN_LAUNCHED(ctx);
@@ -463,13 +463,13 @@ int gnn_graph_from_csr(gnn_ctx_t *ctx, int32_t n_rows, int32_t n_cols, const int
     gnn_graph *g = new gnn_graph();
     g->n_rows = n_rows; g->n_cols = n_cols; g->t_rows = n_cols; g->fill_mode = 2;
     g->nnz = ends[1] - ends[0];
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->rowptr, (size_t)(n_rows + 1) * 4, ctx->stream));
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->colidx, (size_t)(g->nnz ? g->nnz : 1) * 4, ctx->stream));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->rowptr, (size_t)(n_rows + 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->colidx, (size_t)(g->nnz ? g->nnz : 1) * 4));
     rebase_kernel<<<grid_for(n_rows + 1, 256), 256, 0, s>>>(rowptr, n_rows + 1, ends[0], g->rowptr);
     GNN_LAUNCHED(ctx);
     if (g->nnz) GNN_CHECK_CUDA(cudaMemcpyAsync(g->colidx, colidx + ends[0], (size_t)g->nnz * 4, cudaMemcpyDeviceToDevice, s));
     if (val) {
-        GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->val, (size_t)(g->nnz ? g->nnz : 1) * 4, ctx->stream));
+        GNN_CHECK_CUDA(cudaMalloc((void **)&g->val, (size_t)(g->nnz ? g->nnz : 1) * 4));
         if (g->nnz) GNN_CHECK_CUDA(cudaMemcpyAsync(g->val, val + ends[0], (size_t)g->nnz * 4, cudaMemcpyDeviceToDevice, s));
     }
     GNN_TRY(finish_stats(ctx, g));
@@ -483,9 +483,9 @@ int gnn_graph_build_csc(gnn_ctx_t *ctx, gnn_graph_t *g) {
     cudaStream_t s = ctx->stream;
     const int cb = bits_for(g->n_cols);
     const int64_t nnz = g->nnz;
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->colptr, (size_t)(g->n_cols + 1) * 4, ctx->stream));
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->rowidx, (size_t)(nnz ? nnz : 1) * 4, ctx->stream));
-    GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->perm, (size_t)(nnz ? nnz : 1) * 4, ctx->stream));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->colptr, (size_t)(g->n_cols + 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->rowidx, (size_t)(nnz ? nnz : 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&g->perm, (size_t)(nnz ? nnz : 1) * 4));
     if (nnz == 0) {
         GNN_CHECK_CUDA(cudaMemsetAsync(g->colptr, 0, (size_t)(g->n_cols + 1) * 4, s));
         g->symmetric = g->n_rows == g->n_cols;
@@ -531,9 +531,9 @@ int gnn_graph_normalize(gnn_ctx_t *ctx, gnn_graph_t *g) {
     GNN_REQUIRE(g->n_rows == g->n_cols, "gnn_graph_normalize: needs the square (global) graph");
     cudaStream_t s = ctx->stream;
     const int64_t nnz = g->nnz ? g->nnz : 1;
-    if (!g->deg) GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->deg, (size_t)g->n_rows * 4, ctx->stream));
-    if (!g->dinv) GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->dinv, (size_t)g->n_rows * 4, ctx->stream));
-    if (!g->val) GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->val, (size_t)nnz * 4, ctx->stream));
+    if (!g->deg) GNN_CHECK_CUDA(cudaMalloc((void **)&g->deg, (size_t)g->n_rows * 4));
+    if (!g->dinv) GNN_CHECK_CUDA(cudaMalloc((void **)&g->dinv, (size_t)g->n_rows * 4));
+    if (!g->val) GNN_CHECK_CUDA(cudaMalloc((void **)&g->val, (size_t)nnz * 4));
     if (g->val0) { // weighted adjacency: weighted degree, val = (w * dinv[r]) * dinv[c]
         degree_w_kernel<<<grid_for((int64_t)g->n_rows * 32, 256), 256, 0, s>>>(g->rowptr, g->val0, g->n_rows, g->deg, g->dinv);
         GNN_LAUNCHED(ctx);
@@ -548,7 +548,7 @@ int gnn_graph_normalize(gnn_ctx_t *ctx, gnn_graph_t *g) {
         GNN_LAUNCHED(ctx);
     }
     if (g->colptr && !g->valT) {
-        GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->valT, (size_t)nnz * 4, ctx->stream));
+        GNN_CHECK_CUDA(cudaMalloc((void **)&g->valT, (size_t)nnz * 4));
         gather_f32_kernel<<<grid_for(g->nnz, 256), 256, 0, s>>>(g->val, g->perm, g->nnz, g->valT);
         GNN_LAUNCHED(ctx);
     }
@@ -561,10 +561,10 @@ int gnn_graph_normalize_as_written(gnn_ctx_t *ctx, gnn_graph_t *g, float *norm_o
     GNN_REQUIRE(g->fill_mode == 0, "gnn_graph_normalize_as_written: build the graph with fill_mode 0 (add_self_loops(.., 0))");
     cudaStream_t s = ctx->stream;
     const int64_t nnz = g->nnz ? g->nnz : 1;
-    if (!g->deg) GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->deg, (size_t)g->n_rows * 4, ctx->stream));
-    if (!g->dinv) GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->dinv, (size_t)g->n_rows * 4, ctx->stream));
-    if (!g->val) GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->val, (size_t)nnz * 4, ctx->stream));
-    if (g->colptr && !g->valT) GNN_CHECK_CUDA(cudaMallocAsync((void **)&g->valT, (size_t)nnz * 4, ctx->stream));
+    if (!g->deg) GNN_CHECK_CUDA(cudaMalloc((void **)&g->deg, (size_t)g->n_rows * 4));
+    if (!g->dinv) GNN_CHECK_CUDA(cudaMalloc((void **)&g->dinv, (size_t)g->n_rows * 4));
+    if (!g->val) GNN_CHECK_CUDA(cudaMalloc((void **)&g->val, (size_t)nnz * 4));
+    if (g->colptr && !g->valT) GNN_CHECK_CUDA(cudaMalloc((void **)&g->valT, (size_t)nnz * 4));
     float *norm = nullptr;
     GNN_CHECK_CUDA(cudaMallocAsync((void **)&norm, (size_t)g->n_rows * 4, s));
     aswritten_dinv_kernel<<<grid_for(g->n_rows, 256), 256, 0, s>>>(g->rowptr, g->n_rows, g->deg, g->dinv);
@@ -588,10 +588,12 @@ int gnn_graph_normalize_as_written(gnn_ctx_t *ctx, gnn_graph_t *g, float *norm_o
 int gnn_graph_destroy(gnn_ctx_t *ctx, gnn_graph_t *g) {
     if (!g) return 0;
     if (ctx) cudaStreamSynchronize(ctx->stream);
-    // the arrays come from the stream-ordered pool (kept cached: a rebuilt structure costs kernel time only)
-    void *arrays[] = {g->rowptr, g->colidx, g->val, g->val0, g->colptr, g->rowidx, g->perm, g->valT, g->deg, g->dinv};
-    for (void *a : arrays)
-        if (a) { if (ctx) cudaFreeAsync(a, ctx->stream); else cudaFree(a); }
+    // (graph arrays are plain cudaMalloc allocations: taking them from the stream-ordered pool was measured and made a
+    // rebuilt products-shaped structure 4x slower — 130 ms instead of 30 — because the pool grows by mapping fresh
+    // physical memory while the previous structure is still alive; only the sort temporaries live in the pool)
+    cudaFree(g->rowptr); cudaFree(g->colidx); cudaFree(g->val); cudaFree(g->val0);
+    cudaFree(g->colptr); cudaFree(g->rowidx); cudaFree(g->perm); cudaFree(g->valT);
+    cudaFree(g->deg); cudaFree(g->dinv);
     delete g;
     return 0;
 }

@@ -56,6 +56,7 @@ __device__ __forceinline__ float epilogue1(float v, int col, int F, const float 
 
 // output row pointer (see YDest in common.cuh)
 __device__ __forceinline__ float *yd_row(const YDest &d, int32_t row, int64_t ldy) {
+    if (d.row_map) row = __ldg(d.row_map + row);
     if (d.rows_per == 0) return d.base[0] + (int64_t)row * ldy;
     const int32_t q = row / d.rows_per;
     return d.base[q] + (int64_t)(row - q * d.rows_per) * ldy;
@@ -345,7 +346,7 @@ static int launch_rows(gnn_ctx *ctx, int32_t n_out, const int32_t *ptr, const in
     const unsigned grid = (unsigned)ceil_div(n_out, GROUPS);
     float *Y0 = Y.base[0];
 #define ROWS_GO(UV, MU) spmm_rows_kernel<V, LPR, VEC, UV, U, PF, MU><<<grid, SPMM_THREADS, 0, ctx->stream>>>(n_out, ptr, idx, val, P, ldp, F, Y0, Y, ldy, bias, relu, mask, ldm)
-    if (Y.rows_per) { if (val) ROWS_GO(true, true); else ROWS_GO(false, true); }
+    if (Y.rows_per || Y.row_map) { if (val) ROWS_GO(true, true); else ROWS_GO(false, true); }
     else { if (val) ROWS_GO(true, false); else ROWS_GO(false, false); }
 #undef ROWS_GO
     GNN_LAUNCHED(ctx);
@@ -371,7 +372,7 @@ static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz
     spmm_merge_kernel<V, LPR, VEC, UV, U, PF, MU><<<grid, SPMM_THREADS, 0, ctx->stream>>>(                          \
         n_out, (int32_t)k_base, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, val, P, ldp, F, Y0, Y, ldy, bias, relu, mask, ldm, head, \
         tail, head_row, tail_row, ldw)
-    if (Y.rows_per) { if (val) MERGE_GO(true, true); else MERGE_GO(false, true); }
+    if (Y.rows_per || Y.row_map) { if (val) MERGE_GO(true, true); else MERGE_GO(false, true); }
     else { if (val) MERGE_GO(true, false); else MERGE_GO(false, false); }
 #undef MERGE_GO
     GNN_LAUNCHED(ctx);
@@ -381,17 +382,32 @@ static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz
     return 0;
 }
 
-// Variant choice (ctx->spmm_variant: 0 auto, 1 rows, 2 merge).  The nonzero-balanced kernel is the default: it is
-// never slower than one-row-per-group on B200 (products-shaped, mild skew: 33.0 vs 36.3 ms per step; Reddit-shaped,
-// hub rows of 60 K nonzeros: 7.7 vs 15.3 ms) because a lane group streams one row sequentially, so with the rows
-// kernel every hub row is a serial tail, and short rows leave CTA slots idle until the slowest row of the CTA ends.
-// The rows kernel remains for matrices with empty rows (the merge walk needs every row to own a nonzero) and for
-// tiny inputs.
-static bool use_merge(const gnn_ctx *ctx, int64_t nnz, int64_t k_end, int32_t min_nnz_row, int32_t max_nnz_row,
-                      int lpr) {
-    (void)max_nnz_row;
+// Variant choice (ctx->spmm_variant: 0 auto, 1 rows, 2 merge) — by DEGREE SKEW = longest row / mean row length.
+// One-row-per-group (rows kernel) has no chunk bookkeeping, no partial-row workspace and no fix-up launch, but a lane
+// group streams its row sequentially: a row k times the mean length holds its CTA slot k times as long, and a hub row
+// is a serial tail.  The nonzero-balanced merge kernel spreads every row over as many warps as it has 1,024-nonzero
+// chunks.  Measured on B200, ms per launch (tools/spmm_probe.py, profiles/r2_spmm_variant_by_skew.md):
+//   graph (skew)            width   rows    merge
+//   arxiv-shaped (3)          40    0.055   0.093      uniform degrees: rows wins at every width
+//                            128    0.111   0.144
+//                            256    0.242   0.263
+//   pubmed-/cora-shaped (<4)  any   0.016   0.043      launch-bound: one launch instead of two
+//   products-shaped (260)    100    5.64    5.31       power law: merge wins from the middle widths up
+//                            256   12.95   10.4
+//   reddit-shaped (120)       41    5.43    2.05       hub rows of 60 K nonzeros: merge 2-2.6x faster
+//                            128    9.52    4.90
+// Hub rows are therefore not staged through shared memory: cutting them into chunks that go through the ordinary
+// register-accumulating path (and summing the per-chunk partials in fixed order) already runs the Reddit-shaped
+// aggregation at 1.9x the HBM copy peak on B_alg (features are L2-resident there), with no smem capacity limit on the
+// row length.  The rows kernel also serves matrices with empty rows (the merge walk needs every row to own a nonzero).
+constexpr int64_t SPMM_SKEW_MERGE = 16; // longest row >= 16 x the mean -> nonzero-balanced kernel
+static bool use_merge(const gnn_ctx *ctx, int64_t nnz, int64_t k_end, int32_t n_out, int32_t min_nnz_row,
+                      int32_t max_nnz_row, int lpr) {
     if (min_nnz_row < 1 || k_end >= (1ll << 31) || nnz < 4 * (int64_t)merge_chunk(ctx, lpr, nnz)) return false;
-    return ctx->spmm_variant != 1;
+    if (ctx->spmm_variant == 1) return false;
+    if (ctx->spmm_variant == 2) return true;
+    const int64_t mean = nnz / (n_out > 0 ? n_out : 1) + 1;
+    return (int64_t)max_nnz_row >= SPMM_SKEW_MERGE * mean;
 }
 
 // Dispatch on width.  Wide rows are processed in column blocks (separate launches on shifted pointers).
@@ -414,12 +430,13 @@ int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const 
         const float *Pc = P + c0;
         YDest Yc;
         Yc.rows_per = dest ? dest->rows_per : 0;
+        Yc.row_map = dest ? dest->row_map : nullptr;
         for (int q = 0; q < SPMM_MAX_DEST; q++) Yc.base[q] = dest ? (dest->base[q] ? dest->base[q] + c0 : nullptr) : (q == 0 ? Y + c0 : nullptr);
         const float *bc = bias ? bias + c0 : nullptr;
         const float *mc = mask ? mask + c0 : nullptr;
 #define GO2(V, LPR, VEC, U, PF)                                                                                      \
     do {                                                                                                             \
-        if (use_merge(ctx, nnz - k_base, nnz, min_nnz_row, max_nnz_row, LPR))                                       \
+        if (use_merge(ctx, nnz - k_base, nnz, n_out, min_nnz_row, max_nnz_row, LPR))                                       \
             GNN_TRY((launch_merge<V, LPR, VEC, U, PF>(ctx, n_out, k_base, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \
         else                                                                                                         \
             GNN_TRY((launch_rows<V, LPR, VEC, U, PF>(ctx, n_out, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm)));  \
@@ -493,6 +510,15 @@ int gnn_set_spmm_variant(gnn_ctx_t *ctx, int variant) {
     const int ch = variant / 1000;
     ctx->spmm_chunk = ch > 0 ? ch * MERGE_CHUNK_MIN : 0;
     return 0;
+}
+
+int gnn_graph_spmm_variant(gnn_ctx_t *ctx, const gnn_graph_t *g, int transpose) {
+    if (!ctx || !g) return 0;
+    const bool alias = transpose && g->symmetric;
+    const bool fwd = !transpose || alias;
+    const int64_t nnz = fwd ? g->nnz : g->nnz_t;
+    return use_merge(ctx, nnz, nnz, fwd ? g->n_rows : g->t_rows, fwd ? g->min_row_nnz : g->min_col_nnz,
+                     fwd ? g->max_row_nnz : g->max_col_nnz, 32) ? 2 : 1;
 }
 
 int gnn_spmm_fwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *P, int64_t ldp, int32_t F, float *Y, int64_t ldy,

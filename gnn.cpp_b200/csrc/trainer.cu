@@ -447,6 +447,12 @@ int gnn_gcn_destroy(gnn_ctx_t *ctx, gnn_gcn_t *m) {
     cudaFree(m->vel); cudaFree(m->adam_m); cudaFree(m->adam_v);
     if (m->grid) { // activations live in the arena; everything cudaMalloc'ed is listed in `owned`
         for (auto p : m->owned) cudaFree(p);
+        for (int dir = 0; dir < 2; dir++) {
+            for (auto p : m->send_list[dir]) cudaFree(p);
+            for (int k = 0; k < 2; k++) {
+                cudaFree(m->sub[dir][k].ptr); cudaFree(m->sub[dir][k].idx); cudaFree(m->sub[dir][k].rows); cudaFree(m->sub[dir][k].val);
+            }
+        }
         m->loss_d = nullptr;
     } else {
         cudaFree(m->params); cudaFree(m->grads);
@@ -810,6 +816,15 @@ int gnn_gcn_last_spmm_spans(gnn_gcn_t *m, double *ms, double *alg_bytes, int32_t
         k++;
     }
     *n = k;
+    return 0;
+}
+
+int gnn_gcn_exchange_stats(const gnn_gcn_t *m, double *halo_fraction, int *halo_lists, int *split, double *interior_fraction) {
+    GNN_REQUIRE(m, "gnn_gcn_exchange_stats: NULL argument");
+    if (halo_fraction) *halo_fraction = m->halo_fraction;
+    if (halo_lists) *halo_lists = m->halo_lists ? 1 : 0;
+    if (split) *split = m->split ? 1 : 0;
+    if (interior_fraction) *interior_fraction = m->grid && m->grp_rows > 0 ? (double)m->sub[0][0].n / (double)m->grp_rows : 0.0;
     return 0;
 }
 

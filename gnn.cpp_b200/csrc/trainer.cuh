@@ -49,6 +49,16 @@ struct gnn_gcn {
     std::vector<size_t> pc_off, y_off; // per aggregation op: arena offset of the gathered column slice / of the output rows
     std::vector<char> scattered;       // per op: this step's rows -> columns scatter has already been issued
     std::vector<void *> owned;         // cudaMalloc'ed buffers of the grid trainer (the rest lives in the arena)
+    // halo-only exchange + interior/boundary overlap (trainer_grid.cu): per destination rank the rows of this rank it
+    // needs (device lists, [0] forward structure, [1] backward structure), and the structure's rows split into those
+    // that need only the rank's own rows ("interior": aggregated while the exchange is in flight) and the rest
+    struct SubCsr { int32_t n = 0; int64_t nnz = 0; int32_t *ptr = nullptr, *idx = nullptr, *rows = nullptr; float *val = nullptr; int32_t max_nnz = 0; };
+    bool halo_lists = false, split = false;
+    std::vector<int32_t *> send_list[2];
+    std::vector<int64_t> send_cnt[2];
+    SubCsr sub[2][2];                  // [direction][0 interior, 1 boundary]
+    size_t need_off = 0;
+    double halo_fraction = 1.0;        // listed rows / (peers x local rows): 1 = every peer needs every row
     std::vector<float *> H_local;      // grid: local H_l buffers of aggregate-first layers (transform-first H_l is an arena region)
     float *Xs[2] = {nullptr, nullptr};                   // double-buffered staged inputs for *_h entry points
     int32_t *ys[2] = {nullptr, nullptr};
@@ -130,7 +140,8 @@ struct Prof {
 // comm.cu: 2-D partition plumbing
 char *peer_base(gnn_peer_arena *a, int rank);
 int peer_scatter_begin(gnn_ctx *ctx, gnn_peer_arena *a, int slot, const float *src, int64_t ld, int64_t rows, int n_dst,
-                       const int *dst_rank, const size_t *dst_off, const int32_t *c0, const int32_t *w);
+                       const int *dst_rank, const size_t *dst_off, const int32_t *c0, const int32_t *w,
+                       const int32_t *const *lists = nullptr, const int64_t *counts = nullptr);
 int peer_signal(gnn_ctx *ctx, gnn_peer_arena *a, int slot, uint32_t peer_mask);
 int peer_wait_mask(gnn_ctx *ctx, gnn_peer_arena *a, int slot, uint32_t peer_mask, bool after_own_scatter);
 // trainer.cu

@@ -58,26 +58,190 @@ void recompute_stats_grid(gnn_gcn *m) {
     }
 }
 
+
+// ---- halo-only exchange and interior/boundary split: set-up kernels ----------------------------------------------
+__global__ void need_mark_kernel(const int32_t *__restrict__ idx, int64_t nnz, uint8_t *__restrict__ need) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nnz) need[idx[k]] = 1; // benign race: every writer stores 1
+}
+__global__ void need_flags_kernel(const uint8_t *__restrict__ need, int64_t n, uint32_t *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) flags[i] = (i < n && need[i]) ? 1u : 0u;
+}
+__global__ void list_compact_kernel(const uint8_t *__restrict__ need, const uint32_t *__restrict__ pos, int64_t n,
+                                    int32_t *__restrict__ list) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && need[i]) list[pos[i]] = (int32_t)i;
+}
+// one warp per structure row: interior iff every column is one of the rank's own rows [own_lo, own_hi)
+__global__ void interior_flag_kernel(const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx, int32_t n_rows,
+                                     int32_t own_lo, int32_t own_hi, uint32_t *__restrict__ iflag, uint32_t *__restrict__ bflag) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row > n_rows) return;
+    if (row == n_rows) { if (lane == 0) { iflag[row] = 0; bflag[row] = 0; } return; }
+    bool in = true;
+    for (int32_t k = ptr[row] + lane; k < ptr[row + 1]; k += 32) {
+        const int32_t c = idx[k];
+        if (c < own_lo || c >= own_hi) in = false;
+    }
+    in = __all_sync(0xffffffffu, in);
+    if (lane == 0) { iflag[row] = in ? 1u : 0u; bflag[row] = in ? 0u : 1u; }
+}
+__global__ void sub_rows_kernel(const uint32_t *__restrict__ sel, const uint32_t *__restrict__ pos, const int32_t *__restrict__ ptr,
+                                int32_t n_rows, int32_t *__restrict__ rows, uint32_t *__restrict__ len) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rows && sel[r]) { rows[pos[r]] = (int32_t)r; len[pos[r]] = (uint32_t)(ptr[r + 1] - ptr[r]); }
+}
+__global__ void sub_copy_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ sub_ptr, int32_t n_sub,
+                                const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx, const float *__restrict__ val,
+                                int32_t *__restrict__ sub_idx, float *__restrict__ sub_val) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_sub) return;
+    const int32_t r = rows[i], s0 = ptr[r], n = ptr[r + 1] - s0, d0 = sub_ptr[i];
+    for (int32_t k = lane; k < n; k += 32) { sub_idx[d0 + k] = idx[s0 + k]; sub_val[d0 + k] = val[s0 + k]; }
+}
+static inline unsigned g256(int64_t n) { return (unsigned)ceil_div(n > 0 ? n : 1, 256); }
+
+// CSR of the selected rows (sel[r] = 1) of a structure block, with the list of the original row ids
+static int build_sub_csr(gnn_ctx *ctx, const uint32_t *sel, const int32_t *ptr, const int32_t *idx, const float *val,
+                         int32_t n_rows, int32_t parent_max, gnn_gcn::SubCsr *out) {
+    cudaStream_t s = ctx->stream;
+    uint32_t *pos = nullptr, *len = nullptr;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&pos, (size_t)(n_rows + 1) * 4, s));
+    GNN_TRY(exclusive_scan_u32(ctx, sel, pos, n_rows + 1, nullptr));
+    uint32_t n_sub = 0;
+    GNN_CHECK_CUDA(cudaMemcpyAsync(&n_sub, pos + n_rows, 4, cudaMemcpyDeviceToHost, s));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    out->n = (int32_t)n_sub;
+    out->max_nnz = parent_max;
+    GNN_CHECK_CUDA(cudaMalloc((void **)&out->rows, (size_t)(n_sub + 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&out->ptr, (size_t)(n_sub + 2) * 4));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&len, (size_t)(n_sub + 2) * 4, s));
+    GNN_CHECK_CUDA(cudaMemsetAsync(len, 0, (size_t)(n_sub + 2) * 4, s));
+    sub_rows_kernel<<<g256(n_rows), 256, 0, s>>>(sel, pos, ptr, n_rows, out->rows, len);
+    GNN_LAUNCHED(ctx);
+    GNN_TRY(exclusive_scan_u32(ctx, len, reinterpret_cast<uint32_t *>(out->ptr), (int64_t)n_sub + 1, nullptr));
+    int32_t nnz = 0;
+    GNN_CHECK_CUDA(cudaMemcpyAsync(&nnz, out->ptr + n_sub, 4, cudaMemcpyDeviceToHost, s));
+    GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    out->nnz = nnz;
+    GNN_CHECK_CUDA(cudaMalloc((void **)&out->idx, (size_t)(nnz ? nnz : 1) * 4));
+    GNN_CHECK_CUDA(cudaMalloc((void **)&out->val, (size_t)(nnz ? nnz : 1) * 4));
+    sub_copy_kernel<<<g256((int64_t)n_sub * 32), 256, 0, s>>>(out->rows, out->ptr, (int32_t)n_sub, ptr, idx, val, out->idx, out->val);
+    GNN_LAUNCHED(ctx);
+    GNN_CHECK_CUDA(cudaFreeAsync(pos, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(len, s));
+    return 0;
+}
+
+// Collective set-up after the arena exists.  (1) every rank publishes which node rows its structure block reads (forward
+// and backward blocks), (2) reads the peers' flags for its OWN rows and keeps, per destination, the list of rows that
+// destination needs (the halo-only exchange; skipped when the peers need practically everything, as on the synthetic
+// power-law graphs), (3) splits its structure rows into interior (only own rows needed) and boundary rows.
+static int setup_halo(gnn_ctx *ctx, gnn_gcn *m) {
+    const gnn_graph *g = m->g;
+    cudaStream_t s = ctx->stream;
+    const int64_t N = m->n_glob;
+    const int64_t own_lo = std::min<int64_t>(N, (int64_t)ctx->rank * m->chunk), own_hi = own_lo + m->n_loc;
+    const size_t need_stride = (size_t)round_up(N, 256);
+    double listed = 0, possible = 0;
+    for (int dir = 0; dir < 2; dir++) {
+        const int32_t *idx = dir ? g->rowidx : g->colidx;
+        const int64_t nnz = dir ? g->nnz_t : g->nnz;
+        uint8_t *need = reinterpret_cast<uint8_t *>(peer_base(m->arena, ctx->rank) + m->need_off + dir * need_stride);
+        GNN_CHECK_CUDA(cudaMemsetAsync(need, 0, need_stride, s));
+        need_mark_kernel<<<g256(nnz), 256, 0, s>>>(idx, nnz, need);
+        GNN_LAUNCHED(ctx);
+    }
+    GNN_TRY(gnn_allreduce_sum(ctx, m->grads + m->n_params + 1, 1)); // every rank's flags are written
+    GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    uint32_t *flags = nullptr;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&flags, (size_t)(m->n_loc + 2) * 4, s));
+    for (int dir = 0; dir < 2; dir++) {
+        m->send_list[dir].assign(ctx->world, nullptr);
+        m->send_cnt[dir].assign(ctx->world, 0);
+        for (int q = 0; q < ctx->world; q++) {
+            if (q == ctx->rank || m->n_loc == 0) continue;
+            const uint8_t *need_q = reinterpret_cast<const uint8_t *>(peer_base(m->arena, q) + m->need_off + dir * need_stride) + own_lo;
+            need_flags_kernel<<<g256(m->n_loc + 1), 256, 0, s>>>(need_q, m->n_loc, flags);
+            GNN_LAUNCHED(ctx);
+            GNN_TRY(exclusive_scan_u32(ctx, flags, flags, m->n_loc + 1, nullptr));
+            uint32_t cnt = 0;
+            GNN_CHECK_CUDA(cudaMemcpyAsync(&cnt, flags + m->n_loc, 4, cudaMemcpyDeviceToHost, s));
+            GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+            GNN_CHECK_CUDA(cudaMalloc((void **)&m->send_list[dir][q], (size_t)(cnt ? cnt : 1) * 4));
+            list_compact_kernel<<<g256(m->n_loc), 256, 0, s>>>(need_q, flags, m->n_loc, m->send_list[dir][q]);
+            GNN_LAUNCHED(ctx);
+            m->send_cnt[dir][q] = cnt;
+            listed += cnt;
+            possible += (double)m->n_loc;
+        }
+    }
+    GNN_CHECK_CUDA(cudaFreeAsync(flags, s));
+    GNN_TRY(gnn_allreduce_sum(ctx, m->grads + m->n_params + 1, 1)); // nobody is still reading this rank's flags
+    GNN_CHECK_CUDA(cudaStreamSynchronize(s));
+    m->halo_fraction = possible > 0 ? listed / possible : 1.0;
+    m->halo_lists = m->halo_fraction < 0.9;
+    if (const char *e = getenv("GNN_HALO")) m->halo_lists = atoi(e) != 0; // ablation: 0 = always send every row
+    // interior / boundary split of the structure block
+    uint32_t *iflag = nullptr, *bflag = nullptr;
+    const int32_t rows_max = g->n_rows > g->t_rows ? g->n_rows : g->t_rows;
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&iflag, (size_t)(rows_max + 1) * 4, s));
+    GNN_CHECK_CUDA(cudaMallocAsync((void **)&bflag, (size_t)(rows_max + 1) * 4, s));
+    bool want_split = true;
+    for (int dir = 0; dir < 2 && want_split; dir++) {
+        const int32_t *ptr = dir ? g->colptr : g->rowptr, *idx = dir ? g->rowidx : g->colidx;
+        const float *val = dir ? g->valT : g->val;
+        const int32_t n_rows = dir ? g->t_rows : g->n_rows;
+        interior_flag_kernel<<<g256((int64_t)(n_rows + 1) * 32), 256, 0, s>>>(ptr, idx, n_rows, (int32_t)own_lo, (int32_t)own_hi, iflag, bflag);
+        GNN_LAUNCHED(ctx);
+        GNN_TRY(build_sub_csr(ctx, iflag, ptr, idx, val, n_rows, dir ? g->max_col_nnz : g->max_row_nnz, &m->sub[dir][0]));
+        // worth two launches only when a real share of the rows can start early
+        if (m->sub[dir][0].n < n_rows / 10) { want_split = false; break; }
+        GNN_TRY(build_sub_csr(ctx, bflag, ptr, idx, val, n_rows, dir ? g->max_col_nnz : g->max_row_nnz, &m->sub[dir][1]));
+    }
+    GNN_CHECK_CUDA(cudaFreeAsync(iflag, s));
+    GNN_CHECK_CUDA(cudaFreeAsync(bflag, s));
+    m->split = want_split;
+    if (const char *e = getenv("GNN_SPLIT")) m->split = m->split && atoi(e) != 0; // ablation: 0 = one launch over all rows
+    // ranks may decide differently on lists (a sender-side choice) but the split changes nothing a peer can see either
+    return 0;
+}
+
 // step 1: scatter the rank's rows of src[n_loc, ldF] to every rank (each receives its column group's slice)
 static int issue_scatter(gnn_ctx *ctx, gnn_gcn *m, int op, const float *src, int64_t ld_src, int32_t ldF) {
     if (m->scattered[op]) return 0;
     Prof pr(ctx, m, CLS_OTHER);
+    const int dir = op & 1;
     int ranks[16];
     size_t offs[16];
     int32_t c0s[16], ws[16];
+    const int32_t *lists[16];
+    int64_t cnts[16];
     int n = 0;
     for (int i = 1; i <= ctx->world; i++) { // staggered start; the own rank last
         const int q = (ctx->rank + i) % ctx->world;
         int32_t c0, w;
         col_slice(ldF, m->Pc, q % m->Pc, &c0, &w);
         // a column group that gets no columns of a narrow matrix (w == 0) still receives the flag: it waits for every rank
+        if (q == ctx->rank && m->split) { // the own slice is copied on the compute stream: the interior rows start on it at once
+            if (w > 0 && m->n_loc > 0) {
+                float *own = reinterpret_cast<float *>(peer_base(m->arena, q) + m->pc_off[op]) + (size_t)ctx->rank * m->chunk * w;
+                GNN_TRY(copy2d(ctx, own, w, src + c0, ld_src, m->n_loc, w));
+            }
+            continue;
+        }
         ranks[n] = q;
         offs[n] = m->pc_off[op] + (size_t)ctx->rank * m->chunk * w * 4;
         c0s[n] = c0;
         ws[n] = w;
+        lists[n] = (m->halo_lists && q != ctx->rank) ? m->send_list[dir][q] : nullptr; // only the rows q's structure reads
+        cnts[n] = lists[n] ? m->send_cnt[dir][q] : m->n_loc;
         n++;
     }
-    GNN_TRY(peer_scatter_begin(ctx, m->arena, 2 * op, src, ld_src, m->n_loc, n, ranks, offs, c0s, ws));
+    GNN_TRY(peer_scatter_begin(ctx, m->arena, 2 * op, src, ld_src, m->n_loc, n, ranks, offs, c0s, ws, lists, cnts));
     m->scattered[op] = 1;
     return 0;
 }
@@ -91,23 +255,38 @@ static int aggregate_grid(gnn_ctx *ctx, gnn_gcn *m, int op, int transpose, const
     const uint32_t all = ctx->world >= 32 ? 0xffffffffu : ((1u << ctx->world) - 1u);
     uint32_t rowgrp = 0;
     for (int q = 0; q < m->Pc; q++) rowgrp |= 1u << (m->gi * m->Pc + q);
-    {
-        Prof pr(ctx, m, CLS_OTHER);
-        GNN_TRY(peer_wait_mask(ctx, m->arena, 2 * op, all, true));
-    }
     int32_t c0, w;
     col_slice(ldF, m->Pc, m->gj, &c0, &w);
     const int32_t f = F - c0 < w ? F - c0 : w;
-    if (w > 0 && f > 0 && m->grp_rows > 0) {
+    const bool work = w > 0 && f > 0 && m->grp_rows > 0;
+    YDest d;
+    d.row_map = nullptr;
+    d.rows_per = (int32_t)m->chunk;
+    for (int q = 0; q < SPMM_MAX_DEST; q++)
+        d.base[q] = q < m->Pc ? reinterpret_cast<float *>(peer_base(m->arena, m->gi * m->Pc + q) + m->y_off[op]) + c0 : nullptr;
+    const float *PC = reinterpret_cast<const float *>(peer_base(m->arena, ctx->rank) + m->pc_off[op]);
+    const float *bs = bias ? bias + c0 : nullptr;
+    auto sub_spmm = [&](const gnn_gcn::SubCsr &sc) -> int { // aggregation over a row subset, rows routed through row_map
+        if (!work || sc.n == 0) return 0;
+        Prof pr(ctx, m, CLS_SPMM, f, spmm_alg_bytes(sc.n, sc.nnz, f));
+        YDest ds = d;
+        ds.row_map = sc.rows;
+        return spmm_launch(ctx, sc.n, 0, sc.nnz, sc.ptr, sc.idx, sc.val, 1, sc.max_nnz, PC, w, f, nullptr, ldF, bs, relu, nullptr, 0,
+                           true, &ds);
+    };
+    if (m->split) GNN_TRY(sub_spmm(m->sub[transpose ? 1 : 0][0])); // interior rows: only the rank's own rows are read
+    {
+        Prof pr(ctx, m, CLS_OTHER);
+        // also ordered after this rank's own scatter kernel (it reads `src`, which later kernels overwrite); with the
+        // split the interior aggregation is already enqueued, so nothing is lost by waiting here
+        GNN_TRY(peer_wait_mask(ctx, m->arena, 2 * op, all, true));
+    }
+    if (m->split) {
+        GNN_TRY(sub_spmm(m->sub[transpose ? 1 : 0][1]));           // boundary rows: after every peer's rows have landed
+    } else if (work) {
         const int64_t nnz = transpose ? g->nnz_t : g->nnz;
         Prof pr(ctx, m, CLS_SPMM, f, spmm_alg_bytes(m->grp_rows, nnz, f));
-        YDest d;
-        d.rows_per = (int32_t)m->chunk;
-        for (int q = 0; q < SPMM_MAX_DEST; q++)
-            d.base[q] = q < m->Pc ? reinterpret_cast<float *>(peer_base(m->arena, m->gi * m->Pc + q) + m->y_off[op]) + c0 : nullptr;
-        const float *PC = reinterpret_cast<const float *>(peer_base(m->arena, ctx->rank) + m->pc_off[op]);
-        GNN_TRY(spmm_rows_range(ctx, g, transpose, 0, (int32_t)m->grp_rows, 0, nnz, PC, w, f, nullptr, ldF,
-                                bias ? bias + c0 : nullptr, relu, nullptr, 0, &d));
+        GNN_TRY(spmm_rows_range(ctx, g, transpose, 0, (int32_t)m->grp_rows, 0, nnz, PC, w, f, nullptr, ldF, bs, relu, nullptr, 0, &d));
     }
     Prof pr(ctx, m, CLS_OTHER);
     GNN_TRY(peer_signal(ctx, m->arena, 2 * op + 1, rowgrp));
@@ -270,6 +449,8 @@ int gnn_gcn_create_grid(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const i
             m->y_off[op] = aoff;
             aoff += (size_t)round_up(c * (int64_t)wide * 4, 256);
         }
+    m->need_off = aoff;
+    aoff += 2 * (size_t)round_up(N, 256); // which node rows this rank's forward / backward structure block reads (setup_halo)
     const int rc = gnn_peer_arena_create(ctx, aoff, &m->arena);
     if (rc) { // no CPU or NCCL fallback for this mode: the caller picks the row partition instead
         gnn_gcn_destroy(ctx, m);
@@ -285,6 +466,7 @@ int gnn_gcn_create_grid(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const i
     m->H_local.assign(L + 1, nullptr);
     for (int32_t l = 1; l <= L; l++) GNN_TRY(alloc(&m->H_local[l], c * m->ld[l]));
     for (int32_t l = 1; l <= L; l++) m->H[l] = m->agg_first[l] ? m->H_local[l] : y_region(m, op_of(l, 0));
+    GNN_TRY(setup_halo(ctx, m));
     recompute_stats_grid(m);
     *out = m;
     return 0;

@@ -446,6 +446,13 @@ class GCN:
     def exchange_mode(self):
         return capi.load().gnn_gcn_exchange_mode(self.h)
 
+    def exchange_stats(self):
+        hf, idf = C.c_double(1.0), C.c_double(0.0)
+        hl, sp = C.c_int(0), C.c_int(0)
+        capi.call("gnn_gcn_exchange_stats", self.h, C.byref(hf), C.byref(hl), C.byref(sp), C.byref(idf))
+        return {"halo_fraction": hf.value, "halo_only_exchange": bool(hl.value), "interior_boundary_split": bool(sp.value),
+                "interior_fraction": idf.value}
+
     def exchange_desc(self):
         return {0: "no exchange (single GPU)",
                 1: "ncclAllGather of every aggregation input",

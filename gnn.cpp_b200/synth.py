@@ -63,8 +63,11 @@ def _endpoint(h: np.ndarray, N: int, powerlaw: bool) -> np.ndarray:
     return ((np.uint64(pa) * ids + np.uint64(pb)) % np.uint64(N)).astype(np.int32)
 
 
-def edges(seed: int, E: int, N: int, powerlaw: bool = False, chunk: int = 1 << 24):
-    """E directed entries from E//2 undirected pairs (symmetrised); duplicates and self loops kept."""
+def edges(seed: int, E: int, N: int, powerlaw: bool = False, chunk: int = 1 << 24, band: int = 0):
+    """E directed entries from E//2 undirected pairs (symmetrised); duplicates and self loops kept.
+    band > 0: a graph WITH locality (numpy generator only; not one of BASELINE.json's configs): pair k links a uniform
+    node u to u + 1 + (hash mod band), so a contiguous row block only needs feature rows within `band` of its ends —
+    the case the halo-only exchange and the interior/boundary overlap of the partitioned trainer are built for."""
     npairs = E // 2
     src = np.empty(E, dtype=np.int32)
     dst = np.empty(E, dtype=np.int32)
@@ -72,7 +75,11 @@ def edges(seed: int, E: int, N: int, powerlaw: bool = False, chunk: int = 1 << 2
         e = min(npairs + (E & 1), s + chunk)
         k = np.arange(s, e, dtype=np.uint64)
         u = _endpoint(hash3(seed, STREAM_EDGE_U, k), N, powerlaw)
-        v = _endpoint(hash3(seed, STREAM_EDGE_V, k), N, powerlaw)
+        if band > 0:
+            off = (hash3(seed, STREAM_EDGE_V, k) % np.uint64(band)).astype(np.int64) + 1
+            v = ((u.astype(np.int64) + off) % N).astype(np.int32)
+        else:
+            v = _endpoint(hash3(seed, STREAM_EDGE_V, k), N, powerlaw)
         m = min(e, npairs) - s
         if m > 0:
             src[s:s + m] = u[:m]; dst[s:s + m] = v[:m]
@@ -90,6 +97,7 @@ class Config:
     dims: List[int]
     powerlaw: bool = False
     config_id: int = 0
+    band: int = 0            # > 0: locality graph (see edges)
 
     @property
     def seed(self) -> int:
@@ -103,6 +111,9 @@ CONFIGS = {
     "arxiv":    Config("arxiv", 169343, 1170000, [128, 256, 256, 40], False, 3),
     "reddit":   Config("reddit", 232965, 114600000, [602, 128, 41], True, 4),
     "products": Config("products", 2450000, 61900000, [100, 256, 256, 47], True, 5),
+    # NOT a BASELINE config: the products-shaped sizes on a graph with locality (neighbours within 32,768 ids), to show what
+    # the halo-only exchange + interior/boundary overlap do when a row block does not need every remote row
+    "products_local": Config("products_local", 2450000, 61900000, [100, 256, 256, 47], False, 6, 32768),
     # small shapes for tests / smoke
     "toy":      Config("toy", 5, 8, [10, 20, 4], False, 90),
     "tiny":     Config("tiny", 200, 1200, [24, 16, 5], False, 91),
@@ -132,7 +143,7 @@ def weights(cfg: Config):
 
 
 def make_problem(cfg: Config, with_features: bool = True) -> Problem:
-    src, dst = edges(cfg.seed, cfg.E, cfg.N, cfg.powerlaw)
+    src, dst = edges(cfg.seed, cfg.E, cfg.N, cfg.powerlaw, band=cfg.band)
     if cfg.name == "toy":  # the reference's own 8-edge fixture, tests/graph.test.cpp:19-20
         src = np.array([1, 2, 3, 0, 4, 1, 2, 3], dtype=np.int32)
         dst = np.array([1, 2, 0, 1, 2, 2, 1, 1], dtype=np.int32)

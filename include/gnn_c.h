@@ -135,6 +135,9 @@ GNN_API int gnn_dense_to_coo(gnn_ctx_t *ctx, const float *A, int64_t rows, int64
  * aligned with leading dimensions that are multiples of 4 and either F % 4 == 0 or both leading dimensions equal
  * round_up(F, 4) (then the padding columns F..ld-1 of P are read and those of Y are overwritten with the aggregate of
  * P's padding); every other view — e.g. a 47-column slice of a 256-wide matrix — takes the scalar kernels. */
+/* which aggregation kernel the automatic choice takes for this structure (1 = one row per lane group, 2 = nonzero-balanced
+ * merge kernel): by degree skew, longest row >= 16 x the mean row length -> 2 (see csrc/spmm.cu use_merge). */
+GNN_API int gnn_graph_spmm_variant(gnn_ctx_t *ctx, const gnn_graph_t *g, int transpose);
 GNN_API int gnn_spmm_fwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *P, int64_t ldp, int32_t F, float *Y,
                          int64_t ldy, const float *bias, int relu, const float *mask, int64_t ldm, int use_values);
 GNN_API int gnn_spmm_bwd(gnn_ctx_t *ctx, const gnn_graph_t *g, const float *dZ, int64_t ldz, int32_t F, float *dP,
@@ -298,6 +301,11 @@ GNN_API int gnn_gcn_spmm_stats(gnn_gcn_t *m, double *alg_bytes, int32_t *n_spmm,
  * 3 peer-arena pushes by copy engines, 4 pipelined panels with in-place ncclAllGather as transport,
  * 6 2-D partition (gnn_gcn_create_grid: column-slice scatter before, fused row exchange inside every aggregation) */
 GNN_API int gnn_gcn_exchange_mode(const gnn_gcn_t *m);
+/* 2-D partition only.  halo_fraction: rows of this rank its peers' structure blocks read / (peers x local rows) — 1 means
+ * every peer needs every row (the synthetic power-law graphs), small values mean the graph has locality; halo_lists: 1 when
+ * the exchange sends only those rows (chosen when halo_fraction < 0.9); split: 1 when the aggregation runs as interior rows
+ * (only own rows needed, overlapping the exchange) + boundary rows; interior_fraction: interior rows / structure rows. */
+GNN_API int gnn_gcn_exchange_stats(const gnn_gcn_t *m, double *halo_fraction, int *halo_lists, int *split, double *interior_fraction);
 /* Fused trainer under a 2-D partition of the aggregation: world = Pr row groups x Pc feature-column groups, this rank =
  * gi * Pc + gj.  `g` holds the structure rows of row group gi — gnn_graph_slice_rows(global, lo, hi) with
  * lo = min(N, gi Pc c), hi = min(N, (gi+1) Pc c), c = ceil(N / world) — all columns.  Activations, X and y stay 1-D

@@ -69,10 +69,15 @@ def main():
     big = synth.Config("mid_pl", 250000, 5000000, [40, 96, 64, 19], True, 96)     # >= 200 k nodes
     cfgs = [synth.CONFIGS["tiny_pl"], synth.Config("odd", 1237, 9000, [20, 33, 12, 6], True, 95),
             synth.Config("widen", 1500, 12000, [12, 8, 24, 5], True, 97)]      # layer 2 aggregates first with l > 1
+    # a graph with locality: every rank's structure block needs only a band of remote rows, so the halo-only exchange
+    # (send lists) and the interior/boundary split of csrc/trainer_grid.cu are what runs (2-D partition modes)
+    cfgs.append(synth.Config("local", 40000, 600000, [24, 40, 16, 6], False, 99, 1500))
     if os.environ.get("GNN_DIST_BIG", "1") != "0":
         cfgs.append(big)
     for cfg in cfgs:
         for mask in (None, 0, 0xFF):
+            if cfg.name == "local" and mask == 0xFF:
+                continue
             if cfg.name == "mid_pl" and mask is not None:
                 continue                      # the big graph runs the automatic layer order only
             p = synth.make_problem(cfg)
@@ -95,6 +100,13 @@ def main():
             if mask is not None:
                 m.set_option("agg_first_mask", mask)
             m.set_params(p.W, p.b)
+            if cfg.name == "local" and grid is not None:
+                st = m.exchange_stats()
+                if rank == 0:
+                    print("[dist_check] local: %s" % st, flush=True)
+                if os.environ.get("GNN_HALO") is None and os.environ.get("GNN_SPLIT") is None:
+                    ok &= st["halo_only_exchange"] and st["halo_fraction"] < 0.5
+                    ok &= st["interior_boundary_split"] == (st["interior_fraction"] >= 0.1)
             if cfg.name == "mid_pl":
                 ok &= check_big(ctx, m, p, cfg, X, yb, lo, hi, rank, world, grid)
                 m.close(); g.close(); gfull.close()

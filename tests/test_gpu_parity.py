@@ -897,3 +897,26 @@ def test_partition_arrays_bit_exact(ctx, oracle, name, world):
     if name == "local":
         assert seen_interior > 0.8 * 2 * N          # the banded graph is mostly interior: the overlap has work to hide behind
     gfull.close()
+
+
+def test_spmm_variant_follows_degree_skew(ctx, oracle):
+    """north star: "warp-per-row and merge-path variants chosen by degree skew" — the automatic choice takes the rows
+    kernel on a uniform-degree graph and the nonzero-balanced kernel on a power-law graph of the same size, and both
+    give the oracle's result there."""
+    import torch
+    from gnn_cpp_b200 import capi, host, synth
+    N, E, F = 60000, 1500000, 40
+    P = np.random.default_rng(3).uniform(-1, 1, (N, F)).astype(np.float32)
+    for powerlaw, want in ((False, 1), (True, 2)):
+        src, dst = synth.edges(11, E, N, powerlaw=powerlaw)
+        g = host.Graph.build(ctx, src, dst, N)
+        deg = g.export(csc=False)["deg"]
+        skew = deg.max() / deg.mean()
+        assert (skew >= 16) == powerlaw, skew
+        assert capi.load().gnn_graph_spmm_variant(ctx.h, g.h, 0) == want
+        assert capi.load().gnn_graph_spmm_variant(ctx.h, g.h, 1) == want
+        G = oracle.Graph(src, dst, N)
+        ref = oracle.spmm(N, G.rowptr, G.colidx, G.val, P, order=1)
+        got = g.spmm_fwd(_dev(P, ctx)).cpu().numpy()
+        assert rel_err(got, ref) <= TOL
+        g.close()

@@ -20,6 +20,8 @@ widths = [int(a) for a in sys.argv[1:] if a.isdigit()] or [4, 8, 12, 16, 24, 32,
 cfg = synth.CONFIGS[cfg_name]
 src, dst = synth.edges(cfg.seed, cfg.E, cfg.N, cfg.powerlaw)
 ctx = host.Context(0)
+if os.environ.get("PROBE_VARIANT"):          # 1 = one row per lane group, 2 = nonzero-balanced merge kernel, 0 = automatic choice
+    capi.call("gnn_set_spmm_variant", ctx.h, int(os.environ["PROBE_VARIANT"]))
 N = cfg.N
 
 
