@@ -234,7 +234,7 @@ def run_ours(args):
         lo, hi = min(cfg.N, rank * chunk), min(cfg.N, (rank + 1) * chunk)
         # partition of the aggregation: 1-D rows ("row") or Pr x Pc row groups x feature-column groups (csrc/trainer_grid.cu)
         ge = os.environ.get("GNN_GRID", "auto")
-        grid = dist_plan.default_grid(world) if ge == "auto" else (None if ge in ("", "row") else tuple(int(x) for x in ge.lower().split("x")))
+        grid = dist_plan.choose_grid(cfg.N, world, p.src, p.dst) if ge == "auto" else (None if ge in ("", "row") else tuple(int(x) for x in ge.lower().split("x")))
         if grid is not None and os.environ.get("GNN_COMM") == "nccl":
             grid = None                     # the ncclAllGather ablation is a row-partition schedule
         if grid is None:

@@ -91,10 +91,27 @@ def grid_partition(N, world, Pc, rank):
 
 
 def default_grid(world):
-    """(Pr, Pc) bench.py uses per world size (GNN_GRID=PrxPc overrides): the 1-D row partition (None) up to 2 ranks,
-    where its exchange still hides behind the aggregation; 2 row groups beyond, which bounds the loss of SpMM
-    efficiency from narrow column slices while cutting the received bytes ~2x (4 ranks) / ~3x (8 ranks)."""
-    return None if world <= 2 else (2, world // 2)
+    """(Pr, Pc) for a graph WITHOUT locality (every rank needs practically every remote row, as on the synthetic power-law
+    graphs).  Measured on the products-shaped step, ms (profiles/r2_scaling_products.md):
+        2 GPUs: 1-D rows 29.0 | 1x2 27.5          4 GPUs: rows 17.6 | 2x2 16.7 | 1x4 16.9          8 GPUs: rows 14.8 | 2x4 10.2 | 4x2 11.7 | 1x8 12.5
+    Two row groups bound the loss of SpMM efficiency from narrow column slices while cutting the received bytes."""
+    return (1, 2) if world == 2 else (2, world // 2)
+
+
+def choose_grid(N, world, src, dst, sample=2_000_000):
+    """Partition of the aggregation for this graph: when most edges stay inside a rank's contiguous row block (a graph
+    WITH locality) the rows x 1 partition with the halo-only exchange and the interior/boundary overlap moves almost
+    nothing (products-sized band graph, 4 GPUs: 8.3 ms vs 9.8 ms for 2x2 and 13.6 ms for the all-gather); otherwise
+    default_grid.  Decided from a sample of the edge list: fraction of edges whose endpoints live on different ranks."""
+    if world <= 1:
+        return None
+    c = chunk_rows(N, world)
+    E = len(src)
+    if E == 0:
+        return (world, 1)
+    step = max(1, E // sample)
+    remote = float(np.mean((np.asarray(src[::step], dtype=np.int64) // c) != (np.asarray(dst[::step], dtype=np.int64) // c)))
+    return (world, 1) if remote < 0.25 else default_grid(world)
 
 
 def comm_bytes_per_step_grid(N, dims, world, Pc):

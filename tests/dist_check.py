@@ -23,7 +23,7 @@ def parse_grid(world):
     if e in ("", "row"):
         return None
     if e == "auto":
-        return dist_plan.default_grid(world)
+        return dist_plan.default_grid(world)       # (bench.py's choose_grid also looks at the edge list)
     pr, pc = (int(x) for x in e.lower().split("x"))
     assert pr * pc == world, "GNN_GRID=%s does not match world %d" % (e, world)
     return pr, pc
@@ -111,26 +111,29 @@ def main():
                 ok &= check_big(ctx, m, p, cfg, X, yb, lo, hi, rank, world, grid)
                 m.close(); g.close(); gfull.close()
                 continue
-            losses = [float(m.train_step(X, yb, 0.05).cpu()[0]) for _ in range(3)]
+            # three SGD steps, each held to the plain 1e-5 against the oracle stepping from the SAME parameters (the oracle
+            # continues from the product's parameters, so per-step differences do not compound)
             L = len(cfg.dims) - 1
-            grads = [m.grads(l) for l in range(1, L + 1)]
-            params = [m.params(l) for l in range(1, L + 1)]
-            logits = m.activation(L)
-            if rank == 0:
-                from oracle import oracle as orc
-                G = orc.Graph(p.src, p.dst, cfg.N)
-                W = [w.copy() for w in p.W]; b = [x.copy() for x in p.b]
-                for it in range(3):
+            from oracle import oracle as orc
+            G = orc.Graph(p.src, p.dst, cfg.N) if rank == 0 else None
+            W = [w.copy() for w in p.W]; b = [x.copy() for x in p.b]
+            errs, losses = [], []
+            for it in range(3):
+                losses.append(float(m.train_step(X, yb, 0.05).cpu()[0]))
+                grads = [m.grads(l) for l in range(1, L + 1)]
+                params = [m.params(l) for l in range(1, L + 1)]
+                logits = m.activation(L)
+                if rank == 0:
                     ref = orc.train_step(G, cfg.dims, p.X, p.y, W, b, lr=0.05, order=1)
-                    e = abs(losses[it] - ref["loss"]) / abs(ref["loss"])
-                    ok &= e <= 2e-5
-                errs = []
-                for l in range(L):
-                    errs.append(np.abs(grads[l][0] - ref["dW%d" % (l + 1)]).max() / np.abs(ref["dW%d" % (l + 1)]).max())
-                    errs.append(np.abs(grads[l][1] - ref["db%d" % (l + 1)]).max() / np.abs(ref["db%d" % (l + 1)]).max())
-                    errs.append(np.abs(params[l][0] - W[l]).max() / np.abs(W[l]).max())
-                errs.append(np.abs(logits - ref["Z%d" % L][lo:hi]).max() / np.abs(ref["Z%d" % L]).max())
-                ok &= max(errs) <= 2e-5
+                    errs.append(abs(losses[it] - ref["loss"]) / abs(ref["loss"]))
+                    for l in range(L):
+                        errs.append(np.abs(grads[l][0] - ref["dW%d" % (l + 1)]).max() / np.abs(ref["dW%d" % (l + 1)]).max())
+                        errs.append(np.abs(grads[l][1] - ref["db%d" % (l + 1)]).max() / np.abs(ref["db%d" % (l + 1)]).max())
+                        errs.append(np.abs(params[l][0] - W[l]).max() / np.abs(W[l]).max())
+                        W[l][...] = params[l][0]; b[l][...] = params[l][1]
+                    errs.append(np.abs(logits - ref["Z%d" % L][lo:hi]).max() / np.abs(ref["Z%d" % L]).max())
+            if rank == 0:
+                ok &= max(errs) <= 1e-5
                 print("[dist_check] %s world=%d grid=%s mode=%d mask=%s loss=%.6f ref=%.6f max_rel_err=%.2e" %
                       (cfg.name, world, grid, m.exchange_mode(), mask, losses[-1], ref["loss"], max(errs)), flush=True)
             m.close(); g.close(); gfull.close()

@@ -192,6 +192,13 @@ def test_grid_partition_rules():
     assert rows == (5 * 306250, 6 * 306250) and grp == (4 * 306250, 2450000)
     (rows, grp) = dist_plan.grid_partition(10, 4, 2, 3)
     assert rows == (9, 10) and grp == (6, 10)
+    # the automatic choice: power-law endpoints -> 2 row groups x column groups; a band graph -> rows x 1 (halo-only exchange)
+    from gnn_cpp_b200 import synth
+    s1, d1 = synth.edges(5, 200000, 50000, True)
+    s2, d2 = synth.edges(5, 200000, 50000, False, band=500)
+    assert dist_plan.choose_grid(50000, 8, s1, d1) == (2, 4) and dist_plan.choose_grid(50000, 4, s1, d1) == (2, 2)
+    assert dist_plan.choose_grid(50000, 2, s1, d1) == (1, 2) and dist_plan.choose_grid(50000, 1, s1, d1) is None
+    assert dist_plan.choose_grid(50000, 8, s2, d2) == (8, 1) and dist_plan.choose_grid(50000, 4, s2, d2) == (4, 1)
     # received bytes per rank and step, products-shaped: the 2 x 4 grid moves ~2.7x less than the all-gather
     dims = [100, 256, 256, 47]
     ag = dist_plan.comm_bytes_per_step(2450000, dims, 8)

@@ -122,11 +122,18 @@ def test_train_step_full_size_properties(ctx, big):
     y = torch.from_numpy(synth.labels(cfg.seed, synth.STREAM_Y, cfg.N, cfg.dims[-1])).to(ctx.device)
     W, b = synth.weights(cfg)
 
-    def run(precision=1, variant=0, Ws=None, lr=0.0, steps=1):
+    import os
+    from conftest import GOLDEN
+    gold = np.load(os.path.join(GOLDEN, "bench_parity_%s.npz" % cfg.name))   # the exact oracle's first-step gradients + ReLU tie list
+
+    def run(precision=1, variant=0, Ws=None, lr=0.0, steps=1, ties=False):
         capi.call("gnn_set_spmm_variant", ctx.h, variant)
         m = host.GCN(ctx, g, cfg.dims)
         m.set_option("precision", precision)
         m.set_params(Ws if Ws is not None else W, b)
+        if ties:   # hidden pre-activations within 1e-5 max|Z| of zero take the oracle's side of `Z > 0` (gnn_gcn_set_relu_overrides)
+            for l in range(1, L):
+                m.set_relu_overrides(l, gold["kink%d_rows" % l], gold["kink%d_cols" % l].astype(np.int32), gold["kink%d_pos" % l])
         losses = [float(m.train_step(X, y, lr).cpu()[0]) for _ in range(steps)]
         grads = [m.grads(l) for l in range(1, L + 1)]
         m.close()
@@ -136,17 +143,16 @@ def test_train_step_full_size_properties(ctx, big):
     (l1,), g1 = run()
     (l1b,), g1b = run()
     assert l1 == l1b and all(np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1]) for a, c in zip(g1, g1b)), "bit-reproducible"
-    (l0,), g0 = run(precision=0)
-    assert abs(l0 - l1) <= TOL * abs(l0)
-    # dW is a sum over millions of node rows with heavy cancellation (|dW| << sum |terms|): ANY fp32 accumulation
-    # order, the reference's sequential one included, differs from another by ~sqrt(n) ulp of the term magnitude
-    # (measured 1.7e-4 of max|dW1| at n = 2.45 M); the dense transforms are checked against fp64 at this size below
-    for l in range(L):
-        assert rel_err(g1[l][0], g0[l][0]) <= 1e-3 and rel_err(g1[l][1], g0[l][1]) <= 1e-3, ("3xTF32 vs FP32 FMA", l)
-    (lr_,), gr = run(variant=1)
-    assert abs(lr_ - l1) <= TOL * abs(l1)
-    for l in range(L):
-        assert rel_err(gr[l][0], g1[l][0]) <= 1e-3, ("rows vs merge kernel", l)
+    # every code path — tcgen05 3xTF32 and FP32-FMA transforms, the automatic / rows / merge aggregation kernels —
+    # against the EXACT oracle's gradients of this config (tests/golden/bench_parity_*.npz) at the plain 1e-5.  (Round 1
+    # compared the paths with each other at 1e-3: the differences were ReLU ties — a pre-activation within rounding of
+    # zero flips `Z > 0` and moves dW_1 by up to 1e-4 of its tiny largest entry — not accumulation error; with the ties
+    # taken from the oracle every path is within 5e-6.)
+    for kw in (dict(), dict(precision=0), dict(variant=1), dict(variant=2)):
+        (lk,), gk = run(ties=True, **kw)
+        assert abs(lk - float(gold["loss"][0])) <= TOL * abs(float(gold["loss"][0])), kw
+        for l in range(L):
+            assert rel_err(gk[l][0], gold["dW%d" % (l + 1)]) <= TOL and rel_err(gk[l][1], gold["db%d" % (l + 1)]) <= TOL, (kw, l)
     # loss falls over SGD steps
     ls, _ = run(lr=0.05, steps=4)
     assert all(np.isfinite(ls)) and ls[-1] < ls[0]

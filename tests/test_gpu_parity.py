@@ -145,18 +145,24 @@ def test_weighted_adjacency_vs_reference(ctx, oracle, name):
     rows = np.repeat(np.arange(N), np.diff(G.rowptr))
     ref_dense = np.zeros((N, N), np.float32); ref_dense[rows, G.colidx] = G.val0
     assert np.array_equal(dense, ref_dense)
-    # whole train step on the weighted graph vs the restatement
-    ref = oracle.train_step(G, p.cfg.dims, p.X, p.y, [x.copy() for x in p.W], [x.copy() for x in p.b], order=1)
-    m = host.GCN(ctx, g, p.cfg.dims)
+    # whole train step on the weighted graph vs the restatement (plain 1e-5; the backward of the restatement takes the
+    # product's side on ReLU ties, after checking that every differing entry sits within 1e-5 max|Z| of zero)
+    dims, L = p.cfg.dims, len(p.cfg.dims) - 1
+    m = host.GCN(ctx, g, dims)
     m.set_params(p.W, p.b)
     loss = float(m.train_step(_dev(p.X, ctx), _dev(p.y, ctx), 0.0).cpu()[0])
+    Hs, Zs = oracle.forward_composed(G, dims, p.X, p.W, p.b, order=1)
+    masks = []
+    for l in range(1, L):
+        mk = m.activation(l) > 0
+        diff = mk != (Zs[l - 1] > 0)
+        assert np.abs(Zs[l - 1][diff]).max(initial=0.0) <= TOL * np.abs(Zs[l - 1]).max()
+        masks.append(mk)
+    ref = oracle.backward_composed(G, dims, Hs, Zs, p.y, p.W, order=1, masks=masks)
     assert abs(loss - ref["loss"]) <= TOL * abs(ref["loss"])
-    out = {"dZ": m.dlogits()}
-    for l in range(1, len(p.cfg.dims)):
-        out["A%d" % l] = m.activation(l)
-        out["dW%d" % l], out["db%d" % l] = m.grads(l)
-    for l in range(1, len(p.cfg.dims)):
-        assert rel_err(out["dW%d" % l], ref["dW%d" % l]) <= 5 * TOL and rel_err(out["db%d" % l], ref["db%d" % l]) <= 5 * TOL
+    for l in range(1, L + 1):
+        dW, db = m.grads(l)
+        assert rel_err(dW, ref["dW%d" % l]) <= TOL and rel_err(db, ref["db%d" % l]) <= TOL
     m.close(); g.close()
 
 
@@ -482,13 +488,17 @@ def test_trainer_adam_and_train_mask(ctx, oracle):
                 dZ = oracle.relu_bwd(oracle.gemm_nn(dP, W[l], 1), Zs[l - 1])
         grads = grads[::-1]
         loss = float(m.train_step(X, yd, 0.01).cpu()[0])
-        assert abs(loss - loss_ref) <= 2 * TOL * abs(loss_ref), it
+        assert abs(loss - loss_ref) <= TOL * abs(loss_ref), it
         for l in range(L):
             oracle.adam_step(W[l], grads[l][0], mom[l][0], vel[l][0], lr=0.01, step=it + 1)
             oracle.adam_step(b[l], grads[l][1], mom[l][1], vel[l][1], lr=0.01, step=it + 1)
-    for l in range(L):
-        Wg, bg = m.params(l + 1)
-        assert rel_err(Wg, W[l]) <= 1e-4 and rel_err(bg, b[l]) <= 1e-4   # Adam divides by sqrt(v): amplifies rounding
+        # One Adam step moves every parameter by ~lr whatever the gradient's size (g / sqrt(v)), so a 1e-6 relative
+        # difference in a tiny gradient entry is a 1e-6 * lr difference in the parameter: compare the UPDATE, relative
+        # to the step size, then continue from the product's parameters so that nothing compounds over the steps
+        for l in range(L):
+            Wg, bg = m.params(l + 1)
+            assert np.abs(Wg - W[l]).max() <= TOL * max(np.abs(W[l]).max(), 1.0) and np.abs(bg - b[l]).max() <= TOL * max(np.abs(b[l]).max(), 1.0), it
+            W[l][...] = Wg; b[l][...] = bg
     acc = m.accuracy(yd, torch.from_numpy(~mask).to(ctx.device))
     assert 0 <= acc <= int((~mask).sum())
     m.close(); g.close()
@@ -528,7 +538,12 @@ def test_gcnconv_as_written_vs_reference(ctx, oracle, name):
     dZ = np.random.default_rng(5).standard_normal(ref["Z"].shape).astype(np.float32)
     colptr, rowidx, _ = oracle.csc_from_csr(N, ref["rowptr"], ref["colidx"])
     dh_ref = oracle.spmm(N, colptr, rowidx, ref["norm"][rowidx], dZ, order=1)
-    dlin_ref, dg_ref, dbeta_ref = oracle.batchnorm_bwd(ref["lin"], ref["mean"], ref["var"], gamma, dh_ref, relu_out=ref["h"])
+    # the ReLU mask of the backward is the product's own (ties within rounding of zero may fall on either side; the
+    # forward above already pinned h itself to 1e-5)
+    h_gpu = h.cpu().numpy()
+    tie = (h_gpu > 0) != (ref["h"] > 0)
+    assert np.abs(ref["bn"][tie]).max(initial=0.0) <= TOL * np.abs(ref["bn"]).max()
+    dlin_ref, dg_ref, dbeta_ref = oracle.batchnorm_bwd(ref["lin"], ref["mean"], ref["var"], gamma, dh_ref, relu_out=h_gpu)
     dW_ref = oracle.gemm_tn(dlin_ref, p.X, order=1)
     dZd = _dev(dZ, ctx)
     db = host.bias_grad(ctx, dZd)
@@ -537,8 +552,7 @@ def test_gcnconv_as_written_vs_reference(ctx, oracle, name):
     dW = host.gemm_tn(ctx, dlin, X, precision=0)
     assert rel_err(db.cpu().numpy(), oracle.bias_grad(dZ, order=1)) <= TOL
     assert rel_err(dh.cpu().numpy(), dh_ref) <= TOL
-    # pre-activations within rounding of zero may take the other side of the ReLU kink (see _check_grads)
-    tol_b = TOL if name != "cora" else 5 * TOL
+    tol_b = TOL
     assert rel_err(dlin.cpu().numpy(), dlin_ref) <= tol_b and rel_err(dg.cpu().numpy(), dg_ref) <= tol_b
     assert rel_err(dbeta.cpu().numpy(), dbeta_ref) <= tol_b and rel_err(dW.cpu().numpy(), dW_ref) <= tol_b
     g.close()
@@ -579,11 +593,11 @@ def test_mlp_layernorm_tanh_dropout_vs_reference(ctx, oracle, name):
         lin, mean, rstd, gam, Hn = saved
         dY = rng.standard_normal(tuple(lin.shape)).astype(np.float32)
         Yr, mr, rr = oracle.layernorm_fwd(lin.cpu().numpy(), gam, (0.25 * (gam - 1) / 0.5).astype(np.float32), relu=True, order=1)
-        dXr, dgr, dbr = oracle.layernorm_bwd(lin.cpu().numpy(), mr, rr, gam, dY, relu_out=Yr)
+        dXr, dgr, dbr = oracle.layernorm_bwd(lin.cpu().numpy(), mr, rr, gam, dY, relu_out=Hn.cpu().numpy())  # the product's ReLU side on ties
         dX, dg, db = host.layernorm_bwd(ctx, lin, mean, rstd, _dev(gam, ctx), _dev(dY, ctx), relu_out=Hn)
         assert rel_err(Hn.cpu().numpy(), Yr) <= TOL and rel_err(rstd.cpu().numpy(), rr) <= TOL
-        assert rel_err(dX.cpu().numpy(), dXr) <= 2 * TOL and rel_err(dg.cpu().numpy(), dgr) <= 2 * TOL
-        assert rel_err(db.cpu().numpy(), dbr) <= 2 * TOL
+        assert rel_err(dX.cpu().numpy(), dXr) <= TOL and rel_err(dg.cpu().numpy(), dgr) <= TOL
+        assert rel_err(db.cpu().numpy(), dbr) <= TOL
     x = rng.standard_normal(100003).astype(np.float32)
     for pdrop, seed in [(0.0, 1), (0.3, 5), (0.75, 123456789)]:
         assert np.array_equal(host.dropout(ctx, _dev(x, ctx), pdrop, seed).cpu().numpy(), oracle.dropout_fwd(x, pdrop, seed))
@@ -671,10 +685,13 @@ def test_sgd_training_tracks_oracle(ctx, oracle, name):
     for _ in range(5):
         ref = oracle.train_step(G, p.cfg.dims, p.X, p.y, W, b, lr=0.05, order=1)
         loss = float(m.train_step(X, y, 0.05).cpu()[0])
-        assert abs(loss - ref["loss"]) <= 2 * TOL * abs(ref["loss"])
-    for l in range(1, len(p.cfg.dims)):
-        Wg, bg = m.params(l)
-        assert rel_err(Wg, W[l - 1]) <= 2 * TOL and rel_err(bg, b[l - 1]) <= 2 * TOL
+        assert abs(loss - ref["loss"]) <= TOL * abs(ref["loss"])
+        # every step is held to the plain 1e-5; the restatement then continues from the product's parameters so that the
+        # per-step differences do not compound over the five steps
+        for l in range(1, len(p.cfg.dims)):
+            Wg, bg = m.params(l)
+            assert rel_err(Wg, W[l - 1]) <= TOL and rel_err(bg, b[l - 1]) <= TOL
+            W[l - 1][...] = Wg; b[l - 1][...] = bg
     m.close(); g.close()
 
 
