@@ -1,4 +1,4 @@
-"""bench.py contract checks that need no GPU: the JSON line of the last measured run (profiles/r1b_bench_products.json)
+"""bench.py contract checks that need no GPU: the JSON line of the last measured run (profiles/r2_bench_products_1gpu.json)
 carries every key the driver reads, and the reference arm (`--impl reference`) runs on host cores alone."""
 import json
 import os
@@ -23,7 +23,7 @@ def _check_common(d):
 
 
 def test_last_measured_line_has_the_contract_keys():
-    with open(os.path.join(ROOT, "profiles", "r1b_bench_products.json")) as f:
+    with open(os.path.join(ROOT, "profiles", "r2_bench_products_1gpu.json")) as f:
         d = json.loads(f.read().strip().splitlines()[-1])
     _check_common(d)
     r = d["roofline"]
@@ -34,6 +34,13 @@ def test_last_measured_line_has_the_contract_keys():
     assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["clocks"]["sm_mhz"] and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert d["scaling"] == "strong" and d["n_gpus"] == 1 and d["warmup"] >= 3
+    # round 2: the CPU leg ran the SAME config (one full step through the port), parity against the exact oracle is green,
+    # the e2e leg says it is pipelined, the dense transforms carry their own roofline
+    assert d["cpu_baseline"]["same_config"] is True and d["cpu_baseline"]["cores"] >= 1
+    assert d["parity"]["ok"] is True and d["parity"]["max_rel_err"] <= 1e-5
+    assert d["e2e"]["pipelined"] is True and d["roofline"]["traffic_source"].startswith("static")
+    g = d["gemm_roofline"]
+    assert 0 < g["frac"] <= 1.0 and g["tf32_peak_tflops_measured"] > 500
 
 
 def test_reference_arm_runs_on_host_cores():

@@ -269,12 +269,16 @@ def test_spmm_variants_vs_oracle(ctx, oracle, F, variant):
 
 
 def test_spmm_variant_auto_choice(ctx, oracle):
-    """auto (0): graphs whose rows all own a nonzero go to the nonzero-balanced merge kernel (2 launches: kernel +
-    fix-up) whatever the skew; a matrix with an empty row is routed to the rows kernel (1 launch)."""
-    from gnn_cpp_b200 import host
+    """auto (0): the kernel follows the degree skew (longest row >= 16 x the mean -> the nonzero-balanced merge kernel,
+    2 launches: kernel + fix-up; otherwise one row per lane group, 1 launch) and is what gnn_graph_spmm_variant reports;
+    a matrix with an empty row is always routed to the rows kernel."""
+    from gnn_cpp_b200 import capi, host
     F = 64
-    for (src, dst, N), want in [((load_problem("tiny_pl").src, load_problem("tiny_pl").dst, 3000), 2), (_hub_problem(), 2)]:
+    for (src, dst, N), hub in [((load_problem("tiny_pl").src, load_problem("tiny_pl").dst, 3000), False), (_hub_problem(), True)]:
         g = host.Graph.build(ctx, src, dst, N)
+        want = capi.load().gnn_graph_spmm_variant(ctx.h, g.h, 0)
+        deg = g.export(csc=False)["deg"]
+        assert want == (2 if deg.max() >= 16 * (g.nnz // N + 1) else 1) and (not hub or want == 2)
         P = _dev(np.ones((N, F), np.float32), ctx)
         l0 = ctx.launches
         g.spmm_fwd(P)
