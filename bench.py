@@ -257,7 +257,19 @@ def run_ours(args):
     X.copy_(torch.from_numpy(p.X[lo:hi]))
     ybuf = torch.zeros(rows_alloc, dtype=torch.int32, device=ctx.device)
     ybuf[:n_loc].copy_(torch.from_numpy(p.y[lo:hi]))
-    model = host.GCN(ctx, g, cfg.dims) if grid is None else host.GCN(ctx, g, cfg.dims, grid=grid, n_loc=n_loc)
+    if grid is not None:
+        try:
+            model = host.GCN(ctx, g, cfg.dims, grid=grid, n_loc=n_loc)
+        except Exception as e:  # noqa: BLE001  (CUDA IPC peer mapping unavailable on this box: every rank gets the same status)
+            if rank == 0:
+                log("[bench] 2-D partition unavailable (%s): falling back to the 1-D row partition" % e)
+            g.close()
+            gfull = host.Graph.build(ctx, torch.from_numpy(p.src).to(ctx.device), torch.from_numpy(p.dst).to(ctx.device), cfg.N)
+            g = gfull.slice_rows(lo, hi)
+            gfull.close()
+            grid = None
+    if grid is None:
+        model = host.GCN(ctx, g, cfg.dims)
     model.set_option("precision", args.precision)
     model.set_params(p.W, p.b)
     loss_d = torch.zeros(1, dtype=torch.float32, device=ctx.device)
