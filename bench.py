@@ -87,6 +87,37 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+class NvlinkCounter:
+    """NVLink payload bytes this GPU sent / received (NVML throughput counters, summed over its links), read before and
+    after the timed region: the measured exchange volume next to the algorithmic one of the partition plan."""
+
+    def __init__(self, device):
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.ids = [pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX]
+        except Exception:  # noqa: BLE001
+            self.h = None
+
+    def read(self):
+        """(tx_bytes, rx_bytes) or None"""
+        if self.h is None:
+            return None
+        try:
+            vals = []
+            for fid in self.ids:   # scopeId UINT_MAX = all links of the device
+                v = self.nv.nvmlDeviceGetFieldValues(self.h, [(fid, 0xFFFFFFFF)])[0]
+                if v.nvmlReturn != 0:
+                    return None
+                vals.append(int(v.value.ullVal) * 1024)    # the counters are in KiB
+            return tuple(vals)
+        except Exception:  # noqa: BLE001
+            return None
+
+
 # ------------------------------------------------------------------------------------------------ CPU arms
 def host_threads():
     try:
@@ -302,7 +333,10 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = ctx.launches
+    nvl = NvlinkCounter(local_rank) if world > 1 else None
+    nv0 = nvl.read() if nvl else None
     total_ms = timed(step, args.steps)
+    nv1 = nvl.read() if nvl else None
     launches = ctx.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
@@ -437,6 +471,17 @@ def run_ours(args):
                      "mma_floor_ms": mma_ms, "tf32_peak_tflops_measured": tf32.value,
                      "how": "floor = sum over launches of max(operand+output bytes / HBM peak, 3 * 2MNK / measured TF32 peak)"}
 
+    nvlink = None
+    if world > 1:
+        from gnn_cpp_b200 import dist_plan as _dp
+        alg = (_dp.comm_bytes_per_step(cfg.N, cfg.dims, world) if grid is None
+               else _dp.comm_bytes_per_step_grid(cfg.N, cfg.dims, world, grid[1]))
+        nvlink = {"algorithmic_rx_bytes_per_step": int(alg),
+                  "what": "bytes rank 0 receives per step by the partition plan (every needed row once; full halo) vs NVML NVLink payload counters of GPU 0 over the timed region"}
+        if nv0 and nv1:
+            nvlink.update({"measured_tx_bytes_per_step": (nv1[0] - nv0[0]) / args.steps, "measured_rx_bytes_per_step": (nv1[1] - nv0[1]) / args.steps,
+                           "rx_gbs_over_step": (nv1[1] - nv0[1]) / args.steps / (ms_per_step * 1e-3) / 1e9})
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -467,7 +512,7 @@ def run_ours(args):
                 "breakdown_ms": bd,
                 "gemm_tflops": st["gemm_flops"] / (bd["gemm"] * 1e-3) / 1e12 if bd["gemm"] > 0 else None,
                 "gemm_roofline": gemm_roof,
-                "cpu_baseline": cpu, "parity": parity,
+                "cpu_baseline": cpu, "parity": parity, "nvlink": nvlink,
                 "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(Xh.numel() * 4 + yh.numel() * 4),
                         "d2h_bytes_per_step": 4, "api": "gnn_gcn_train_step_h (pinned host buffers)", "pipelined": True,
                         "pipelining": "the upload of step i+1's inputs (copy stream, double-buffered) overlaps step i's kernels; every step's inputs cross PCIe once inside the timed region and its loss is read back"},
