@@ -91,15 +91,17 @@ void *gnn_ctx_stream(gnn_ctx_t *ctx) { return (void *)ctx->stream; }
 int gnn_ctx_sm_count(gnn_ctx_t *ctx) { return ctx->sm_count; }
 int64_t gnn_ctx_launch_count(gnn_ctx_t *ctx) { return ctx->launches; }
 
+// Tensor storage comes from the stream-ordered pool (release threshold = keep everything, see gnn_ctx_create): the op-node
+// path of the C++ surface allocates an output per operation, ~40 per train step — with cudaMalloc / synchronising cudaFree
+// each of them was a device-wide synchronisation; from the pool a steady-state step allocates nothing new.
 int gnn_malloc(gnn_ctx_t *ctx, void **ptr, size_t bytes) {
     GNN_CHECK_CUDA(cudaSetDevice(ctx->device));
-    GNN_CHECK_CUDA(cudaMalloc(ptr, bytes ? bytes : 4));
+    GNN_CHECK_CUDA(cudaMallocAsync(ptr, bytes ? bytes : 4, ctx->stream));
     return 0;
 }
 int gnn_free(gnn_ctx_t *ctx, void *ptr) {
     if (!ptr) return 0;
-    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-    GNN_CHECK_CUDA(cudaFree(ptr));
+    GNN_CHECK_CUDA(cudaFreeAsync(ptr, ctx->stream)); // ordered after everything already enqueued on the context's stream
     return 0;
 }
 int gnn_memset(gnn_ctx_t *ctx, void *ptr, int value, size_t bytes) {
