@@ -102,19 +102,31 @@ class NvlinkCounter:
         except Exception:  # noqa: BLE001
             self.h = None
 
+    def _field(self, fid, scope):
+        v = self.nv.nvmlDeviceGetFieldValues(self.h, [(fid, scope)])[0]
+        if v.nvmlReturn != 0:
+            return None
+        t = v.valueType   # NVML_VALUE_TYPE_*: 0 double, 1 unsigned int, 2 unsigned long, 3 unsigned long long, 4 signed long long
+        return int({0: v.value.dVal, 1: v.value.uiVal, 2: v.value.ulVal, 3: v.value.ullVal, 4: v.value.sllVal}.get(t, v.value.ullVal))
+
     def read(self):
         """(tx_bytes, rx_bytes) or None"""
         if self.h is None:
             return None
         try:
             vals = []
-            for fid in self.ids:   # scopeId UINT_MAX = all links of the device
-                v = self.nv.nvmlDeviceGetFieldValues(self.h, [(fid, 0xFFFFFFFF)])[0]
-                if v.nvmlReturn != 0:
-                    return None
-                vals.append(int(v.value.ullVal) * 1024)    # the counters are in KiB
+            for fid in self.ids:
+                v = self._field(fid, 0xFFFFFFFF)            # scope UINT_MAX = all links of the device
+                if v is None:                               # older drivers: per-link scopes only
+                    per = [self._field(fid, l) for l in range(18)]
+                    per = [x for x in per if x is not None]
+                    if not per:
+                        return None
+                    v = sum(per)
+                vals.append(v * 1024)                       # the counters are in KiB
             return tuple(vals)
-        except Exception:  # noqa: BLE001
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
             return None
 
 

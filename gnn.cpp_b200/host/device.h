@@ -31,6 +31,15 @@ inline gnn_ctx_t *ctx() {
     return c;
 }
 inline void sync() { check(gnn_ctx_sync(ctx())); }
+/** dense-transform arithmetic of the layer nodes: 1 = 3xTF32 on tcgen05 (FP32-accurate to ~1e-6, falls back per shape to the
+ *  FP32-FMA kernel; the fused trainer's default), 0 = FP32 FMA everywhere.  GNN_GEMM_PRECISION overrides. */
+inline int default_gemm_precision() {
+    static const int p = [] {
+        const char *e = std::getenv("GNN_GEMM_PRECISION");
+        return e ? std::atoi(e) : 1;
+    }();
+    return p;
+}
 
 // ---- one process per GPU: nodes are 1-D row-partitioned, rank r owns rows [lo, hi) ----------------
 struct Dist {

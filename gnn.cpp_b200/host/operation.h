@@ -326,7 +326,7 @@ template <class T> class LinearOp : public Operation<T> {
     device::buffer_ptr out_; // output buffer kept for the ReLU mask (a buffer, not the tensor: no ownership cycle)
 
   public:
-    int precision = 0;
+    int precision = device::default_gemm_precision(); // round 1 left this at 0 (FP32 FMA): the op-node path ran 83 ms per products-shaped step against the fused trainer's 46
     LinearOp() { this->name = "Linear"; }
     std::shared_ptr<T> forward(const std::shared_ptr<T> &x, const std::shared_ptr<T> &W, const std::shared_ptr<T> &b, bool relu = false) {
         if (x->rank() != 2 || W->rank() != 2 || x->shape()[1] != W->shape()[1]) throw std::runtime_error(err::mm_compatible());
