@@ -490,6 +490,8 @@ def run_ours(args):
                else _dp.comm_bytes_per_step_grid(cfg.N, cfg.dims, world, grid[1]))
         nvlink = {"algorithmic_rx_bytes_per_step": int(alg),
                   "what": "bytes rank 0 receives per step by the partition plan (every needed row once; full halo) vs NVML NVLink payload counters of GPU 0 over the timed region"}
+        if not (nv0 and nv1):
+            nvlink["measured"] = "unavailable: NVML reports the NVLink throughput fields (NVML_FI_DEV_NVLINK_THROUGHPUT_*) as NOT_SUPPORTED on this box"
         if nv0 and nv1:
             nvlink.update({"measured_tx_bytes_per_step": (nv1[0] - nv0[0]) / args.steps, "measured_rx_bytes_per_step": (nv1[1] - nv0[1]) / args.steps,
                            "rx_gbs_over_step": (nv1[1] - nv0[1]) / args.steps / (ms_per_step * 1e-3) / 1e9})

@@ -91,17 +91,19 @@ void *gnn_ctx_stream(gnn_ctx_t *ctx) { return (void *)ctx->stream; }
 int gnn_ctx_sm_count(gnn_ctx_t *ctx) { return ctx->sm_count; }
 int64_t gnn_ctx_launch_count(gnn_ctx_t *ctx) { return ctx->launches; }
 
-// Tensor storage comes from the stream-ordered pool (release threshold = keep everything, see gnn_ctx_create): the op-node
-// path of the C++ surface allocates an output per operation, ~40 per train step — with cudaMalloc / synchronising cudaFree
-// each of them was a device-wide synchronisation; from the pool a steady-state step allocates nothing new.
+// Plain device allocations.  (Serving them from the stream-ordered pool was measured in round 2 and reverted: with
+// multi-GB tensors of many different sizes the pool keeps remapping physical memory — the op-node train step of the C++
+// surface went from a steady 83 ms to an erratic 120-670 ms.  Callers that allocate per operation cache blocks themselves:
+// gnn.cpp_b200/host/device.h keeps freed blocks by size, so a steady-state step allocates nothing.)
 int gnn_malloc(gnn_ctx_t *ctx, void **ptr, size_t bytes) {
     GNN_CHECK_CUDA(cudaSetDevice(ctx->device));
-    GNN_CHECK_CUDA(cudaMallocAsync(ptr, bytes ? bytes : 4, ctx->stream));
+    GNN_CHECK_CUDA(cudaMalloc(ptr, bytes ? bytes : 4));
     return 0;
 }
 int gnn_free(gnn_ctx_t *ctx, void *ptr) {
     if (!ptr) return 0;
-    GNN_CHECK_CUDA(cudaFreeAsync(ptr, ctx->stream)); // ordered after everything already enqueued on the context's stream
+    GNN_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    GNN_CHECK_CUDA(cudaFree(ptr));
     return 0;
 }
 int gnn_memset(gnn_ctx_t *ctx, void *ptr, int value, size_t bytes) {

@@ -9,6 +9,8 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
+#include <vector>
 
 #include "../../include/gnn_c.h"
 
@@ -59,13 +61,45 @@ inline void allreduce_sum(float *dptr, int64_t n) {
     if (dist().active()) check(gnn_allreduce_sum(ctx(), dptr, n));
 }
 
+// Freed tensor blocks, kept by exact size: the autograd path allocates an output per operation (~40 per train step, the
+// same sizes every step), and cudaMalloc / cudaFree each synchronise the device.  Everything in this layer runs on the
+// context's single stream, so a block handed out again is only touched by work enqueued after its previous user.
+struct BlockCache {
+    std::unordered_map<size_t, std::vector<void *>> free_blocks;
+    size_t cached_bytes = 0;
+    static constexpr size_t LIMIT = 96ull << 30; // beyond this, blocks go back to the driver
+    void *take(size_t n) {
+        auto it = free_blocks.find(n);
+        if (it == free_blocks.end() || it->second.empty()) return nullptr;
+        void *p = it->second.back();
+        it->second.pop_back();
+        cached_bytes -= n;
+        return p;
+    }
+    bool give(size_t n, void *p) {
+        if (cached_bytes + n > LIMIT) return false;
+        free_blocks[n].push_back(p);
+        cached_bytes += n;
+        return true;
+    }
+};
+inline BlockCache &block_cache() {
+    static BlockCache *c = new BlockCache(); // intentionally never destroyed: tensors with static lifetime may outlive it
+    return *c;
+}
+
 struct Buffer {
     void *ptr = nullptr;
     size_t bytes = 0;
-    explicit Buffer(size_t n) : bytes(n) { check(gnn_malloc(ctx(), &ptr, n)); }
+    explicit Buffer(size_t n) : bytes(n) {
+        ptr = block_cache().take(n);
+        if (!ptr) check(gnn_malloc(ctx(), &ptr, n));
+    }
     Buffer(const Buffer &) = delete;
     Buffer &operator=(const Buffer &) = delete;
-    ~Buffer() { gnn_free(ctx(), ptr); }
+    ~Buffer() {
+        if (ptr && !block_cache().give(bytes, ptr)) gnn_free(ctx(), ptr);
+    }
 };
 using buffer_ptr = std::shared_ptr<Buffer>;
 inline buffer_ptr alloc(size_t bytes) { return std::make_shared<Buffer>(bytes); }

@@ -49,9 +49,8 @@ GNN_API int gnn_ctx_sm_count(gnn_ctx_t *ctx);
 GNN_API int64_t gnn_ctx_launch_count(gnn_ctx_t *ctx);
 
 /* ---------------------------------------------------------------- storage -------------------------
- * Replaces the heap std::valarray storage of cyg::tensor (reference include/tensor.h:825-828).  gnn_malloc / gnn_free are
- * ordered on the context's stream (stream-ordered memory pool): a buffer may be used by work enqueued after gnn_malloc
- * and is released after the work enqueued before gnn_free; neither call synchronises the device. */
+ * Replaces the heap std::valarray storage of cyg::tensor (reference include/tensor.h:825-828).  gnn_free waits for the
+ * context's stream before releasing the block. */
 GNN_API int gnn_malloc(gnn_ctx_t *ctx, void **ptr, size_t bytes);
 GNN_API int gnn_free(gnn_ctx_t *ctx, void *ptr);
 GNN_API int gnn_memset(gnn_ctx_t *ctx, void *ptr, int value, size_t bytes);
