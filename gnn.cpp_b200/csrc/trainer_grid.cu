@@ -386,6 +386,8 @@ using namespace gnn;
 
 extern "C" {
 
+static int create_grid_impl(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_t *dims, int32_t Pr, int32_t Pc, gnn_gcn *m);
+
 int gnn_gcn_create_grid(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_t *dims, int32_t Pr, int32_t Pc,
                         gnn_gcn_t **out) {
     GNN_REQUIRE(ctx && g && dims && out && L >= 1, "gnn_gcn_create_grid: bad argument");
@@ -402,6 +404,20 @@ int gnn_gcn_create_grid(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const i
     gnn_gcn *m = new gnn_gcn();
     m->g = g; m->L = L; m->grid = true; m->dist = true;
     m->Pr = Pr; m->Pc = Pc; m->gi = gi; m->gj = gj;
+    m->n_glob = N; m->chunk = c; m->grp_rows = g->n_rows;
+    const int rc = create_grid_impl(ctx, g, L, dims, Pr, Pc, m);
+    if (rc) { // nothing half-built survives a failed set-up (every rank fails together: the set-up is collective)
+        const std::string msg = gnn_last_error();
+        gnn_gcn_destroy(ctx, m);
+        set_error("%s", msg.c_str());
+        return rc;
+    }
+    *out = m;
+    return 0;
+}
+
+static int create_grid_impl(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const int32_t *dims, int32_t Pr, int32_t Pc, gnn_gcn *m) {
+    const int64_t N = g->n_cols, c = m->chunk;
     m->n_glob = N; m->chunk = c; m->grp_rows = g->n_rows;
     m->n_loc = std::max<int64_t>(0, std::min<int64_t>(N, (int64_t)(ctx->rank + 1) * c) - std::min<int64_t>(N, (int64_t)ctx->rank * c));
     m->dims.assign(dims, dims + L + 1);
@@ -451,11 +467,7 @@ int gnn_gcn_create_grid(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const i
         }
     m->need_off = aoff;
     aoff += 2 * (size_t)round_up(N, 256); // which node rows this rank's forward / backward structure block reads (setup_halo)
-    const int rc = gnn_peer_arena_create(ctx, aoff, &m->arena);
-    if (rc) { // no CPU or NCCL fallback for this mode: the caller picks the row partition instead
-        gnn_gcn_destroy(ctx, m);
-        return rc;
-    }
+    GNN_TRY(gnn_peer_arena_create(ctx, aoff, &m->arena)); // no NCCL variant of this mode: on failure the caller picks the row partition
     m->H.assign(L + 1, nullptr);
     m->M.assign(L + 1, nullptr);
     for (int32_t l = 1; l <= L; l++) {
@@ -468,7 +480,6 @@ int gnn_gcn_create_grid(gnn_ctx_t *ctx, const gnn_graph_t *g, int32_t L, const i
     for (int32_t l = 1; l <= L; l++) m->H[l] = m->agg_first[l] ? m->H_local[l] : y_region(m, op_of(l, 0));
     GNN_TRY(setup_halo(ctx, m));
     recompute_stats_grid(m);
-    *out = m;
     return 0;
 }
 
