@@ -201,9 +201,31 @@ static int gemm_dispatch(gnn_ctx *ctx, int64_t M, int32_t N, int64_t K, const fl
 int gemm_tc_nt(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B, int64_t ldb,
                float *C, int64_t ldc, const float *bias, int relu);
 int gemm_tc_nn(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B, int64_t ldb,
-               float *C, int64_t ldc, const float *mask, int64_t ldm);
+               float *C, int64_t ldc, const float *mask, int64_t ldm, float *colsum_out = nullptr);
 int gemm_tc_tn(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float *A, int64_t lda, const float *B,
                int64_t ldb, float *C, int64_t ldc);
+
+// dH = (dP W) . [mask > 0] as gnn_gemm_nn, plus db = column sums of the result (the bias gradient of the layer that
+// consumes dH as its dZ): fused into the tensor-core epilogue when the shape allows (*fused = true), otherwise the plain
+// product and the caller sums the columns itself.
+int gemm_nn_bias_grad(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B,
+                      int64_t ldb, float *C, int64_t ldc, const float *mask, int64_t ldm, int precision, float *db,
+                      bool *fused) {
+    *fused = false;
+    static const bool enabled = [] { // TODO(bring-up): default flips to on once the GPU suite has passed with it
+        const char *e = getenv("GNN_FUSED_BIAS_GRAD");
+        return e && atoi(e) != 0;
+    }();
+    if (enabled && precision == 1 && db && M > 0 && N > 0 && K > 0) {
+        const int r = gemm_tc_nn(ctx, M, N, K, A, lda, B, ldb, C, ldc, mask, ldm, db);
+        if (r == 0) {
+            *fused = true;
+            return 0;
+        }
+        if (r > 0) return r;
+    }
+    return gnn_gemm_nn(ctx, M, N, K, A, lda, B, ldb, C, ldc, mask, ldm, precision);
+}
 
 } // namespace gnn
 

@@ -74,12 +74,87 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of one TPC run ONE tcgen05.mma of 256 rows; each
+// CTA stages its own 128 rows of A and only HALF of B in shared memory (the pair's tensor cores exchange the halves), so
+// the per-SM shared-memory traffic of the B operand — TMA fill and MMA reads — is halved.  CTA rank 0 (the leader)
+// issues the MMAs and owns the barriers the other CTA signals remotely.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_shared_cluster_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+// arrive on a barrier that may live in the other CTA of the pair (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// the same with the default (.release.cta) semantics — what CUTLASS' ClusterBarrier::arrive(cta_id) issues; no
+// MEMBAR.GPU in front of the arrive (A/B switch GNN_GEMM_DEBUG bit 8, see pair_arrive)
+__device__ __forceinline__ void mbar_arrive_cluster_light(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// wait on a local barrier whose arrivals come from both CTAs of the pair (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// fence between the generic and the async proxy for every state space (pair mode: the tile this CTA rewrote is consumed
+// by an MMA the OTHER CTA issues)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// A warp of either CTA publishes "my part of this stage is in shared memory, visible to the tensor core" on the
+// leader's barrier.  Default: full-space proxy fence + release at cluster scope (what the PTX memory model asks for when
+// the waiting thread is in the other CTA).  light: shared::cta proxy fence + default-scope arrive.
+__device__ __forceinline__ void pair_publish(uint32_t leader_bar, int lane, bool light) {
+    if (light) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_light(leader_bar);
+    } else {
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_bar);
+    }
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// Pair kernels allocate per CTA with the cta_group::1 forms above (same amount from an empty TMEM in both CTAs -> same
+// columns; the kernels check it).  The cta_group::2 forms (the same warp of BOTH CTAs executes them) are kept behind
+// GNN_GEMM_DEBUG bit 16 for bring-up.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread for the CTA
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -93,6 +168,31 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t 
 // arrives on the mbarrier when every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// pair forms: one MMA over both CTAs' operands (issued by the leader); the commit arrives on the barrier at the same
+// shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+                 :
+                 : "r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(z)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+template <int NCTA> __device__ __forceinline__ void mma_issue(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    if constexpr (NCTA == 2) mma_tf32_pair(d, da, db, idesc, acc);
+    else mma_tf32(d, da, db, idesc, acc);
+}
+template <int NCTA> __device__ __forceinline__ void mma_done(uint32_t bar) {
+    if constexpr (NCTA == 2) mma_commit_pair(bar);
+    else mma_commit(bar);
 }
 // 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base+i), columns c..c+15
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
@@ -163,8 +263,34 @@ struct RowsArgs {
     int relu;
     const float *mask;
     int64_t ldm;
+    // bias gradient fused into the epilogue (TMA epilogue only): per epilogue warp the column sums of the tiles it wrote,
+    // [gridDim.x * 4][256]; a fixed-order pass adds the partials (rows_colsum_final_kernel).  NULL = not wanted.
+    float *colsum_part;
 };
 
+// Column sums over the 32 rows a warp holds (lane = row, x[j] = column j): a butterfly that halves the columns a lane
+// keeps at every step — after 5 steps lane j holds, in x[0], the sum of column j over all 32 lanes.  31 shuffles, fixed
+// order (deterministic).
+__device__ __forceinline__ float warp_column_sums(float (&x)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            const float send = upper ? x[i] : x[i + s];
+            const float keep = upper ? x[i + s] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return x[0];
+}
+
+// NCTA = 1: one CTA per 128-row tile.  NCTA = 2: a CTA pair (cluster of 2, launched with the cluster attribute) per
+// 256-row tile — every CTA runs the same roles on its own 128 rows and its own half of the weights' output columns;
+// only the leader's MMA thread issues (cta_group::2, M = 256).  Barriers signalled by threads of both CTAs (converted
+// tile ready, accumulator drained) live in the leader and count both CTAs' warps; barriers signalled by the tensor core
+// (stage free, accumulator full) are local in each CTA and receive a multicast commit.
+template <int NCTA>
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
     tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmM, const RowsArgs a) {
@@ -181,6 +307,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
     const uint32_t stage0 = bres + a.b_resident;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+    // the leader's copies of the barriers that threads of both CTAs arrive on
+    const uint32_t bar_conv_l = NCTA == 2 ? mapa_shared(bar_conv, 0) : bar_conv;
+    const uint32_t bar_tempty_l = NCTA == 2 ? mapa_shared(bar_tempty, 0) : bar_tempty;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -193,12 +323,12 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
         }
         for (int s = 0; s < a.stages; s++) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_conv + 8 * s, 4);
+            mbar_init(bar_conv + 8 * s, 4 * NCTA);
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 4);
+            mbar_init(bar_tempty + 8 * i, 4 * NCTA);
         }
         fence_barrier_init();
     }
@@ -206,22 +336,34 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
         float *bias_s = reinterpret_cast<float *>(gbase + 1024);
         for (int i = threadIdx.x - 192; i < 256; i += 128) bias_s[i] = (a.bias && i < a.N) ? __ldg(a.bias + i) : 0.f;
     }
-    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+    if (warp == 1) {
+        if (NCTA == 2 && (a.debug & 16)) tmem_alloc_pair(tmem_slot, a.tmem_cols);
+        else tmem_alloc(tmem_slot, a.tmem_cols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (NCTA == 2) cluster_sync_all(); // also: the other CTA's barriers exist before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gbase + 224);
+    if constexpr (NCTA == 2) {
+        // one MMA addresses the accumulator at the same TMEM columns in both CTAs: each CTA allocates the same amount
+        // from an empty TMEM (1 CTA per SM), so the bases agree — anything else must fail loudly
+        if (threadIdx.x == 0 && ld_shared_cluster_u32(mapa_shared(tmem_slot, cta_rank ^ 1u)) != tmem_base) __trap();
+    }
 
-    const int32_t first_tile = blockIdx.x, tile_step = gridDim.x;
+    // tiles are NCTA * 128 rows; this CTA's rows of tile t start at row_of(t)
+    const int32_t first_tile = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
+    auto row_of = [&](int32_t tile) { return (tile * NCTA + (int32_t)cta_rank) * TILE_M; };
+    const int32_t b_row0 = (int32_t)cta_rank * (a.Npad / NCTA); // this CTA's rows of the (hi | lo) weight halves
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            if (a.b_resident) { // the whole split weight matrix, once: [k-block][hi | lo]
+            if (a.b_resident) { // the whole split weight matrix (this CTA's output columns), once: [k-block][hi | lo]
                 mbar_arrive_expect_tx(bar_bres, a.b_resident);
                 for (int32_t kb = 0; kb < a.kblocks; kb++) {
-                    tma_load_2d(bres + kb * 2 * a.b_bytes, &tmB, bar_bres, kb * a.bk, 0);
-                    tma_load_2d(bres + kb * 2 * a.b_bytes + a.b_bytes, &tmB, bar_bres, kb * a.bk, a.Npad);
+                    tma_load_2d(bres + kb * 2 * a.b_bytes, &tmB, bar_bres, kb * a.bk, b_row0);
+                    tma_load_2d(bres + kb * 2 * a.b_bytes + a.b_bytes, &tmB, bar_bres, kb * a.bk, a.Npad + b_row0);
                 }
             }
             const uint32_t tx = a.a_bytes + (a.b_resident ? 0 : 2 * a.b_bytes);
@@ -231,28 +373,35 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     const uint32_t st = stage0 + s * a.stage_bytes;
                     mbar_arrive_expect_tx(bar_full + 8 * s, tx);
-                    tma_load_2d(st, &tmA, bar_full + 8 * s, kb * a.bk, tile * TILE_M);
+                    tma_load_2d(st, &tmA, bar_full + 8 * s, kb * a.bk, row_of(tile));
                     if (!a.b_resident) {
-                        tma_load_2d(st + 2 * a.a_bytes, &tmB, bar_full + 8 * s, kb * a.bk, 0);
-                        tma_load_2d(st + 2 * a.a_bytes + a.b_bytes, &tmB, bar_full + 8 * s, kb * a.bk, a.Npad);
+                        tma_load_2d(st + 2 * a.a_bytes, &tmB, bar_full + 8 * s, kb * a.bk, b_row0);
+                        tma_load_2d(st + 2 * a.a_bytes + a.b_bytes, &tmB, bar_full + 8 * s, kb * a.bk, a.Npad + b_row0);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc(TILE_M, (uint32_t)a.Npad, 0, 0);
+        if (lane == 0 && cta_rank == 0) {
+            const uint32_t idesc = instr_desc(TILE_M * NCTA, (uint32_t)a.Npad, 0, 0);
             uint32_t it = 0, tile_it = 0;
-            if (a.b_resident) mbar_wait(bar_bres, 0);
+            if (NCTA == 1 && a.b_resident) mbar_wait(bar_bres, 0);
             for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step, tile_it++) {
                 const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
+                if constexpr (NCTA == 2) mbar_wait_cluster(bar_tempty + 8 * acc, acc_ph ^ 1);
+                else mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * a.acc_stride;
                 for (int32_t kb = 0; kb < a.kblocks; kb++, it++) {
                     const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
-                    mbar_wait(bar_full + 8 * s, ph);
-                    mbar_wait(bar_conv + 8 * s, ph);
+                    if constexpr (NCTA == 2) {
+                        // the converter warps of BOTH CTAs arrive here, each after it saw its own CTA's stage (A tile
+                        // and weight half) land: one wait covers all four operand tiles of the pair
+                        mbar_wait_cluster(bar_conv + 8 * s, ph);
+                    } else {
+                        mbar_wait(bar_full + 8 * s, ph);
+                        mbar_wait(bar_conv + 8 * s, ph);
+                    }
                     tc_fence_after();
                     const uint32_t st = stage0 + s * a.stage_bytes;
                     // K-major operands: 8-row groups are sbo bytes apart (8 rows x one swizzle row of bk floats)
@@ -264,18 +413,19 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                     const uint64_t b_lo = smem_desc(bst + a.b_bytes, 16, sbo, lay);
                     for (uint32_t k = 0; k < (uint32_t)a.bk / 8; k++) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4); // 8 tf32 = 32 bytes along the swizzled row
-                        mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-                        mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-                        mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+                        mma_issue<NCTA>(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+                        mma_issue<NCTA>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+                        mma_issue<NCTA>(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
                     }
-                    mma_commit(bar_empty + 8 * s);
+                    mma_done<NCTA>(bar_empty + 8 * s);
                 }
-                mma_commit(bar_tfull + 8 * acc);
+                mma_done<NCTA>(bar_tfull + 8 * acc);
             }
         }
     } else if (warp < 6) {
         const int t = threadIdx.x - 64; // 0..127
         uint32_t it = 0;
+        if (NCTA == 2 && a.b_resident) mbar_wait(bar_bres, 0); // pair mode: "converted" also vouches for the weights
         for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step) {
             for (int32_t kb = 0; kb < a.kblocks; kb++, it++) {
                 const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
@@ -287,9 +437,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                     float4 *hp = reinterpret_cast<float4 *>(st) + (i * 128 + t);
                     split4(hp, hp + a.a_bytes / 16);
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+                if constexpr (NCTA == 2) {
+                    pair_publish(bar_conv_l + 8 * s, lane, a.debug & 8);
+                } else {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+                }
             }
         }
     } else if (a.tma_epi) {
@@ -311,10 +465,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
             const int32_t tile = first_tile + (int32_t)(ci / nch) * tile_step;
             const int32_t c0 = (int32_t)(ci % nch) * 32;
             mbar_arrive_expect_tx(mbar + 8 * (ci & 1), 4096);
-            tma_load_2d(msk0 + (uint32_t)(ci & 1) * 4096, &tmM, mbar + 8 * (ci & 1), c0, tile * TILE_M + q * 32);
+            tma_load_2d(msk0 + (uint32_t)(ci & 1) * 4096, &tmM, mbar + 8 * (ci & 1), c0, row_of(tile) + q * 32);
         };
         if (a.mask && lane == 0)
             for (int64_t ci = 0; ci < 2 && ci < total_ch; ci++) issue_mask(ci);
+        float csum[8]; // fused bias gradient: lane j, slot k = running sum of output column 32 k + j over this warp's rows
+#pragma unroll
+        for (int k = 0; k < 8; k++) csum[k] = 0.f;
         int64_t ci = 0;
         uint32_t tile_it = 0;
         for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step, tile_it++) {
@@ -322,7 +479,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
             mbar_wait(bar_tfull + 8 * acc, acc_ph);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * a.acc_stride;
-            const int32_t row0 = tile * TILE_M + q * 32;
+            const int32_t row0 = row_of(tile) + q * 32;
             for (int32_t c0 = 0; c0 < a.Npad; c0 += 32, ci++) {
                 const uint32_t b = (uint32_t)(ci & 1);
                 uint32_t r[32];
@@ -337,7 +494,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                 if (c0 + 32 >= a.Npad) { // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    if (lane == 0) {
+                        if constexpr (NCTA == 2) mbar_arrive_cluster(bar_tempty_l + 8 * acc);
+                        else mbar_arrive(bar_tempty + 8 * acc);
+                    }
                 }
                 // the TMA store issued two chunks ago must have finished reading staging tile b
                 if (lane == 0) bulk_wait_read1();
@@ -362,6 +522,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                         v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
                     }
                     *reinterpret_cast<float4 *>(srow + sw) = v;
+                    if (a.colsum_part) { // keep what was written (rows past M contribute nothing)
+                        r[4 * c] = __float_as_uint(v.x); r[4 * c + 1] = __float_as_uint(v.y);
+                        r[4 * c + 2] = __float_as_uint(v.z); r[4 * c + 3] = __float_as_uint(v.w);
+                    }
                 }
                 fence_proxy_async(); // staging writes (generic proxy) -> visible to the TMA store (async proxy)
                 __syncwarp();
@@ -370,7 +534,23 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                     bulk_commit();
                     if (a.mask && ci + 2 < total_ch) issue_mask(ci + 2); // mask tile b has been consumed by every lane
                 }
+                if (a.colsum_part) {
+                    const bool live = (int64_t)row0 + lane < a.M;
+                    float x[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) x[i] = live ? __uint_as_float(r[i]) : 0.f;
+                    const float colv = warp_column_sums(x, lane);
+                    const int ch = c0 >> 5;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) csum[k] += k == ch ? colv : 0.f;
+                }
             }
+        }
+        if (a.colsum_part) {
+            float *dst = a.colsum_part + ((size_t)blockIdx.x * 4 + q) * 256;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (k * 32 < a.Npad) dst[k * 32 + lane] = csum[k];
         }
         if (lane == 0) bulk_wait_all();
     } else {
@@ -383,7 +563,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
             mbar_wait(bar_tfull + 8 * acc, acc_ph);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * a.acc_stride;
-            const int64_t row0 = (int64_t)tile * TILE_M + q * 32;
+            const int64_t row0 = (int64_t)row_of(tile) + q * 32;
             for (int32_t c0 = 0; c0 < a.Npad; c0 += 32) {
                 uint32_t r[32];
                 const bool two = c0 + 16 < a.Npad;
@@ -393,7 +573,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                 if (c0 + 32 >= a.Npad) { // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    if (lane == 0) {
+                        if constexpr (NCTA == 2) mbar_arrive_cluster(bar_tempty_l + 8 * acc);
+                        else mbar_arrive(bar_tempty + 8 * acc);
+                    }
                 }
                 // phase 1: thread = row, scatter its 32 columns into the warp's staging rows (xor-swizzled chunks)
 #pragma unroll
@@ -460,10 +643,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
     }
 
     tc_fence_before();
-    __syncthreads();
+    __syncwarp(); // the single-lane roles rejoin their warps before the (warp-aligned) barrier
+    if constexpr (NCTA == 2) cluster_sync_all(); // neither CTA's shared memory / TMEM goes away under the other's feet
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, a.tmem_cols);
+        if (NCTA == 2 && (a.debug & 16)) tmem_dealloc_pair(tmem_base, a.tmem_cols);
+        else tmem_dealloc(tmem_base, a.tmem_cols);
     }
 }
 
@@ -480,12 +666,17 @@ constexpr uint32_t BOX_BYTES = TN_BK * 128; // one TMA box: 16 node rows x 32 fl
 
 struct TnArgs {
     int64_t M, nodes_per_cta;
-    int32_t K1, nbB, N, stages;
+    int32_t K1, nbB, N, stages; // nbB = B boxes (32 columns each) staged by ONE CTA; N = MMA width (all of B's columns)
     uint32_t tmem_cols, stage_bytes, hi_bytes;
-    int64_t part_stride; // floats per node split: gridDim.y * 128 * N
-    float *partial;      // [splits][gridDim.y*128][N]
+    int64_t part_stride; // floats per node split: halves * 128 * N
+    float *partial;      // [splits][halves*128][N]
+    uint32_t debug;      // GNN_GEMM_DEBUG bit 8: light pair synchronisation (see pair_publish)
 };
 
+// NCTA = 2 (K1 > 128): the two 128-row halves of the output are a CTA pair (cluster (2,1,1)) on ONE cta_group::2 MMA of
+// M = 256 — each CTA stages and splits its half of A's columns and only HALF of B's columns (NCTA = 1 stages all of B in
+// both halves' CTAs), and keeps its 128 output rows in its own TMEM.
+template <int NCTA>
 __global__ void __launch_bounds__(TN_THREADS, 1)
     tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -498,7 +689,11 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
     const uint32_t stage0 = base + CTRL_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int32_t half = blockIdx.y;
+    // NCTA = 1: grid (node splits, halves).  NCTA = 2: grid (2 * node splits), cluster (2,1,1): rank in the pair = half
+    const int32_t half = NCTA == 2 ? (int32_t)(blockIdx.x & 1) : (int32_t)blockIdx.y;
+    const int32_t split = NCTA == 2 ? (int32_t)(blockIdx.x >> 1) : (int32_t)blockIdx.x;
+    const uint32_t bar_conv_l = NCTA == 2 ? mapa_shared(bar_conv, 0) : bar_conv;
+    const uint32_t bar_tempty_l = NCTA == 2 ? mapa_shared(bar_tempty, 0) : bar_tempty;
     const int32_t colsA = min(128, a.K1 - half * 128);  // output rows of this half
     const int32_t nbA = (colsA + 31) / 32;              // real A boxes (of the 4 the MMA reads)
 
@@ -507,29 +702,38 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
         float4 *z = reinterpret_cast<float4 *>(gbase + CTRL_BYTES);
         const uint32_t n16 = (uint32_t)a.stages * a.stage_bytes / 16;
         for (uint32_t i = threadIdx.x; i < n16; i += TN_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        fence_proxy_async();
+        if constexpr (NCTA == 2) fence_proxy_async_all();
+        else fence_proxy_async();
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < a.stages; s++) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_conv + 8 * s, 8);
+            mbar_init(bar_conv + 8 * s, 8 * NCTA);
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 8);
+            mbar_init(bar_tempty + 8 * i, 8 * NCTA);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+    if (warp == 1) {
+        if (NCTA == 2 && (a.debug & 16)) tmem_alloc_pair(tmem_slot, a.tmem_cols);
+        else tmem_alloc(tmem_slot, a.tmem_cols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (NCTA == 2) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gbase + 224);
+    if constexpr (NCTA == 2) { // see tc_rows_kernel: the pair's accumulators must sit at the same TMEM columns
+        if (threadIdx.x == 0 && ld_shared_cluster_u32(mapa_shared(tmem_slot, (uint32_t)half ^ 1u)) != tmem_base) __trap();
+    }
+    const int32_t b_box0 = NCTA == 2 ? half * a.nbB : 0; // first of B's column boxes this CTA stages
 
-    const int64_t n_begin = (int64_t)blockIdx.x * a.nodes_per_cta;
+    const int64_t n_begin = (int64_t)split * a.nodes_per_cta;
     const int64_t n_end = min(a.M, n_begin + a.nodes_per_cta);
     const int32_t iters = (int32_t)((n_end - n_begin + TN_BK - 1) / TN_BK);
     const int32_t nchunks = (iters + TN_CHUNK - 1) / TN_CHUNK;
@@ -547,23 +751,28 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
                 for (int32_t b = 0; b < nbA; b++)
                     tma_load_2d(st + b * BOX_BYTES, &tmA, bar_full + 8 * s, half * 128 + b * 32, node);
                 for (int32_t b = 0; b < a.nbB; b++)
-                    tma_load_2d(st + A_HI_BYTES + b * BOX_BYTES, &tmB, bar_full + 8 * s, b * 32, node);
+                    tma_load_2d(st + A_HI_BYTES + b * BOX_BYTES, &tmB, bar_full + 8 * s, (b_box0 + b) * 32, node);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc(128, (uint32_t)a.N, 1, 1);
+        if (lane == 0 && (NCTA == 1 || half == 0)) {
+            const uint32_t idesc = instr_desc(128 * NCTA, (uint32_t)a.N, 1, 1);
             int32_t it = 0;
             for (int32_t chunk = 0; chunk < nchunks; chunk++) {
                 const uint32_t accb = chunk & 1, acc_ph = (chunk >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * accb, acc_ph ^ 1);
+                if constexpr (NCTA == 2) mbar_wait_cluster(bar_tempty + 8 * accb, acc_ph ^ 1);
+                else mbar_wait(bar_tempty + 8 * accb, acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + accb * a.N;
                 const int32_t nst = min(TN_CHUNK, iters - chunk * TN_CHUNK);
                 for (int32_t jst = 0; jst < nst; jst++, it++) {
                     const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
-                    mbar_wait(bar_full + 8 * s, ph);
-                    mbar_wait(bar_conv + 8 * s, ph);
+                    if constexpr (NCTA == 2) {
+                        mbar_wait_cluster(bar_conv + 8 * s, ph); // both CTAs' converters, each after its own stage landed
+                    } else {
+                        mbar_wait(bar_full + 8 * s, ph);
+                        mbar_wait(bar_conv + 8 * s, ph);
+                    }
                     tc_fence_after();
                     const uint32_t st = stage0 + s * a.stage_bytes;
                     // MN-major, 32-byte-atom 128-byte swizzle: LBO = distance between 32-float column boxes,
@@ -575,13 +784,13 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
 #pragma unroll
                     for (uint32_t k = 0; k < TN_BK / 8; k++) {
                         const uint64_t adv = (uint64_t)(k * 1024 >> 4); // next group of 8 node rows
-                        mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (jst | k) != 0);
-                        mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-                        mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+                        mma_issue<NCTA>(d_tmem, a_lo + adv, b_hi + adv, idesc, (jst | k) != 0);
+                        mma_issue<NCTA>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+                        mma_issue<NCTA>(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
                     }
-                    mma_commit(bar_empty + 8 * s);
+                    mma_done<NCTA>(bar_empty + 8 * s);
                 }
-                mma_commit(bar_tfull + 8 * accb);
+                mma_done<NCTA>(bar_tfull + 8 * accb);
             }
         }
     } else {
@@ -610,7 +819,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * accb);
+            if (lane == 0) {
+                if constexpr (NCTA == 2) mbar_arrive_cluster(bar_tempty_l + 8 * accb);
+                else mbar_arrive(bar_tempty + 8 * accb);
+            }
         };
 
         int32_t drained = 0;
@@ -625,15 +837,19 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
                 float4 *hp = reinterpret_cast<float4 *>(st + off);
                 split4(hp, hp + a.hi_bytes / 16);
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+            if constexpr (NCTA == 2) {
+                pair_publish(bar_conv_l + 8 * s, lane, a.debug & 8);
+            } else {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+            }
             // chunk `drained` is complete once the pipeline has moved a.stages stages past its end
             if (it + 1 == (drained + 1) * TN_CHUNK + a.stages) drain(drained++);
         }
         while (drained < nchunks) drain(drained++);
 
-        float *orow = a.partial + (size_t)blockIdx.x * a.part_stride + (size_t)(half * 128 + q * 32 + lane) * a.N +
+        float *orow = a.partial + (size_t)split * a.part_stride + (size_t)(half * 128 + q * 32 + lane) * a.N +
                       colhalf * Nh;
 #pragma unroll
         for (int c = 0; c < 32; c++)
@@ -643,10 +859,13 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
     }
 
     tc_fence_before();
-    __syncthreads();
+    __syncwarp();
+    if constexpr (NCTA == 2) cluster_sync_all();
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, a.tmem_cols);
+        if (NCTA == 2 && (a.debug & 16)) tmem_dealloc_pair(tmem_base, a.tmem_cols);
+        else tmem_dealloc(tmem_base, a.tmem_cols);
     }
 }
 
@@ -660,6 +879,15 @@ __global__ void tn_reduce_kernel(const float *__restrict__ partial, int32_t n_pa
     float s = 0.f;
     for (int32_t z = 0; z < n_parts; z++) s += p[(size_t)z * part_stride];
     C[(int64_t)r * ldc + c] = s;
+}
+
+// out[c] = sum over the epilogue warps' partials (ascending) of part[p][c], c < F
+__global__ void rows_colsum_final_kernel(const float *__restrict__ part, int32_t n_parts, int32_t F, float *__restrict__ out) {
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= F) return;
+    float s = 0.f;
+    for (int32_t p = 0; p < n_parts; p++) s += part[(size_t)p * 256 + c];
+    out[c] = s;
 }
 
 // weights -> [2*Npad, Kpad]: rows [0,Npad) = hi, rows [Npad,2Npad) = lo of Bt[n][k], zero padded.
@@ -761,13 +989,44 @@ static uint32_t pow2_cols(uint32_t c) {
 }
 constexpr uint32_t SMEM_MAX = 227 * 1024;
 
+// GNN_GEMM_PAIR: bit 0 = CTA pairs in the rows kernel (NT, NN), bit 1 = in the TN kernel; default both
+static int pair_mask() {
+    const char *e = getenv("GNN_GEMM_PAIR");
+    return e ? atoi(e) : 0; // TODO(bring-up): flips to 3 once the GPU suite has passed with it
+}
+
+// CTA pairs of `fn` (1 CTA per SM, cluster of 2) that can be resident at once: the persistent grids are sized to it.
+// Falls back to SMs / 2 when the occupancy query is not answered.
+static int pair_capacity(gnn_ctx *ctx, const void *fn, cudaLaunchConfig_t *cfg) {
+    struct Entry { const void *fn; int device; size_t smem; int n; };
+    static Entry cache[16];
+    static int cached = 0;
+    for (int i = 0; i < cached; i++)
+        if (cache[i].fn == fn && cache[i].device == ctx->device && cache[i].smem == cfg->dynamicSmemBytes) return cache[i].n;
+    cfg->gridDim = dim3(2 * (unsigned)(ctx->sm_count / 2));
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fn, cfg) != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = ctx->sm_count / 2;
+    }
+    if (n > ctx->sm_count / 2) n = ctx->sm_count / 2;
+    if (n < 1) n = 1;
+    if (getenv("GNN_GEMM_DEBUG_PRINT")) fprintf(stderr, "gemm_tc: %d CTA pairs resident (smem %zu)\n", n, cfg->dynamicSmemBytes);
+    if (cached < 16) cache[cached++] = Entry{fn, ctx->device, cfg->dynamicSmemBytes, n};
+    return n;
+}
+
 // C[M, N] (N <= 256) = A[M,K] * Bt^T with Bt given through `transpose` as in prep_weights_kernel
 static int rows_gemm(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B,
                      int64_t ldb, int transpose, float *C, int64_t ldc, const float *bias, int relu, const float *mask,
-                     int64_t ldm) {
+                     int64_t ldm, float *colsum_out = nullptr) {
     const int32_t Npad = (int32_t)round_up(N, 16), Kpad = (int32_t)round_up(K, BK);
+    const bool lsu_epi = (N % 4 != 0) || (getenv("GNN_GEMM_EPI") && !strcmp(getenv("GNN_GEMM_EPI"), "lsu"));
+    if (colsum_out && lsu_epi) return -1; // the fused column sums live in the TMA epilogue
     void *ws = nullptr;
-    GNN_TRY(ctx->workspace((size_t)2 * Npad * Kpad * 4, &ws));
+    const size_t bs_bytes = (size_t)round_up((int64_t)2 * Npad * Kpad * 4, 256);
+    const size_t part_bytes = colsum_out ? (size_t)ctx->sm_count * 4 * 256 * 4 : 0;
+    GNN_TRY(ctx->workspace(bs_bytes + part_bytes, &ws));
     float *Bs = (float *)ws;
     {
         const int64_t n = (int64_t)Npad * Kpad;
@@ -778,33 +1037,37 @@ static int rows_gemm(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float 
     // 256-wide output leaves room for only 2 stages (96 KB each) and the TMA -> convert -> MMA chain of a stage
     // cannot overlap enough; 16-float k-blocks (64-byte swizzle) halve the stage and double the depth.
     RowsArgs a;
+    // CTA pairs (cta_group::2, 256-row tiles) unless GNN_GEMM_PAIR clears bit 0: each CTA stages half of the weights' output columns
+    const int ncta = !(pair_mask() & 1) || ctx->sm_count < 2 || M <= TILE_M ? 1 : 2;
+    const uint32_t nb = (uint32_t)Npad / ncta; // weight rows (output columns) staged per CTA: a multiple of 8
     // TMA stores clip the tensor edge in 16-byte units (observed: column 47 of a 47-wide, ld 48 output was written),
     // so an output whose width is not a multiple of 4 keeps the per-lane store epilogue with its exact guards
-    a.tma_epi = (N % 4 != 0) || (getenv("GNN_GEMM_EPI") && !strcmp(getenv("GNN_GEMM_EPI"), "lsu")) ? 0 : 1;
+    a.tma_epi = lsu_epi ? 0 : 1;
+    a.colsum_part = colsum_out ? (float *)((uint8_t *)ws + bs_bytes) : nullptr;
     a.epi_bytes = a.tma_epi ? (mask ? 65536u : 32768u) : STAGING_BYTES;
     const uint32_t fixed = 1024 /*align slack*/ + CTRL_BYTES + a.epi_bytes;
     a.bk = BK;
     // Short reductions: the whole split weight matrix (2 * Npad * Kpad floats) stays resident in shared memory and
     // only A is streamed (otherwise every k-block of every tile re-fetches 2 * Npad * bk weights from L2).
-    const uint32_t b_all = 2u * (uint32_t)Npad * (uint32_t)Kpad * 4u;
+    const uint32_t b_all = 2u * nb * (uint32_t)Kpad * 4u;
     const bool resident = Kpad <= 64 && b_all + 3 * (2 * A_TILE_BYTES) <= SMEM_MAX - fixed && !getenv("GNN_GEMM_NO_RESIDENT");
     // 32-float k-blocks unless that leaves fewer than 3 pipeline stages (measured: N=47, K=256 runs 1.06 ms with
     // four 32-float stages and 1.50 ms with 16-float ones; a 256-wide output only fits 16-float stages)
-    const uint32_t stage32 = 2 * A_TILE_BYTES + (resident ? 0 : 2 * (uint32_t)Npad * 128);
+    const uint32_t stage32 = 2 * A_TILE_BYTES + (resident ? 0 : 2 * nb * 128);
     if ((SMEM_MAX - fixed - (resident ? b_all : 0)) / stage32 < 3) a.bk = 16;
     if (getenv("GNN_GEMM_BK")) a.bk = atoi(getenv("GNN_GEMM_BK")) == 16 ? 16 : 32;
     a.a_bytes = (uint32_t)TILE_M * a.bk * 4;
-    a.b_bytes = (uint32_t)Npad * a.bk * 4;
+    a.b_bytes = nb * a.bk * 4;
     a.b_resident = resident ? b_all : 0;
     a.debug = getenv("GNN_GEMM_DEBUG") ? (uint32_t)atoi(getenv("GNN_GEMM_DEBUG")) : 0;
     a.stage_bytes = 2 * a.a_bytes + (resident ? 0 : 2 * a.b_bytes);
     CUtensorMap tmA, tmB;
     const CUtensorMapSwizzle sw = a.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     GNN_TRY(make_map(&tmA, A, M, K, lda, TILE_M, sw, (uint32_t)a.bk));
-    GNN_TRY(make_map(&tmB, Bs, 2 * (int64_t)Npad, Kpad, Kpad, (uint32_t)Npad, sw, (uint32_t)a.bk));
+    GNN_TRY(make_map(&tmB, Bs, 2 * (int64_t)Npad, Kpad, Kpad, nb, sw, (uint32_t)a.bk));
 
     a.M = M; a.N = N; a.Npad = Npad; a.kblocks = Kpad / a.bk;
-    a.num_tiles = (int32_t)ceil_div(M, TILE_M);
+    a.num_tiles = (int32_t)ceil_div(M, TILE_M * ncta);
     int stages = (int)((SMEM_MAX - fixed - a.b_resident) / a.stage_bytes);
     if (stages > 8) stages = 8;
     GNN_REQUIRE(stages >= 2, "gemm_tc: tile does not fit shared memory");
@@ -815,37 +1078,78 @@ static int rows_gemm(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float 
     const uint32_t smem = fixed + a.b_resident + (uint32_t)stages * a.stage_bytes;
     static uint64_t attr_set = 0; // function attributes are per device: one bit per device ordinal
     if (!(attr_set >> (ctx->device & 63) & 1)) {
-        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         attr_set |= 1ull << (ctx->device & 63);
     }
-    const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
     CUtensorMap tmC, tmM;
     GNN_TRY(make_map(&tmC, C, M, N, ldc, 32));
     if (mask) GNN_TRY(make_map(&tmM, mask, M, N, ldm, 32));
     else tmM = tmC;
-    tc_rows_kernel<<<grid, ROWS_THREADS, smem, ctx->stream>>>(tmA, tmB, tmC, tmM, a);
+    int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count; // persistent: one CTA per SM
+    if (ncta == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(ROWS_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int pairs = pair_capacity(ctx, (const void *)tc_rows_kernel<2>, &cfg); // one CTA pair per TPC
+        if (pairs > a.num_tiles) pairs = a.num_tiles;
+        grid = 2 * pairs;
+        cfg.gridDim = dim3((unsigned)grid);
+        GNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_rows_kernel<2>, tmA, tmB, tmC, tmM, a));
+    } else {
+        tc_rows_kernel<1><<<grid, ROWS_THREADS, smem, ctx->stream>>>(tmA, tmB, tmC, tmM, a);
+    }
     GNN_LAUNCHED(ctx);
+    if (colsum_out) {
+        rows_colsum_final_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, ctx->stream>>>(a.colsum_part, grid * 4, N, colsum_out);
+        GNN_LAUNCHED(ctx);
+    }
     return 0;
 }
 
+static uint64_t tn_attr_set = 0; // per-device function attributes of the TN kernels: one bit per device ordinal
 // C[K1, K2 (<=256)] = A[M,K1]^T B[M,K2]
 static int tn_gemm(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float *A, int64_t lda, const float *B,
                    int64_t ldb, float *C, int64_t ldc) {
+    if (!(tn_attr_set >> (ctx->device & 63) & 1)) {
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        tn_attr_set |= 1ull << (ctx->device & 63);
+    }
     TnArgs a;
     a.M = M;
     a.K1 = K1;
     const int32_t halves = (int32_t)ceil_div(K1, 128);
-    a.nbB = (int32_t)ceil_div(K2, 32);
-    a.N = a.nbB * 32;
+    // two halves = one CTA pair (cta_group::2) unless GNN_GEMM_PAIR clears bit 1: each CTA then stages half of B's columns
+    const int ncta = halves == 2 && (pair_mask() & 2) && ctx->sm_count >= 2 ? 2 : 1;
+    a.N = (int32_t)round_up(K2, 32 * ncta);
+    a.nbB = a.N / (32 * ncta);
     a.hi_bytes = (uint32_t)(4 + a.nbB) * BOX_BYTES;
     a.stage_bytes = 2 * a.hi_bytes;
     const uint32_t fixed = 1024 + CTRL_BYTES;
     int stages = (int)((SMEM_MAX - fixed) / a.stage_bytes);
-    if (stages > 6) stages = 6;
+    if (stages > (ncta == 2 ? 8 : 6)) stages = ncta == 2 ? 8 : 6;
     GNN_REQUIRE(stages >= 2, "gemm_tc: tile does not fit shared memory");
     a.stages = stages;
     a.tmem_cols = pow2_cols((uint32_t)(2 * a.N));
     int64_t splits = ctx->sm_count / halves;
+    if (ncta == 2) { // one CTA pair per TPC that can hold one
+        cudaLaunchConfig_t q = {};
+        q.blockDim = dim3(TN_THREADS);
+        q.dynamicSmemBytes = fixed + (uint32_t)stages * a.stage_bytes;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        q.attrs = qa;
+        q.numAttrs = 1;
+        splits = pair_capacity(ctx, (const void *)tc_tn_kernel<2>, &q);
+    }
     if (splits < 1) splits = 1;
     const int64_t max_splits = ceil_div(M, TN_BK);
     if (splits > max_splits) splits = max_splits;
@@ -855,16 +1159,26 @@ static int tn_gemm(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float 
     void *ws = nullptr;
     GNN_TRY(ctx->workspace((size_t)splits * a.part_stride * 4, &ws));
     a.partial = (float *)ws;
+    a.debug = getenv("GNN_GEMM_DEBUG") ? (uint32_t)atoi(getenv("GNN_GEMM_DEBUG")) : 0;
     CUtensorMap tmA, tmB;
     GNN_TRY(make_map(&tmA, A, M, K1, lda, TN_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     GNN_TRY(make_map(&tmB, B, M, K2, ldb, TN_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     const uint32_t smem = fixed + (uint32_t)stages * a.stage_bytes;
-    static uint64_t attr_set = 0;
-    if (!(attr_set >> (ctx->device & 63) & 1)) {
-        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-        attr_set |= 1ull << (ctx->device & 63);
+    if (ncta == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (unsigned)splits);
+        cfg.blockDim = dim3(TN_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        GNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_tn_kernel<2>, tmA, tmB, a));
+    } else {
+        tc_tn_kernel<1><<<dim3((unsigned)splits, (unsigned)halves), TN_THREADS, smem, ctx->stream>>>(tmA, tmB, a);
     }
-    tc_tn_kernel<<<dim3((unsigned)splits, (unsigned)halves), TN_THREADS, smem, ctx->stream>>>(tmA, tmB, a);
     GNN_LAUNCHED(ctx);
     const int64_t n = (int64_t)K1 * K2;
     tn_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(a.partial, (int32_t)splits, a.part_stride, a.N,
@@ -906,7 +1220,7 @@ constexpr int32_t TC_MAX_K = 512;
 int gemm_tc_nt(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B, int64_t ldb,
                float *C, int64_t ldc, const float *bias, int relu) {
     if (!tc::aligned16(A) || !tc::aligned16(C) || (lda & 3) || (ldc & 3)) return -1;
-    if (M >= (1ll << 31) || K > TC_MAX_K) return -1;
+    if (M >= (1ll << 31) - 512 || K > TC_MAX_K) return -1;
     for (int32_t n0 = 0; n0 < N; n0 += 256) { // wider outputs: column panels of 256
         const int32_t nn = N - n0 < 256 ? N - n0 : 256;
         GNN_TRY(tc::rows_gemm(ctx, M, nn, K, A, lda, B + (int64_t)n0 * ldb, ldb, 0, C + n0, ldc, bias ? bias + n0 : nullptr,
@@ -915,15 +1229,18 @@ int gemm_tc_nt(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, in
     return 0;
 }
 
+// colsum_out != NULL: also the column sums of C (the bias gradient of the layer below), from the same epilogue; only for
+// a single 256-column panel with the TMA epilogue — otherwise -1 before anything is launched
 int gemm_tc_nn(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B, int64_t ldb,
-               float *C, int64_t ldc, const float *mask, int64_t ldm) {
+               float *C, int64_t ldc, const float *mask, int64_t ldm, float *colsum_out) {
     if (!tc::aligned16(A) || !tc::aligned16(C) || (lda & 3) || (ldc & 3)) return -1;
+    if (colsum_out && (N > 256 || (N & 3))) return -1;
     if (mask && (!tc::aligned16(mask) || (ldm & 3))) return -1;
-    if (M >= (1ll << 31) || K > TC_MAX_K) return -1;
+    if (M >= (1ll << 31) - 512 || K > TC_MAX_K) return -1;
     for (int32_t n0 = 0; n0 < N; n0 += 256) {
         const int32_t nn = N - n0 < 256 ? N - n0 : 256;
         GNN_TRY(tc::rows_gemm(ctx, M, nn, K, A, lda, B + n0, ldb, 1, C + n0, ldc, nullptr, 0, mask ? mask + n0 : nullptr,
-                              ldm));
+                              ldm, colsum_out));
     }
     return 0;
 }

@@ -230,6 +230,7 @@ static int forward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
 static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
     if (m->grid) return backward_grid(ctx, m, X, ldx);
     const gnn_graph *g = m->g;
+    bool db_fused = false; // db_l already came out of the epilogue of the GEMM that produced dZ_l
     for (int32_t l = m->L; l >= 1; l--) {
         const int32_t Fi = m->dims[l - 1], Fo = m->dims[l];
         const float *W = m->params + m->w_off[l];
@@ -237,12 +238,14 @@ static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
         const float *Hin = l > 1 ? m->H[l - 1] : X;
         const int64_t ld_in = l > 1 ? m->ld[l - 1] : ldx;
         const int op = op_of(l, 1);
+        const bool db_done = db_fused;
+        db_fused = false;
         const Panels Po = panels_of(m, m->ld[l]);                 // panels of dZ_l (width F_l)
         const Panels Pi = panels_of(m, m->ld[l > 1 ? l - 1 : l]); // panels of dZ_{l-1} (width F_{l-1})
         // dZ_{l-1} feeds a transform-first layer's aggregation: produced panel-major and pushed tile by tile
         const bool next_pm = m->arena && l > 1 && !m->agg_first[l - 1];
         const bool dz_pm = m->arena && !m->agg_first[l];
-        for (int p = 0; l < m->L && p < (dz_pm ? Po.n : 1); p++) { // db_L comes out of the loss kernel
+        for (int p = 0; l < m->L && !db_done && p < (dz_pm ? Po.n : 1); p++) { // db_L comes out of the loss kernel
             Prof pr(ctx, m, CLS_BIAS);
             const View dz = dz_view(ctx, m, l, Po, p);
             GNN_TRY(colsum(ctx, m->n_loc, dz_pm ? panel_f(Po, p, Fo) : Fo, dz.ptr, dz.ld, db + (dz_pm ? Po.c0[p] : 0)));
@@ -317,7 +320,13 @@ static int backward(gnn_ctx *ctx, gnn_gcn *m, const float *X, int64_t ldx) {
                     // the remaining row blocks and the dW GEMM below)
                     for (int p2 = 0; p2 < (next_pm ? Pi.n : 1); p2++) {
                         const View dn = dz_view(ctx, m, l - 1, Pi, p2);
-                        if (r1 > r0) {
+                        if (r1 > r0 && !m->arena && m->n_rb == 1) {
+                            // one launch covers all of dZ_{l-1}: its column sums (db_{l-1}) come out of the same epilogue
+                            Prof pr(ctx, m, CLS_GEMM);
+                            GNN_TRY(gemm_nn_bias_grad(ctx, r1 - r0, Fi, Fo, m->S1 + r0 * m->ld[l], m->ld[l], W, Fi, dn.row(r0),
+                                                      dn.ld, Hin + r0 * ld_in, ld_in, m->precision,
+                                                      m->grads + m->b_off[l - 1], &db_fused));
+                        } else if (r1 > r0) {
                             Prof pr(ctx, m, CLS_GEMM);
                             GNN_TRY(gnn_gemm_nn(ctx, r1 - r0, next_pm ? panel_f(Pi, p2, Fi) : Fi, Fo, m->S1 + r0 * m->ld[l],
                                                 m->ld[l], W + (next_pm ? Pi.c0[p2] : 0), Fi, dn.row(r0), dn.ld,

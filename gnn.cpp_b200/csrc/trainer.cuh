@@ -9,6 +9,10 @@
 int gnn_peer_arena_transport(const gnn_peer_arena_t *a); // comm.cu: 1 SM store kernel, 0 copy engines, 2 ncclAllGather
 namespace gnn {
 int colsum(gnn_ctx *ctx, int64_t N, int32_t F, const float *A, int64_t lda, float *out);
+// gemm.cu: gnn_gemm_nn plus db = column sums of the result, fused into the tensor-core epilogue when possible (*fused)
+int gemm_nn_bias_grad(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B,
+                      int64_t ldb, float *C, int64_t ldc, const float *mask, int64_t ldm, int precision, float *db,
+                      bool *fused);
 int softmax_xent_launch(gnn_ctx *ctx, int64_t N, int32_t C, const float *Z, int64_t ldz, const int32_t *y,
                         int64_t n_total, float *loss, float *dZ, int64_t ldd, float *db, bool may_touch_padding);
 int copy2d(gnn_ctx *ctx, float *dst, int64_t ldd, const float *src, int64_t lds, int64_t rows, int32_t cols);
