@@ -59,6 +59,7 @@ struct gnn_ctx {
     int64_t launches = 0;
     int spmm_variant = 0, spmm_tune_u = 0, spmm_tune_pf = 1, spmm_chunk = 0;
     int spmm_alt = 0; // lane mapping for non-power-of-two vector counts (GNN_SPMM_ALT, see spmm_launch)
+    int spmm_async = 0; // FIFO depth of the shared-memory-staged merge kernel for widths <= 128 (GNN_SPMM_ASYNC; 0 = register gathers)
     // grow-only scratch (sort double buffers, scan levels, split-K partials ...)
     void *ws = nullptr;
     size_t ws_bytes = 0;

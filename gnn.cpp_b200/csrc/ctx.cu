@@ -62,6 +62,7 @@ int gnn_ctx_create(int device, void *stream, gnn_ctx_t **out) {
     c->sm_count = prop.multiProcessorCount;
     c->l2_bytes = (size_t)prop.l2CacheSize;
     if (const char *e = getenv("GNN_SPMM_ALT")) c->spmm_alt = atoi(e);
+    if (const char *e = getenv("GNN_SPMM_ASYNC")) c->spmm_async = atoi(e);
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {

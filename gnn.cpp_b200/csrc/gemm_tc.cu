@@ -99,7 +99,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // the same with the default (.release.cta) semantics — what CUTLASS' ClusterBarrier::arrive(cta_id) issues; no
-// MEMBAR.GPU in front of the arrive (A/B switch GNN_GEMM_DEBUG bit 8, see pair_arrive)
+// MEMBAR.GPU in front of the arrive (see pair_publish)
 __device__ __forceinline__ void mbar_arrive_cluster_light(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
@@ -125,10 +125,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 // by an MMA the OTHER CTA issues)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // A warp of either CTA publishes "my part of this stage is in shared memory, visible to the tensor core" on the
-// leader's barrier.  Default: full-space proxy fence + release at cluster scope (what the PTX memory model asks for when
-// the waiting thread is in the other CTA).  light: shared::cta proxy fence + default-scope arrive.
-__device__ __forceinline__ void pair_publish(uint32_t leader_bar, int lane, bool light) {
-    if (light) {
+// leader's barrier, once per pipeline stage.  Default: proxy fence on the CTA's own shared memory (where the tile lives
+// and where the tensor core reads it) + a default-scope remote arrive — the sequence CUTLASS' 2-SM kernels use for
+// operand tiles written by threads.  The formally stronger form (full-space proxy fence + release at cluster scope) puts
+// two MEMBAR.ALL.GPU on the path of every stage and made the pair kernels 1.5x SLOWER than the single-CTA ones
+// (profiles/r2b_gemm_pair.md); it is kept behind GNN_GEMM_DEBUG bit 8 for A/B runs.
+__device__ __forceinline__ void pair_publish(uint32_t leader_bar, int lane, bool heavy) {
+    if (!heavy) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_light(leader_bar);
@@ -146,16 +149,8 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-// Pair kernels allocate per CTA with the cta_group::1 forms above (same amount from an empty TMEM in both CTAs -> same
-// columns; the kernels check it).  The cta_group::2 forms (the same warp of BOTH CTAs executes them) are kept behind
-// GNN_GEMM_DEBUG bit 16 for bring-up.
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
+// The pair kernels also allocate per CTA with these cta_group::1 forms: the same amount from an empty TMEM (one CTA per
+// SM) lands on the same columns in both CTAs, which is what one cta_group::2 MMA needs; the kernels check it and trap.
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread for the CTA
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\t"
@@ -336,10 +331,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
         float *bias_s = reinterpret_cast<float *>(gbase + 1024);
         for (int i = threadIdx.x - 192; i < 256; i += 128) bias_s[i] = (a.bias && i < a.N) ? __ldg(a.bias + i) : 0.f;
     }
-    if (warp == 1) {
-        if (NCTA == 2 && (a.debug & 16)) tmem_alloc_pair(tmem_slot, a.tmem_cols);
-        else tmem_alloc(tmem_slot, a.tmem_cols);
-    }
+    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
     tc_fence_before();
     if constexpr (NCTA == 2) cluster_sync_all(); // also: the other CTA's barriers exist before anything signals them
     else __syncthreads();
@@ -388,7 +380,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
             if (NCTA == 1 && a.b_resident) mbar_wait(bar_bres, 0);
             for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step, tile_it++) {
                 const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
-                if constexpr (NCTA == 2) mbar_wait_cluster(bar_tempty + 8 * acc, acc_ph ^ 1);
+                if (NCTA == 2 && (a.debug & 8)) mbar_wait_cluster(bar_tempty + 8 * acc, acc_ph ^ 1);
                 else mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * a.acc_stride;
@@ -397,7 +389,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                     if constexpr (NCTA == 2) {
                         // the converter warps of BOTH CTAs arrive here, each after it saw its own CTA's stage (A tile
                         // and weight half) land: one wait covers all four operand tiles of the pair
-                        mbar_wait_cluster(bar_conv + 8 * s, ph);
+                        if (a.debug & 8) mbar_wait_cluster(bar_conv + 8 * s, ph);
+                        else mbar_wait(bar_conv + 8 * s, ph);
                     } else {
                         mbar_wait(bar_full + 8 * s, ph);
                         mbar_wait(bar_conv + 8 * s, ph);
@@ -495,7 +488,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if constexpr (NCTA == 2) mbar_arrive_cluster(bar_tempty_l + 8 * acc);
+                        // nothing but "my tcgen05.ld of this accumulator are complete" is published: no memory fence
+                        if constexpr (NCTA == 2) mbar_arrive_cluster_light(bar_tempty_l + 8 * acc);
                         else mbar_arrive(bar_tempty + 8 * acc);
                     }
                 }
@@ -574,7 +568,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if constexpr (NCTA == 2) mbar_arrive_cluster(bar_tempty_l + 8 * acc);
+                        // nothing but "my tcgen05.ld of this accumulator are complete" is published: no memory fence
+                        if constexpr (NCTA == 2) mbar_arrive_cluster_light(bar_tempty_l + 8 * acc);
                         else mbar_arrive(bar_tempty + 8 * acc);
                     }
                 }
@@ -648,8 +643,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        if (NCTA == 2 && (a.debug & 16)) tmem_dealloc_pair(tmem_base, a.tmem_cols);
-        else tmem_dealloc(tmem_base, a.tmem_cols);
+        tmem_dealloc(tmem_base, a.tmem_cols);
     }
 }
 
@@ -670,7 +664,7 @@ struct TnArgs {
     uint32_t tmem_cols, stage_bytes, hi_bytes;
     int64_t part_stride; // floats per node split: halves * 128 * N
     float *partial;      // [splits][halves*128][N]
-    uint32_t debug;      // GNN_GEMM_DEBUG bit 8: light pair synchronisation (see pair_publish)
+    uint32_t debug;      // GNN_GEMM_DEBUG bit 8: cluster-scope release for the pair synchronisation (see pair_publish)
 };
 
 // NCTA = 2 (K1 > 128): the two 128-row halves of the output are a CTA pair (cluster (2,1,1)) on ONE cta_group::2 MMA of
@@ -719,10 +713,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
         }
         fence_barrier_init();
     }
-    if (warp == 1) {
-        if (NCTA == 2 && (a.debug & 16)) tmem_alloc_pair(tmem_slot, a.tmem_cols);
-        else tmem_alloc(tmem_slot, a.tmem_cols);
-    }
+    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
     tc_fence_before();
     if constexpr (NCTA == 2) cluster_sync_all();
     else __syncthreads();
@@ -760,7 +751,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
             int32_t it = 0;
             for (int32_t chunk = 0; chunk < nchunks; chunk++) {
                 const uint32_t accb = chunk & 1, acc_ph = (chunk >> 1) & 1;
-                if constexpr (NCTA == 2) mbar_wait_cluster(bar_tempty + 8 * accb, acc_ph ^ 1);
+                if (NCTA == 2 && (a.debug & 8)) mbar_wait_cluster(bar_tempty + 8 * accb, acc_ph ^ 1);
                 else mbar_wait(bar_tempty + 8 * accb, acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + accb * a.N;
@@ -768,7 +759,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
                 for (int32_t jst = 0; jst < nst; jst++, it++) {
                     const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
                     if constexpr (NCTA == 2) {
-                        mbar_wait_cluster(bar_conv + 8 * s, ph); // both CTAs' converters, each after its own stage landed
+                        // both CTAs' converters arrive here, each after its own stage landed
+                        if (a.debug & 8) mbar_wait_cluster(bar_conv + 8 * s, ph);
+                        else mbar_wait(bar_conv + 8 * s, ph);
                     } else {
                         mbar_wait(bar_full + 8 * s, ph);
                         mbar_wait(bar_conv + 8 * s, ph);
@@ -820,7 +813,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if constexpr (NCTA == 2) mbar_arrive_cluster(bar_tempty_l + 8 * accb);
+                if constexpr (NCTA == 2) mbar_arrive_cluster_light(bar_tempty_l + 8 * accb);
                 else mbar_arrive(bar_tempty + 8 * accb);
             }
         };
@@ -864,8 +857,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        if (NCTA == 2 && (a.debug & 16)) tmem_dealloc_pair(tmem_base, a.tmem_cols);
-        else tmem_dealloc(tmem_base, a.tmem_cols);
+        tmem_dealloc(tmem_base, a.tmem_cols);
     }
 }
 
@@ -992,7 +984,7 @@ constexpr uint32_t SMEM_MAX = 227 * 1024;
 // GNN_GEMM_PAIR: bit 0 = CTA pairs in the rows kernel (NT, NN), bit 1 = in the TN kernel; default both
 static int pair_mask() {
     const char *e = getenv("GNN_GEMM_PAIR");
-    return e ? atoi(e) : 0; // TODO(bring-up): flips to 3 once the GPU suite has passed with it
+    return e ? atoi(e) : 3;
 }
 
 // CTA pairs of `fn` (1 CTA per SM, cluster of 2) that can be resident at once: the persistent grids are sized to it.
@@ -1038,7 +1030,10 @@ static int rows_gemm(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float 
     // cannot overlap enough; 16-float k-blocks (64-byte swizzle) halve the stage and double the depth.
     RowsArgs a;
     // CTA pairs (cta_group::2, 256-row tiles) unless GNN_GEMM_PAIR clears bit 0: each CTA stages half of the weights' output columns
-    const int ncta = !(pair_mask() & 1) || ctx->sm_count < 2 || M <= TILE_M ? 1 : 2;
+    // — which pays where the weight traffic is large: wide outputs whose reduction is too long to keep the weights
+    // resident (measured, ms per launch, single -> pair: K=256,N=256 1.70 -> 1.38; K=100,N=256 0.93 -> 0.93;
+    // K=256,N=47 1.08 -> 1.06; K=47,N=256 (resident) 1.31 -> 1.41)
+    const int ncta = !(pair_mask() & 1) || ctx->sm_count < 2 || M <= TILE_M || Npad < 128 || Kpad <= 64 ? 1 : 2;
     const uint32_t nb = (uint32_t)Npad / ncta; // weight rows (output columns) staged per CTA: a multiple of 8
     // TMA stores clip the tensor edge in 16-byte units (observed: column 47 of a 47-wide, ld 48 output was written),
     // so an output whose width is not a multiple of 4 keeps the per-lane store epilogue with its exact guards

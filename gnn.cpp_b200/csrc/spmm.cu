@@ -327,6 +327,158 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---- variant 2a: the nonzero-balanced walk with the gathers staged through shared memory ----------------------------
+// The one-vector-per-lane widths (F <= 128) are latency-bound gathers: a lane can only keep U = 4 feature-row loads in
+// flight in registers, and every row segment restarts the chain "load (column, value) -> load the rows -> accumulate".
+// Here every lane owns a FIFO of D 16-byte slots in shared memory that it fills with cp.async (LDGSTS: no destination
+// registers, so the depth costs nothing but shared memory) and drains D steps later with a 128-bit shared load.  The
+// fill side ("producer") walks the chunk's nonzeros D steps ahead of the accumulate side ("consumer") ACROSS row
+// boundaries, and streams the (column, value) pairs in chunk order, so the gather pipeline never drains at a row end.
+// Both sides are the same warp and use the same row-aligned step sequence (step = S consecutive nonzeros of one row,
+// one per slot), hence the summation order — and every bit of the result — is that of spmm_merge_kernel.
+// A lane only ever reads back what it copied itself: no barrier of any kind is needed.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+template <int LPR, int D, bool USE_VAL, bool MULTI>
+__global__ void __launch_bounds__(SPMM_THREADS, SPMM_MIN_CTAS_NARROW)
+    spmm_merge_async_kernel(int32_t n_out, int32_t k_base, int32_t nnz, int32_t n_chunks, int32_t MERGE_CHUNK,
+                            const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx, const float *__restrict__ val,
+                            const float *__restrict__ P, int64_t ldp, int32_t F, float *__restrict__ Y,
+                            const __grid_constant__ YDest yd, int64_t ldy, const float *__restrict__ bias, int relu,
+                            const float *__restrict__ mask, int64_t ldm, float *__restrict__ head, float *__restrict__ tail,
+                            int32_t *__restrict__ head_row, int32_t *__restrict__ tail_row, int32_t ldw) {
+    using V = float4;
+    using T = VecTraits<V>;
+    constexpr int S = 32 / LPR;
+    constexpr int GROUPS = SPMM_THREADS / 32;
+    extern __shared__ __align__(16) uint8_t fifo_raw[];
+    float4 *fifo_p = reinterpret_cast<float4 *>(fifo_raw);                         // [D][SPMM_THREADS]
+    float *fifo_a = reinterpret_cast<float *>(fifo_raw + (size_t)D * SPMM_THREADS * 16); // [D][SPMM_THREADS]
+    const int lig = threadIdx.x & 31, sub = lig % LPR, slot = lig / LPR;
+    const int32_t g = blockIdx.x * GROUPS + (threadIdx.x >> 5);
+    if (g >= n_chunks) return;
+    const unsigned gmask = 0xffffffffu;
+    const int nvec = (F + 3) / 4;
+    const int nvec_st = slot == 0 ? nvec : 0;
+    const bool lane_ok = sub < nvec;
+    const int32_t k0 = k_base + g * MERGE_CHUNK, k1 = min(nnz, k0 + MERGE_CHUNK);
+    const uint32_t my_p = (uint32_t)__cvta_generic_to_shared(fifo_p + threadIdx.x);
+
+    int32_t lo = 0, hi = n_out; // invariant: ptr[lo] <= k0 < ptr[hi]
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (__ldg(ptr + mid) <= k0) lo = mid;
+        else hi = mid;
+    }
+    // ---- producer cursor: next step = nonzeros p_k + slot of row p_row, while < p_end (the row's end inside the chunk)
+    int32_t p_row = lo, p_k = k0;
+    int32_t p_end = min(__ldg(ptr + p_row + 1), k1);
+    // (column, value) pairs in chunk order: cur covers [bk, bk + 32), nxt the 32 after it
+    int32_t bk = k0;
+    int32_t cur_c = 0, nxt_c = 0;
+    float cur_a = 1.f, nxt_a = 1.f;
+    if (bk + lig < nnz) {
+        cur_c = ld_stream_i32(idx + bk + lig);
+        if (USE_VAL) cur_a = ld_stream_f32(val + bk + lig);
+    }
+    if (bk + 32 + lig < nnz) {
+        nxt_c = ld_stream_i32(idx + bk + 32 + lig);
+        if (USE_VAL) nxt_a = ld_stream_f32(val + bk + 32 + lig);
+    }
+    auto produce = [&](int fslot) { // one step into FIFO slot fslot — or an empty group once the chunk is exhausted
+        if (p_k < k1) {
+            const int32_t kk = p_k + slot;
+            const bool live = kk < p_end;
+            const int rel = (kk - bk) & 63; // < 40 for live lanes
+            const int32_t c0 = __shfl_sync(gmask, cur_c, rel & 31), c1 = __shfl_sync(gmask, nxt_c, rel & 31);
+            const int32_t c = rel < 32 ? c0 : c1;
+            float a = 1.f;
+            if (USE_VAL) {
+                const float a0 = __shfl_sync(gmask, cur_a, rel & 31), a1 = __shfl_sync(gmask, nxt_a, rel & 31);
+                a = rel < 32 ? a0 : a1;
+            }
+            const bool fetch = live && lane_ok;
+            const float *src = fetch ? P + (int64_t)c * ldp + sub * 4 : P;
+            cp_async16(my_p + (uint32_t)fslot * (SPMM_THREADS * 16), src, fetch ? 16u : 0u); // 0 bytes: the slot is zero-filled
+            fifo_a[fslot * SPMM_THREADS + threadIdx.x] = live ? a : 0.f;
+            p_k += S;
+            if (p_k >= p_end) { // row finished (inside this chunk): the next step starts the next row
+                p_k = p_end;
+                if (p_k < k1) {
+                    p_row++;
+                    if ((p_row & 31) == 0) prefetch_l1(ptr + min(p_row + 32, n_out)); // next line of row pointers
+                    p_end = min(__ldg(ptr + p_row + 1), k1);
+                }
+            }
+            if (p_k - bk >= 32) { // slide the (column, value) window; the batch after next is requested now
+                bk += 32;
+                cur_c = nxt_c;
+                cur_a = nxt_a;
+                if (bk + 32 + lig < nnz) {
+                    nxt_c = ld_stream_i32(idx + bk + 32 + lig);
+                    if (USE_VAL) nxt_a = ld_stream_f32(val + bk + 32 + lig);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    // ---- consumer cursor (same step sequence, D - 1 steps behind)
+    int32_t row = lo, k = k0;
+    int32_t re = __ldg(ptr + row + 1);
+    int32_t seg_end = min(re, k1);
+    bool starts = __ldg(ptr + row) == k0; // only the chunk's first row can have begun in an earlier chunk
+    int32_t hrow = -1, trow = -1;
+    V acc = T::zero();
+#pragma unroll
+    for (int i = 0; i < D - 1; i++) produce(i);
+    int fs = 0; // FIFO slot of the step consumed next
+    while (k < k1) {
+        produce(fs == 0 ? D - 1 : fs - 1); // the slot consumed in the previous iteration
+        cp_async_wait<D - 1>();
+        const float4 pv = fifo_p[fs * SPMM_THREADS + threadIdx.x];
+        const float av = fifo_a[fs * SPMM_THREADS + threadIdx.x];
+        T::fma(acc, av, pv);
+        fs = fs + 1 == D ? 0 : fs + 1;
+        k += S;
+        if (k >= seg_end) { // the row's nonzeros inside this chunk are summed
+            V accv[1] = {acc};
+            reduce_slots<V, LPR, S, 1>(accv, gmask);
+            acc = accv[0];
+            const bool ends = (seg_end == re);
+            if (starts && ends) {
+                float *yrow;
+                if constexpr (MULTI) yrow = yd_row(yd, row, ldy);
+                else yrow = Y + (int64_t)row * ldy;
+                store_row<V, LPR, 1>(accv, yrow, nvec_st, sub, F, bias, relu, mask ? mask + (int64_t)row * ldm : nullptr);
+            } else {
+                float *dst = (ends ? head : tail) + (int64_t)g * ldw;
+                if (ends) hrow = row;
+                else trow = row;
+                if (sub < nvec_st) reinterpret_cast<V *>(dst)[sub] = acc;
+            }
+            acc = T::zero();
+            k = seg_end;
+            starts = true;
+            if (k < k1) {
+                row++;
+                re = __ldg(ptr + row + 1);
+                seg_end = min(re, k1);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (lig == 0) {
+        head_row[g] = hrow;
+        tail_row[g] = trow;
+    }
+}
+
 // nonzeros per warp of the merge kernel; a small launch (e.g. a row block of a partition) is cut finer so that it
 // still spans >= 4 waves of resident warps
 static inline int32_t merge_chunk(const gnn_ctx *ctx, int lpr, int64_t nnz) {
@@ -375,6 +527,46 @@ static int launch_merge(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz
     if (Y.rows_per || Y.row_map) { if (val) MERGE_GO(true, true); else MERGE_GO(false, true); }
     else { if (val) MERGE_GO(true, false); else MERGE_GO(false, false); }
 #undef MERGE_GO
+    GNN_LAUNCHED(ctx);
+    spmm_merge_fixup_kernel<<<(unsigned)ceil_div((int64_t)n_chunks * 32, 256), 256, 0, ctx->stream>>>(
+        n_chunks, F, head, tail, head_row, tail_row, ldw, Y, ldy, bias, relu, mask, ldm);
+    GNN_LAUNCHED(ctx);
+    return 0;
+}
+
+// the shared-memory-staged walk (spmm_merge_async_kernel) for the one-vector-per-lane widths; D = FIFO depth
+template <int LPR, int D>
+static int launch_merge_async(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const int32_t *ptr, const int32_t *idx,
+                              const float *val, const float *P, int64_t ldp, int32_t F, const YDest &Y, int64_t ldy,
+                              const float *bias, int relu, const float *mask, int64_t ldm) {
+    constexpr int GROUPS = SPMM_THREADS / 32;
+    const int32_t MERGE_CHUNK = merge_chunk(ctx, LPR, nnz - k_base);
+    const int32_t n_chunks = (int32_t)ceil_div(nnz - k_base, MERGE_CHUNK);
+    const int32_t ldw = (int32_t)round_up(F, 4);
+    void *ws = nullptr;
+    const size_t part = (size_t)n_chunks * ldw * 4;
+    GNN_TRY(ctx->workspace(2 * part + (size_t)n_chunks * 8 + 64, &ws));
+    float *head = (float *)ws, *tail = head + (size_t)n_chunks * ldw;
+    int32_t *head_row = (int32_t *)(tail + (size_t)n_chunks * ldw), *tail_row = head_row + n_chunks;
+    const unsigned grid = (unsigned)ceil_div(n_chunks, GROUPS);
+    constexpr size_t smem = (size_t)D * SPMM_THREADS * 20;
+    float *Y0 = Y.base[0];
+#define ASYNC_GO(UV, MU)                                                                                            \
+    do {                                                                                                            \
+        auto kern = spmm_merge_async_kernel<LPR, D, UV, MU>;                                                        \
+        static uint64_t attr_set = 0; /* per device ordinal */                                                      \
+        if (!(attr_set >> (ctx->device & 63) & 1)) {                                                                \
+            GNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+            GNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));        \
+            attr_set |= 1ull << (ctx->device & 63);                                                                 \
+        }                                                                                                           \
+        kern<<<grid, SPMM_THREADS, smem, ctx->stream>>>(n_out, (int32_t)k_base, (int32_t)nnz, n_chunks, MERGE_CHUNK, ptr, idx, \
+                                                        val, P, ldp, F, Y0, Y, ldy, bias, relu, mask, ldm, head, tail,     \
+                                                        head_row, tail_row, ldw);                                   \
+    } while (0)
+    if (Y.rows_per || Y.row_map) { if (val) ASYNC_GO(true, true); else ASYNC_GO(false, true); }
+    else { if (val) ASYNC_GO(true, false); else ASYNC_GO(false, false); }
+#undef ASYNC_GO
     GNN_LAUNCHED(ctx);
     spmm_merge_fixup_kernel<<<(unsigned)ceil_div((int64_t)n_chunks * 32, 256), 256, 0, ctx->stream>>>(
         n_chunks, F, head, tail, head_row, tail_row, ldw, Y, ldy, bias, relu, mask, ldm);
@@ -436,9 +628,14 @@ int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const 
         const float *mc = mask ? mask + c0 : nullptr;
 #define GO2(V, LPR, VEC, U, PF)                                                                                      \
     do {                                                                                                             \
-        if (use_merge(ctx, nnz - k_base, nnz, n_out, min_nnz_row, max_nnz_row, LPR))                                       \
-            GNN_TRY((launch_merge<V, LPR, VEC, U, PF>(ctx, n_out, k_base, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \
-        else                                                                                                         \
+        if (use_merge(ctx, nnz - k_base, nnz, n_out, min_nnz_row, max_nnz_row, LPR)) {                                     \
+            if (sizeof(V) == 16 && VEC == 1 && ctx->spmm_async >= 12)                                                \
+                GNN_TRY((launch_merge_async<LPR, 12>(ctx, n_out, k_base, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \
+            else if (sizeof(V) == 16 && VEC == 1 && ctx->spmm_async > 0)                                             \
+                GNN_TRY((launch_merge_async<LPR, 8>(ctx, n_out, k_base, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \
+            else                                                                                                     \
+                GNN_TRY((launch_merge<V, LPR, VEC, U, PF>(ctx, n_out, k_base, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \
+        } else                                                                                                       \
             GNN_TRY((launch_rows<V, LPR, VEC, U, PF>(ctx, n_out, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm)));  \
     } while (0)
 #ifdef GNN_SPMM_TUNE /* experiment build: (U, prefetch) selectable at run time for the float4 kernels */
