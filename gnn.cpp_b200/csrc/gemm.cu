@@ -212,10 +212,8 @@ int gemm_nn_bias_grad(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float
                       int64_t ldb, float *C, int64_t ldc, const float *mask, int64_t ldm, int precision, float *db,
                       bool *fused) {
     *fused = false;
-    static const bool enabled = [] { // GNN_FUSED_BIAS_GRAD=0: separate column-sum kernel (A/B runs)
-        const char *e = getenv("GNN_FUSED_BIAS_GRAD");
-        return !e || atoi(e) != 0;
-    }();
+    const char *e = getenv("GNN_FUSED_BIAS_GRAD"); // =0: separate column-sum kernel (A/B runs, tests)
+    const bool enabled = !e || atoi(e) != 0;
     if (enabled && precision == 1 && db && M > 0 && N > 0 && K > 0) {
         const int r = gemm_tc_nn(ctx, M, N, K, A, lda, B, ldb, C, ldc, mask, ldm, db);
         if (r == 0) {

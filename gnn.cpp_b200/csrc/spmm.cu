@@ -337,6 +337,16 @@ __global__ void __launch_bounds__(256)
 // Both sides are the same warp and use the same row-aligned step sequence (step = S consecutive nonzeros of one row,
 // one per slot), hence the summation order — and every bit of the result — is that of spmm_merge_kernel.
 // A lane only ever reads back what it copied itself: no barrier of any kind is needed.
+//
+// MEASURED (tools/spmm_async_probe.py, products-shaped, 1x B200, ms per launch; profiles/r2b_spmm_async.md): bit-identical
+// at every width, but only the narrowest width gains —
+//   width               16     32     47     64    100    128
+//   register gathers   1.36   1.87   2.99   2.95   5.27   5.27
+//   staged, depth 8    1.26   1.87   3.13   3.09   5.59   5.83      (depth 12, 3 resident CTAs: 1.58 ... 6.29)
+// so doubling the loads in flight does not buy bandwidth: the narrow aggregations are not short of memory-level
+// parallelism (a 192-byte row costs what a 256-byte row costs — the limit is per request, not per byte), and the staged
+// walk pays ~2.7x the instructions per nonzero plus the shared-memory round trip.  NOT the default: kept behind
+// GNN_SPMM_ASYNC=8 (context option) as the recorded shared-memory-staging ablation the north star asks for.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -629,9 +639,7 @@ int spmm_launch(gnn_ctx *ctx, int32_t n_out, int64_t k_base, int64_t nnz, const 
 #define GO2(V, LPR, VEC, U, PF)                                                                                      \
     do {                                                                                                             \
         if (use_merge(ctx, nnz - k_base, nnz, n_out, min_nnz_row, max_nnz_row, LPR)) {                                     \
-            if (sizeof(V) == 16 && VEC == 1 && ctx->spmm_async >= 12)                                                \
-                GNN_TRY((launch_merge_async<LPR, 12>(ctx, n_out, k_base, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \
-            else if (sizeof(V) == 16 && VEC == 1 && ctx->spmm_async > 0)                                             \
+            if (sizeof(V) == 16 && VEC == 1 && ctx->spmm_async > 0)                                                  \
                 GNN_TRY((launch_merge_async<LPR, 8>(ctx, n_out, k_base, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \
             else                                                                                                     \
                 GNN_TRY((launch_merge<V, LPR, VEC, U, PF>(ctx, n_out, k_base, nnz, ptr, idx, val, Pc, ldp, f, Yc, ldy, bc, relu, mc, ldm))); \

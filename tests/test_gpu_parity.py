@@ -348,7 +348,7 @@ def _padded(a, ctx):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 16, 32), (200, 16, 24), (3001, 47, 256), (4099, 256, 100), (1000, 130, 257),
-                                   (777, 3, 64), (20000, 300, 100), (2708, 16, 1433), (40000, 256, 256)])
+                                   (777, 3, 64), (20000, 300, 100), (2708, 16, 1433), (40000, 256, 256), (257, 200, 96)])
 def test_gemms_tensor_core_vs_oracle(ctx, oracle, M, N, K):
     """3xTF32 on tcgen05 (precision=1) against the fp64-accumulate oracle, ragged shapes included; the launch
     counter proves the tensor-core kernels ran (weight split + GEMM, or GEMM + partial reduction = 2 launches)
@@ -388,6 +388,97 @@ def test_gemms_tensor_core_vs_oracle(ctx, oracle, M, N, K):
     assert n == 2 * ((K + 255) // 256)
     assert rel_err(got.cpu().numpy(), dW) <= TOL
     assert torch.equal(got, host.gemm_tn(ctx, dPd, Ad, precision=1))  # deterministic: fixed-order partial sum
+
+
+@pytest.mark.parametrize("M,N,K", [(257, 200, 96), (5000, 256, 256), (33000, 256, 100)])
+def test_gemm_cta_pairs_match_single_cta(ctx, oracle, M, N, K, monkeypatch):
+    """The cta_group::2 kernels (a CTA pair per 256-row tile / per 256 output rows of the TN product, each CTA staging half
+    of the B operand) against the single-CTA kernels on the same inputs: the per-element accumulation order is the same, so
+    the results agree (bitwise on the B200s measured; asserted to 1e-6); (257, ...) leaves the odd CTA of the second tile without any row."""
+    from gnn_cpp_b200 import host
+    import torch
+    rng = np.random.default_rng(M * 7 + N + K)
+    A = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    W = rng.uniform(-1, 1, (N, K)).astype(np.float32)
+    dP = rng.uniform(-1, 1, (M, N)).astype(np.float32)
+    bias = rng.uniform(-1, 1, N).astype(np.float32)
+    Ad, dPd, Wd, bd = _padded(A, ctx), _padded(dP, ctx), _dev(W, ctx), _dev(bias, ctx)
+    res = {}
+    for pair in ("0", "3"):
+        monkeypatch.setenv("GNN_GEMM_PAIR", pair)
+        res[pair] = (host.gemm_nt(ctx, Ad, Wd, bias=bd, relu=True, precision=1).clone(),
+                     host.gemm_nn(ctx, dPd, Wd, mask=Ad, precision=1).clone(),
+                     host.gemm_tn(ctx, dPd, Ad, precision=1).clone())
+    torch.cuda.synchronize()
+    for a, b, what in zip(res["0"], res["3"], ("NT", "NN", "TN")):
+        assert rel_err(b.cpu().numpy(), a.cpu().numpy()) <= 1e-6, "%s: CTA-pair result differs from the single-CTA kernel" % what
+        print("%s M=%d N=%d K=%d: pair == single bitwise: %s" % (what, M, N, K, torch.equal(a, b)))
+    assert rel_err(res["3"][0].cpu().numpy(), oracle.bias_relu(oracle.gemm_nt(A, W, order=1), bias)[1]) <= TOL
+
+
+def test_fused_bias_gradient_matches_column_sum_kernel(ctx, oracle, monkeypatch):
+    """db_l out of the epilogue of the GEMM that writes dZ_l (default) against the separate column-sum kernel
+    (GNN_FUSED_BIAS_GRAD=0): same dZ, different summation order -> equal within rounding; dW and the loss bit-identical."""
+    from gnn_cpp_b200 import host, synth
+    import torch
+    cfg = synth.Config("fused_db", 9000, 90000, [64, 256, 128, 10], True, 77)   # transform-first layers 2 and 3: db_1, db_2 fused
+    p = synth.make_problem(cfg)
+    g = host.Graph.build(ctx, p.src, p.dst, cfg.N)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("GNN_FUSED_BIAS_GRAD", fused)
+        m = host.GCN(ctx, g, cfg.dims)
+        m.set_params(p.W, p.b)
+        l0 = ctx.launches
+        loss = float(m.train_step(torch.from_numpy(p.X).to(ctx.device), torch.from_numpy(p.y).to(ctx.device), 0.0).cpu()[0])
+        out[fused] = (loss, [m.grads(l) for l in range(1, len(cfg.dims))], ctx.launches - l0)
+        m.close()
+    g.close()
+    assert out["1"][0] == out["0"][0]
+    assert out["1"][2] < out["0"][2], "the fused path must launch fewer kernels"
+    for (dW1, db1), (dW0, db0) in zip(out["1"][1], out["0"][1]):
+        assert np.array_equal(dW1, dW0)
+        assert rel_err(db1, db0) <= 1e-6
+
+
+def test_spmm_staged_gathers_bit_identical(oracle):
+    """GNN_SPMM_ASYNC (context option): the nonzero-balanced walk with its gathers staged through per-lane cp.async FIFOs
+    in shared memory sums in the same order as the register-gather merge kernel -> bit-identical, epilogues included."""
+    import os
+    import torch
+    from gnn_cpp_b200 import capi, host
+    from gnn_cpp_b200.host import _ptr
+    old = os.environ.pop("GNN_SPMM_ASYNC", None)
+    c0 = host.Context(0)
+    os.environ["GNN_SPMM_ASYNC"] = "8"
+    c1 = host.Context(0)
+    if old is None:
+        del os.environ["GNN_SPMM_ASYNC"]
+    else:
+        os.environ["GNN_SPMM_ASYNC"] = old
+    try:
+        for c in (c0, c1):
+            capi.call("gnn_set_spmm_variant", c.h, 2)
+        for src, dst, N in [(load_problem("tiny_pl").src, load_problem("tiny_pl").dst, 3000), _hub_problem()]:
+            g = host.Graph.build(c0, src, dst, N)
+            for F in (7, 12, 32, 47, 100, 128):
+                rng = np.random.default_rng(F + N)
+                ld = (F + 3) // 4 * 4
+                P = torch.zeros((N, ld), device=c0.device); P[:, :F] = torch.from_numpy(rng.uniform(-1, 1, (N, F)).astype(np.float32))
+                bias = torch.from_numpy(rng.uniform(-1, 1, F).astype(np.float32)).to(c0.device)
+                mask = torch.zeros((N, ld), device=c0.device); mask[:, :F] = torch.from_numpy(rng.uniform(-1, 1, (N, F)).astype(np.float32))
+                outs = []
+                for c in (c0, c1):
+                    Y = torch.full((N, ld), 7.0, device=c0.device)
+                    capi.call("gnn_spmm_fwd", c.h, g.h, _ptr(P), ld, F, _ptr(Y), ld, _ptr(bias), 1, _ptr(mask), ld, 1)
+                    Z = torch.full((N, ld), 7.0, device=c0.device)
+                    capi.call("gnn_spmm_bwd", c.h, g.h, _ptr(P), ld, F, _ptr(Z), ld, None, 0, 1)
+                    outs.append((Y, Z))
+                torch.cuda.synchronize()
+                assert torch.equal(outs[0][0][:, :F], outs[1][0][:, :F]) and torch.equal(outs[0][1][:, :F], outs[1][1][:, :F]), F
+            g.close()
+    finally:
+        c1.close(); c0.close()
 
 
 @pytest.mark.parametrize("N,C", [(5, 4), (200, 5), (2708, 7), (19717, 3), (5000, 47), (1234, 70)])
