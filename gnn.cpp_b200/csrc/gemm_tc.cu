@@ -205,9 +205,8 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return u;
 }
-// in-place hi, separate lo for one 16-byte vector
-__device__ __forceinline__ void split4(float4 *hi_ptr, float4 *lo_ptr) {
-    const float4 v = *hi_ptr;
+// hi (rounded to TF32) and lo (the rounded remainder) of one 16-byte vector already in registers
+__device__ __forceinline__ void split4_from(const float4 v, float4 *hi_ptr, float4 *lo_ptr) {
     float4 h, l;
     h.x = __uint_as_float(rna_tf32(v.x)); l.x = __uint_as_float(rna_tf32(v.x - h.x));
     h.y = __uint_as_float(rna_tf32(v.y)); l.y = __uint_as_float(rna_tf32(v.y - h.y));
@@ -235,6 +234,18 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 __host__ __device__ constexpr uint32_t instr_desc(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+
+// pipeline position: stage index and phase parity advanced incrementally (a runtime `it % stages` is an integer division
+// on the per-stage path of every warp role — ~25 instructions in the ncu source view)
+struct StagePos {
+    uint32_t s = 0, ph = 0;
+    __device__ __forceinline__ void next(uint32_t stages) {
+        if (++s == stages) {
+            s = 0;
+            ph ^= 1u;
+        }
+    }
+};
 
 // ------------------------------------------------------------------------------------------------ rows kernel
 constexpr int ROWS_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2-5 converters, warps 6-9 epilogue
@@ -350,7 +361,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
+            StagePos pos;
             if (a.b_resident) { // the whole split weight matrix (this CTA's output columns), once: [k-block][hi | lo]
                 mbar_arrive_expect_tx(bar_bres, a.b_resident);
                 for (int32_t kb = 0; kb < a.kblocks; kb++) {
@@ -360,8 +371,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
             }
             const uint32_t tx = a.a_bytes + (a.b_resident ? 0 : 2 * a.b_bytes);
             for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step) {
-                for (int32_t kb = 0; kb < a.kblocks; kb++, it++) {
-                    const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                for (int32_t kb = 0; kb < a.kblocks; kb++, pos.next(a.stages)) {
+                    const uint32_t s = pos.s, ph = pos.ph;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     const uint32_t st = stage0 + s * a.stage_bytes;
                     mbar_arrive_expect_tx(bar_full + 8 * s, tx);
@@ -376,7 +387,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
     } else if (warp == 1) {
         if (lane == 0 && cta_rank == 0) {
             const uint32_t idesc = instr_desc(TILE_M * NCTA, (uint32_t)a.Npad, 0, 0);
-            uint32_t it = 0, tile_it = 0;
+            uint32_t tile_it = 0;
+            StagePos pos;
             if (NCTA == 1 && a.b_resident) mbar_wait(bar_bres, 0);
             for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step, tile_it++) {
                 const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
@@ -384,8 +396,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
                 else mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * a.acc_stride;
-                for (int32_t kb = 0; kb < a.kblocks; kb++, it++) {
-                    const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                for (int32_t kb = 0; kb < a.kblocks; kb++, pos.next(a.stages)) {
+                    const uint32_t s = pos.s, ph = pos.ph;
                     if constexpr (NCTA == 2) {
                         // the converter warps of BOTH CTAs arrive here, each after it saw its own CTA's stage (A tile
                         // and weight half) land: one wait covers all four operand tiles of the pair
@@ -417,18 +429,23 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
         }
     } else if (warp < 6) {
         const int t = threadIdx.x - 64; // 0..127
-        uint32_t it = 0;
+        StagePos pos;
         if (NCTA == 2 && a.b_resident) mbar_wait(bar_bres, 0); // pair mode: "converted" also vouches for the weights
         for (int32_t tile = first_tile; tile < a.num_tiles; tile += tile_step) {
-            for (int32_t kb = 0; kb < a.kblocks; kb++, it++) {
-                const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+            for (int32_t kb = 0; kb < a.kblocks; kb++, pos.next(a.stages)) {
+                const uint32_t s = pos.s, ph = pos.ph;
                 mbar_wait(bar_full + 8 * s, ph);
                 uint8_t *st = gbase + CTRL_BYTES + a.epi_bytes + a.b_resident + (size_t)s * a.stage_bytes;
                 const int nit = (a.debug & 2) ? 0 : a.bk / 4; // 128 x bk floats = 32 bk float4 over 128 threads
-#pragma unroll 4
-                for (int i = 0; i < nit; i++) {
-                    float4 *hp = reinterpret_cast<float4 *>(st) + (i * 128 + t);
-                    split4(hp, hp + a.a_bytes / 16);
+                for (int i0 = 0; i0 < nit; i0 += 4) { // nit is 4 or 8; four loads in flight, then the conversions and stores
+                    float4 raw[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) raw[j] = reinterpret_cast<const float4 *>(st)[(i0 + j) * 128 + t];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float4 *hp = reinterpret_cast<float4 *>(st) + ((i0 + j) * 128 + t);
+                        split4_from(raw[j], hp, hp + a.a_bytes / 16);
+                    }
                 }
                 if constexpr (NCTA == 2) {
                     pair_publish(bar_conv_l + 8 * s, lane, a.debug & 8);
@@ -733,8 +750,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
     if (warp == 0) {
         if (lane == 0) {
             const uint32_t tx = (uint32_t)(nbA + a.nbB) * BOX_BYTES;
-            for (int32_t it = 0; it < iters; it++) {
-                const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+            StagePos pos;
+            for (int32_t it = 0; it < iters; it++, pos.next(a.stages)) {
+                const uint32_t s = pos.s, ph = pos.ph;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 const uint32_t st = stage0 + s * a.stage_bytes;
                 const int32_t node = (int32_t)(n_begin + (int64_t)it * TN_BK);
@@ -748,7 +766,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
     } else if (warp == 1) {
         if (lane == 0 && (NCTA == 1 || half == 0)) {
             const uint32_t idesc = instr_desc(128 * NCTA, (uint32_t)a.N, 1, 1);
-            int32_t it = 0;
+            StagePos pos;
             for (int32_t chunk = 0; chunk < nchunks; chunk++) {
                 const uint32_t accb = chunk & 1, acc_ph = (chunk >> 1) & 1;
                 if (NCTA == 2 && (a.debug & 8)) mbar_wait_cluster(bar_tempty + 8 * accb, acc_ph ^ 1);
@@ -756,8 +774,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + accb * a.N;
                 const int32_t nst = min(TN_CHUNK, iters - chunk * TN_CHUNK);
-                for (int32_t jst = 0; jst < nst; jst++, it++) {
-                    const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+                for (int32_t jst = 0; jst < nst; jst++, pos.next(a.stages)) {
+                    const uint32_t s = pos.s, ph = pos.ph;
                     if constexpr (NCTA == 2) {
                         // both CTAs' converters arrive here, each after its own stage landed
                         if (a.debug & 8) mbar_wait_cluster(bar_conv + 8 * s, ph);
@@ -820,15 +838,32 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
 
         int32_t drained = 0;
         const int32_t nboxes = nbA + a.nbB; // a box is 2 KB = 128 float4
-        for (int32_t it = 0; it < iters; it++) {
-            const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
+        StagePos pos;
+        for (int32_t it = 0; it < iters; it++, pos.next(a.stages)) {
+            const uint32_t s = pos.s, ph = pos.ph;
             mbar_wait(bar_full + 8 * s, ph);
-            uint8_t *st = gbase + CTRL_BYTES + (size_t)s * a.stage_bytes;
-            for (int32_t i = t; i < nboxes * 128; i += 256) {
-                const int32_t b = i >> 7, e = i & 127;
-                const uint32_t off = (b < nbA ? b * BOX_BYTES : A_HI_BYTES + (b - nbA) * BOX_BYTES) + e * 16;
-                float4 *hp = reinterpret_cast<float4 *>(st + off);
-                split4(hp, hp + a.hi_bytes / 16);
+            uint8_t *st = gbase + CTRL_BYTES + (size_t)s * a.stage_bytes + (t & 127) * 16;
+            // thread t converts vector (t & 127) of boxes (t >> 7), (t >> 7) + 2, ...: up to 6 boxes (4 of A + 8 of B over
+            // 256 threads), unrolled so that the shared-memory loads of all of them are in flight together (ncu: the
+            // rolled loop made this warp role a ~100-cycle dependent chain per box, 300 instructions per warp and stage)
+#pragma unroll
+            for (int j0 = 0; j0 < 6; j0 += 2) { // two boxes at a time (more would spill: 168 registers is the cap of 3 warps per scheduler): loads first, then the conversions and stores
+                float4 raw[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int32_t b = (t >> 7) + 2 * (j0 + j);
+                    const uint32_t off = b < nbA ? b * BOX_BYTES : A_HI_BYTES + (b - nbA) * BOX_BYTES;
+                    if (b < nboxes) raw[j] = *reinterpret_cast<const float4 *>(st + off);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int32_t b = (t >> 7) + 2 * (j0 + j);
+                    const uint32_t off = b < nbA ? b * BOX_BYTES : A_HI_BYTES + (b - nbA) * BOX_BYTES;
+                    if (b < nboxes) {
+                        float4 *hp = reinterpret_cast<float4 *>(st + off);
+                        split4_from(raw[j], hp, hp + a.hi_bytes / 16);
+                    }
+                }
             }
             if constexpr (NCTA == 2) {
                 pair_publish(bar_conv_l + 8 * s, lane, a.debug & 8);
