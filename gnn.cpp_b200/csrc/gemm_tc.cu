@@ -1,10 +1,13 @@
 // gemm_tc.cu — tensor-core (tcgen05, 3xTF32) variants of the dense feature transforms K6.
 //
-// Every FP32 operand a is split as a = hi + lo with hi = rna_tf32(a), lo = rna_tf32(a - hi); the product is
-// accumulated in FP32 (TMEM) as  lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  (error ~2^-21, inside the 1e-5 contract;
-// the dropped lo*lo term is ~2^-22).  The big, streamed operand is split ON CHIP: TMA lands the raw FP32 tile in
-// shared memory (128-byte swizzle), four converter warps rewrite it as hi (in place) + lo (second buffer), and one
-// thread issues the tcgen05.mma triple.  The small operand (weights) is pre-split once per call.
+// Every FP32 operand a is split as a = hi + lo; the product is accumulated in FP32 (TMEM) as
+// lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  (error ~2^-20, inside the 1e-5 contract; the dropped lo*lo term is ~2^-21).
+// The small operand (weights) is pre-split once per call with hi = rna_tf32(b), lo = rna_tf32(b - hi).  The big,
+// streamed operand is split ON CHIP: TMA lands the raw FP32 tile in shared memory (128-byte swizzle) and converter
+// warps write lo next to it.  Default (TRUNC): the tensor core only reads the upper 19 bits of a TF32 operand, so the
+// raw tile IS hi = trunc(a) and only lo = a - trunc(a) is written (2 instructions per element); TRUNC = false is the
+// round-to-nearest split (hi rewritten in place; two emulated cvt.rna per element).  One thread issues the tcgen05.mma
+// triple.
 //
 //   rows kernel (NT, NN):  C[M,N] = A[M,K] * Bt[N,K]^T   A streamed by 128-row tiles, persistent CTAs,
 //                          two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1,
@@ -216,6 +219,20 @@ __device__ __forceinline__ void split4_from(const float4 v, float4 *hi_ptr, floa
     *lo_ptr = l;
 }
 
+// Truncating split: the tensor core reads only the upper 19 bits of a TF32 operand, so the raw FP32 tile as TMA landed
+// it already IS the hi operand (hi = v with the low 13 mantissa bits ignored); only lo = v - trunc(v) has to be
+// written (exact in FP32; the tensor core again keeps its upper 11 significand bits).  2 instructions per element
+// instead of two emulated cvt.rna (~5 SASS instructions each) + subtract, and no rewrite of the hi tile.
+// |v - (hi + lo_eff)| < 2^-20 |v|, one-sided (rna: 2^-22, symmetric).
+__device__ __forceinline__ void split4_trunc(const float4 v, float4 *lo_ptr) {
+    float4 l;
+    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    *lo_ptr = l;
+}
+
 // shared-memory matrix descriptor, descriptor version 1 (sm_100).  layout 2 = 128-byte swizzle of 16-byte chunks
 // (TMA SWIZZLE_128B), layout 1 = 128-byte swizzle of 32-byte chunks (TMA SWIZZLE_128B_ATOM_32B) — the only layout
 // the tensor core accepts for MN-major 32-bit operands.
@@ -296,7 +313,7 @@ __device__ __forceinline__ float warp_column_sums(float (&x)[32], int lane) {
 // only the leader's MMA thread issues (cta_group::2, M = 256).  Barriers signalled by threads of both CTAs (converted
 // tile ready, accumulator drained) live in the leader and count both CTAs' warps; barriers signalled by the tensor core
 // (stage free, accumulator full) are local in each CTA and receive a multicast commit.
-template <int NCTA>
+template <int NCTA, bool TRUNC>
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
     tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmM, const RowsArgs a) {
@@ -444,7 +461,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1)
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         float4 *hp = reinterpret_cast<float4 *>(st) + ((i0 + j) * 128 + t);
-                        split4_from(raw[j], hp, hp + a.a_bytes / 16);
+                        if constexpr (TRUNC) split4_trunc(raw[j], hp + a.a_bytes / 16);
+                        else split4_from(raw[j], hp, hp + a.a_bytes / 16);
                     }
                 }
                 if constexpr (NCTA == 2) {
@@ -687,7 +705,7 @@ struct TnArgs {
 // NCTA = 2 (K1 > 128): the two 128-row halves of the output are a CTA pair (cluster (2,1,1)) on ONE cta_group::2 MMA of
 // M = 256 — each CTA stages and splits its half of A's columns and only HALF of B's columns (NCTA = 1 stages all of B in
 // both halves' CTAs), and keeps its 128 output rows in its own TMEM.
-template <int NCTA>
+template <int NCTA, bool TRUNC>
 __global__ void __launch_bounds__(TN_THREADS, 1)
     tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -861,7 +879,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
                     const uint32_t off = b < nbA ? b * BOX_BYTES : A_HI_BYTES + (b - nbA) * BOX_BYTES;
                     if (b < nboxes) {
                         float4 *hp = reinterpret_cast<float4 *>(st + off);
-                        split4_from(raw[j], hp, hp + a.hi_bytes / 16);
+                        if constexpr (TRUNC) split4_trunc(raw[j], hp + a.hi_bytes / 16);
+                        else split4_from(raw[j], hp, hp + a.hi_bytes / 16);
                     }
                 }
             }
@@ -1016,6 +1035,15 @@ static uint32_t pow2_cols(uint32_t c) {
 }
 constexpr uint32_t SMEM_MAX = 227 * 1024;
 
+// GNN_GEMM_SPLIT: 1 (default) = truncating hi/lo split of the streamed operand, 0 = round-to-nearest (two cvt.rna per
+// element).  Measured (profiles/r2b_gemm_pair.md): the eight GEMMs of a products-shaped step 11.00 -> 9.54 ms, the TN
+// kernels (both operands streamed and split) 0.97 / 2.02 / 1.84 -> 0.70 / 1.44 / 1.41 ms; worst error against the fp64
+// oracle 2.6e-6 -> 2.8e-6 (isolated products), 4.5e-6 -> 5.3e-6 (dW_1 of the full train step); bar 1e-5.
+static int split_mode() {
+    const char *e = getenv("GNN_GEMM_SPLIT");
+    return e ? atoi(e) : 1;
+}
+
 // GNN_GEMM_PAIR: bit 0 = CTA pairs in the rows kernel (NT, NN), bit 1 = in the TN kernel; default both
 static int pair_mask() {
     const char *e = getenv("GNN_GEMM_PAIR");
@@ -1090,6 +1118,7 @@ static int rows_gemm(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float 
     a.b_bytes = nb * a.bk * 4;
     a.b_resident = resident ? b_all : 0;
     a.debug = getenv("GNN_GEMM_DEBUG") ? (uint32_t)atoi(getenv("GNN_GEMM_DEBUG")) : 0;
+    const bool trunc = split_mode() != 0;
     a.stage_bytes = 2 * a.a_bytes + (resident ? 0 : 2 * a.b_bytes);
     CUtensorMap tmA, tmB;
     const CUtensorMapSwizzle sw = a.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -1108,8 +1137,10 @@ static int rows_gemm(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float 
     const uint32_t smem = fixed + a.b_resident + (uint32_t)stages * a.stage_bytes;
     static uint64_t attr_set = 0; // function attributes are per device: one bit per device ordinal
     if (!(attr_set >> (ctx->device & 63) & 1)) {
-        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         attr_set |= 1ull << (ctx->device & 63);
     }
     CUtensorMap tmC, tmM;
@@ -1127,13 +1158,16 @@ static int rows_gemm(gnn_ctx *ctx, int64_t M, int32_t N, int32_t K, const float 
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        int pairs = pair_capacity(ctx, (const void *)tc_rows_kernel<2>, &cfg); // one CTA pair per TPC
+        int pairs = pair_capacity(ctx, (const void *)tc_rows_kernel<2, false>, &cfg); // one CTA pair per TPC
         if (pairs > a.num_tiles) pairs = a.num_tiles;
         grid = 2 * pairs;
         cfg.gridDim = dim3((unsigned)grid);
-        GNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_rows_kernel<2>, tmA, tmB, tmC, tmM, a));
+        if (trunc) GNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_rows_kernel<2, true>, tmA, tmB, tmC, tmM, a));
+        else GNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_rows_kernel<2, false>, tmA, tmB, tmC, tmM, a));
+    } else if (trunc) {
+        tc_rows_kernel<1, true><<<grid, ROWS_THREADS, smem, ctx->stream>>>(tmA, tmB, tmC, tmM, a);
     } else {
-        tc_rows_kernel<1><<<grid, ROWS_THREADS, smem, ctx->stream>>>(tmA, tmB, tmC, tmM, a);
+        tc_rows_kernel<1, false><<<grid, ROWS_THREADS, smem, ctx->stream>>>(tmA, tmB, tmC, tmM, a);
     }
     GNN_LAUNCHED(ctx);
     if (colsum_out) {
@@ -1148,8 +1182,10 @@ static uint64_t tn_attr_set = 0; // per-device function attributes of the TN ker
 static int tn_gemm(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float *A, int64_t lda, const float *B,
                    int64_t ldb, float *C, int64_t ldc) {
     if (!(tn_attr_set >> (ctx->device & 63) & 1)) {
-        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        GNN_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         tn_attr_set |= 1ull << (ctx->device & 63);
     }
     TnArgs a;
@@ -1178,7 +1214,7 @@ static int tn_gemm(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float 
         qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
         q.attrs = qa;
         q.numAttrs = 1;
-        splits = pair_capacity(ctx, (const void *)tc_tn_kernel<2>, &q);
+        splits = pair_capacity(ctx, (const void *)tc_tn_kernel<2, false>, &q);
     }
     if (splits < 1) splits = 1;
     const int64_t max_splits = ceil_div(M, TN_BK);
@@ -1190,6 +1226,7 @@ static int tn_gemm(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float 
     GNN_TRY(ctx->workspace((size_t)splits * a.part_stride * 4, &ws));
     a.partial = (float *)ws;
     a.debug = getenv("GNN_GEMM_DEBUG") ? (uint32_t)atoi(getenv("GNN_GEMM_DEBUG")) : 0;
+    const bool trunc = split_mode() != 0;
     CUtensorMap tmA, tmB;
     GNN_TRY(make_map(&tmA, A, M, K1, lda, TN_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     GNN_TRY(make_map(&tmB, B, M, K2, ldb, TN_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
@@ -1205,9 +1242,12 @@ static int tn_gemm(gnn_ctx *ctx, int64_t M, int32_t K1, int32_t K2, const float 
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        GNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_tn_kernel<2>, tmA, tmB, a));
+        if (trunc) GNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_tn_kernel<2, true>, tmA, tmB, a));
+        else GNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_tn_kernel<2, false>, tmA, tmB, a));
+    } else if (trunc) {
+        tc_tn_kernel<1, true><<<dim3((unsigned)splits, (unsigned)halves), TN_THREADS, smem, ctx->stream>>>(tmA, tmB, a);
     } else {
-        tc_tn_kernel<1><<<dim3((unsigned)splits, (unsigned)halves), TN_THREADS, smem, ctx->stream>>>(tmA, tmB, a);
+        tc_tn_kernel<1, false><<<dim3((unsigned)splits, (unsigned)halves), TN_THREADS, smem, ctx->stream>>>(tmA, tmB, a);
     }
     GNN_LAUNCHED(ctx);
     const int64_t n = (int64_t)K1 * K2;

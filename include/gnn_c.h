@@ -154,7 +154,11 @@ GNN_API int gnn_set_spmm_variant(gnn_ctx_t *ctx, int variant);
  *   gnn_gemm_nn: C[M,N] = A[M,K] * B[K,N] (mask)                — MatMul::_backward lhs branch, operation.h:516-523
  *   gnn_gemm_tn: C[K1,K2] = A[M,K1]^T * B[M,K2]                 — rhs branch + Transpose::_backward,
  *                                                                  operation.h:524-531,416-433 (fixed-order split over M)
- * precision: 0 = FP32 FMA (CUDA cores), 1 = 3xTF32 on tcgen05 tensor cores (error ~2^-21, inside 1e-5). */
+ * precision: 0 = FP32 FMA (CUDA cores), 1 = 3xTF32 on tcgen05 tensor cores (error ~2^-21, inside 1e-5); wide products
+ * (N >= 128 with K > 64; K1 > 128 for gnn_gemm_tn) run on CTA pairs (tcgen05.mma.cta_group::2, clusters of 2), with
+ * results bit-identical to the single-CTA kernels.  Environment switches for A/B runs: GNN_GEMM_PAIR (bit 0 NT/NN,
+ * bit 1 TN; default 3), GNN_FUSED_BIAS_GRAD=0 (fused trainer: separate bias-gradient kernel), GNN_SPMM_ASYNC=8
+ * (read at gnn_ctx_create: aggregation gathers staged through shared memory, an ablation). */
 GNN_API int gnn_gemm_nt(gnn_ctx_t *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B,
                         int64_t ldb, float *C, int64_t ldc, const float *bias, int relu, int precision);
 GNN_API int gnn_gemm_nn(gnn_ctx_t *ctx, int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *B,
