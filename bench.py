@@ -478,7 +478,7 @@ def run_ours(args):
                 fl = 2.0 * n_loc * fi * fo * 3                      # three TF32 MMAs per product
                 h, c = by / (peak * 1e9) * 1e3, fl / (tf32.value * 1e12) * 1e3
                 hbm_ms += h; mma_ms += c; floor_ms += max(h, c)
-        gemm_roof = {"kernels": "tc_rows_kernel / tc_tn_kernel (tcgen05 3xTF32), %d launches per step" % (3 * L - 1),
+        gemm_roof = {"kernels": "tc_rows_kernel / tc_tn_kernel (tcgen05 3xTF32; bias gradients fused into the NN epilogues on 1 GPU), %d launches per step" % (3 * L - 1),
                      "ms": bd["gemm"], "floor_ms": floor_ms, "frac": floor_ms / bd["gemm"], "hbm_floor_ms": hbm_ms,
                      "mma_floor_ms": mma_ms, "tf32_peak_tflops_measured": tf32.value,
                      "how": "floor = sum over launches of max(operand+output bytes / HBM peak, 3 * 2MNK / measured TF32 peak)"}
@@ -505,7 +505,7 @@ def run_ours(args):
         cfgd.update({"parallelism": ("%s x%d, %s + NCCL grad all-reduce" % ("1-D row partition" if grid is None else "activations 1-D row-partitioned, aggregation %d x %d" % grid, world, model.exchange_desc())) if world > 1 else "single GPU",
                      "l2_policy": "working set (feature matrices %.1f GB) larger than L2; no flush needed" % (cfg.N * max(cfg.dims) * 4 / 1e9)
                      if cfg.N * max(cfg.dims) * 4 > 2.5e8 else "small working set (L2-resident): launch-bound config",
-                     "gemm_precision": "fp32 FMA" if args.precision == 0 else "3xTF32 tcgen05",
+                     "gemm_precision": "fp32 FMA" if args.precision == 0 else "3xTF32 tcgen05 (CTA pairs, cta_group::2, on the wide products; truncating hi/lo split of the streamed operand)",
                      "exchange": model.exchange_stats() if grid is not None else None, "spmm_launches_per_step": st["n_spmm"], "structure_build_ms": build_ms, "structure_build_warm_ms": build_warm_ms, "final_loss": final_loss})
         line = {"metric": "gcn_train_step_ms", "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",

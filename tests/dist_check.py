@@ -104,8 +104,11 @@ def main():
                 st = m.exchange_stats()
                 if rank == 0:
                     print("[dist_check] local: %s" % st, flush=True)
-                if os.environ.get("GNN_HALO") is None and os.environ.get("GNN_SPLIT") is None:
+                if os.environ.get("GNN_HALO") is None and os.environ.get("GNN_SPLIT") is None and grid[0] > 1:
+                    # with ONE row group (1 x P) every rank's structure block spans all rows and needs every row of its
+                    # column slice: halo fraction 1.0 by construction, nothing to assert
                     ok &= st["halo_only_exchange"] and st["halo_fraction"] < 0.9   # (2 row groups of 4 ranks: 0.58; rows x 1: 0.03-0.09)
+                if os.environ.get("GNN_HALO") is None and os.environ.get("GNN_SPLIT") is None:
                     ok &= st["interior_boundary_split"] == (st["interior_fraction"] >= 0.1)
             if cfg.name == "mid_pl":
                 ok &= check_big(ctx, m, p, cfg, X, yb, lo, hi, rank, world, grid)
