@@ -5,7 +5,7 @@
 // The small operand (weights) is pre-split once per call with hi = rna_tf32(b), lo = rna_tf32(b - hi).  The big,
 // streamed operand is split ON CHIP: TMA lands the raw FP32 tile in shared memory (128-byte swizzle) and converter
 // warps write lo next to it.  Default (TRUNC): the tensor core only reads the upper 19 bits of a TF32 operand, so the
-// raw tile IS hi = trunc(a) and only lo = a - trunc(a) is written (2 instructions per element); TRUNC = false is the
+// raw tile IS hi = trunc(a) and only lo = rna_tf32(a - trunc(a)) is written (3 instructions per element); TRUNC = false is the
 // round-to-nearest split (hi rewritten in place; two emulated cvt.rna per element).  One thread issues the tcgen05.mma
 // triple.
 //
@@ -220,17 +220,18 @@ __device__ __forceinline__ void split4_from(const float4 v, float4 *hi_ptr, floa
 }
 
 // Truncating split: the tensor core reads only the upper 19 bits of a TF32 operand, so the raw FP32 tile as TMA landed
-// it already IS the hi operand (hi = v with the low 13 mantissa bits ignored); only lo = v - trunc(v) has to be
-// written (exact in FP32; the tensor core again keeps its upper 11 significand bits).  2 instructions per element
-// instead of two emulated cvt.rna (~5 SASS instructions each) + subtract, and no rewrite of the hi tile.
-// |v - (hi + lo_eff)| < 2^-20 |v|, one-sided (rna: 2^-22, symmetric).
+// it already IS the hi operand (hi = trunc(v): the low 13 mantissa bits are ignored); only lo has to be written.
+// d = v - trunc(v) is exact in FP32; adding 0x1000 to its bit pattern makes the hardware's truncation of lo a
+// round-to-nearest (ties away), so lo = rna_tf32(d) for one integer add.  3 instructions per element instead of two
+// emulated cvt.rna (~5 SASS instructions each) + subtract, and no rewrite of the hi tile.
+// |v - (hi + lo)| <= 2^-21 |v|, zero-mean (round-to-nearest split: 2^-22).  (d = 0 -> 0x1000, which the tensor core
+// reads as 0; a non-finite v leaves hi non-finite, which is what propagates.)
+__device__ __forceinline__ float lo_of(float v) {
+    const float d = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    return __uint_as_float(__float_as_uint(d) + 0x1000u);
+}
 __device__ __forceinline__ void split4_trunc(const float4 v, float4 *lo_ptr) {
-    float4 l;
-    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-    *lo_ptr = l;
+    *lo_ptr = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
 }
 
 // shared-memory matrix descriptor, descriptor version 1 (sm_100).  layout 2 = 128-byte swizzle of 16-byte chunks
