@@ -1,5 +1,5 @@
-"""bench.py contract checks that need no GPU: the JSON line of the last measured run (profiles/r2_bench_products_1gpu.json)
-carries every key the driver reads, and the reference arm (`--impl reference`) runs on host cores alone."""
+"""bench.py contract checks that need no GPU: the JSON lines of the last measured runs (profiles/r2b_bench_products_1gpu.json,
+the final library; profiles/r2_bench_products_1gpu.json, first session of round 2) carry every key the driver reads, and the reference arm (`--impl reference`) runs on host cores alone."""
 import json
 import os
 import subprocess
@@ -22,8 +22,12 @@ def _check_common(d):
     assert d["cpu_baseline"]["kind"] in ("reference", "port")
 
 
-def test_last_measured_line_has_the_contract_keys():
-    with open(os.path.join(ROOT, "profiles", "r2_bench_products_1gpu.json")) as f:
+import pytest
+
+
+@pytest.mark.parametrize("name", ["r2b_bench_products_1gpu.json", "r2_bench_products_1gpu.json"])
+def test_last_measured_line_has_the_contract_keys(name):
+    with open(os.path.join(ROOT, "profiles", name)) as f:
         d = json.loads(f.read().strip().splitlines()[-1])
     _check_common(d)
     r = d["roofline"]
@@ -46,7 +50,6 @@ def test_last_measured_line_has_the_contract_keys():
 def test_reference_arm_runs_on_host_cores():
     """`bench.py --impl reference --config cora`: the REAL reference binary (oracle/_ref/ref_gcn), one dense step"""
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_gcn")):
-        import pytest
         pytest.skip("oracle/_ref/ref_gcn not built")
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "cora",
                                    "--steps", "1", "--warmup", "0"], text=True, timeout=600)
